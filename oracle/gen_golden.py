@@ -1,0 +1,247 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference on CPU.  TEST INFRASTRUCTURE.
+
+Run in the build container (needs /root/reference):  ``python -m oracle.gen_golden``
+Every case: inputs from ``oracle/cases.py``, weights from ``oracle.restate.make_state_dicts``
+loaded into the reference modules with strict key checking, reference outputs stored (fp32,
+small).  The script also asserts that the oracle restatement reproduces each output, so a
+golden file is only ever written from a run in which oracle == reference.
+"""
+import os
+import random
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from oracle import cases, ref_harness, restate as R                     # noqa: E402
+from scene_generation_b200 import synthetic                             # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+
+
+def close(a, b, tol, name):
+    err = (a - b).abs().max().item()
+    scale = max(b.abs().max().item(), 1e-6)
+    print('  %-34s max|diff| %.3e (max|ref| %.3e)' % (name, err, scale))
+    assert err <= tol * max(scale, 1.0), (name, err)
+
+
+def ops_golden():
+    ref = ref_harness.modules()
+    torch.manual_seed(0)
+    cfg = cases.CFG_SMALLG
+    sds = R.make_state_dicts(cfg, seed=11)
+    sg = sds['g']
+    vocab = synthetic.make_vocab(cfg['num_objs'])
+    g = {}
+
+    # ---- graph.py ------------------------------------------------------------------
+    for tag, batch in (('cfg1', cases.cfg1_batch()), ('ragged', cases.ragged_batch())):
+        imgs, objs, boxes, masks, triples, o2i, t2i, attrs = batch
+        conv1 = ref.graph.GraphTripleConv(128, attributes_dim=35, output_dim=128, hidden_dim=512)
+        ref_harness.load(conv1, {k[len('gconv.'):]: v for k, v in sg.items() if k.startswith('gconv.')})
+        net = ref.graph.GraphTripleConvNet(128, num_layers=4, hidden_dim=512)
+        ref_harness.load(net, {k[len('gconv_net.'):]: v for k, v in sg.items() if k.startswith('gconv_net.')})
+        s, p, o = triples[:, 0], triples[:, 1], triples[:, 2]
+        edges = torch.stack([s, o], dim=1)
+        ov = torch.cat([sg['obj_embeddings.weight'][objs], attrs], dim=1)
+        pv = sg['pred_embeddings.weight'][p]
+        with torch.no_grad():
+            o1, p1 = conv1(ov, pv, edges)
+            o5, p5 = net(o1, p1, edges)
+            mo, mp = R.scene_graph_to_vectors(sg, objs, triples, attrs)
+        close(mo, o5, 1e-5, 'gconv obj ' + tag)
+        close(mp, p5, 1e-5, 'gconv pred ' + tag)
+        g['gconv_%s_obj1' % tag], g['gconv_%s_pred1' % tag] = o1, p1
+        g['gconv_%s_obj5' % tag], g['gconv_%s_pred5' % tag] = o5, p5
+
+    # ---- layout.py -----------------------------------------------------------------
+    vecs, boxes, masks, o2i = cases.layout_literals()
+    with torch.no_grad():
+        lit = ref.layout.masks_to_layout(vecs, boxes, masks, o2i, 24, 20)
+        lit_t = ref.layout.masks_to_layout(vecs, boxes, masks, o2i, 24, 20, test_mode=True)
+    close(R.masks_to_layout(vecs, boxes, masks, o2i, 24, 20), lit, 1e-5, 'layout literals')
+    close(R.masks_to_layout(vecs, boxes, masks, o2i, 24, 20, test_mode=True), lit_t, 1e-5, 'layout literals test')
+    g['layout_lit'], g['layout_lit_test'] = lit, lit_t
+    imgs, objs, boxes, masks, triples, o2i, t2i, attrs = cases.ragged_batch()
+    lv = cases.rand((objs.numel(), 42), 3)
+    pm = cases.rand((objs.numel(), 32, 32), 4, 0.0, 1.0)
+    with torch.no_grad():
+        l1 = ref.layout.masks_to_layout(lv, boxes, masks, o2i, 32, 32)
+        l2 = ref.layout.masks_to_layout(lv, boxes, pm, o2i, 32, 32)
+        l3 = ref.layout.masks_to_layout(lv, boxes, masks, o2i, 32, 32, test_mode=True)
+    close(R.masks_to_layout(lv, boxes, masks, o2i, 32), l1, 1e-5, 'layout ragged int masks')
+    close(R.masks_to_layout(lv, boxes, pm, o2i, 32), l2, 1e-5, 'layout ragged float masks')
+    close(R.masks_to_layout(lv, boxes, masks, o2i, 32, test_mode=True), l3, 1e-5, 'layout ragged test_mode')
+    g['layout_ragged_int'], g['layout_ragged_float'], g['layout_ragged_test'] = l1, l2, l3
+
+    # ---- bilinear.py ---------------------------------------------------------------
+    feats, bb, b2f = cases.crop_literals()
+    with torch.no_grad():
+        c1 = ref.bilinear.crop_bbox_batch(feats, bb, b2f, 8, 6)
+    close(R.crop_bbox_batch(feats, bb, b2f, 8, 6), c1, 1e-5, 'crop literals (perm)')
+    g['crop_lit'] = c1
+    with torch.no_grad():
+        c2 = ref.bilinear.crop_bbox_batch(imgs, boxes, o2i, 32)
+    close(R.crop_bbox_batch(imgs, boxes, o2i, 32), c2, 1e-5, 'crop ragged')
+    g['crop_ragged'] = c2
+
+    # ---- generators.py -------------------------------------------------------------
+    with ref_harness.pretend_cuda():
+        G = ref.generators.define_G(42, 3, cfg['ngf'], 4, cfg['n_blocks'], 'instance')
+    ref_harness.load(G, {k[len('layout_to_image.'):]: v for k, v in sg.items() if k.startswith('layout_to_image.')})
+    x = cases.rand((2, 42, 64, 64), 5, 0.0, 1.0)
+    with torch.no_grad():
+        y = G(x)
+    close(R.global_generator(sg, x, n_blocks=cfg['n_blocks']), y, 1e-4, 'GlobalGenerator (ngf 8)')
+    g['generator_small'] = y
+    mn = ref.generators.mask_net(192, 32)
+    ref_harness.load(mn, {k[len('mask_net.'):]: v for k, v in sg.items() if k.startswith('mask_net.')})
+    mn.train()
+    mv = cases.rand((8, 192), 6)
+    with torch.no_grad():
+        ms = mn(mv.view(8, 192, 1, 1))
+    sd_copy = {k: v.clone() for k, v in sg.items()}
+    close(R.mask_net(sd_copy, mv, update=True), ms, 1e-4, 'mask_net (train BN)')
+    close(sd_copy['mask_net.2.running_var'], mn.state_dict()['2.running_var'], 1e-5, 'mask_net BN running_var')
+    g['mask_net'] = ms
+    g['mask_net_running_var'] = mn.state_dict()['2.running_var'].clone()
+    enc = ref.generators.AppearanceEncoder(vocab, 'C4-64-2,C4-128-2,C4-256-2', normalization='batch',
+                                           activation='leakyrelu-0.2', padding='valid', vecs_size=192)
+    ref_harness.load(enc, {k[len('image_encoder.'):]: v for k, v in sg.items() if k.startswith('image_encoder.')})
+    enc.train()
+    cr = cases.rand((8, 3, 64, 64), 8)
+    with torch.no_grad():
+        ev = enc(cr)
+    close(R.appearance_encoder(sg, cr), ev, 1e-4, 'AppearanceEncoder')
+    g['appearance_encoder'] = ev
+
+    # ---- discriminators.py ---------------------------------------------------------
+    objD = ref.discriminators.AcCropDiscriminator(vocab, 'C4-64-2,C4-128-2,C4-256-2', 'batch', 'leakyrelu-0.2',
+                                                  object_size=32, padding='valid')
+    ref_harness.load(objD, sds['obj'])
+    objD.train()
+    with torch.no_grad():
+        rs, ac, crops = objD(imgs, objs, boxes, o2i)
+    mrs, mac, mcrops = R.ac_crop_discriminator(sds['obj'], imgs, objs, boxes, o2i)
+    close(mrs, rs, 1e-4, 'AcCropDiscriminator scores')
+    close(mac.view(1), ac.view(1), 1e-4, 'AcCropDiscriminator ac_loss')
+    g['objd_scores'], g['objd_ac'] = rs, ac
+    with ref_harness.pretend_cuda():
+        netD = ref.discriminators.define_D(45, 64, 3, 'instance', False, 2)
+        maskD = ref.discriminators.define_mask_D(1, 64, 2, 'instance', False, 1, 10)
+    ref_harness.load(netD, sds['img'])
+    ref_harness.load(maskD, sds['mask'])
+    xin = cases.rand((2, 45, 64, 64), 9)
+    with torch.no_grad():
+        fd = netD(xin)
+    md = R.multiscale_discriminator(sds['img'], xin)
+    for i in range(2):
+        for j in range(5):
+            close(md[i][j], fd[i][j], 1e-4, 'netD scale-slot %d feat %d' % (i, j))
+            g['netD_%d_%d' % (i, j)] = fd[i][j]
+    oh = R.one_hot(objs, 10)
+    with torch.no_grad():
+        fm = maskD(pm.unsqueeze(1), oh)
+    mm = R.mask_discriminator(sds['mask'], pm.unsqueeze(1), oh)
+    for j in range(4):
+        close(mm[0][j], fm[0][j], 1e-4, 'maskD feat %d' % j)
+        g['maskD_%d' % j] = fm[0][j]
+    torch.save({k: v.clone() for k, v in g.items()}, os.path.join(OUT, 'ops.pt'))
+    print('wrote ops.pt (%d tensors)' % len(g))
+
+
+def _param_close(mine, ref, name, lr=1e-4):
+    """After one Adam step every element moved by ~lr*sign(grad) (first step: m/sqrt(v) = +-1), so
+    elements whose true gradient is ~0 (e.g. conv biases in front of a norm layer) can legitimately land
+    2*lr apart.  Check: nothing differs by more than 2.2*lr and the bulk agrees to 2e-6."""
+    d = (mine.float() - ref.float()).abs()
+    frac = (d <= 2e-6).float().mean().item()
+    print('  %-52s max %.2e  frac(<=2e-6) %.4f' % (name, d.max().item(), frac))
+    assert d.max().item() <= 2.2 * lr + 1e-6, name
+    return frac
+
+
+STEP_PARAMS = {
+    'g': ['gconv.net1.0.weight', 'gconv_net.gconvs.3.net2.2.weight', 'box_net.2.bias', 'mask_net.1.weight',
+          'mask_net.2.running_mean', 'mask_net.2.running_var', 'image_encoder.cnn.0.0.weight',
+          'image_encoder.cnn.0.1.running_var', 'repr_net.2.weight', 'layout_to_image.model.38.weight',
+          'layout_to_image.model.38.bias'],
+    'obj': ['discriminator.cnn.0.1.running_var', 'discriminator.real_classifier.weight',
+            'discriminator.obj_classifier.bias'],
+    'mask': ['scale0_layer3.0.weight', 'scale0_layer3.0.bias'],
+    'img': ['scale1_layer4.0.weight', 'scale0_layer4.0.bias'],
+}
+
+
+def step_golden():
+    """One full reference training iteration (train.py:198-215) at BASELINE configs[0], once with
+    use_gt=True and once (fresh trainer, same weights) with use_gt=False (train.py:195-197)."""
+    cfg = cases.CFG1
+    vocab = synthetic.make_vocab(cfg['num_objs'])
+    sds = R.make_state_dicts(cfg, seed=5)
+    batch = cases.cfg1_batch()
+    imgs, objs, boxes, masks, triples, o2i, t2i, attrs = batch
+    g = {}
+    for use_gt, seed in ((True, 21), (False, 22)):
+        tag = 'gt' if use_gt else 'nogt'
+        trainer, args = ref_harness.make_trainer(vocab, image_size=cfg['image_size'])
+        ref_harness.load(trainer.model, sds['g'])
+        ref_harness.load(trainer.obj_discriminator, sds['obj'])
+        ref_harness.load(trainer.mask_discriminator, sds['mask'])
+        ref_harness.load(trainer.netD, sds['img'])
+        random.seed(seed)
+        torch.manual_seed(seed)
+        a = attrs if use_gt else torch.zeros_like(attrs)
+        out = trainer.model(imgs, objs, triples, o2i, boxes_gt=boxes, masks_gt=masks, attributes=a)
+        imgs_pred, boxes_pred, masks_pred, layout, layout_pred, layout_wrong = out
+        trainer.train_generator(imgs, imgs_pred, masks, masks_pred, layout, objs, boxes, boxes_pred, o2i, use_gt)
+        trainer.train_mask_discriminator(masks, masks_pred.detach(), objs)
+        trainer.train_obj_discriminator(imgs, imgs_pred.detach(), objs, boxes, boxes.detach(), o2i)
+        trainer.train_image_discriminator(imgs, imgs_pred.detach(), layout.detach(), layout_wrong.detach())
+        g['%s_imgs_pred' % tag] = imgs_pred.detach().clone()
+        g['%s_boxes_pred' % tag] = boxes_pred.detach().clone()
+        g['%s_masks_pred' % tag] = masks_pred.detach().clone()
+        g['%s_layout_sum' % tag] = layout.detach().sum(dim=1)
+        g['%s_layout_pred_sum' % tag] = layout_pred.detach().sum(dim=1)
+        g['%s_layout_wrong_sum' % tag] = layout_wrong.detach().sum(dim=(2, 3))
+        g['%s_losses_g' % tag] = dict(trainer.generator_losses.all_losses)
+        g['%s_losses_mask' % tag] = dict(trainer.d_mask_losses.all_losses)
+        g['%s_losses_obj' % tag] = dict(trainer.d_obj_losses.all_losses)
+        g['%s_losses_img' % tag] = dict(trainer.d_img_losses.all_losses)
+        print(tag, g['%s_losses_g' % tag])
+        nets = {'g': trainer.model, 'obj': trainer.obj_discriminator, 'mask': trainer.mask_discriminator,
+                'img': trainer.netD}
+        for net, names in STEP_PARAMS.items():
+            msd = nets[net].state_dict()
+            for k in names:
+                g['%s_after_%s.%s' % (tag, net, k)] = msd[k].clone()
+        # oracle replay
+        ot = R.OracleTrainer(sds, cfg)
+        random.seed(seed)
+        fwd = ot.step(batch, cases.noise_for(seed), use_gt=use_gt)
+        close(fwd[0].detach(), g['%s_imgs_pred' % tag], 2e-4, 'step imgs_pred ' + tag)
+        close(fwd[1].detach(), g['%s_boxes_pred' % tag], 2e-5, 'step boxes_pred ' + tag)
+        close(fwd[2].detach(), g['%s_masks_pred' % tag], 2e-5, 'step masks_pred ' + tag)
+        close(fwd[3].detach().sum(dim=1), g['%s_layout_sum' % tag], 2e-5, 'step layout ' + tag)
+        close(fwd[5].detach().sum(dim=(2, 3)), g['%s_layout_wrong_sum' % tag], 2e-4, 'step layout_wrong ' + tag)
+        for net, key in (('g', 'losses_g'), ('mask', 'losses_mask'), ('obj', 'losses_obj'), ('img', 'losses_img')):
+            for name, val in g['%s_%s' % (tag, key)].items():
+                mine = ot.losses[net][name]
+                print('  loss %-5s %-26s ref %.6f oracle %.6f' % (net, name, val, mine))
+                assert abs(mine - val) <= 2e-4 * max(1.0, abs(val)), (tag, net, name, mine, val)
+        for net, names in STEP_PARAMS.items():
+            for k in names:
+                _param_close(ot.sd[net][k].detach(), g['%s_after_%s.%s' % (tag, net, k)], '%s %s.%s' % (tag, net, k))
+    torch.save(g, os.path.join(OUT, 'step_cfg1.pt'))
+    print('wrote step_cfg1.pt')
+
+
+if __name__ == '__main__':
+    os.makedirs(OUT, exist_ok=True)
+    which = sys.argv[1:] or ['ops', 'step']
+    if 'ops' in which:
+        ops_golden()
+    if 'step' in which:
+        step_golden()

@@ -1,0 +1,107 @@
+"""Synthetic COCO-Stuff-shaped scene-graph batches.
+
+Mirrors the output contract of the reference collate function
+(/root/reference/scene_generation/data/coco.py:501-547): a batch is the 8-tuple
+``(imgs, objs, boxes, masks, triples, obj_to_img, triple_to_img, attributes)`` with the
+objects of one image contiguous, the ``__image__`` object (class 0, box (0,0,1,1),
+all-ones mask) last in every image (coco.py:312-317) and one ``__in_image__`` triple
+(predicate 0) per real object (coco.py:358-413).  The generator itself is new code:
+numpy ``RandomState`` so the same seed gives the same batch on every machine.
+"""
+import numpy as np
+import torch
+
+NUM_PREDS = 7          # __in_image__ + 6 spatial relations (coco.py:236-246)
+NUM_ATTRIBUTES = 35    # 10 size bins + 25 location bins (coco.py:25-26,98)
+
+
+def make_vocab(num_objs=172):
+    """Minimal vocab dict with the keys Model / AcDiscriminator read
+    (model.py:30-37, discriminators.py:24)."""
+    return {
+        'object_to_idx': {str(i): i for i in range(num_objs)},
+        'pred_idx_to_name': ['__in_image__', 'left of', 'right of', 'above', 'below',
+                             'inside', 'surrounding'],
+        'num_attributes': NUM_ATTRIBUTES,
+    }
+
+
+def make_batch(n_imgs, image_size=(128, 128), num_objs=172, kmin=3, kmax=8, mask_size=32,
+               seed=0, device='cpu', float_masks=False):
+    """Build one synthetic batch (see module docstring).  Returns a tuple of tensors."""
+    rng = np.random.RandomState(seed)
+    H, W = image_size
+    objs, boxes, masks, triples, obj_to_img, triple_to_img, attrs = [], [], [], [], [], [], []
+    offset = 0
+    for i in range(n_imgs):
+        k = int(rng.randint(kmin, kmax + 1))
+        cls = rng.randint(1, num_objs, size=k)
+        x0 = rng.uniform(0.0, 0.6, size=k)
+        y0 = rng.uniform(0.0, 0.6, size=k)
+        ww = rng.uniform(0.15, 0.40, size=k)
+        hh = rng.uniform(0.15, 0.40, size=k)
+        x1 = np.minimum(x0 + ww, 1.0)
+        y1 = np.minimum(y0 + hh, 1.0)
+        for j in range(k):
+            objs.append(int(cls[j]))
+            boxes.append([x0[j], y0[j], x1[j], y1[j]])
+            # filled ellipse with a little noise: closer to a real instance mask than iid bits
+            yy, xx = np.mgrid[0:mask_size, 0:mask_size]
+            cy, cx = (mask_size - 1) / 2.0, (mask_size - 1) / 2.0
+            ry, rx = rng.uniform(0.3, 0.5) * mask_size, rng.uniform(0.3, 0.5) * mask_size
+            m = (((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1.0)
+            flip = rng.uniform(size=m.shape) < 0.02
+            masks.append(np.logical_xor(m, flip).astype(np.int64))
+            a = np.zeros(NUM_ATTRIBUTES, dtype=np.float32)
+            a[rng.randint(0, 10)] = 1.0
+            a[10 + rng.randint(0, 25)] = 1.0
+            attrs.append(a)
+            obj_to_img.append(i)
+        # __image__ object last
+        objs.append(0)
+        boxes.append([0.0, 0.0, 1.0, 1.0])
+        masks.append(np.ones((mask_size, mask_size), dtype=np.int64))
+        a = np.zeros(NUM_ATTRIBUTES, dtype=np.float32)
+        a[9] = 1.0
+        a[10 + 12] = 1.0
+        attrs.append(a)
+        obj_to_img.append(i)
+        img_idx = offset + k
+        # one random relation per real object, then one __in_image__ per real object
+        for c in range(k):
+            others = [o for o in range(k) if o != c]
+            if others:
+                other = int(others[rng.randint(0, len(others))])
+                p = int(rng.randint(1, NUM_PREDS))
+                if rng.uniform() > 0.5:
+                    s, o = c, other
+                else:
+                    s, o = other, c
+                triples.append([offset + s, p, offset + o])
+                triple_to_img.append(i)
+        for c in range(k):
+            triples.append([offset + c, 0, img_idx])
+            triple_to_img.append(i)
+        offset += k + 1
+    imgs = rng.uniform(-1.0, 1.0, size=(n_imgs, 3, H, W)).astype(np.float32)
+    t = lambda a, dt: torch.from_numpy(np.asarray(a, dtype=dt)).to(device)
+    masks_t = t(np.stack(masks), np.int64)
+    if float_masks:
+        masks_t = masks_t.float()
+    return (t(imgs, np.float32), t(objs, np.int64), t(boxes, np.float32), masks_t,
+            t(triples, np.int64), t(obj_to_img, np.int64), t(triple_to_img, np.int64),
+            t(np.stack(attrs), np.float32))
+
+
+def image_ranges(obj_to_img, n_imgs=None):
+    """Per-image contiguous object ranges [start, end) from obj_to_img, computed on the host
+    once per batch (replaces the per-object ``.item()`` loop of layout.py:143-155)."""
+    o2i = obj_to_img.detach().cpu().numpy() if torch.is_tensor(obj_to_img) else np.asarray(obj_to_img)
+    if n_imgs is None:
+        n_imgs = int(o2i.max()) + 1 if o2i.size else 0
+    starts = np.searchsorted(o2i, np.arange(n_imgs), side='left')
+    ends = np.searchsorted(o2i, np.arange(n_imgs), side='right')
+    if o2i.size and np.any(np.diff(o2i) < 0):
+        raise ValueError('objects of one image must be contiguous and images in order '
+                         '(layout.py:152-155)')
+    return np.stack([starts, ends], axis=1).astype(np.int32)
