@@ -1,0 +1,143 @@
+/* libsg_b200 — C ABI of the B200-native scene-graph -> image hot path.
+ *
+ * The reference (ashual/scene_generation) is pure PyTorch and has no FFI of its own;
+ * each entry point below replaces the ATen/cuDNN dispatch of the cited reference call site and is
+ * what a maintainer would bind (ctypes stub: INTEGRATION.md).  Conventions:
+ *   - plain pointers + sizes, no torch types; all pointers are DEVICE pointers unless noted;
+ *   - the caller owns every buffer (inputs, outputs, workspaces); nothing is retained after return;
+ *   - every call only ENQUEUES work on `stream` (no device synchronisation, no default stream);
+ *   - return 0 on success, non-zero on error; sg_last_error() gives the message (thread local);
+ *   - there is no CPU fallback: without an sm_100a device the calls fail.
+ * Tensor formats: "NCHW f32" is the reference's layout; "NHWC bf16" is channels-last bf16 with a
+ * physical channel count Cp (multiple of 8, channels >= C are zero) — the operand format of the
+ * tensor-core kernels.
+ */
+#ifndef SG_B200_H
+#define SG_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* sg_stream_t; /* cudaStream_t */
+
+/* ---- runtime ------------------------------------------------------------------------------- */
+const char* sg_last_error(void);
+const char* sg_version(void);
+int sg_arch(void);                       /* 100 = built for sm_100a */
+unsigned long long sg_launch_count(void);/* kernels launched by this library in this process */
+void sg_reset_launch_count(void);
+
+/* ---- layout.py:64-184  masks_to_layout / _boxes_to_grid / _pool_samples ---------------------- */
+/* mask_dtype: 0 f32, 1 i64, 2 u8.  img_ranges: int32 (N,2) object range [start,end) per image
+ * (objects of an image are contiguous, layout.py:152-155).  out_format: 0 NCHW f32 (N,D,H,W),
+ * 1 NHWC bf16 (N,H,W,Cp). */
+int sg_masks_to_layout_fwd(const float* vecs, const float* boxes, const void* masks, int mask_dtype,
+                           const int* img_ranges, int O, int D, int M, int N, int H, int W,
+                           int align_corners, int out_format, int Cp, void* out, sg_stream_t stream);
+/* d vecs (O,D) f32 always; d masks (O,M,M) f32 when dmasks != NULL. */
+int sg_masks_to_layout_bwd(const float* vecs, const float* boxes, const void* masks, int mask_dtype,
+                           const int* img_ranges, int O, int D, int M, int N, int H, int W,
+                           int align_corners, int grad_format, int Cp, const void* grad_out,
+                           float* dvecs, float* dmasks, sg_stream_t stream);
+/* test_mode=True compositing (layout.py:157-169); mass_ws: O floats of workspace. */
+int sg_masks_to_layout_test(const float* vecs, const float* boxes, const void* masks, int mask_dtype,
+                            const int* img_ranges, int O, int D, int M, int N, int H, int W,
+                            int align_corners, int out_format, int Cp, float* mass_ws, void* out,
+                            sg_stream_t stream);
+
+/* ---- graph.py:74-116  GraphTripleConv gather / pooled scatter -------------------------------- */
+/* edges: int64 (T,2) [subject, object] (graph.py:75-76).  CSR of incidences per object:
+ * seg_ptr int32 (O+1), seg_src int32 (2T) with seg_src = 2*t + role (role 1 = object slot), in the
+ * reference's accumulation order (all subject uses in triple order, then all object uses). */
+int sg_gconv_gather_fwd(const float* obj_vecs, const float* pred_vecs, const long long* edges, int O, int T,
+                        int Do, int Dp, int out_dtype, int ld_out, void* out, sg_stream_t stream);
+int sg_gconv_pool_fwd(const float* new_t, int ldt, int col_o, const int* seg_ptr, const int* seg_src, int O,
+                      int H, int avg, int out_dtype, int ld_out, void* out, sg_stream_t stream);
+int sg_gconv_pool_bwd(const float* dpooled, const float* dnew_p, const long long* edges, const int* seg_ptr,
+                      int T, int H, int Dout, int avg, int ld_out, float* dnew_t, sg_stream_t stream);
+int sg_gconv_gather_bwd(const float* dcur, int ldc, const int* seg_ptr, const int* seg_src, int O, int T,
+                        int Do, int Dp, float* dobj, float* dpred, sg_stream_t stream);
+
+/* ---- bilinear.py:26-130,246-275  crop_bbox_batch ---------------------------------------------- */
+int sg_crop_bbox_fwd(const float* feats, const float* boxes, const long long* box_to_feats, int N, int C,
+                     int H, int W, int B, int HH, int WW, int align_corners, int out_format, int Cp,
+                     void* out, sg_stream_t stream);
+int sg_crop_bbox_bwd(const float* boxes, const long long* box_to_feats, int N, int C, int H, int W, int B,
+                     int HH, int WW, int align_corners, int grad_format, int Cp, const void* grad_out,
+                     float* dfeats, sg_stream_t stream);
+
+/* ---- generators.py:62-91, layers.py:234-273, discriminators.py:87-245, graph.py:85,120 --------
+ * Dense contractions (nn.Conv2d / ConvTranspose2d / Linear fprop + dgrad) as ONE tcgen05
+ * implicit-GEMM kernel:   y[img,h,w,co] = epi( sum_{tap} sum_{ci} x[img, plane(tap), h+dh(tap)+in_h0,
+ *                                                    w+dw(tap)+in_w0, ci] * wgt[co, wtap(tap), ci] )
+ * x is NHWC bf16 viewed as [N][P][H][W][C] (P = parity planes for stride-2, else 1); out-of-range
+ * coordinates read as zero (TMA fill) which implements zero padding.  Up to 4 output "phases"
+ * (sub-pixel decomposition of transposed / strided-adjoint convs) each with its own tap list and
+ * output offset; output address = img*os_img + (h*oh_mul+oh_off)*os_h + (w*ow_mul+ow_off)*os_w + co. */
+#define SG_MAX_TAPS 64
+#define SG_ACT_NONE 0
+#define SG_ACT_RELU 1
+#define SG_ACT_LEAKY 2
+#define SG_ACT_TANH 3
+#define SG_ACT_SIGMOID 4
+typedef struct {
+  int16_t dh, dw, plane, wtap;
+} sg_tap_t;
+typedef struct {
+  int tap_begin, ntaps, oh_off, ow_off;
+} sg_phase_t;
+typedef struct {
+  const void* x;          /* bf16 [x_N][x_P][x_H][x_W][x_C], x_C % 8 == 0 */
+  int x_N, x_P, x_H, x_W, x_C;
+  const void* w;          /* bf16 [w_Cout][w_taps][w_C], w_C % 8 == 0 */
+  int w_Cout, w_taps, w_C;
+  void* y;                /* f32 or bf16 */
+  int y_dtype;            /* 0 f32, 1 bf16 */
+  long long y_os_img, y_os_h, y_os_w;
+  int Hout, Wout;         /* per-phase logical output extent */
+  int oh_mul, ow_mul;
+  int in_h0, in_w0;
+  int nphases;
+  sg_phase_t phases[4];
+  int ntaps;
+  sg_tap_t taps[SG_MAX_TAPS];
+  const float* bias;      /* (Cout) or NULL */
+  int act;
+  float slope;
+  float* stats;           /* (x_N, Cout, 2) f32 sum / sum-of-squares of the pre-activation output, or NULL
+                             (caller zeroes it); feeds InstanceNorm / BatchNorm */
+} sg_conv_desc_t;
+int sg_conv_tc(const sg_conv_desc_t* desc, sg_stream_t stream);
+
+/* Weight gradient (cuDNN wgrad in the reference):
+ *   dw[co, wtap, ci] += sum_{img,h,w} dy[img, pa, h+dha, w+dwa, co] * x[img, pb, h+dhb, w+dwb, ci]
+ * for every entry of the tap table (a = dy side, b = x side).  dw is f32 [Cout][w_taps][dw_C]
+ * and is ACCUMULATED into (split-K atomics) — the caller zeroes it. */
+typedef struct {
+  int16_t dha, dwa, pa, dhb, dwb, pb, wtap, pad;
+} sg_wtap_t;
+typedef struct {
+  const void* dy;         /* bf16 [N][dy_P][dy_H][dy_W][dy_C] */
+  int N, dy_P, dy_H, dy_W, dy_C;
+  const void* x;          /* bf16 [N][x_P][x_H][x_W][x_C] */
+  int x_P, x_H, x_W, x_C;
+  int Hred, Wred;         /* reduction extent (h in [0,Hred), w in [0,Wred)) */
+  float* dw;              /* f32 [Cout][w_taps][dw_C] */
+  int Cout, Cin, w_taps, dw_C;
+  int ntaps;
+  sg_wtap_t taps[SG_MAX_TAPS];
+  int ksplit;             /* 0 = auto */
+} sg_wgrad_desc_t;
+int sg_wgrad_tc(const sg_wgrad_desc_t* desc, sg_stream_t stream);
+
+/* ---- operand preparation ------------------------------------------------------------------ */
+/* f32 (rows, cols) with row pitch ld_src -> bf16 (rows, ld_dst); columns >= cols are zero. */
+int sg_cast_pad_bf16(const float* src, long long rows, int cols, long long ld_src, int ld_dst, void* dst,
+                     sg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SG_B200_H */

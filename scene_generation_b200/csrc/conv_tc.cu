@@ -1,0 +1,530 @@
+// tcgen05 / TMA implicit-GEMM convolution family for sm_100a.
+//
+// Replaces the cuDNN fprop/dgrad/wgrad + cuBLAS GEMM dispatch behind nn.Conv2d / nn.ConvTranspose2d /
+// nn.Linear on the reference hot path (generators.py:62-91, layers.py:234-273,
+// discriminators.py:87-245, graph.py:85,120).
+//
+//   conv_tc_kernel : D[128 pixels, BN couts] = sum_taps sum_kblocks A_tap[128, 64] * B_tap[BN, 64]^T
+//     A tile = one 5-D TMA box (64 ch, BW, BH, 1 plane, BI imgs) of the NHWC bf16 activation at a
+//     tap-shifted coordinate (out-of-range -> zero = padding);  B tile = 3-D TMA box (64 ch, 1 tap, BN)
+//     of the [Cout][taps][Cin] bf16 weights.  Both K-major, SWIZZLE_128B; fp32 accumulators in TMEM.
+//     Warp roles: w0 TMA producer, w1 TMEM alloc + single-thread tcgen05.mma issuer, w2-5 epilogue
+//     (tcgen05.ld -> bias -> InstanceNorm/BatchNorm partial sums -> activation -> vector stores).
+//   wgrad_tc_kernel : D[128 couts, BN cins] = sum over 64-pixel boxes dy[pix, co]^T x[pix(+tap), ci]
+//     both operands MN-major (pixel = K is the strided smem dimension), split-K with fp32 atomics.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "../../include/sg_b200.h"
+
+namespace {
+
+using namespace ptx;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// bf16 tensor [d4][d3][d2][d1][d0] (d0 innermost, contiguous) -> tiled map with the given box
+int make_tmap(CUtensorMap* m, const void* base, int rank, const long long* dims, const int* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return sg_fail(SG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[5];
+  cuuint64_t gstride[4];
+  cuuint32_t bdim[5], estr[5];
+  unsigned long long stride = 2;
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = (cuuint64_t)dims[i];
+    bdim[i] = (cuuint32_t)box[i];
+    estr[i] = 1;
+    stride *= (unsigned long long)dims[i];
+    if (i < rank - 1) gstride[i] = stride;
+  }
+  if (((uintptr_t)base & 15) != 0) return sg_fail(SG_ERR_ARG, "tensor base %p not 16-byte aligned", base);
+  if ((dims[0] * 2) % 16 != 0) return sg_fail(SG_ERR_ARG, "innermost extent %lld not a multiple of 8 elements", dims[0]);
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstride, bdim,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return sg_fail(SG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return SG_OK;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  switch (act) {
+    case SG_ACT_RELU: return fmaxf(v, 0.f);
+    case SG_ACT_LEAKY: return v >= 0.f ? v : v * slope;
+    case SG_ACT_TANH: return tanhf(v);
+    case SG_ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
+    default: return v;
+  }
+}
+
+// lane l ends up with the sum over the warp of v[l]
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      float send = up ? v[i] : v[i + s];
+      float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+struct ConvKParams {
+  int Hout, Wout, tiles_w, tiles_h, BW, BH, BI, n_img;
+  int kblocks, Cout;
+  int in_h0, in_w0;
+  long long os_img, os_h, os_w;
+  int oh_mul, ow_mul;
+  void* y;
+  int y_dtype;
+  const float* bias;
+  int act;
+  float slope;
+  float* stats;
+  int vec_ok;
+  sg_phase_t phases[4];
+  sg_tap_t taps[SG_MAX_TAPS];
+};
+
+constexpr int A_BYTES = 128 * 128;   // 128 rows x 64 bf16
+
+template <int BN>
+struct ConvCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int TM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int SMEM = STAGES * (A_BYTES + (B_BYTES < 1024 ? 1024 : B_BYTES)) + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int B_STRIDE = (B_BYTES < 1024 ? 1024 : B_BYTES);
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ ConvKParams p) {
+  using Cfg = ConvCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_STRIDE);
+  uint64_t* empty = full + STAGES;
+  uint64_t* accum_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.x;
+  const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, ti = mt / (p.tiles_w * p.tiles_h);
+  const int w0 = tw * p.BW, h0 = th * p.BH, img0 = ti * p.BI;
+  const int n0 = blockIdx.y * BN;
+  const sg_phase_t ph = p.phases[blockIdx.z];
+  const int iters = ph.ntaps * p.kblocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum_full, 1);
+    fence_barrier_init();
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1) tmem_alloc<Cfg::TM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t par = (it / STAGES) & 1;
+        mbar_wait(&empty[s], par ^ 1);
+        const int tap_i = it / p.kblocks, kb = it - tap_i * p.kblocks;
+        const sg_tap_t tp = p.taps[ph.tap_begin + tap_i];
+        mbar_expect_tx(&full[s], A_BYTES + Cfg::B_BYTES);
+        tma_load_5d(sA + s * A_BYTES, &tmA, &full[s], kb * 64, w0 + tp.dw + p.in_w0, h0 + tp.dh + p.in_h0, tp.plane, img0);
+        tma_load_3d(sB + s * Cfg::B_STRIDE, &tmB, &full[s], kb * 64, tp.wtap, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t par = (it / STAGES) & 1;
+        mbar_wait(&full[s], par);
+        tc_fence_after();
+        const uint64_t ad = umma_desc_sw128(smem_u32(sA + s * A_BYTES), 16, 1024);
+        const uint64_t bd = umma_desc_sw128(smem_u32(sB + s * Cfg::B_STRIDE), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mma_bf16(tmem, ad + 2 * k, bd + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+        mma_commit(&empty[s]);   // frees the smem slot once these MMAs have read it
+      }
+      mma_commit(accum_full);
+    }
+  } else {
+    // ---------------- epilogue: warps 2..5 own TMEM lane quarters (warp % 4) -------------------
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int ww = r % p.BW, hh = (r / p.BW) % p.BH, ii = r / (p.BW * p.BH);
+    const int img = img0 + ii, h = h0 + hh, w = w0 + ww;
+    const bool valid = (img < p.n_img) && (h < p.Hout) && (w < p.Wout);
+    const long long off = (long long)img * p.os_img + (long long)(h * p.oh_mul + ph.oh_off) * p.os_h +
+                          (long long)(w * p.ow_mul + ph.ow_off) * p.os_w;
+    const bool seg_full = (p.BI == 1) || ((p.BW * p.BH) % 32 == 0);
+    mbar_wait(accum_full, 0);
+    tc_fence_after();
+    constexpr int CH = (BN >= 32) ? 32 : 16;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += CH) {
+      if (n0 + c0 >= p.Cout) break;
+      uint32_t raw[32];
+      if (CH == 32) tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, raw);
+      else tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c0, raw);
+      tmem_ld_wait();
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < CH) {
+          const int c = n0 + c0 + j;
+          float b = (p.bias != nullptr && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
+          f[j] = __uint_as_float(raw[j]) + b;
+        } else {
+          f[j] = 0.f;
+        }
+      }
+      if (p.stats != nullptr) {
+        if (seg_full) {
+          float s1[32], s2[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float v = valid ? f[j] : 0.f;
+            s1[j] = v;
+            s2[j] = v * v;
+          }
+          float t1 = warp_transpose_reduce(s1, lane);
+          float t2 = warp_transpose_reduce(s2, lane);
+          const int simg = __shfl_sync(0xffffffffu, img, 0);
+          const int c = n0 + c0 + lane;
+          if (lane < CH && c < p.Cout && simg < p.n_img) {
+            atomicAdd(p.stats + ((long long)simg * p.Cout + c) * 2, t1);
+            atomicAdd(p.stats + ((long long)simg * p.Cout + c) * 2 + 1, t2);
+          }
+        } else if (valid) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            const int c = n0 + c0 + j;
+            if (c < p.Cout) {
+              atomicAdd(p.stats + ((long long)img * p.Cout + c) * 2, f[j]);
+              atomicAdd(p.stats + ((long long)img * p.Cout + c) * 2 + 1, f[j] * f[j]);
+            }
+          }
+        }
+      }
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) f[j] = apply_act(f[j], p.act, p.slope);
+        const bool full_chunk = (n0 + c0 + CH <= p.Cout) && p.vec_ok;
+        if (p.y_dtype == 1) {
+          __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + off + n0 + c0;
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < CH; j += 8) {
+              __align__(16) __nv_bfloat162 pk[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) pk[t] = __floats2bfloat162_rn(f[j + 2 * t], f[j + 2 * t + 1]);
+              *reinterpret_cast<uint4*>(yp + j) = *reinterpret_cast<uint4*>(pk);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (n0 + c0 + j < p.Cout) yp[j] = __float2bfloat16(f[j]);
+          }
+        } else {
+          float* yp = reinterpret_cast<float*>(p.y) + off + n0 + c0;
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < CH; j += 4) *reinterpret_cast<float4*>(yp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (n0 + c0 + j < p.Cout) yp[j] = f[j];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::TM_COLS>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------
+struct WgradKParams {
+  int tiles_w, tiles_h, BW, BH, BI;
+  int ktiles_total, ktiles_per_split;
+  int Cout, Cin, w_taps, dw_C, n_ci_tiles;
+  float* dw;
+  sg_wtap_t taps[SG_MAX_TAPS];
+};
+
+constexpr int WG_BOX_BYTES = 64 * 128;   // 64 pixels x 64 channels bf16
+
+template <int BN>
+struct WgradCfg {
+  static constexpr int NB = BN / 64;
+  static constexpr int STAGE_BYTES = (2 + NB) * WG_BOX_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ WgradKParams p) {
+  using Cfg = WgradCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* accum_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ci_tile = blockIdx.x % p.n_ci_tiles, co_tile = blockIdx.x / p.n_ci_tiles;
+  const int co0 = co_tile * 128, ci0 = ci_tile * BN;
+  const sg_wtap_t tp = p.taps[blockIdx.y];
+  const int kt_begin = blockIdx.z * p.ktiles_per_split;
+  const int kt_end = min(kt_begin + p.ktiles_per_split, p.ktiles_total);
+  const int iters = max(kt_end - kt_begin, 0);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum_full, 1);
+    fence_barrier_init();
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t par = (it / STAGES) & 1;
+        mbar_wait(&empty[s], par ^ 1);
+        const int kt = kt_begin + it;
+        const int tw = kt % p.tiles_w, th = (kt / p.tiles_w) % p.tiles_h, ti = kt / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.BW, h0 = th * p.BH, img0 = ti * p.BI;
+        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+        mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+        tma_load_5d(st, &tmA, &full[s], co0, w0 + tp.dwa, h0 + tp.dha, tp.pa, img0);
+        tma_load_5d(st + WG_BOX_BYTES, &tmA, &full[s], co0 + 64, w0 + tp.dwa, h0 + tp.dha, tp.pa, img0);
+#pragma unroll
+        for (int j = 0; j < Cfg::NB; ++j)
+          tma_load_5d(st + (2 + j) * WG_BOX_BYTES, &tmB, &full[s], ci0 + 64 * j, w0 + tp.dwb, h0 + tp.dhb, tp.pb, img0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && iters > 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t par = (it / STAGES) & 1;
+        mbar_wait(&full[s], par);
+        tc_fence_after();
+        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+        // MN-major SW128: 64 MN-elements contiguous (128 B), 8 K-rows per 1024 B group (SBO),
+        // next 64-element MN block one TMA box further (LBO)
+        const uint64_t ad = umma_desc_sw128(smem_u32(st), WG_BOX_BYTES, 1024);
+        const uint64_t bd = umma_desc_sw128(smem_u32(st + 2 * WG_BOX_BYTES), WG_BOX_BYTES, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mma_bf16(tmem, ad + 128 * k, bd + 128 * k, idesc, (it | k) != 0 ? 1u : 0u);
+        mma_commit(&empty[s]);
+      }
+      mma_commit(accum_full);
+    }
+  } else if (iters > 0) {
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    mbar_wait(accum_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (ci0 + c0 >= p.Cin) break;
+      uint32_t raw[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, raw);
+      tmem_ld_wait();
+      if (co < p.Cout) {
+        float* dst = p.dw + ((long long)co * p.w_taps + tp.wtap) * p.dw_C + ci0 + c0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (ci0 + c0 + j < p.Cin) atomicAdd(dst + j, __uint_as_float(raw[j]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<BN>(tmem);
+}
+
+// choose the 128-row (or `rows`-row) tile box (BW, BH, BI) minimising padded work
+void choose_tile(int rows, int H, int W, int N, int* BW, int* BH, int* BI) {
+  long best = -1;
+  for (int bw = 1; bw <= rows; bw <<= 1) {
+    for (int bh = 1; bw * bh <= rows; bh <<= 1) {
+      int bi = rows / (bw * bh);
+      if (bw > 256 || bh > 256 || bi > 256) continue;
+      if (bi > 1 && (bw < W || bh < H)) continue;   // several images per tile only if one image fits
+      if (bw * bh * bi != rows) continue;
+      long cost = (long)sg_cdiv(W, bw) * sg_cdiv(H, bh) * sg_cdiv(N, bi);
+      if (best < 0 || cost < best || (cost == best && bw > *BW)) {
+        best = cost;
+        *BW = bw; *BH = bh; *BI = bi;
+      }
+    }
+  }
+}
+
+template <int BN>
+int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKParams& kp, dim3 grid, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN>::SMEM);
+    if (e != cudaSuccess) return sg_fail(SG_ERR_CUDA, "conv_tc smem attribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  conv_tc_kernel<BN><<<grid, 192, ConvCfg<BN>::SMEM, stream>>>(tmA, tmB, kp);
+  SG_CHECK_LAUNCH("sg_conv_tc");
+  return SG_OK;
+}
+
+template <int BN>
+int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const WgradKParams& kp, dim3 grid, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradCfg<BN>::SMEM);
+    if (e != cudaSuccess) return sg_fail(SG_ERR_CUDA, "wgrad_tc smem attribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  wgrad_tc_kernel<BN><<<grid, 192, WgradCfg<BN>::SMEM, stream>>>(tmA, tmB, kp);
+  SG_CHECK_LAUNCH("sg_wgrad_tc");
+  return SG_OK;
+}
+
+}  // namespace
+
+extern "C" int sg_conv_tc(const sg_conv_desc_t* d, sg_stream_t stream) {
+  SG_CHECK_ARG(d != nullptr, "sg_conv_tc: null descriptor");
+  SG_CHECK_ARG(d->x && d->w && d->y, "sg_conv_tc: null tensor pointer");
+  SG_CHECK_ARG(d->x_C % 8 == 0 && d->w_C % 8 == 0, "sg_conv_tc: channel counts must be multiples of 8 (x_C=%d w_C=%d)", d->x_C, d->w_C);
+  SG_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= SG_MAX_TAPS, "sg_conv_tc: ntaps %d out of range", d->ntaps);
+  SG_CHECK_ARG(d->nphases >= 1 && d->nphases <= 4, "sg_conv_tc: nphases %d out of range", d->nphases);
+  SG_CHECK_ARG(d->Hout > 0 && d->Wout > 0 && d->x_N > 0 && d->w_Cout > 0, "sg_conv_tc: empty problem");
+  SG_CHECK_ARG(d->y_dtype == 0 || d->y_dtype == 1, "sg_conv_tc: y_dtype must be 0 (f32) or 1 (bf16)");
+  for (int i = 0; i < d->nphases; ++i)
+    SG_CHECK_ARG(d->phases[i].ntaps >= 1 && d->phases[i].tap_begin >= 0 && d->phases[i].tap_begin + d->phases[i].ntaps <= d->ntaps,
+                 "sg_conv_tc: phase %d tap range invalid", i);
+  ConvKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  choose_tile(128, d->Hout, d->Wout, d->x_N, &kp.BW, &kp.BH, &kp.BI);
+  kp.Hout = d->Hout; kp.Wout = d->Wout;
+  kp.tiles_w = sg_cdiv(d->Wout, kp.BW); kp.tiles_h = sg_cdiv(d->Hout, kp.BH);
+  const int img_tiles = sg_cdiv(d->x_N, kp.BI);
+  kp.n_img = d->x_N;
+  kp.kblocks = sg_cdiv(d->x_C < d->w_C ? d->x_C : d->w_C, 64);
+  kp.Cout = d->w_Cout;
+  kp.in_h0 = d->in_h0; kp.in_w0 = d->in_w0;
+  kp.os_img = d->y_os_img; kp.os_h = d->y_os_h; kp.os_w = d->y_os_w;
+  kp.oh_mul = d->oh_mul; kp.ow_mul = d->ow_mul;
+  kp.y = d->y; kp.y_dtype = d->y_dtype; kp.bias = d->bias; kp.act = d->act; kp.slope = d->slope; kp.stats = d->stats;
+  const int va = d->y_dtype == 1 ? 8 : 4;
+  kp.vec_ok = (d->y_os_img % va == 0) && (d->y_os_h % va == 0) && (d->y_os_w % va == 0) &&
+              (((uintptr_t)d->y) % 16 == 0);
+  for (int i = 0; i < 4; ++i) kp.phases[i] = d->phases[i < d->nphases ? i : 0];
+  for (int i = 0; i < d->ntaps; ++i) kp.taps[i] = d->taps[i];
+
+  CUtensorMap tmA, tmB;
+  long long adims[5] = {d->x_C, d->x_W, d->x_H, d->x_P, d->x_N};
+  int abox[5] = {64, kp.BW, kp.BH, 1, kp.BI};
+  if (int e = make_tmap(&tmA, d->x, 5, adims, abox)) return e;
+  const int BN = d->w_Cout > 128 ? 256 : (d->w_Cout > 64 ? 128 : (d->w_Cout > 16 ? 64 : 16));
+  long long bdims[3] = {d->w_C, d->w_taps, d->w_Cout};
+  int bbox[3] = {64, 1, BN};
+  if (int e = make_tmap(&tmB, d->w, 3, bdims, bbox)) return e;
+  dim3 grid(kp.tiles_w * kp.tiles_h * img_tiles, sg_cdiv(d->w_Cout, BN), d->nphases);
+  switch (BN) {
+    case 256: return launch_conv<256>(tmA, tmB, kp, grid, stream);
+    case 128: return launch_conv<128>(tmA, tmB, kp, grid, stream);
+    case 64: return launch_conv<64>(tmA, tmB, kp, grid, stream);
+    default: return launch_conv<16>(tmA, tmB, kp, grid, stream);
+  }
+}
+
+extern "C" int sg_wgrad_tc(const sg_wgrad_desc_t* d, sg_stream_t stream) {
+  SG_CHECK_ARG(d != nullptr && d->dy && d->x && d->dw, "sg_wgrad_tc: null pointer");
+  SG_CHECK_ARG(d->dy_C % 8 == 0 && d->x_C % 8 == 0, "sg_wgrad_tc: channel counts must be multiples of 8");
+  SG_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= SG_MAX_TAPS, "sg_wgrad_tc: ntaps %d out of range", d->ntaps);
+  SG_CHECK_ARG(d->Hred > 0 && d->Wred > 0 && d->N > 0 && d->Cout > 0 && d->Cin > 0, "sg_wgrad_tc: empty problem");
+  WgradKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  choose_tile(64, d->Hred, d->Wred, d->N, &kp.BW, &kp.BH, &kp.BI);
+  kp.tiles_w = sg_cdiv(d->Wred, kp.BW); kp.tiles_h = sg_cdiv(d->Hred, kp.BH);
+  kp.ktiles_total = kp.tiles_w * kp.tiles_h * sg_cdiv(d->N, kp.BI);
+  kp.Cout = d->Cout; kp.Cin = d->Cin; kp.w_taps = d->w_taps; kp.dw_C = d->dw_C; kp.dw = d->dw;
+  for (int i = 0; i < d->ntaps; ++i) kp.taps[i] = d->taps[i];
+  const int BN = d->Cin > 128 ? 256 : (d->Cin > 64 ? 128 : 64);
+  kp.n_ci_tiles = sg_cdiv(d->Cin, BN);
+  const int co_tiles = sg_cdiv(d->Cout, 128);
+  int ksplit = d->ksplit;
+  if (ksplit <= 0) {
+    long base_ctas = (long)co_tiles * kp.n_ci_tiles * d->ntaps;
+    ksplit = (int)((2 * 148 + base_ctas - 1) / base_ctas);
+    if (ksplit > kp.ktiles_total) ksplit = kp.ktiles_total;
+    if (ksplit < 1) ksplit = 1;
+    // keep at least 8 k-tiles per split so the pipeline prologue amortises
+    while (ksplit > 1 && kp.ktiles_total / ksplit < 8) --ksplit;
+  }
+  kp.ktiles_per_split = sg_cdiv(kp.ktiles_total, ksplit);
+  ksplit = sg_cdiv(kp.ktiles_total, kp.ktiles_per_split);
+  CUtensorMap tmA, tmB;
+  long long adims[5] = {d->dy_C, d->dy_W, d->dy_H, d->dy_P, d->N};
+  long long bdims[5] = {d->x_C, d->x_W, d->x_H, d->x_P, d->N};
+  int box[5] = {64, kp.BW, kp.BH, 1, kp.BI};
+  if (int e = make_tmap(&tmA, d->dy, 5, adims, box)) return e;
+  if (int e = make_tmap(&tmB, d->x, 5, bdims, box)) return e;
+  dim3 grid(co_tiles * kp.n_ci_tiles, d->ntaps, ksplit);
+  switch (BN) {
+    case 256: return launch_wgrad<256>(tmA, tmB, kp, grid, stream);
+    case 128: return launch_wgrad<128>(tmA, tmB, kp, grid, stream);
+    default: return launch_wgrad<64>(tmA, tmB, kp, grid, stream);
+  }
+}

@@ -1,0 +1,408 @@
+// masks/boxes -> spatial layout composition (reference: scene_generation/layout.py:64-184).
+//
+//   out[n, c, h, w] = sum_{o in image n} vecs[o, c] * S_o(h, w)
+//   S_o(h, w)       = bilinear, zero-padded sample of mask_o at the box grid of layout.py:96-128
+//
+// The reference materialises (O,D,M,M) and (O,D,H,W) tensors; here S_o is evaluated once per
+// (object, pixel) into shared memory and the D channels are produced by FMAs from it, so the only
+// HBM traffic is the output write (fwd) / the gradient read (bwd): N*Cp*H*W*s bytes.
+#include "common.cuh"
+#include "../../include/sg_b200.h"
+
+namespace {
+
+constexpr int TP = 64;        // pixels per tile (contiguous in the flattened H*W index)
+constexpr int MAXO = 32;      // objects processed per shared-memory chunk
+constexpr int THREADS = 256;
+
+struct LayoutArgs {
+  const float* vecs;      // (O, D) fp32
+  const float* boxes;     // (O, 4) fp32 xyxy
+  const void* masks;      // (O, M, M) f32 / i64 / u8
+  const int* ranges;      // (N, 2) object range per image
+  int mask_dtype;         // 0 f32, 1 i64, 2 u8
+  int O, D, M, N, H, W;
+  int Cp;                 // physical channel count of NHWC tensors (>= D, multiple of 8)
+  int align_corners;
+};
+
+__device__ __forceinline__ float load_mask(const void* masks, int dtype, long idx) {
+  if (dtype == 0) return ((const float*)masks)[idx];
+  if (dtype == 1) return (float)((const long long*)masks)[idx];
+  return (float)((const unsigned char*)masks)[idx];
+}
+
+// S_o(h,w) and (optionally) the 4 corner indices/weights
+__device__ __forceinline__ float sample_mask(const LayoutArgs& a, int o, int h, int w, const float* bx) {
+  float x0 = bx[0], y0 = bx[1];
+  float ww = __fsub_rn(bx[2], x0), hh = __fsub_rn(bx[3], y0);
+  float gx = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(sg_linspace01(w, a.W), x0), ww), 2.f), 1.f);
+  float gy = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(sg_linspace01(h, a.H), y0), hh), 2.f), 1.f);
+  SgBilin ax = sg_axis(gx, a.M, a.align_corners);
+  SgBilin ay = sg_axis(gy, a.M, a.align_corners);
+  const long base = (long)o * a.M * a.M;
+  float s = 0.f;
+  if (ay.ok0 && ax.ok0) s = __fmaf_rn(__fmul_rn(ax.w0, ay.w0), load_mask(a.masks, a.mask_dtype, base + (long)ay.i0 * a.M + ax.i0), s);
+  if (ay.ok0 && ax.ok1) s = __fmaf_rn(__fmul_rn(ax.w1, ay.w0), load_mask(a.masks, a.mask_dtype, base + (long)ay.i0 * a.M + ax.i0 + 1), s);
+  if (ay.ok1 && ax.ok0) s = __fmaf_rn(__fmul_rn(ax.w0, ay.w1), load_mask(a.masks, a.mask_dtype, base + (long)(ay.i0 + 1) * a.M + ax.i0), s);
+  if (ay.ok1 && ax.ok1) s = __fmaf_rn(__fmul_rn(ax.w1, ay.w1), load_mask(a.masks, a.mask_dtype, base + (long)(ay.i0 + 1) * a.M + ax.i0 + 1), s);
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward, train branch (layout.py:149-155): NHWC bf16 (Cp channels, zero padded) or NCHW fp32
+// ------------------------------------------------------------------------------------------------
+template <bool NHWC_BF16>
+__global__ void __launch_bounds__(THREADS) layout_fwd_kernel(LayoutArgs a, void* out) {
+  extern __shared__ float smem[];
+  float* sS = smem;                       // [MAXO][TP]
+  float* sV = smem + MAXO * TP;           // [MAXO][Cp]
+  __shared__ int sActive[MAXO];
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * TP;
+  const int HW = a.H * a.W;
+  const int o_begin = a.ranges[2 * n], o_end = a.ranges[2 * n + 1];
+  const int chunks = a.Cp / 8;
+  constexpr int MAX_ITEMS = 8;            // TP*chunks/THREADS <= 8  (Cp <= 256)
+  float acc[MAX_ITEMS][8];
+#pragma unroll
+  for (int i = 0; i < MAX_ITEMS; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  for (int ob = o_begin; ob < o_end; ob += MAXO) {
+    const int nobj = min(MAXO, o_end - ob);
+    __syncthreads();
+    if (threadIdx.x < MAXO) sActive[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < nobj * a.Cp; i += THREADS) {
+      int o = i / a.Cp, c = i % a.Cp;
+      sV[o * a.Cp + c] = (c < a.D) ? a.vecs[(long)(ob + o) * a.D + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nobj * TP; i += THREADS) {
+      int o = i / TP, px = i % TP;
+      int p = p0 + px;
+      float s = 0.f;
+      if (p < HW) s = sample_mask(a, ob + o, p / a.W, p % a.W, a.boxes + 4 * (ob + o));
+      sS[o * TP + px] = s;
+      if (s != 0.f) sActive[o] = 1;
+    }
+    __syncthreads();
+    if (NHWC_BF16) {
+#pragma unroll
+      for (int it = 0; it < MAX_ITEMS; ++it) {
+        int idx = it * THREADS + threadIdx.x;
+        if (idx >= TP * chunks) break;
+        int px = idx / chunks, ch = idx % chunks;
+        for (int o = 0; o < nobj; ++o) {
+          if (!sActive[o]) continue;
+          float s = sS[o * TP + px];
+          if (s == 0.f) continue;
+          const float4* v = reinterpret_cast<const float4*>(sV + o * a.Cp + ch * 8);
+          float4 v0 = v[0], v1 = v[1];
+          acc[it][0] = __fmaf_rn(v0.x, s, acc[it][0]); acc[it][1] = __fmaf_rn(v0.y, s, acc[it][1]);
+          acc[it][2] = __fmaf_rn(v0.z, s, acc[it][2]); acc[it][3] = __fmaf_rn(v0.w, s, acc[it][3]);
+          acc[it][4] = __fmaf_rn(v1.x, s, acc[it][4]); acc[it][5] = __fmaf_rn(v1.y, s, acc[it][5]);
+          acc[it][6] = __fmaf_rn(v1.z, s, acc[it][6]); acc[it][7] = __fmaf_rn(v1.w, s, acc[it][7]);
+        }
+      }
+    } else {
+      // NCHW: item = (channel group of 8 strided channels?) -> keep it simple: one (c, px) per slot
+#pragma unroll
+      for (int it = 0; it < MAX_ITEMS; ++it) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          int idx = (it * 8 + j) * THREADS + threadIdx.x;   // over D*TP, px fastest
+          if (idx >= a.D * TP) break;
+          int c = idx / TP, px = idx % TP;
+          float r = acc[it][j];
+          for (int o = 0; o < nobj; ++o) {
+            float s = sS[o * TP + px];
+            if (s != 0.f) r = __fmaf_rn(sV[o * a.Cp + c], s, r);
+          }
+          acc[it][j] = r;
+        }
+      }
+    }
+  }
+  if (NHWC_BF16) {
+    __nv_bfloat16* o16 = (__nv_bfloat16*)out;
+#pragma unroll
+    for (int it = 0; it < MAX_ITEMS; ++it) {
+      int idx = it * THREADS + threadIdx.x;
+      if (idx >= TP * chunks) break;
+      int px = idx / chunks, ch = idx % chunks;
+      int p = p0 + px;
+      if (p >= HW) continue;
+      __align__(16) __nv_bfloat162 pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pk[j] = __floats2bfloat162_rn(acc[it][2 * j], acc[it][2 * j + 1]);
+      *reinterpret_cast<uint4*>(o16 + ((long)n * HW + p) * a.Cp + ch * 8) = *reinterpret_cast<uint4*>(pk);
+    }
+  } else {
+    float* o32 = (float*)out;
+#pragma unroll
+    for (int it = 0; it < MAX_ITEMS; ++it) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int idx = (it * 8 + j) * THREADS + threadIdx.x;
+        if (idx >= a.D * TP) break;
+        int c = idx / TP, px = idx % TP;
+        int p = p0 + px;
+        if (p < HW) o32[((long)n * a.D + c) * HW + p] = acc[it][j];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward (train branch): dvecs[o,c] = sum_p S_o(p) g[n,c,p];  dmask via the 4 bilinear corners.
+// ------------------------------------------------------------------------------------------------
+template <bool NHWC_BF16>
+__global__ void __launch_bounds__(THREADS) layout_bwd_kernel(LayoutArgs a, const void* grad, float* dvecs, float* dmasks) {
+  extern __shared__ float smem[];
+  float* sS = smem;                         // [MAXO][TP]
+  float* sG = smem + MAXO * TP;             // [TP][Cp+1]
+  float* sV = sG + TP * (a.Cp + 1);         // [MAXO][Cp] only when dmasks
+  __shared__ int sActive[MAXO];
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * TP;
+  const int HW = a.H * a.W;
+  const int o_begin = a.ranges[2 * n], o_end = a.ranges[2 * n + 1];
+  const int ldg = a.Cp + 1;
+  // stage the gradient tile as fp32
+  if (NHWC_BF16) {
+    const __nv_bfloat16* g16 = (const __nv_bfloat16*)grad;
+    const int chunks = a.Cp / 8;
+    for (int idx = threadIdx.x; idx < TP * chunks; idx += THREADS) {
+      int px = idx / chunks, ch = idx % chunks;
+      int p = p0 + px;
+      uint4 raw = make_uint4(0, 0, 0, 0);
+      if (p < HW) raw = *reinterpret_cast<const uint4*>(g16 + ((long)n * HW + p) * a.Cp + ch * 8);
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __bfloat1622float2(h2[j]);
+        sG[px * ldg + ch * 8 + 2 * j] = f.x;
+        sG[px * ldg + ch * 8 + 2 * j + 1] = f.y;
+      }
+    }
+  } else {
+    const float* g32 = (const float*)grad;
+    for (int idx = threadIdx.x; idx < a.D * TP; idx += THREADS) {
+      int c = idx / TP, px = idx % TP;
+      int p = p0 + px;
+      sG[px * ldg + c] = (p < HW) ? g32[((long)n * a.D + c) * HW + p] : 0.f;
+    }
+  }
+  for (int ob = o_begin; ob < o_end; ob += MAXO) {
+    const int nobj = min(MAXO, o_end - ob);
+    __syncthreads();
+    if (threadIdx.x < MAXO) sActive[threadIdx.x] = 0;
+    if (dmasks) {
+      for (int i = threadIdx.x; i < nobj * a.Cp; i += THREADS) {
+        int o = i / a.Cp, c = i % a.Cp;
+        sV[o * a.Cp + c] = (c < a.D) ? a.vecs[(long)(ob + o) * a.D + c] : 0.f;
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nobj * TP; i += THREADS) {
+      int o = i / TP, px = i % TP;
+      int p = p0 + px;
+      float s = 0.f;
+      if (p < HW) s = sample_mask(a, ob + o, p / a.W, p % a.W, a.boxes + 4 * (ob + o));
+      sS[o * TP + px] = s;
+      if (s != 0.f) sActive[o] = 1;
+    }
+    __syncthreads();
+    // dvecs: thread per (o, c); serial over the tile's pixels
+    for (int i = threadIdx.x; i < nobj * a.D; i += THREADS) {
+      int o = i / a.D, c = i % a.D;
+      if (!sActive[o]) continue;
+      float r = 0.f;
+      for (int px = 0; px < TP; ++px) r = __fmaf_rn(sS[o * TP + px], sG[px * ldg + c], r);
+      atomicAdd(dvecs + (long)(ob + o) * a.D + c, r);
+    }
+    if (dmasks) {
+      // dS[o,px] = sum_c vecs[o,c] g[px,c]; then scatter through the bilinear corners
+      for (int i = threadIdx.x; i < nobj * TP; i += THREADS) {
+        int o = i / TP, px = i % TP;
+        int p = p0 + px;
+        if (p >= HW) continue;
+        float ds = 0.f;
+        for (int c = 0; c < a.D; ++c) ds = __fmaf_rn(sV[o * a.Cp + c], sG[px * ldg + c], ds);
+        if (ds == 0.f) continue;
+        const float* bx = a.boxes + 4 * (ob + o);
+        int h = p / a.W, w = p % a.W;
+        float x0 = bx[0], y0 = bx[1];
+        float ww = __fsub_rn(bx[2], x0), hh = __fsub_rn(bx[3], y0);
+        float gx = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(sg_linspace01(w, a.W), x0), ww), 2.f), 1.f);
+        float gy = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(sg_linspace01(h, a.H), y0), hh), 2.f), 1.f);
+        SgBilin ax = sg_axis(gx, a.M, a.align_corners);
+        SgBilin ay = sg_axis(gy, a.M, a.align_corners);
+        float* dm = dmasks + (long)(ob + o) * a.M * a.M;
+        if (ay.ok0 && ax.ok0) atomicAdd(dm + ay.i0 * a.M + ax.i0, ax.w0 * ay.w0 * ds);
+        if (ay.ok0 && ax.ok1) atomicAdd(dm + ay.i0 * a.M + ax.i0 + 1, ax.w1 * ay.w0 * ds);
+        if (ay.ok1 && ax.ok0) atomicAdd(dm + (ay.i0 + 1) * a.M + ax.i0, ax.w0 * ay.w1 * ds);
+        if (ay.ok1 && ax.ok1) atomicAdd(dm + (ay.i0 + 1) * a.M + ax.i0 + 1, ax.w1 * ay.w1 * ds);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// test-mode compositing (layout.py:157-169)
+//   mass[o] = sum_{c,h,w} vecs[o,c] S_o(h,w);  objects of an image painted in ascending mass order,
+//   a pixel is owned by the first object (in that order) whose clean mask sample S_o > 0.5.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS) layout_mass_kernel(LayoutArgs a, float* mass) {
+  __shared__ float red[THREADS / 32];
+  const int o = blockIdx.x;
+  float vs = 0.f;
+  for (int c = threadIdx.x; c < a.D; c += THREADS) vs += a.vecs[(long)o * a.D + c];
+  float ss = 0.f;
+  for (int p = threadIdx.x; p < a.H * a.W; p += THREADS) ss += sample_mask(a, o, p / a.W, p % a.W, a.boxes + 4 * o);
+  // block reduce both
+  for (int pass = 0; pass < 2; ++pass) {
+    float v = pass == 0 ? vs : ss;
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int i = 0; i < THREADS / 32; ++i) t += red[i];
+    if (pass == 0) vs = t; else ss = t;
+  }
+  if (threadIdx.x == 0) mass[o] = vs * ss;
+}
+
+template <bool NHWC_BF16>
+__global__ void __launch_bounds__(THREADS) layout_test_kernel(LayoutArgs a, const float* mass, void* out) {
+  extern __shared__ float smem[];
+  int* sOwner = (int*)smem;               // [TP]
+  float* sOwnS = smem + TP;               // [TP]
+  __shared__ int sOrder[1024];
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * TP;
+  const int HW = a.H * a.W;
+  const int o_begin = a.ranges[2 * n], o_end = a.ranges[2 * n + 1];
+  const int nobj = min(o_end - o_begin, 1024);
+  // rank by (mass, index): stable ascending order
+  for (int i = threadIdx.x; i < nobj; i += THREADS) {
+    float mi = mass[o_begin + i];
+    int rank = 0;
+    for (int j = 0; j < nobj; ++j) {
+      float mj = mass[o_begin + j];
+      rank += (mj < mi) || (mj == mi && j < i);
+    }
+    sOrder[rank] = i;
+  }
+  __syncthreads();
+  for (int px = threadIdx.x; px < TP; px += THREADS) {
+    int p = p0 + px;
+    int owner = -1;
+    float os = 0.f;
+    if (p < HW) {
+      for (int r = 0; r < nobj; ++r) {
+        int o = o_begin + sOrder[r];
+        float s = sample_mask(a, o, p / a.W, p % a.W, a.boxes + 4 * o);
+        if (s > 0.5f) { owner = o; os = s; break; }
+      }
+    }
+    sOwner[px] = owner;
+    sOwnS[px] = os;
+  }
+  __syncthreads();
+  if (NHWC_BF16) {
+    __nv_bfloat16* o16 = (__nv_bfloat16*)out;
+    for (int idx = threadIdx.x; idx < TP * a.Cp; idx += THREADS) {
+      int px = idx / a.Cp, c = idx % a.Cp;
+      int p = p0 + px;
+      if (p >= HW) continue;
+      int o = sOwner[px];
+      float v = (o >= 0 && c < a.D) ? a.vecs[(long)o * a.D + c] * sOwnS[px] : 0.f;
+      o16[((long)n * HW + p) * a.Cp + c] = __float2bfloat16(v);
+    }
+  } else {
+    float* o32 = (float*)out;
+    for (int idx = threadIdx.x; idx < TP * a.D; idx += THREADS) {
+      int c = idx / TP, px = idx % TP;
+      int p = p0 + px;
+      if (p >= HW) continue;
+      int o = sOwner[px];
+      o32[((long)n * a.D + c) * HW + p] = (o >= 0) ? a.vecs[(long)o * a.D + c] * sOwnS[px] : 0.f;
+    }
+  }
+}
+
+int check_args(const LayoutArgs& a, int out_format) {
+  SG_CHECK_ARG(a.O >= 0 && a.D > 0 && a.M > 0 && a.N >= 0 && a.H > 0 && a.W > 0, "masks_to_layout: bad sizes");
+  SG_CHECK_ARG(a.mask_dtype >= 0 && a.mask_dtype <= 2, "masks_to_layout: mask_dtype must be 0 (f32), 1 (i64) or 2 (u8)");
+  SG_CHECK_ARG(out_format == 0 || out_format == 1, "masks_to_layout: out_format must be 0 (NCHW f32) or 1 (NHWC bf16)");
+  SG_CHECK_ARG(a.Cp >= a.D && a.Cp % 8 == 0 && a.Cp <= 256, "masks_to_layout: Cp must be a multiple of 8 in [D, 256] (got D=%d Cp=%d)", a.D, a.Cp);
+  return SG_OK;
+}
+
+}  // namespace
+
+extern "C" int sg_masks_to_layout_fwd(const float* vecs, const float* boxes, const void* masks, int mask_dtype,
+                                      const int* img_ranges, int O, int D, int M, int N, int H, int W,
+                                      int align_corners, int out_format, int Cp, void* out, cudaStream_t stream) {
+  LayoutArgs a{vecs, boxes, masks, img_ranges, mask_dtype, O, D, M, N, H, W, Cp, align_corners};
+  if (int e = check_args(a, out_format)) return e;
+  if (N == 0) return SG_OK;
+  dim3 grid(sg_cdiv((long)H * W, TP), N);
+  size_t smem = sizeof(float) * (MAXO * TP + MAXO * Cp);
+  if (out_format == 1) {
+    cudaFuncSetAttribute(layout_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    layout_fwd_kernel<true><<<grid, THREADS, smem, stream>>>(a, out);
+  } else {
+    cudaFuncSetAttribute(layout_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    layout_fwd_kernel<false><<<grid, THREADS, smem, stream>>>(a, out);
+  }
+  SG_CHECK_LAUNCH("sg_masks_to_layout_fwd");
+  return SG_OK;
+}
+
+extern "C" int sg_masks_to_layout_bwd(const float* vecs, const float* boxes, const void* masks, int mask_dtype,
+                                      const int* img_ranges, int O, int D, int M, int N, int H, int W,
+                                      int align_corners, int grad_format, int Cp, const void* grad_out,
+                                      float* dvecs, float* dmasks, cudaStream_t stream) {
+  LayoutArgs a{vecs, boxes, masks, img_ranges, mask_dtype, O, D, M, N, H, W, Cp, align_corners};
+  if (int e = check_args(a, grad_format)) return e;
+  SG_CHECK_ARG(dvecs != nullptr, "masks_to_layout_bwd: dvecs is null");
+  cudaMemsetAsync(dvecs, 0, sizeof(float) * (size_t)O * D, stream);
+  if (dmasks) cudaMemsetAsync(dmasks, 0, sizeof(float) * (size_t)O * M * M, stream);
+  if (N == 0 || O == 0) return SG_OK;
+  dim3 grid(sg_cdiv((long)H * W, TP), N);
+  size_t smem = sizeof(float) * (MAXO * TP + TP * (Cp + 1) + (dmasks ? MAXO * Cp : 0));
+  if (grad_format == 1) {
+    cudaFuncSetAttribute(layout_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    layout_bwd_kernel<true><<<grid, THREADS, smem, stream>>>(a, grad_out, dvecs, dmasks);
+  } else {
+    cudaFuncSetAttribute(layout_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    layout_bwd_kernel<false><<<grid, THREADS, smem, stream>>>(a, grad_out, dvecs, dmasks);
+  }
+  SG_CHECK_LAUNCH("sg_masks_to_layout_bwd");
+  return SG_OK;
+}
+
+extern "C" int sg_masks_to_layout_test(const float* vecs, const float* boxes, const void* masks, int mask_dtype,
+                                       const int* img_ranges, int O, int D, int M, int N, int H, int W,
+                                       int align_corners, int out_format, int Cp, float* mass_ws, void* out,
+                                       cudaStream_t stream) {
+  LayoutArgs a{vecs, boxes, masks, img_ranges, mask_dtype, O, D, M, N, H, W, Cp, align_corners};
+  if (int e = check_args(a, out_format)) return e;
+  SG_CHECK_ARG(mass_ws != nullptr, "masks_to_layout_test: mass workspace (O floats) is null");
+  if (N == 0) return SG_OK;
+  if (O > 0) {
+    layout_mass_kernel<<<O, THREADS, 0, stream>>>(a, mass_ws);
+    SG_CHECK_LAUNCH("sg_masks_to_layout_test(mass)");
+  }
+  dim3 grid(sg_cdiv((long)H * W, TP), N);
+  size_t smem = sizeof(float) * 2 * TP;
+  if (out_format == 1) layout_test_kernel<true><<<grid, THREADS, smem, stream>>>(a, mass_ws, out);
+  else layout_test_kernel<false><<<grid, THREADS, smem, stream>>>(a, mass_ws, out);
+  SG_CHECK_LAUNCH("sg_masks_to_layout_test");
+  return SG_OK;
+}

@@ -1,0 +1,226 @@
+"""Low-level tensor -> C-ABI wrappers (PyTorch tensors in, PyTorch tensors out).
+
+Only plumbing lives here: pointer extraction, output allocation, descriptor filling.  All arithmetic
+happens in libsg_b200.so.  Every wrapper enqueues on the current torch CUDA stream.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, Phase, Tap, WgradDesc, WTap
+
+F32, BF16 = 0, 1
+NCHW_F32, NHWC_BF16 = 0, 1
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('libsg_b200 ops need CUDA tensors (there is no CPU fallback)')
+
+
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+_MASK_DT = {torch.float32: 0, torch.int64: 1, torch.uint8: 2}
+
+
+# ---------------------------------------------------------------------------------------------
+# layout
+# ---------------------------------------------------------------------------------------------
+def masks_to_layout_fwd(vecs, boxes, masks, ranges, H, W, align_corners=False, out_format=NCHW_F32, test_mode=False):
+    """ranges: int32 (N,2) device tensor.  Returns (N,D,H,W) f32, or a (N,D,H,W) *view* of a
+    channels-last bf16 buffer with Cp = round_up(D, 8) physical channels."""
+    _need_cuda(vecs, boxes, masks, ranges)
+    O, D = vecs.shape
+    M = masks.shape[1]
+    N = ranges.shape[0]
+    vecs, boxes, masks = vecs.contiguous().float(), boxes.contiguous().float(), masks.contiguous()
+    Cp = round_up(D, 8)
+    if out_format == NHWC_BF16:
+        buf = torch.empty((N, H, W, Cp), dtype=torch.bfloat16, device=vecs.device)
+    else:
+        buf = torch.empty((N, D, H, W), dtype=torch.float32, device=vecs.device)
+    args = [_ptr(vecs), _ptr(boxes), _ptr(masks), _MASK_DT[masks.dtype], _ptr(ranges), O, D, M, N, H, W,
+            int(align_corners), out_format, Cp]
+    if test_mode:
+        ws = torch.empty(max(O, 1), dtype=torch.float32, device=vecs.device)
+        _lib.call('sg_masks_to_layout_test', *args, _ptr(ws), _ptr(buf), _stream())
+    else:
+        _lib.call('sg_masks_to_layout_fwd', *args, _ptr(buf), _stream())
+    if out_format == NHWC_BF16:
+        return buf.permute(0, 3, 1, 2)[:, :D]
+    return buf
+
+
+def masks_to_layout_bwd(vecs, boxes, masks, ranges, H, W, grad, align_corners=False, need_dmasks=False):
+    """grad: (N,D,H,W) f32 contiguous, or a channels-last bf16 tensor whose storage is (N,H,W,Cp)."""
+    O, D = vecs.shape
+    M = masks.shape[1]
+    N = ranges.shape[0]
+    vecs, boxes, masks = vecs.contiguous().float(), boxes.contiguous().float(), masks.contiguous()
+    if grad.dtype == torch.bfloat16:
+        g = grad.permute(0, 2, 3, 1)
+        Cp = g.stride(2)
+        if not (g.stride(3) == 1 and Cp % 8 == 0 and g.stride(1) == W * Cp and g.stride(0) == H * W * Cp):
+            Cp = round_up(D, 8)
+            gb = torch.zeros((N, H, W, Cp), dtype=torch.bfloat16, device=grad.device)
+            gb[..., :D] = g
+            g = gb
+        fmt = NHWC_BF16
+    else:
+        g = grad.contiguous().float()
+        Cp = round_up(D, 8)
+        fmt = NCHW_F32
+    dvecs = torch.empty((O, D), dtype=torch.float32, device=vecs.device)
+    dmasks = torch.empty((O, M, M), dtype=torch.float32, device=vecs.device) if need_dmasks else None
+    _lib.call('sg_masks_to_layout_bwd', _ptr(vecs), _ptr(boxes), _ptr(masks), _MASK_DT[masks.dtype], _ptr(ranges),
+              O, D, M, N, H, W, int(align_corners), fmt, Cp, _ptr(g), _ptr(dvecs), _ptr(dmasks), _stream())
+    return dvecs, dmasks
+
+
+# ---------------------------------------------------------------------------------------------
+# graph
+# ---------------------------------------------------------------------------------------------
+def build_incidence_csr(edges_cpu, O):
+    """CSR of (triple, role) incidences per object in the reference's accumulation order
+    (graph.py:100-101: all subject uses in triple order, then all object uses).  Host side, numpy."""
+    e = np.asarray(edges_cpu, dtype=np.int64).reshape(-1, 2)
+    T = e.shape[0]
+    if T and (e.min() < 0 or e.max() >= O):
+        raise IndexError('edge index out of range [0, %d)' % O)
+    obj = np.concatenate([e[:, 0], e[:, 1]])
+    src = np.concatenate([2 * np.arange(T), 2 * np.arange(T) + 1])
+    order = np.argsort(obj, kind='stable')
+    counts = np.bincount(obj, minlength=O)
+    ptr = np.zeros(O + 1, dtype=np.int32)
+    np.cumsum(counts, out=ptr[1:])
+    return ptr, src[order].astype(np.int32)
+
+
+def gconv_gather(obj_vecs, pred_vecs, edges, out_dtype=torch.float32, ld_out=None):
+    _need_cuda(obj_vecs, pred_vecs, edges)
+    O, Do = obj_vecs.shape
+    T, Dp = pred_vecs.shape
+    ld = ld_out or (2 * Do + Dp)
+    out = torch.empty((T, ld), dtype=out_dtype, device=obj_vecs.device)
+    _lib.call('sg_gconv_gather_fwd', _ptr(obj_vecs.contiguous()), _ptr(pred_vecs.contiguous()), _ptr(edges.contiguous()),
+              O, T, Do, Dp, BF16 if out_dtype == torch.bfloat16 else F32, ld, _ptr(out), _stream())
+    return out
+
+
+def gconv_pool(new_t, col_o, seg_ptr, seg_src, O, H, avg=True, out_dtype=torch.float32, ld_out=None):
+    ld = ld_out or H
+    out = torch.empty((O, ld), dtype=out_dtype, device=new_t.device)
+    assert new_t.dtype == torch.float32 and new_t.stride(1) == 1
+    _lib.call('sg_gconv_pool_fwd', _ptr(new_t), new_t.stride(0), col_o, _ptr(seg_ptr), _ptr(seg_src), O, H, int(avg),
+              BF16 if out_dtype == torch.bfloat16 else F32, ld, _ptr(out), _stream())
+    return out
+
+
+def gconv_pool_bwd(dpooled, dnew_p, edges, seg_ptr, T, H, Dout, avg=True):
+    out = torch.empty((T, 2 * H + Dout), dtype=torch.float32, device=dpooled.device)
+    _lib.call('sg_gconv_pool_bwd', _ptr(dpooled.contiguous()), _ptr(None if dnew_p is None else dnew_p.contiguous()),
+              _ptr(edges.contiguous()), _ptr(seg_ptr), T, H, Dout, int(avg), 2 * H + Dout, _ptr(out), _stream())
+    return out
+
+
+def gconv_gather_bwd(dcur, seg_ptr, seg_src, O, T, Do, Dp):
+    dcur = dcur.contiguous()
+    dobj = torch.empty((O, Do), dtype=torch.float32, device=dcur.device)
+    dpred = torch.empty((T, Dp), dtype=torch.float32, device=dcur.device)
+    _lib.call('sg_gconv_gather_bwd', _ptr(dcur), dcur.stride(0), _ptr(seg_ptr), _ptr(seg_src), O, T, Do, Dp,
+              _ptr(dobj), _ptr(dpred), _stream())
+    return dobj, dpred
+
+
+# ---------------------------------------------------------------------------------------------
+# crop
+# ---------------------------------------------------------------------------------------------
+def crop_bbox_fwd(feats, boxes, box_to_feats, HH, WW, align_corners=False, out_format=NCHW_F32):
+    _need_cuda(feats, boxes, box_to_feats)
+    N, C, H, W = feats.shape
+    B = boxes.shape[0]
+    feats, boxes, m = feats.contiguous().float(), boxes.contiguous().float(), box_to_feats.contiguous()
+    Cp = round_up(C, 8)
+    if out_format == NHWC_BF16:
+        out = torch.empty((B, HH, WW, Cp), dtype=torch.bfloat16, device=feats.device)
+    else:
+        out = torch.empty((B, C, HH, WW), dtype=torch.float32, device=feats.device)
+    _lib.call('sg_crop_bbox_fwd', _ptr(feats), _ptr(boxes), _ptr(m), N, C, H, W, B, HH, WW, int(align_corners),
+              out_format, Cp, _ptr(out), _stream())
+    return out
+
+
+def crop_bbox_bwd(grad, boxes, box_to_feats, N, C, H, W, align_corners=False, grad_format=NCHW_F32):
+    B = boxes.shape[0]
+    if grad_format == NHWC_BF16:
+        HH, WW, Cp = grad.shape[1], grad.shape[2], grad.shape[3]
+    else:
+        HH, WW, Cp = grad.shape[2], grad.shape[3], round_up(C, 8)
+    dfeats = torch.empty((N, C, H, W), dtype=torch.float32, device=grad.device)
+    _lib.call('sg_crop_bbox_bwd', _ptr(boxes.contiguous().float()), _ptr(box_to_feats.contiguous()), N, C, H, W, B,
+              HH, WW, int(align_corners), grad_format, Cp, _ptr(grad.contiguous()), _ptr(dfeats), _stream())
+    return dfeats
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core conv / gemm
+# ---------------------------------------------------------------------------------------------
+def conv_tc(x5, w3, y, y_strides, Hout, Wout, taps, phases=None, oh_mul=1, ow_mul=1, in_h0=0, in_w0=0,
+            bias=None, act=_lib.ACT_NONE, slope=0.0, stats=None):
+    """x5: bf16 (N,P,H,W,C) contiguous; w3: bf16 (Cout,taps,C) contiguous; y: f32/bf16 output storage
+    addressed as img*os_img + (h*oh_mul+oh_off)*os_h + (w*ow_mul+ow_off)*os_w + co with
+    y_strides=(os_img, os_h, os_w) in elements.  taps: list of (dh, dw, plane, wtap).
+    phases: list of (tap_begin, ntaps, oh_off, ow_off) or None for a single phase."""
+    _need_cuda(x5, w3, y)
+    assert x5.dtype == torch.bfloat16 and w3.dtype == torch.bfloat16 and x5.is_contiguous() and w3.is_contiguous()
+    d = ConvDesc()
+    d.x, (d.x_N, d.x_P, d.x_H, d.x_W, d.x_C) = x5.data_ptr(), x5.shape
+    d.w, (d.w_Cout, d.w_taps, d.w_C) = w3.data_ptr(), w3.shape
+    d.y, d.y_dtype = y.data_ptr(), (BF16 if y.dtype == torch.bfloat16 else F32)
+    d.y_os_img, d.y_os_h, d.y_os_w = y_strides
+    d.Hout, d.Wout, d.oh_mul, d.ow_mul, d.in_h0, d.in_w0 = Hout, Wout, oh_mul, ow_mul, in_h0, in_w0
+    if phases is None:
+        phases = [(0, len(taps), 0, 0)]
+    d.nphases = len(phases)
+    for i, ph in enumerate(phases):
+        d.phases[i] = Phase(*ph)
+    d.ntaps = len(taps)
+    for i, tp in enumerate(taps):
+        d.taps[i] = Tap(*tp)
+    d.bias = None if bias is None else bias.data_ptr()
+    d.act, d.slope = act, slope
+    d.stats = None if stats is None else stats.data_ptr()
+    _lib.call('sg_conv_tc', ctypes.byref(d), _stream())
+    return y
+
+
+def wgrad_tc(dy5, x5, dw, Hred, Wred, taps, Cout, Cin, ksplit=0):
+    """dy5: bf16 (N,P,H,W,Cd); x5: bf16 (N,P,H,W,Cx); dw: f32 (Cout, w_taps, dw_C) ACCUMULATED into.
+    taps: list of (dha, dwa, pa, dhb, dwb, pb, wtap)."""
+    _need_cuda(dy5, x5, dw)
+    assert dy5.dtype == torch.bfloat16 and x5.dtype == torch.bfloat16 and dw.dtype == torch.float32
+    assert dy5.is_contiguous() and x5.is_contiguous() and dw.is_contiguous()
+    d = WgradDesc()
+    d.dy, (d.N, d.dy_P, d.dy_H, d.dy_W, d.dy_C) = dy5.data_ptr(), dy5.shape
+    d.x, (_, d.x_P, d.x_H, d.x_W, d.x_C) = x5.data_ptr(), x5.shape
+    d.Hred, d.Wred = Hred, Wred
+    d.dw, d.Cout, d.Cin, d.w_taps, d.dw_C = dw.data_ptr(), Cout, Cin, dw.shape[1], dw.shape[2]
+    d.ntaps = len(taps)
+    for i, tp in enumerate(taps):
+        d.taps[i] = WTap(*tp, 0)
+    d.ksplit = ksplit
+    _lib.call('sg_wgrad_tc', ctypes.byref(d), _stream())
+    return dw
