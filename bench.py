@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: images/sec of the full training iteration (Model.forward + generator step
++ mask/object/image discriminator steps, incl. Adam and — multi-GPU — the gradient all-reduce) on
+synthetic COCO-Stuff-shaped scene graphs, 128x128, batch 32 per GPU (BASELINE.json configs[1]/[2]).
+
+    python bench.py --gpus N --steps K --warmup W             # this framework (one process per GPU)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on host cores
+                                                             #   (oracle port; rank 0 only)
+Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for how every field is produced.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_IMAGE_STEP = 224.1e9     # algorithmic FLOPs of one image through one train step
+NUM_OBJS = 172
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=32, help='images per GPU')
+    ap.add_argument('--image-size', type=int, default=128)
+    ap.add_argument('--kmin', type=int, default=3)
+    ap.add_argument('--kmax', type=int, default=8)
+    ap.add_argument('--cpu-batch', type=int, default=2, help='images per step of the CPU baseline sample')
+    ap.add_argument('--cpu-steps', type=int, default=3)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's train step on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(image_size, n_imgs, steps, warmup, kmin, kmax):
+    """images/sec of the reference algorithm (oracle/restate.py OracleTrainer: fp32, torch CPU kernels for the
+    dense contractions) on all host threads, on a bounded sample of the bench workload."""
+    from oracle import restate as R
+    from scene_generation_b200 import synthetic
+    import random
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = dict(image_size=(image_size, image_size), num_objs=NUM_OBJS, rep_size=32, mask_size=32, n_downsample_global=4,
+               gconv_num_layers=5, crop_size=32, ngf=64, n_blocks=9)
+    sds = R.make_state_dicts(cfg, seed=0)
+    tr = R.OracleTrainer(sds, cfg)
+    random.seed(0)
+    times = []
+    for s in range(warmup + steps):
+        batch = synthetic.make_batch(n_imgs, (image_size, image_size), NUM_OBJS, kmin, kmax, seed=1000 + s)
+        noise = torch.randn((1, 64))
+        t0 = time.perf_counter()
+        tr.step(batch, noise, use_gt=(s % 2 == 0))
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    mean = sum(times) / len(times)
+    return n_imgs / mean, mean, cores
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    rate, mean, cores = cpu_reference_rate(a.image_size, a.cpu_batch, a.steps, max(a.warmup, 1), a.kmin, a.kmax)
+    sample = '%d images/step x %d steps of the %dx%d, <=%d-object workload (fp32, %d host threads)' % (
+        a.cpu_batch, a.steps, a.image_size, a.image_size, a.kmax, cores)
+    line = {
+        'impl': 'reference', 'metric': 'images/sec (train step, %dx%d, bs32/GPU)' % (a.image_size, a.image_size),
+        'value': rate, 'unit': 'images/s', 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': max(a.warmup, 1),
+        'ms_per_step': mean * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': {'workload': 'COCO-Stuff-shaped synthetic scene graphs (<=%d obj), %dx%d, full train step '
+                               '(no VGG loss: pretrained weights unavailable offline)' % (a.kmax, a.image_size, a.image_size),
+                   'global_batch': a.cpu_batch, 'parallelism': 'cpu x%d threads' % cores},
+        'cpu_baseline': {'value': rate, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': rate, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# clock sampling
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.FIELDS,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for s in self.samples:
+            f = [x.strip() for x in s.split(',')]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# per-launch instrumentation of the tensor-core kernels (one extra, untimed step)
+# ------------------------------------------------------------------------------------------------
+class KernelProbe:
+    """Wraps ops.conv_tc / ops.wgrad_tc with CUDA events on the launching stream and accounts the
+    ALGORITHMIC FLOPs of every launch (2 * output pixels * Cout * real Cin * taps)."""
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        from scene_generation_b200 import ops
+        self.ops = ops
+        self.orig_conv, self.orig_wgrad = ops.conv_tc, ops.wgrad_tc
+        probe = self
+
+        def conv_tc(x5, w3, y, y_strides, Hout, Wout, taps, phases=None, **kw):
+            N, Cout, Cin = x5.shape[0], w3.shape[0], min(x5.shape[4], w3.shape[2])
+            nph = len(phases) if phases else 1
+            ntap = sum(p[1] for p in phases) if phases else len(taps)
+            flops = 2.0 * N * Hout * Wout * Cout * Cin * ntap
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = probe.orig_conv(x5, w3, y, y_strides, Hout, Wout, taps, phases=phases, **kw)
+            e1.record()
+            probe.records.append(('conv_tc', flops, e0, e1, (N, Hout, Wout, Cout, Cin, ntap, nph)))
+            return r
+
+        def wgrad_tc(dy5, x5, dw, Hred, Wred, taps, Cout, Cin, ksplit=0):
+            flops = 2.0 * dy5.shape[0] * Hred * Wred * Cout * Cin * len(taps)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = probe.orig_wgrad(dy5, x5, dw, Hred, Wred, taps, Cout, Cin, ksplit)
+            e1.record()
+            probe.records.append(('wgrad_tc', flops, e0, e1, (dy5.shape[0], Hred, Wred, Cout, Cin, len(taps), 1)))
+            return r
+        ops.conv_tc, ops.wgrad_tc = conv_tc, wgrad_tc
+        return self
+
+    def __exit__(self, *exc):
+        self.ops.conv_tc, self.ops.wgrad_tc = self.orig_conv, self.orig_wgrad
+
+    def summary(self):
+        torch.cuda.synchronize()
+        fam = {}
+        top = {}
+        for name, flops, e0, e1, shape in self.records:
+            ms = e0.elapsed_time(e1)
+            f = fam.setdefault(name, {'launches': 0, 'flops': 0.0, 'ms': 0.0})
+            f['launches'] += 1
+            f['flops'] += flops
+            f['ms'] += ms
+            t = top.setdefault((name, shape), {'launches': 0, 'flops': 0.0, 'ms': 0.0})
+            t['launches'] += 1
+            t['flops'] += flops
+            t['ms'] += ms
+        return fam, top
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('bf16_tflops_sustained', 1441.7), d.get('hbm_gbs', 6572.9), 'measured (MEASURED_PEAKS.json, sustained)'
+    return 1400.0, 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    a = parse()
+    if a.impl == 'reference':
+        return run_reference_arm(a)
+
+    import torch.distributed as dist
+    from scene_generation_b200 import _lib, args as sgargs, synthetic
+    from scene_generation_b200.trainer import Trainer
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    assert world == a.gpus or world == 1, 'launch with torchrun --nproc-per-node %d' % a.gpus
+
+    H = a.image_size
+    targs = sgargs.default_args(image_size=(H, H), num_objs=NUM_OBJS)
+    torch.manual_seed(1234)           # identical replicas; the reducers broadcast rank 0's weights anyway
+    tr = Trainer(targs, synthetic.make_vocab(NUM_OBJS), {})
+    # distinct synthetic batches per rank and per step, pre-built in pinned host memory
+    n_distinct = 4
+    host_batches = []
+    for i in range(n_distinct):
+        hb = synthetic.make_batch(a.batch, (H, H), NUM_OBJS, a.kmin, a.kmax, seed=7919 * rank + i)
+        host_batches.append(tuple(t.pin_memory() for t in hb))
+    dev_batches = [tuple(t.to(dev, non_blocking=True) for t in hb) for hb in host_batches]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host_batches[0])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(i):
+        tr.train_step(dev_batches[i % n_distinct], use_gt=(i % 2 == 0))
+
+    def step_e2e(i):
+        hb = host_batches[i % n_distinct]
+        batch = tuple(t.to(dev, non_blocking=True) for t in hb)
+        tr.train_step(batch, use_gt=(i % 2 == 0))
+        return float(tr.generator_losses.total_loss)      # device -> host read of the step's result
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for i in range(max(a.warmup, 3)):
+        step_resident(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.reset_launch_count()
+    ms_total = timed(step_resident, a.steps)
+    launches = _lib.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    images = a.batch * world * a.steps
+    value = images / (ms_total / 1e3)
+
+    e2e = None
+    if not a.no_e2e:
+        step_e2e(0)
+        ms_e2e = timed(step_e2e, a.steps)
+        e2e = {'value': images / (ms_e2e / 1e3), 'unit': 'images/s', 'h2d_bytes_per_step': h2d_bytes * world,
+               'd2h_bytes_per_step': 4 * world, 'ms_per_step': ms_e2e / a.steps}
+
+    # one instrumented (untimed) step: per-launch device time + algorithmic FLOPs of the tensor-core kernels
+    roofline, kernels = None, None
+    if rank == 0:
+        with KernelProbe() as probe:
+            step_resident(0)
+            fam, top = probe.summary()
+        peak_tf, peak_hbm, which = load_peaks()
+        dom = max(fam.items(), key=lambda kv: kv[1]['ms'])
+        achieved = dom[1]['flops'] / (dom[1]['ms'] * 1e-3) / 1e12
+        roofline = {'kernel': dom[0], 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                    'frac': achieved / peak_tf, 'traffic': None, 'peak_source': which,
+                    'launches_per_step': dom[1]['launches'], 'ms_per_step': dom[1]['ms']}
+        kernels = {k: {'launches': v['launches'], 'ms': round(v['ms'], 3),
+                       'tflops': round(v['flops'] / (v['ms'] * 1e-3) / 1e12, 1)} for k, v in fam.items()}
+        worst = sorted(top.items(), key=lambda kv: -kv[1]['ms'])[:6]
+        kernels['top_shapes'] = [{'kernel': k[0], 'N,H,W,Cout,Cin,taps,phases': list(k[1]), 'launches': v['launches'],
+                                  'ms': round(v['ms'], 3), 'tflops': round(v['flops'] / (v['ms'] * 1e-3) / 1e12, 1)}
+                                 for k, v in worst]
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        rate, mean, cores = cpu_reference_rate(H, a.cpu_batch, a.cpu_steps, 1, a.kmin, a.kmax)
+        cpu = {'value': rate, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+               'sample': '%d images/step x %d steps (+1 warm-up) of the same workload, fp32, %d host threads, %.2f s/step'
+                         % (a.cpu_batch, a.cpu_steps, cores, mean)}
+
+    if rank == 0:
+        line = {
+            'metric': 'images/sec (train step, %dx%d, bs%d/GPU)' % (H, H, a.batch), 'value': value, 'unit': 'images/s',
+            'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3), 'ms_per_step': ms_total / a.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': 'COCO-Stuff-shaped synthetic scene graphs (%d-%d objects + __image__), %dx%d, full '
+                                   'train step: Model.forward + G step + mask/obj/image D steps + 4x Adam%s; VGG loss off '
+                                   '(no pretrained weights offline)' % (a.kmin, a.kmax, H, H,
+                                                                        ' + NCCL grad all-reduce' if world > 1 else ''),
+                       'global_batch': a.batch * world, 'parallelism': 'dp%d' % world,
+                       'l2': 'working set (732 MB of f32 weights + activations) >> 126 MB L2; %d distinct batches cycled'
+                             % n_distinct,
+                       'algorithmic_gflop_per_image': FLOPS_PER_IMAGE_STEP / 1e9},
+            'model_tflops': value * FLOPS_PER_IMAGE_STEP / 1e12,
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'kernels': kernels,
+            'cpu_baseline': cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -75,7 +75,7 @@ int sg_crop_bbox_bwd(const float* boxes, const long long* box_to_feats, int N, i
  * x is NHWC bf16 viewed as [N][P][H][W][C] (P = parity planes for stride-2, else 1); out-of-range
  * coordinates read as zero (TMA fill) which implements zero padding.  Up to 4 output "phases"
  * (sub-pixel decomposition of transposed / strided-adjoint convs) each with its own tap list and
- * output offset; output address = img*os_img + (h*oh_mul+oh_off)*os_h + (w*ow_mul+ow_off)*os_w + co. */
+ * output offset; output address = img*os_img + (h*oh_mul+oh_off)*os_h + (w*ow_mul+ow_off)*os_w + co*os_c. */
 #define SG_MAX_TAPS 64
 #define SG_ACT_NONE 0
 #define SG_ACT_RELU 1
@@ -95,7 +95,7 @@ typedef struct {
   int w_Cout, w_taps, w_C;
   void* y;                /* f32 or bf16 */
   int y_dtype;            /* 0 f32, 1 bf16 */
-  long long y_os_img, y_os_h, y_os_w;
+  long long y_os_img, y_os_h, y_os_w, y_os_c; /* element strides; y_os_c = 1 for NHWC */
   int Hout, Wout;         /* per-phase logical output extent */
   int oh_mul, ow_mul;
   int in_h0, in_w0;
@@ -133,9 +133,69 @@ typedef struct {
 int sg_wgrad_tc(const sg_wgrad_desc_t* desc, sg_stream_t stream);
 
 /* ---- operand preparation ------------------------------------------------------------------ */
-/* f32 (rows, cols) with row pitch ld_src -> bf16 (rows, ld_dst); columns >= cols are zero. */
-int sg_cast_pad_bf16(const float* src, long long rows, int cols, long long ld_src, int ld_dst, void* dst,
-                     sg_stream_t stream);
+/* f32 (rows, cols) with row pitch ld_src -> bf16 (rows, ld_dst); columns >= cols are zero.  With
+ * mask_y != NULL the value is multiplied by relu'/leaky' derived from the layer OUTPUT mask_y
+ * (same shape/pitch as src): 1 where mask_y > 0 else `slope` (adjoint of the fused Linear+ReLU,
+ * layers.py:215-231). */
+int sg_cast_pad_bf16(const float* src, long long rows, int cols, long long ld_src, int ld_dst,
+                     const float* mask_y, float slope, void* dst, sg_stream_t stream);
+/* master weights f32 [Cout][taps][Cin] -> bf16 operand [Cout][taps][Cin_p] (fprop / wgrad-free B
+ * operand) and, when wt != NULL, the transposed bf16 [Cin][taps][Cout_p] used by dgrad. */
+int sg_pack_weight(const float* w, int Cout, int taps, int Cin, int Cin_p, int Cout_p, void* wk, void* wt,
+                   sg_stream_t stream);
+
+/* ---- layers.py:292-301 InstanceNorm2d / BatchNorm2d, ReLU / LeakyReLU, ReflectionPad2d,
+ *      Interpolate(nearest x2), fused into one operand-writer pass (and its adjoint) ----------- */
+/* conv-epilogue sums (n_img, C, 2) -> scale/shift/mean/rstd (n_img*C each).  mode 0: InstanceNorm2d
+ * (affine=False), mode 1: BatchNorm2d train mode (statistics over all n_img*count elements, running
+ * stats updated in place with the unbiased variance when running_mean != NULL). */
+int sg_norm_finalize(const float* stats, int mode, int n_img, int C, float count, float eps, const float* gamma,
+                     const float* beta, float* running_mean, float* running_var, float momentum, float* scale,
+                     float* shift, float* save_mean, float* save_rstd, sg_stream_t stream);
+typedef struct {
+  const void* src;        /* bf16 NHWC [N][H][W][C], C % 8 == 0 (raw conv output) */
+  int N, H, W, C;
+  const float* scale;     /* (N*C) or NULL (identity) */
+  const float* shift;
+  int act;                /* SG_ACT_NONE / RELU / LEAKY */
+  float slope;
+  const void* res;        /* bf16 residual addressed img*res_os_img + h*res_os_h + w*res_os_w + c, or NULL */
+  long long res_os_img, res_os_h, res_os_w;
+  int up;                 /* 1, or 2 = nearest-neighbour x2 upsampling before padding */
+  int pad;                /* halo width */
+  int pad_mode;           /* 0 zeros, 1 reflection */
+  int planes;             /* 0: out [N][1][Hp][Wp][C]; 1: parity planes [N][4][ceil(Hp/2)][ceil(Wp/2)][C] */
+} sg_nap_desc_t;
+int sg_norm_act_pad_fwd(const sg_nap_desc_t* d, void* out, sg_stream_t stream);
+/* adjoint: grad has the layout of the forward output.  With save_mean != NULL the norm backward
+ * dsrc = scale * (g' - mean(g') - xhat * mean(g' xhat)) is applied (bn=1: statistics over all images);
+ * sums is (N*C*2) [bn=0] / (C*2) [bn=1] f32 scratch that returns S1 = sum g', S2 = sum g' xhat
+ * (= d beta, d gamma for BatchNorm).  dsrc is plain bf16 NHWC or (out_planes=1) parity planes.
+ * dres (optional, bf16, addressed with the residual's res_os_* strides) receives the folded
+ * gradient of the residual input. */
+int sg_norm_act_pad_bwd(const sg_nap_desc_t* d, const void* grad, const float* save_mean, const float* save_rstd,
+                        int bn, float count, float* sums, int out_planes, void* dsrc, void* dres,
+                        sg_stream_t stream);
+/* f32 NCHW grad * act'(y) (tanh / sigmoid heads, generators.py:87, model.py:107) -> bf16 NHWC (Cp). */
+int sg_act_bwd_nchw(const float* dy, const float* y, int N, int C, int H, int W, int act, int Cp, void* out,
+                    sg_stream_t stream);
+/* NCHW (f32: dtype 0, i64: dtype 1) -> channels [c0, c0+C) of a bf16 NHWC (Cp) tensor, and back. */
+int sg_nchw_to_nhwc(const void* src, int src_dtype, int N, int C, int H, int W, int Cp, int c0, void* out,
+                    sg_stream_t stream);
+int sg_nhwc_to_nchw(const void* src, int N, int C, int H, int W, int Cp, int c0, float* out, sg_stream_t stream);
+/* discriminators.py:107-109: concat a broadcast one-hot class vector (cls int64 per image, n_cls wide)
+ * behind the Cs feature channels -> [rows][Cd]; and the adjoint channel slice. */
+int sg_concat_cond(const void* src, long long rows_per_img, int n_img, int Cs, int Cd, const long long* cls,
+                   int n_cls, void* out, sg_stream_t stream);
+int sg_slice_channels(const void* src, long long rows, int Cd, int Cs, void* out, sg_stream_t stream);
+/* discriminators.py:99,184: AvgPool2d(3, stride 2, pad 1, count_include_pad=False), bf16 NHWC. */
+int sg_avgpool3x3s2_fwd(const void* x, int N, int H, int W, int C, void* y, sg_stream_t stream);
+int sg_avgpool3x3s2_bwd(const void* gy, int N, int H, int W, int C, void* gx, sg_stream_t stream);
+/* layers.py:82-85 GlobalAvgPool: bf16 [N][HW][C] -> f32 [N][C], and the adjoint. */
+int sg_gap_fwd(const void* x, int N, int HW, int C, float* y, sg_stream_t stream);
+int sg_gap_bwd(const float* gy, int N, int HW, int C, void* gx, sg_stream_t stream);
+/* bias gradient: column sums of bf16 [rows][ld] (first C columns) ACCUMULATED into f32 out[C]. */
+int sg_colsum_bf16(const void* x, long long rows, int C, int ld, float* out, sg_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -33,12 +33,21 @@ class ConvDesc(ctypes.Structure):
         ('x', c_void_p), ('x_N', c_int), ('x_P', c_int), ('x_H', c_int), ('x_W', c_int), ('x_C', c_int),
         ('w', c_void_p), ('w_Cout', c_int), ('w_taps', c_int), ('w_C', c_int),
         ('y', c_void_p), ('y_dtype', c_int),
-        ('y_os_img', c_long), ('y_os_h', c_long), ('y_os_w', c_long),
+        ('y_os_img', c_long), ('y_os_h', c_long), ('y_os_w', c_long), ('y_os_c', c_long),
         ('Hout', c_int), ('Wout', c_int), ('oh_mul', c_int), ('ow_mul', c_int),
         ('in_h0', c_int), ('in_w0', c_int),
         ('nphases', c_int), ('phases', Phase * 4),
         ('ntaps', c_int), ('taps', Tap * SG_MAX_TAPS),
         ('bias', c_void_p), ('act', c_int), ('slope', c_float), ('stats', c_void_p),
+    ]
+
+
+class NapDesc(ctypes.Structure):
+    _fields_ = [
+        ('src', c_void_p), ('N', c_int), ('H', c_int), ('W', c_int), ('C', c_int),
+        ('scale', c_void_p), ('shift', c_void_p), ('act', c_int), ('slope', c_float),
+        ('res', c_void_p), ('res_os_img', c_long), ('res_os_h', c_long), ('res_os_w', c_long),
+        ('up', c_int), ('pad', c_int), ('pad_mode', c_int), ('planes', c_int),
     ]
 
 
@@ -95,6 +104,21 @@ _SIGS = {
     'sg_crop_bbox_fwd': [_P, _P, _P] + [c_int] * 10 + [_P, _P],
     'sg_crop_bbox_bwd': [_P, _P] + [c_int] * 10 + [_P, _P, _P],
     'sg_conv_tc': [ctypes.POINTER(ConvDesc), _P],
+    'sg_cast_pad_bf16': [_P, c_long, c_int, c_long, c_int, _P, c_float, _P, _P],
+    'sg_pack_weight': [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P],
+    'sg_norm_finalize': [_P, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, c_float, _P, _P, _P, _P, _P],
+    'sg_norm_act_pad_fwd': [ctypes.POINTER(NapDesc), _P, _P],
+    'sg_norm_act_pad_bwd': [ctypes.POINTER(NapDesc), _P, _P, _P, c_int, c_float, _P, c_int, _P, _P, _P],
+    'sg_act_bwd_nchw': [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
+    'sg_nchw_to_nhwc': [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
+    'sg_nhwc_to_nchw': [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
+    'sg_concat_cond': [_P, c_long, c_int, c_int, c_int, _P, c_int, _P, _P],
+    'sg_slice_channels': [_P, c_long, c_int, c_int, _P, _P],
+    'sg_avgpool3x3s2_fwd': [_P, c_int, c_int, c_int, c_int, _P, _P],
+    'sg_avgpool3x3s2_bwd': [_P, c_int, c_int, c_int, c_int, _P, _P],
+    'sg_gap_fwd': [_P, c_int, c_int, c_int, _P, _P],
+    'sg_gap_bwd': [_P, c_int, c_int, c_int, _P, _P],
+    'sg_colsum_bf16': [_P, c_long, c_int, c_int, _P, _P],
     'sg_wgrad_tc': [ctypes.POINTER(WgradDesc), _P],
 }
 _RESTYPES = {'sg_last_error': ctypes.c_char_p, 'sg_version': ctypes.c_char_p, 'sg_arch': c_int,

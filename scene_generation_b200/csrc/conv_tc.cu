@@ -90,7 +90,7 @@ struct ConvKParams {
   int Hout, Wout, tiles_w, tiles_h, BW, BH, BI, n_img;
   int kblocks, Cout;
   int in_h0, in_w0;
-  long long os_img, os_h, os_w;
+  long long os_img, os_h, os_w, os_c;
   int oh_mul, ow_mul;
   void* y;
   int y_dtype;
@@ -246,7 +246,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int j = 0; j < CH; ++j) f[j] = apply_act(f[j], p.act, p.slope);
         const bool full_chunk = (n0 + c0 + CH <= p.Cout) && p.vec_ok;
         if (p.y_dtype == 1) {
-          __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + off + n0 + c0;
+          __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + off + (long long)(n0 + c0) * p.os_c;
           if (full_chunk) {
 #pragma unroll
             for (int j = 0; j < CH; j += 8) {
@@ -258,17 +258,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
 #pragma unroll
             for (int j = 0; j < CH; ++j)
-              if (n0 + c0 + j < p.Cout) yp[j] = __float2bfloat16(f[j]);
+              if (n0 + c0 + j < p.Cout) yp[(long long)j * p.os_c] = __float2bfloat16(f[j]);
           }
         } else {
-          float* yp = reinterpret_cast<float*>(p.y) + off + n0 + c0;
+          float* yp = reinterpret_cast<float*>(p.y) + off + (long long)(n0 + c0) * p.os_c;
           if (full_chunk) {
 #pragma unroll
             for (int j = 0; j < CH; j += 4) *reinterpret_cast<float4*>(yp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
           } else {
 #pragma unroll
             for (int j = 0; j < CH; ++j)
-              if (n0 + c0 + j < p.Cout) yp[j] = f[j];
+              if (n0 + c0 + j < p.Cout) yp[(long long)j * p.os_c] = f[j];
           }
         }
       }
@@ -450,6 +450,7 @@ extern "C" int sg_conv_tc(const sg_conv_desc_t* d, sg_stream_t stream) {
   SG_CHECK_ARG(d->nphases >= 1 && d->nphases <= 4, "sg_conv_tc: nphases %d out of range", d->nphases);
   SG_CHECK_ARG(d->Hout > 0 && d->Wout > 0 && d->x_N > 0 && d->w_Cout > 0, "sg_conv_tc: empty problem");
   SG_CHECK_ARG(d->y_dtype == 0 || d->y_dtype == 1, "sg_conv_tc: y_dtype must be 0 (f32) or 1 (bf16)");
+  SG_CHECK_ARG(d->y_os_c >= 1, "sg_conv_tc: y_os_c (channel stride) must be >= 1");
   for (int i = 0; i < d->nphases; ++i)
     SG_CHECK_ARG(d->phases[i].ntaps >= 1 && d->phases[i].tap_begin >= 0 && d->phases[i].tap_begin + d->phases[i].ntaps <= d->ntaps,
                  "sg_conv_tc: phase %d tap range invalid", i);
@@ -463,11 +464,11 @@ extern "C" int sg_conv_tc(const sg_conv_desc_t* d, sg_stream_t stream) {
   kp.kblocks = sg_cdiv(d->x_C < d->w_C ? d->x_C : d->w_C, 64);
   kp.Cout = d->w_Cout;
   kp.in_h0 = d->in_h0; kp.in_w0 = d->in_w0;
-  kp.os_img = d->y_os_img; kp.os_h = d->y_os_h; kp.os_w = d->y_os_w;
+  kp.os_img = d->y_os_img; kp.os_h = d->y_os_h; kp.os_w = d->y_os_w; kp.os_c = d->y_os_c;
   kp.oh_mul = d->oh_mul; kp.ow_mul = d->ow_mul;
   kp.y = d->y; kp.y_dtype = d->y_dtype; kp.bias = d->bias; kp.act = d->act; kp.slope = d->slope; kp.stats = d->stats;
   const int va = d->y_dtype == 1 ? 8 : 4;
-  kp.vec_ok = (d->y_os_img % va == 0) && (d->y_os_h % va == 0) && (d->y_os_w % va == 0) &&
+  kp.vec_ok = (d->y_os_c == 1) && (d->y_os_img % va == 0) && (d->y_os_h % va == 0) && (d->y_os_w % va == 0) &&
               (((uintptr_t)d->y) % 16 == 0);
   for (int i = 0; i < 4; ++i) kp.phases[i] = d->phases[i < d->nphases ? i : 0];
   for (int i = 0; i < d->ntaps; ++i) kp.taps[i] = d->taps[i];

@@ -1,28 +1,663 @@
 // Element-wise / normalisation / re-layout kernels around the tensor-core convolutions.
+//
+// The reference runs InstanceNorm2d / BatchNorm2d / ReLU / LeakyReLU / ReflectionPad2d / nearest
+// upsampling / AvgPool2d / GlobalAvgPool / concat as separate ATen kernels (generators.py:16-91,
+// layers.py:82-85,234-314, discriminators.py:99-110,184).  Here the conv epilogue already produced the
+// per-(image,channel) sum / sum-of-squares, so one "operand writer" pass applies
+//     out = pad/planes/upsample( act( src * scale + shift ) + residual )
+// and writes the bf16 NHWC operand of the next convolution; its adjoint folds the padding halo,
+// applies act' and the norm backward in a reduce + apply pair.
 #include "common.cuh"
 #include "../../include/sg_b200.h"
 
 namespace {
 
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ void load8(const bf16* p, float* f) {
+  uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float2 v = __bfloat1622float2(h2[j]);
+    f[2 * j] = v.x;
+    f[2 * j + 1] = v.y;
+  }
+}
+__device__ __forceinline__ void store8(bf16* p, const float* f) {
+  __align__(16) __nv_bfloat162 pk[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) pk[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+  *reinterpret_cast<uint4*>(p) = *reinterpret_cast<uint4*>(pk);
+}
+__device__ __forceinline__ float act_fwd(float v, int act, float slope) {
+  if (act == SG_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == SG_ACT_LEAKY) return v >= 0.f ? v : v * slope;
+  return v;
+}
+__device__ __forceinline__ float act_grad(float z, int act, float slope) {
+  if (act == SG_ACT_RELU) return z > 0.f ? 1.f : 0.f;
+  if (act == SG_ACT_LEAKY) return z >= 0.f ? 1.f : slope;
+  return 1.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cast / pack
+// ---------------------------------------------------------------------------------------------
 __global__ void cast_pad_kernel(const float* __restrict__ src, long rows, int cols, long ld_src, int ld_dst,
-                                __nv_bfloat16* __restrict__ dst) {
+                                const float* __restrict__ mask_y, float slope, bf16* __restrict__ dst) {
   long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   long total = rows * ld_dst;
   if (idx >= total) return;
   long r = idx / ld_dst;
   int c = (int)(idx - r * ld_dst);
-  dst[idx] = __float2bfloat16(c < cols ? src[r * ld_src + c] : 0.f);
+  float v = 0.f;
+  if (c < cols) {
+    v = src[r * ld_src + c];
+    if (mask_y != nullptr && !(mask_y[r * ld_src + c] > 0.f)) v *= slope;   // relu'/leaky' from the output
+  }
+  dst[idx] = __float2bfloat16(v);
+}
+
+// f32 [Cout][taps][Cin] -> bf16 [Cout][taps][Cin_p]  and (optionally) bf16 [Cin][taps][Cout_p]
+__global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int taps, int Cin, int Cin_p, int Cout_p,
+                                   bf16* __restrict__ wk, bf16* __restrict__ wt) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long n1 = (long)Cout * taps * Cin_p;
+  long n2 = wt ? (long)Cin * taps * Cout_p : 0;
+  if (idx < n1) {
+    int ci = idx % Cin_p;
+    long r = idx / Cin_p;   // co*taps + t
+    wk[idx] = __float2bfloat16(ci < Cin ? w[r * Cin + ci] : 0.f);
+  } else if (idx < n1 + n2) {
+    long j = idx - n1;
+    int co = j % Cout_p;
+    long r = j / Cout_p;    // ci*taps + t
+    int t = r % taps, ci = r / taps;
+    wt[j] = __float2bfloat16(co < Cout ? w[((long)co * taps + t) * Cin + ci] : 0.f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// norm finalize: conv-epilogue sums -> per-(image,channel) scale/shift (+ saved mean/rstd)
+// ---------------------------------------------------------------------------------------------
+__global__ void norm_finalize_kernel(const float* __restrict__ stats, int mode, int n_img, int C, float count, float eps,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     float* running_mean, float* running_var, float momentum,
+                                     float* __restrict__ scale, float* __restrict__ shift,
+                                     float* __restrict__ save_mean, float* __restrict__ save_rstd) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (mode == 0) {   // InstanceNorm2d(affine=False)
+    if (idx >= n_img * C) return;
+    float mean = stats[2 * idx] / count;
+    float var = fmaxf(stats[2 * idx + 1] / count - mean * mean, 0.f);
+    float rstd = rsqrtf(var + eps);
+    scale[idx] = rstd;
+    shift[idx] = -mean * rstd;
+    save_mean[idx] = mean;
+    save_rstd[idx] = rstd;
+  } else {           // BatchNorm2d (train): statistics over all images
+    if (idx >= C) return;
+    float s = 0.f, ss = 0.f;
+    for (int n = 0; n < n_img; ++n) {
+      s += stats[2 * (n * C + idx)];
+      ss += stats[2 * (n * C + idx) + 1];
+    }
+    float tot = count * n_img;
+    float mean = s / tot;
+    float var = fmaxf(ss / tot - mean * mean, 0.f);
+    float rstd = rsqrtf(var + eps);
+    float g = gamma ? gamma[idx] : 1.f, b = beta ? beta[idx] : 0.f;
+    if (running_mean) {
+      running_mean[idx] = (1.f - momentum) * running_mean[idx] + momentum * mean;
+      running_var[idx] = (1.f - momentum) * running_var[idx] + momentum * var * (tot / fmaxf(tot - 1.f, 1.f));
+    }
+    for (int n = 0; n < n_img; ++n) {
+      scale[n * C + idx] = g * rstd;
+      shift[n * C + idx] = b - mean * g * rstd;
+      save_mean[n * C + idx] = mean;
+      save_rstd[n * C + idx] = rstd;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// operand writer (forward)
+// ---------------------------------------------------------------------------------------------
+struct NapArgs {
+  const bf16* src;   // plain NHWC [N][H][W][C]
+  int N, H, W, C;
+  const float* scale;   // (N*C) or null
+  const float* shift;
+  int act;
+  float slope;
+  const bf16* res;      // residual, addressed in source coordinates; null if none
+  long long res_os_img, res_os_h, res_os_w;
+  int up, pad, pad_mode, planes;
+};
+
+__device__ __forceinline__ int src_coord(int hp, int pad, int pad_mode, int Hu) {
+  int hu = hp - pad;
+  if (hu < 0) return pad_mode ? -hu : -1;
+  if (hu >= Hu) return pad_mode ? 2 * (Hu - 1) - hu : -1;
+  return hu;
+}
+
+__global__ void nap_fwd_kernel(NapArgs a, bf16* __restrict__ out) {
+  const int nC = a.C / 8;
+  const int Hu = a.H * a.up, Wu = a.W * a.up;
+  const int Hp = Hu + 2 * a.pad, Wp = Wu + 2 * a.pad;
+  const int Ho = a.planes ? (Hp + 1) / 2 : Hp, Wo = a.planes ? (Wp + 1) / 2 : Wp;
+  const int P = a.planes ? 4 : 1;
+  long total = (long)a.N * P * Ho * Wo * nC;
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int ch = idx % nC;
+  long r = idx / nC;
+  int j = r % Wo; r /= Wo;
+  int i = r % Ho; r /= Ho;
+  int pl = r % P;
+  int n = r / P;
+  int hp = a.planes ? 2 * i + (pl >> 1) : i;
+  int wp = a.planes ? 2 * j + (pl & 1) : j;
+  float f[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) f[k] = 0.f;
+  if (hp < Hp && wp < Wp) {
+    int hu = src_coord(hp, a.pad, a.pad_mode, Hu), wu = src_coord(wp, a.pad, a.pad_mode, Wu);
+    if (hu >= 0 && wu >= 0 && hu < Hu && wu < Wu) {
+      int h = hu / a.up, w = wu / a.up;
+      load8(a.src + (((long)n * a.H + h) * a.W + w) * a.C + ch * 8, f);
+      if (a.scale) {
+        const float4* sc = reinterpret_cast<const float4*>(a.scale + (long)n * a.C + ch * 8);
+        const float4* sh = reinterpret_cast<const float4*>(a.shift + (long)n * a.C + ch * 8);
+        float4 s0 = sc[0], s1 = sc[1], h0 = sh[0], h1 = sh[1];
+        f[0] = fmaf(f[0], s0.x, h0.x); f[1] = fmaf(f[1], s0.y, h0.y); f[2] = fmaf(f[2], s0.z, h0.z); f[3] = fmaf(f[3], s0.w, h0.w);
+        f[4] = fmaf(f[4], s1.x, h1.x); f[5] = fmaf(f[5], s1.y, h1.y); f[6] = fmaf(f[6], s1.z, h1.z); f[7] = fmaf(f[7], s1.w, h1.w);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = act_fwd(f[k], a.act, a.slope);
+      if (a.res) {
+        float rr[8];
+        load8(a.res + (long)n * a.res_os_img + (long)h * a.res_os_h + (long)w * a.res_os_w + ch * 8, rr);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] += rr[k];
+      }
+    }
+  }
+  store8(out + idx * 8, f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// operand writer (backward): fold halo/planes/upsample, act', norm backward
+// ---------------------------------------------------------------------------------------------
+struct NapBwdArgs {
+  NapArgs f;
+  const bf16* g;          // grad in the forward operand's format
+  const float* save_mean; // (N*C) or null (no norm)
+  const float* save_rstd;
+  int bn;                 // 1: statistics shared over images (BatchNorm)
+  float count;            // elements per statistic
+  float* sums;            // (N*C*2) [IN]  or (C*2) [BN] : S1 = sum g', S2 = sum g' * xhat
+  int out_planes;         // dsrc written as parity planes (for transposed-conv producers)
+  bf16* dsrc;             // [N][H][W][C] plain, or planes [N][4][ceil(H/2)][ceil(W/2)][C]
+  bf16* dres;             // optional: folded grad (no act') in plain source layout
+};
+
+// accumulate the folded output-gradient for source pixel (n,h,w), channels ch*8..+8
+__device__ __forceinline__ void fold_grad(const NapArgs& a, const bf16* g, int n, int h, int w, int ch, float* acc) {
+  const int Hu = a.H * a.up, Wu = a.W * a.up;
+  const int Hp = Hu + 2 * a.pad, Wp = Wu + 2 * a.pad;
+  const int Ho = a.planes ? (Hp + 1) / 2 : Hp, Wo = a.planes ? (Wp + 1) / 2 : Wp;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (int uh = 0; uh < a.up; ++uh) {
+    const int hu = h * a.up + uh;
+    int rows[3];
+    int nr = 0;
+    rows[nr++] = hu + a.pad;
+    if (a.pad_mode && a.pad > 0) {
+      if (hu >= 1 && hu <= a.pad) rows[nr++] = a.pad - hu;
+      if (hu <= Hu - 2 && hu >= Hu - 1 - a.pad) rows[nr++] = a.pad + 2 * (Hu - 1) - hu;
+    }
+    for (int uw = 0; uw < a.up; ++uw) {
+      const int wu = w * a.up + uw;
+      int cols[3];
+      int nc = 0;
+      cols[nc++] = wu + a.pad;
+      if (a.pad_mode && a.pad > 0) {
+        if (wu >= 1 && wu <= a.pad) cols[nc++] = a.pad - wu;
+        if (wu <= Wu - 2 && wu >= Wu - 1 - a.pad) cols[nc++] = a.pad + 2 * (Wu - 1) - wu;
+      }
+      for (int ri = 0; ri < nr; ++ri)
+        for (int ci = 0; ci < nc; ++ci) {
+          int hp = rows[ri], wp = cols[ci];
+          long off;
+          if (a.planes) off = ((((long)n * 4 + (hp & 1) * 2 + (wp & 1)) * Ho + (hp >> 1)) * Wo + (wp >> 1)) * a.C;
+          else off = (((long)n * Ho + hp) * Wo + wp) * a.C;
+          float t[8];
+          load8(g + off + ch * 8, t);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] += t[k];
+        }
+    }
+  }
+}
+
+// g' = fold(g) * act'(z), xhat; returns both
+__device__ __forceinline__ void gprime(const NapBwdArgs& b, int n, int h, int w, int ch, float* gp, float* xh) {
+  const NapArgs& a = b.f;
+  fold_grad(a, b.g, n, h, w, ch, gp);
+  float x[8];
+  load8(a.src + (((long)n * a.H + h) * a.W + w) * a.C + ch * 8, x);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = ch * 8 + k;
+    float z = x[k];
+    if (a.scale) z = fmaf(x[k], a.scale[(long)n * a.C + c], a.shift[(long)n * a.C + c]);
+    gp[k] *= act_grad(z, a.act, a.slope);
+    xh[k] = b.save_mean ? (x[k] - b.save_mean[(long)n * a.C + c]) * b.save_rstd[(long)n * a.C + c] : 0.f;
+  }
+}
+
+__global__ void nap_bwd_reduce_kernel(NapBwdArgs b, int pix_per_block) {
+  const NapArgs& a = b.f;
+  const int nC = a.C / 8;
+  const int lanes = blockDim.x / nC;            // pixel lanes per block
+  const int ch = threadIdx.x % nC, lane = threadIdx.x / nC;
+  const int n = blockIdx.y;
+  const int HW = a.H * a.W;
+  const int p_begin = blockIdx.x * pix_per_block;
+  const int p_end = min(p_begin + pix_per_block, HW);
+  if (lane >= lanes) return;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
+  for (int p = p_begin + lane; p < p_end; p += lanes) {
+    float gp[8], xh[8];
+    gprime(b, n, p / a.W, p % a.W, ch, gp, xh);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s1[k] += gp[k];
+      s2[k] += gp[k] * xh[k];
+    }
+  }
+  float* dst = b.sums + ((b.bn ? 0 : (long)n * a.C) + ch * 8) * 2;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    atomicAdd(dst + 2 * k, s1[k]);
+    atomicAdd(dst + 2 * k + 1, s2[k]);
+  }
+}
+
+__global__ void nap_bwd_apply_kernel(NapBwdArgs b) {
+  const NapArgs& a = b.f;
+  const int nC = a.C / 8;
+  long total = (long)a.N * a.H * a.W * nC;
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int ch = idx % nC;
+  long r = idx / nC;
+  int w = r % a.W; r /= a.W;
+  int h = r % a.H;
+  int n = r / a.H;
+  float gp[8], xh[8];
+  if (b.dres) {
+    float fg[8];
+    fold_grad(a, b.g, n, h, w, ch, fg);
+    store8(b.dres + (long)n * a.res_os_img + (long)h * a.res_os_h + (long)w * a.res_os_w + ch * 8, fg);
+  }
+  gprime(b, n, h, w, ch, gp, xh);
+  float o[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = ch * 8 + k;
+    if (b.save_mean) {
+      const float* sm = b.sums + ((b.bn ? 0 : (long)n * a.C) + c) * 2;
+      float m1 = sm[0] / b.count, m2 = sm[1] / b.count;
+      o[k] = a.scale[(long)n * a.C + c] * (gp[k] - m1 - xh[k] * m2);   // scale = rstd (* gamma)
+    } else {
+      float sc = a.scale ? a.scale[(long)n * a.C + c] : 1.f;
+      o[k] = gp[k] * sc;
+    }
+  }
+  long off;
+  if (b.out_planes) {
+    const int Hh = (a.H + 1) / 2, Wh = (a.W + 1) / 2;
+    off = ((((long)n * 4 + (h & 1) * 2 + (w & 1)) * Hh + (h >> 1)) * Wh + (w >> 1)) * a.C + ch * 8;
+  } else {
+    off = idx * 8;
+  }
+  store8(b.dsrc + off, o);
+}
+
+// ---------------------------------------------------------------------------------------------
+// small layout / pooling kernels
+// ---------------------------------------------------------------------------------------------
+// f32 NCHW grad * act'(y) -> bf16 NHWC [N][H][W][Cp]   (tanh / sigmoid heads)
+__global__ void act_bwd_nchw_kernel(const float* __restrict__ dy, const float* __restrict__ y, int N, int C, int H, int W,
+                                    int act, int Cp, bf16* __restrict__ out) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long total = (long)N * H * W;
+  if (idx >= total) return;
+  int n = idx / ((long)H * W);
+  long p = idx % ((long)H * W);
+  for (int c = 0; c < Cp; ++c) {
+    float v = 0.f;
+    if (c < C) {
+      long s = ((long)n * C + c) * H * W + p;
+      float yy = y[s], g = dy[s];
+      v = act == SG_ACT_TANH ? g * (1.f - yy * yy) : (act == SG_ACT_SIGMOID ? g * yy * (1.f - yy) : g);
+    }
+    out[idx * Cp + c] = __float2bfloat16(v);
+  }
+}
+
+// f32 NCHW (or f32/i64 single-channel) -> bf16 NHWC [N][H][W][Cp] at channel offset c0 (other channels untouched)
+__global__ void nchw_to_nhwc_kernel(const void* __restrict__ src, int src_dtype, int N, int C, int H, int W, int Cp, int c0,
+                                    bf16* __restrict__ out) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long total = (long)N * H * W;
+  if (idx >= total) return;
+  int n = idx / ((long)H * W);
+  long p = idx % ((long)H * W);
+  for (int c = 0; c < C; ++c) {
+    long s = ((long)n * C + c) * H * W + p;
+    float v = src_dtype == 0 ? ((const float*)src)[s] : (float)((const long long*)src)[s];
+    out[idx * Cp + c0 + c] = __float2bfloat16(v);
+  }
+}
+// bf16 NHWC channels [c0, c0+C) -> f32 NCHW
+__global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ src, int N, int C, int H, int W, int Cp, int c0,
+                                    float* __restrict__ out) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long total = (long)N * H * W;
+  if (idx >= total) return;
+  int n = idx / ((long)H * W);
+  long p = idx % ((long)H * W);
+  for (int c = 0; c < C; ++c) out[((long)n * C + c) * H * W + p] = __bfloat162float(src[idx * Cp + c0 + c]);
+}
+
+// copy bf16 NHWC [rows][Cs] into channels [0,Cs) of [rows][Cd] and zero-fill / one-hot the rest
+__global__ void concat_cond_kernel(const bf16* __restrict__ src, long rows_per_img, int n_img, int Cs, int Cd,
+                                   const long long* __restrict__ cls, int n_cls, bf16* __restrict__ out) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long total = (long)n_img * rows_per_img * Cd;
+  if (idx >= total) return;
+  int c = idx % Cd;
+  long r = idx / Cd;
+  int n = r / rows_per_img;
+  bf16 v;
+  if (c < Cs) v = src[r * Cs + c];
+  else v = __float2bfloat16((cls != nullptr && c - Cs < n_cls && cls[n] == c - Cs) ? 1.f : 0.f);
+  out[idx] = v;
+}
+// adjoint: channels [0,Cs) of [rows][Cd] -> [rows][Cs]
+__global__ void slice_channels_kernel(const bf16* __restrict__ src, long rows, int Cd, int Cs, bf16* __restrict__ out) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * Cs) return;
+  int c = idx % Cs;
+  long r = idx / Cs;
+  out[idx] = src[r * Cd + c];
+}
+
+// AvgPool2d(3, stride 2, pad 1, count_include_pad=False) on bf16 NHWC
+__global__ void avgpool_fwd_kernel(const bf16* __restrict__ x, int N, int H, int W, int C, int Ho, int Wo, bf16* __restrict__ y) {
+  const int nC = C / 8;
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long total = (long)N * Ho * Wo * nC;
+  if (idx >= total) return;
+  int ch = idx % nC;
+  long r = idx / nC;
+  int j = r % Wo; r /= Wo;
+  int i = r % Ho;
+  int n = r / Ho;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  int cnt = 0;
+  for (int dy = -1; dy <= 1; ++dy)
+    for (int dx = -1; dx <= 1; ++dx) {
+      int h = 2 * i + dy, w = 2 * j + dx;
+      if (h < 0 || h >= H || w < 0 || w >= W) continue;
+      float t[8];
+      load8(x + (((long)n * H + h) * W + w) * C + ch * 8, t);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += t[k];
+      ++cnt;
+    }
+  float inv = 1.f / (float)cnt;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] *= inv;
+  store8(y + idx * 8, acc);
+}
+__global__ void avgpool_bwd_kernel(const bf16* __restrict__ gy, int N, int H, int W, int C, int Ho, int Wo, bf16* __restrict__ gx) {
+  const int nC = C / 8;
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long total = (long)N * H * W * nC;
+  if (idx >= total) return;
+  int ch = idx % nC;
+  long r = idx / nC;
+  int w = r % W; r /= W;
+  int h = r % H;
+  int n = r / H;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (int i = max((h - 1) / 2, 0); i <= (h + 1) / 2; ++i) {
+    if (i >= Ho || abs(2 * i - h) > 1) continue;
+    for (int j = max((w - 1) / 2, 0); j <= (w + 1) / 2; ++j) {
+      if (j >= Wo || abs(2 * j - w) > 1) continue;
+      int ch_cnt = (min(2 * i + 1, H - 1) - max(2 * i - 1, 0) + 1) * (min(2 * j + 1, W - 1) - max(2 * j - 1, 0) + 1);
+      float t[8];
+      load8(gy + (((long)n * Ho + i) * Wo + j) * C + ch * 8, t);
+      float inv = 1.f / (float)ch_cnt;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += t[k] * inv;
+    }
+  }
+  store8(gx + idx * 8, acc);
+}
+
+// GlobalAvgPool: bf16 [N][HW][C] -> f32 [N][C]   (layers.py:82-85)
+__global__ void gap_fwd_kernel(const bf16* __restrict__ x, int N, int HW, int C, float* __restrict__ y) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * C) return;
+  int c = idx % C, n = idx / C;
+  float s = 0.f;
+  for (int p = 0; p < HW; ++p) s += __bfloat162float(x[((long)n * HW + p) * C + c]);
+  y[idx] = s / (float)HW;
+}
+__global__ void gap_bwd_kernel(const float* __restrict__ gy, int N, int HW, int C, bf16* __restrict__ gx) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)N * HW * C) return;
+  int c = idx % C;
+  int n = idx / ((long)HW * C);
+  gx[idx] = __float2bfloat16(gy[(long)n * C + c] / (float)HW);
+}
+
+// column sums of a bf16 [rows][C] matrix into f32 [C] (bias gradient), accumulated atomically
+__global__ void colsum_kernel(const bf16* __restrict__ x, long rows, int C, int ld, int rows_per_block, float* __restrict__ out) {
+  long r0 = (long)blockIdx.x * rows_per_block;
+  long r1 = min(r0 + rows_per_block, rows);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (long r = r0; r < r1; ++r) s += __bfloat162float(x[r * ld + c]);
+    atomicAdd(out + c, s);
+  }
 }
 
 }  // namespace
 
-// f32 (rows, cols) with row pitch ld_src -> bf16 (rows, ld_dst), columns >= cols zero filled
-extern "C" int sg_cast_pad_bf16(const float* src, long long rows, int cols, long long ld_src, int ld_dst, void* dst,
-                                sg_stream_t stream) {
+#define LAUNCH_1D(kernel, total, stream, ...) kernel<<<sg_cdiv((total), 256), 256, 0, stream>>>(__VA_ARGS__)
+
+extern "C" int sg_cast_pad_bf16(const float* src, long long rows, int cols, long long ld_src, int ld_dst,
+                                const float* mask_y, float slope, void* dst, sg_stream_t stream) {
   SG_CHECK_ARG(rows >= 0 && cols > 0 && ld_dst >= cols && ld_src >= cols, "cast_pad_bf16: bad sizes");
   if (rows == 0) return SG_OK;
-  long total = rows * ld_dst;
-  cast_pad_kernel<<<sg_cdiv(total, 256), 256, 0, stream>>>(src, rows, cols, ld_src, ld_dst, (__nv_bfloat16*)dst);
+  LAUNCH_1D(cast_pad_kernel, rows * ld_dst, stream, src, rows, cols, ld_src, ld_dst, mask_y, slope, (bf16*)dst);
   SG_CHECK_LAUNCH("sg_cast_pad_bf16");
+  return SG_OK;
+}
+
+extern "C" int sg_pack_weight(const float* w, int Cout, int taps, int Cin, int Cin_p, int Cout_p, void* wk, void* wt,
+                              sg_stream_t stream) {
+  SG_CHECK_ARG(Cout > 0 && taps > 0 && Cin > 0 && Cin_p >= Cin && Cin_p % 8 == 0, "pack_weight: bad sizes");
+  SG_CHECK_ARG(wt == nullptr || (Cout_p >= Cout && Cout_p % 8 == 0), "pack_weight: bad Cout_p");
+  long total = (long)Cout * taps * Cin_p + (wt ? (long)Cin * taps * Cout_p : 0);
+  LAUNCH_1D(pack_weight_kernel, total, stream, w, Cout, taps, Cin, Cin_p, Cout_p, (bf16*)wk, (bf16*)wt);
+  SG_CHECK_LAUNCH("sg_pack_weight");
+  return SG_OK;
+}
+
+extern "C" int sg_norm_finalize(const float* stats, int mode, int n_img, int C, float count, float eps, const float* gamma,
+                                const float* beta, float* running_mean, float* running_var, float momentum, float* scale,
+                                float* shift, float* save_mean, float* save_rstd, sg_stream_t stream) {
+  SG_CHECK_ARG(stats && scale && shift && save_mean && save_rstd, "norm_finalize: null pointer");
+  SG_CHECK_ARG((mode == 0 || mode == 1) && n_img > 0 && C > 0 && count > 0, "norm_finalize: bad arguments");
+  int total = mode == 0 ? n_img * C : C;
+  LAUNCH_1D(norm_finalize_kernel, total, stream, stats, mode, n_img, C, count, eps, gamma, beta, running_mean, running_var,
+            momentum, scale, shift, save_mean, save_rstd);
+  SG_CHECK_LAUNCH("sg_norm_finalize");
+  return SG_OK;
+}
+
+static int nap_check(const sg_nap_desc_t* d) {
+  SG_CHECK_ARG(d && d->src, "norm_act_pad: null pointer");
+  SG_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0 && d->C > 0 && d->C % 8 == 0, "norm_act_pad: bad sizes (C must be a multiple of 8)");
+  SG_CHECK_ARG(d->up == 1 || d->up == 2, "norm_act_pad: up must be 1 or 2");
+  SG_CHECK_ARG(d->pad >= 0 && (d->pad_mode == 0 || d->pad_mode == 1), "norm_act_pad: bad padding");
+  SG_CHECK_ARG(!(d->pad_mode == 1 && d->pad >= d->H * d->up), "norm_act_pad: reflection pad must be smaller than the input");
+  SG_CHECK_ARG(d->act == SG_ACT_NONE || d->act == SG_ACT_RELU || d->act == SG_ACT_LEAKY, "norm_act_pad: unsupported activation");
+  return SG_OK;
+}
+static NapArgs nap_args(const sg_nap_desc_t* d) {
+  NapArgs a;
+  a.src = (const bf16*)d->src; a.N = d->N; a.H = d->H; a.W = d->W; a.C = d->C;
+  a.scale = d->scale; a.shift = d->shift; a.act = d->act; a.slope = d->slope;
+  a.res = (const bf16*)d->res; a.res_os_img = d->res_os_img; a.res_os_h = d->res_os_h; a.res_os_w = d->res_os_w;
+  a.up = d->up; a.pad = d->pad; a.pad_mode = d->pad_mode; a.planes = d->planes;
+  return a;
+}
+
+extern "C" int sg_norm_act_pad_fwd(const sg_nap_desc_t* d, void* out, sg_stream_t stream) {
+  if (int e = nap_check(d)) return e;
+  SG_CHECK_ARG(out != nullptr, "norm_act_pad_fwd: null output");
+  NapArgs a = nap_args(d);
+  const int Hp = d->H * d->up + 2 * d->pad, Wp = d->W * d->up + 2 * d->pad;
+  const long per_img = d->planes ? 4L * ((Hp + 1) / 2) * ((Wp + 1) / 2) : (long)Hp * Wp;
+  long total = (long)d->N * per_img * (d->C / 8);
+  LAUNCH_1D(nap_fwd_kernel, total, stream, a, (bf16*)out);
+  SG_CHECK_LAUNCH("sg_norm_act_pad_fwd");
+  return SG_OK;
+}
+
+extern "C" int sg_norm_act_pad_bwd(const sg_nap_desc_t* d, const void* grad, const float* save_mean, const float* save_rstd,
+                                   int bn, float count, float* sums, int out_planes, void* dsrc, void* dres,
+                                   sg_stream_t stream) {
+  if (int e = nap_check(d)) return e;
+  SG_CHECK_ARG(grad && dsrc, "norm_act_pad_bwd: null pointer");
+  SG_CHECK_ARG(save_mean == nullptr || (save_rstd && sums && count > 0), "norm_act_pad_bwd: norm backward needs rstd/sums/count");
+  NapBwdArgs b;
+  b.f = nap_args(d);
+  b.g = (const bf16*)grad; b.save_mean = save_mean; b.save_rstd = save_rstd; b.bn = bn; b.count = count; b.sums = sums;
+  b.out_planes = out_planes; b.dsrc = (bf16*)dsrc; b.dres = (bf16*)dres;
+  const int nC = d->C / 8;
+  if (save_mean) {
+    cudaMemsetAsync(sums, 0, sizeof(float) * 2 * (size_t)(bn ? d->C : (size_t)d->N * d->C), stream);
+    int threads = nC >= 256 ? nC : 256;
+    threads = (threads / nC) * nC;
+    SG_CHECK_ARG(threads <= 1024, "norm_act_pad_bwd: too many channels");
+    int pix_per_block = 1024;
+    dim3 grid(sg_cdiv((long)d->H * d->W, pix_per_block), d->N);
+    nap_bwd_reduce_kernel<<<grid, threads, 0, stream>>>(b, pix_per_block);
+    SG_CHECK_LAUNCH("sg_norm_act_pad_bwd(reduce)");
+  }
+  long total = (long)d->N * d->H * d->W * nC;
+  if (out_planes) {
+    // odd sizes leave unwritten slots in the parity planes: zero them first
+    if ((d->H & 1) || (d->W & 1))
+      cudaMemsetAsync(dsrc, 0, sizeof(bf16) * 4 * (size_t)d->N * ((d->H + 1) / 2) * ((d->W + 1) / 2) * d->C, stream);
+  }
+  LAUNCH_1D(nap_bwd_apply_kernel, total, stream, b);
+  SG_CHECK_LAUNCH("sg_norm_act_pad_bwd(apply)");
+  return SG_OK;
+}
+
+extern "C" int sg_act_bwd_nchw(const float* dy, const float* y, int N, int C, int H, int W, int act, int Cp, void* out,
+                               sg_stream_t stream) {
+  SG_CHECK_ARG(dy && y && out && Cp >= C && Cp % 8 == 0, "act_bwd_nchw: bad arguments");
+  LAUNCH_1D(act_bwd_nchw_kernel, (long)N * H * W, stream, dy, y, N, C, H, W, act, Cp, (bf16*)out);
+  SG_CHECK_LAUNCH("sg_act_bwd_nchw");
+  return SG_OK;
+}
+
+extern "C" int sg_nchw_to_nhwc(const void* src, int src_dtype, int N, int C, int H, int W, int Cp, int c0, void* out,
+                               sg_stream_t stream) {
+  SG_CHECK_ARG(src && out && c0 >= 0 && c0 + C <= Cp && (src_dtype == 0 || src_dtype == 1), "nchw_to_nhwc: bad arguments");
+  LAUNCH_1D(nchw_to_nhwc_kernel, (long)N * H * W, stream, src, src_dtype, N, C, H, W, Cp, c0, (bf16*)out);
+  SG_CHECK_LAUNCH("sg_nchw_to_nhwc");
+  return SG_OK;
+}
+
+extern "C" int sg_nhwc_to_nchw(const void* src, int N, int C, int H, int W, int Cp, int c0, float* out, sg_stream_t stream) {
+  SG_CHECK_ARG(src && out && c0 >= 0 && c0 + C <= Cp, "nhwc_to_nchw: bad arguments");
+  LAUNCH_1D(nhwc_to_nchw_kernel, (long)N * H * W, stream, (const bf16*)src, N, C, H, W, Cp, c0, out);
+  SG_CHECK_LAUNCH("sg_nhwc_to_nchw");
+  return SG_OK;
+}
+
+extern "C" int sg_concat_cond(const void* src, long long rows_per_img, int n_img, int Cs, int Cd, const long long* cls,
+                              int n_cls, void* out, sg_stream_t stream) {
+  SG_CHECK_ARG(src && out && Cd >= Cs && rows_per_img > 0 && n_img > 0, "concat_cond: bad arguments");
+  LAUNCH_1D(concat_cond_kernel, (long)n_img * rows_per_img * Cd, stream, (const bf16*)src, rows_per_img, n_img, Cs, Cd, cls,
+            n_cls, (bf16*)out);
+  SG_CHECK_LAUNCH("sg_concat_cond");
+  return SG_OK;
+}
+
+extern "C" int sg_slice_channels(const void* src, long long rows, int Cd, int Cs, void* out, sg_stream_t stream) {
+  SG_CHECK_ARG(src && out && Cd >= Cs && rows > 0, "slice_channels: bad arguments");
+  LAUNCH_1D(slice_channels_kernel, rows * Cs, stream, (const bf16*)src, rows, Cd, Cs, (bf16*)out);
+  SG_CHECK_LAUNCH("sg_slice_channels");
+  return SG_OK;
+}
+
+extern "C" int sg_avgpool3x3s2_fwd(const void* x, int N, int H, int W, int C, void* y, sg_stream_t stream) {
+  SG_CHECK_ARG(x && y && C % 8 == 0, "avgpool_fwd: bad arguments");
+  int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  LAUNCH_1D(avgpool_fwd_kernel, (long)N * Ho * Wo * (C / 8), stream, (const bf16*)x, N, H, W, C, Ho, Wo, (bf16*)y);
+  SG_CHECK_LAUNCH("sg_avgpool3x3s2_fwd");
+  return SG_OK;
+}
+
+extern "C" int sg_avgpool3x3s2_bwd(const void* gy, int N, int H, int W, int C, void* gx, sg_stream_t stream) {
+  SG_CHECK_ARG(gy && gx && C % 8 == 0, "avgpool_bwd: bad arguments");
+  int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  LAUNCH_1D(avgpool_bwd_kernel, (long)N * H * W * (C / 8), stream, (const bf16*)gy, N, H, W, C, Ho, Wo, (bf16*)gx);
+  SG_CHECK_LAUNCH("sg_avgpool3x3s2_bwd");
+  return SG_OK;
+}
+
+extern "C" int sg_gap_fwd(const void* x, int N, int HW, int C, float* y, sg_stream_t stream) {
+  SG_CHECK_ARG(x && y && N > 0 && HW > 0 && C > 0, "gap_fwd: bad arguments");
+  LAUNCH_1D(gap_fwd_kernel, (long)N * C, stream, (const bf16*)x, N, HW, C, y);
+  SG_CHECK_LAUNCH("sg_gap_fwd");
+  return SG_OK;
+}
+
+extern "C" int sg_gap_bwd(const float* gy, int N, int HW, int C, void* gx, sg_stream_t stream) {
+  SG_CHECK_ARG(gy && gx && N > 0 && HW > 0 && C > 0, "gap_bwd: bad arguments");
+  LAUNCH_1D(gap_bwd_kernel, (long)N * HW * C, stream, gy, N, HW, C, (bf16*)gx);
+  SG_CHECK_LAUNCH("sg_gap_bwd");
+  return SG_OK;
+}
+
+extern "C" int sg_colsum_bf16(const void* x, long long rows, int C, int ld, float* out, sg_stream_t stream) {
+  SG_CHECK_ARG(x && out && rows > 0 && C > 0 && ld >= C, "colsum: bad arguments");
+  int rpb = (int)((rows + 592 - 1) / 592);
+  if (rpb < 32) rpb = 32;
+  colsum_kernel<<<sg_cdiv(rows, rpb), 256, 0, stream>>>((const bf16*)x, rows, C, ld, rpb, out);
+  SG_CHECK_LAUNCH("sg_colsum_bf16");
   return SG_OK;
 }

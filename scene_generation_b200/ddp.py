@@ -1,0 +1,49 @@
+"""Data-parallel plumbing: one process per GPU, torch.distributed (NCCL over NVLink/NVSwitch; gloo on
+CPU for tests).  The path shards over the batch of scene graphs; the only exchange is
+the gradient all-reduce per network per optimizer step, done on ONE flat f32 buffer whose slices are the
+parameters' .grad tensors (no packing copies)."""
+import torch
+import torch.distributed as dist
+
+
+def world_size():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def rank():
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def broadcast_parameters(module, src=0):
+    """identical replicas at start (and BN buffers from rank 0, PyTorch-DDP style)."""
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src)
+
+
+class FlatGradReducer:
+    """Owns a flat f32 gradient buffer; every parameter's .grad is a (stride-preserving) view into it.
+    Parameters that received no gradient in a step contribute zeros (covers the use_gt coin flip,
+    train.py:195, where box_net gets no gradient)."""
+
+    def __init__(self, module):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            # same physical layout as the parameter (dense, possibly permuted)
+            g = torch.as_strided(self.flat, p.shape, p.stride(), off)
+            p.grad = g
+            off += n
+
+    def zero(self):
+        self.flat.zero_()
+
+    def allreduce(self):
+        ws = world_size()
+        if ws > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.div_(ws)

@@ -1,0 +1,605 @@
+"""torch.autograd glue over the C ABI: every Function's forward AND backward call libsg_b200 kernels.
+
+PyTorch is used for what the tier allows — device memory, streams, the autograd tape — not for
+arithmetic.  Activations between tensor-core convolutions live in two bf16 formats:
+  * "raw"     : plain NHWC (N,H,W,C), the output of a convolution;
+  * "operand" : (N,P,Hp,Wp,C), what the next convolution's TMA boxes read (P=1 padded plane, or
+                P=4 parity planes for stride-2 access).
+"""
+import ctypes
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib, convspec, ops
+from ._lib import NapDesc
+from .ops import _ptr, _stream, round_up
+
+BF = torch.bfloat16
+
+
+# ---------------------------------------------------------------------------------------------
+# weights: f32 masters are stored physically as [Cout][taps][Cin]; bf16 operands are repacked
+# whenever the master's version counter changes (i.e. after an optimizer step)
+# ---------------------------------------------------------------------------------------------
+_pack_cache = {}
+
+
+def master3(weight, kind):
+    """f32 view (Cout, taps, Cin) of a Conv2d / ConvTranspose2d / Linear weight (no copy)."""
+    if weight.dim() == 2:
+        assert weight.is_contiguous()
+        return weight.view(weight.shape[0], 1, weight.shape[1])
+    kh, kw = weight.shape[2], weight.shape[3]
+    v = weight.permute(1, 2, 3, 0) if kind == 'T' else weight.permute(0, 2, 3, 1)
+    if not v.is_contiguous():
+        raise RuntimeError('conv weights must be stored channels-last ([Cout][kh][kw][Cin]); use '
+                           'scene_generation_b200.layers to build the modules')
+    return v.reshape(v.shape[0], kh * kw, v.shape[3])
+
+
+def grad_like_weight(g3, weight, kind):
+    """(Cout,taps,Cin) f32 gradient -> tensor with the logical shape of `weight` (no copy)."""
+    if weight.dim() == 2:
+        return g3.view(weight.shape)
+    kh, kw = weight.shape[2], weight.shape[3]
+    v = g3.view(g3.shape[0], kh, kw, g3.shape[2])
+    return v.permute(3, 0, 1, 2) if kind == 'T' else v.permute(0, 3, 1, 2)
+
+
+def packed_weights(weight, kind):
+    key = id(weight)
+    ent = _pack_cache.get(key)
+    if ent is not None and ent[0] == weight._version and ent[3] is weight:
+        return ent[1], ent[2]
+    m3 = master3(weight.detach(), kind)
+    Cout, taps, Cin = m3.shape
+    wk = torch.empty((Cout, taps, round_up(Cin, 8)), dtype=BF, device=weight.device)
+    wt = torch.empty((Cin, taps, round_up(Cout, 8)), dtype=BF, device=weight.device)
+    _lib.call('sg_pack_weight', _ptr(m3), Cout, taps, Cin, wk.shape[2], wt.shape[2], _ptr(wk), _ptr(wt), _stream())
+    _pack_cache[key] = (weight._version, wk, wt, weight)
+    return wk, wt
+
+
+def clear_weight_cache():
+    _pack_cache.clear()
+
+
+# ---------------------------------------------------------------------------------------------
+# small kernel wrappers
+# ---------------------------------------------------------------------------------------------
+def cast_pad(x, ld_dst=None, mask_y=None, slope=0.0):
+    """f32 (rows, cols) -> bf16 (rows, ld_dst) zero padded; optional relu'/leaky' mask from the output."""
+    x = x.contiguous()
+    rows, cols = x.shape
+    ld = ld_dst or round_up(cols, 8)
+    out = torch.empty((rows, ld), dtype=BF, device=x.device)
+    _lib.call('sg_cast_pad_bf16', _ptr(x), rows, cols, x.stride(0), ld, _ptr(mask_y), float(slope), _ptr(out), _stream())
+    return out
+
+
+def _nap_desc(src, scale, shift, act, slope, res, res_strides, up, pad, pad_mode, planes):
+    N, H, W, C = src.shape
+    d = NapDesc()
+    d.src, d.N, d.H, d.W, d.C = src.data_ptr(), N, H, W, C
+    d.scale = None if scale is None else scale.data_ptr()
+    d.shift = None if shift is None else shift.data_ptr()
+    d.act, d.slope = act, slope
+    d.res = None if res is None else res
+    d.res_os_img, d.res_os_h, d.res_os_w = res_strides
+    d.up, d.pad, d.pad_mode, d.planes = up, pad, pad_mode, int(planes)
+    return d
+
+
+def operand_shape(N, H, W, C, up=1, pad=0, planes=False):
+    Hp, Wp = H * up + 2 * pad, W * up + 2 * pad
+    return (N, 4, (Hp + 1) // 2, (Wp + 1) // 2, C) if planes else (N, 1, Hp, Wp, C)
+
+
+def nap_forward(src, scale=None, shift=None, act=_lib.ACT_NONE, slope=0.0, res_ptr=None, res_strides=(0, 0, 0),
+                up=1, pad=0, pad_mode=0, planes=False):
+    src = src.contiguous()
+    N, H, W, C = src.shape
+    out = torch.empty(operand_shape(N, H, W, C, up, pad, planes), dtype=BF, device=src.device)
+    d = _nap_desc(src, scale, shift, act, slope, res_ptr, res_strides, up, pad, pad_mode, planes)
+    _lib.call('sg_norm_act_pad_fwd', ctypes.byref(d), _ptr(out), _stream())
+    return out
+
+
+def to_planes(raw):
+    """plain bf16 NHWC -> 4 parity planes (N,4,ceil(H/2),ceil(W/2),C)."""
+    return nap_forward(raw, planes=True)
+
+
+def act_bwd_from_output(dy, y, act, slope, out_planes=False):
+    """dz = dy * act'(.) for relu / leaky fused in a conv epilogue (sign of the output = sign of the
+    pre-activation).  dy, y: plain bf16 NHWC."""
+    N, H, W, C = y.shape
+    d = _nap_desc(y, None, None, act, slope, None, (0, 0, 0), 1, 0, 0, False)
+    shape = (N, 4, (H + 1) // 2, (W + 1) // 2, C) if out_planes else (N, H, W, C)
+    out = torch.empty(shape, dtype=BF, device=y.device)
+    _lib.call('sg_norm_act_pad_bwd', ctypes.byref(d), _ptr(dy), None, None, 0, 1.0, None, int(out_planes), _ptr(out), None,
+              _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# convolution
+# ---------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class ConvSpec:
+    kind: str = 's1'          # 's1' stride-1, 's2' stride-2 over parity planes, 'T' ConvTranspose2d(k3,s2,p1,op1)
+    k: int = 3
+    pad: int = 0              # zero padding realised by the TMA out-of-bounds fill
+    in_hw: tuple = None       # logical (H, W) of the un-planed input (needed for 's2')
+    act: int = _lib.ACT_NONE  # epilogue activation
+    slope: float = 0.0
+    stats: bool = False       # emit per-(image,channel) sum / sum-sq for a following norm
+    out: str = 'bf16'         # 'bf16' NHWC | 'f32_nchw' | 'f32_nhwc'
+    need_dx: bool = True
+    dx_channels: tuple = None  # restrict dgrad to input channels [c0, c1)
+
+
+def _out_hw(spec, x5):
+    _, _, Hx, Wx, _ = x5.shape
+    if spec.kind == 's1':
+        return Hx + 2 * spec.pad - spec.k + 1, Wx + 2 * spec.pad - spec.k + 1
+    if spec.kind == 's2':
+        H, W = spec.in_hw
+        return (H + 2 * spec.pad - spec.k) // 2 + 1, (W + 2 * spec.pad - spec.k) // 2 + 1
+    return 2 * Hx, 2 * Wx
+
+
+def _conv_forward(x5, wk, bias, spec, Cout):
+    N = x5.shape[0]
+    Ho, Wo = _out_hw(spec, x5)
+    dev = x5.device
+    if spec.out == 'bf16':
+        assert Cout % 8 == 0
+        y = torch.empty((N, Ho, Wo, Cout), dtype=BF, device=dev)
+        strides = (Ho * Wo * Cout, Wo * Cout, Cout, 1)
+    elif spec.out == 'f32_nhwc':
+        y = torch.empty((N, Ho, Wo, Cout), dtype=torch.float32, device=dev)
+        strides = (Ho * Wo * Cout, Wo * Cout, Cout, 1)
+    else:
+        y = torch.empty((N, Cout, Ho, Wo), dtype=torch.float32, device=dev)
+        strides = (Cout * Ho * Wo, Wo, 1, Ho * Wo)
+    stats = torch.zeros((N, Cout, 2), dtype=torch.float32, device=dev) if spec.stats else None
+    kw = dict(bias=bias, act=spec.act, slope=spec.slope, stats=stats)
+    if spec.kind == 's1':
+        taps, off = convspec.conv_s1(spec.k, spec.pad)
+        ops.conv_tc(x5, wk, y, strides, Ho, Wo, taps, in_h0=off, in_w0=off, **kw)
+    elif spec.kind == 's2':
+        ops.conv_tc(x5, wk, y, strides, Ho, Wo, convspec.conv_s2(spec.k, spec.pad), **kw)
+    else:
+        taps, phases = convspec.convT_s2(spec.k, 1)
+        ops.conv_tc(x5, wk, y, strides, Ho // 2, Wo // 2, taps, phases=phases, oh_mul=2, ow_mul=2, **kw)
+    return y, stats
+
+
+class ConvFn(torch.autograd.Function):
+    """nn.Conv2d / nn.ConvTranspose2d fprop + dgrad + wgrad on tcgen05 (generators.py:69-87,
+    layers.py:251,266, discriminators.py:134-156,211-233)."""
+
+    @staticmethod
+    def forward(ctx, x5, weight, bias, spec):
+        wk, _ = packed_weights(weight, spec.kind)
+        Cout = wk.shape[0]
+        y, stats = _conv_forward(x5, wk, bias, spec, Cout)
+        ctx.spec = spec
+        ctx.save_for_backward(x5, weight, bias, y if spec.act != _lib.ACT_NONE else None)
+        if stats is None:
+            stats = torch.empty(0, device=x5.device)
+        ctx.mark_non_differentiable(stats)
+        return y, stats
+
+    @staticmethod
+    def backward(ctx, dy, _dstats):
+        spec = ctx.spec
+        x5, weight, bias, y = ctx.saved_tensors
+        _, wt = packed_weights(weight, spec.kind)
+        Cin, taps_n, Coutp = wt.shape
+        m3 = master3(weight, spec.kind)
+        Cout = m3.shape[0]
+        N = x5.shape[0]
+        want_planes = spec.kind == 'T'
+        # ---- dz: gradient w.r.t. the pre-activation conv output, as a bf16 operand -------------
+        if spec.out == 'f32_nchw':
+            _, _, Ho, Wo = dy.shape
+            dz = torch.empty((N, Ho, Wo, Coutp), dtype=BF, device=dy.device)
+            _lib.call('sg_act_bwd_nchw', _ptr(dy.contiguous()), _ptr(y if y is not None else dy), N, Cout, Ho, Wo,
+                      spec.act, Coutp, _ptr(dz), _stream())
+        elif spec.out == 'f32_nhwc':
+            _, Ho, Wo, _ = dy.shape
+            assert spec.act in (_lib.ACT_NONE, _lib.ACT_RELU, _lib.ACT_LEAKY)
+            mask = y.view(-1, Cout) if spec.act != _lib.ACT_NONE else None
+            dz = cast_pad(dy.reshape(-1, Cout), Coutp, mask_y=mask, slope=spec.slope).view(N, Ho, Wo, Coutp)
+        else:
+            _, Ho, Wo, _ = dy.shape
+            dy = dy.contiguous()
+            if spec.act != _lib.ACT_NONE:
+                dz = act_bwd_from_output(dy, y, spec.act, spec.slope, out_planes=want_planes)
+            else:
+                dz = to_planes(dy) if want_planes else dy
+        if dz.dim() == 4:
+            dz5 = to_planes(dz) if want_planes else dz.unsqueeze(1)
+        else:
+            dz5 = dz
+        # ---- bias gradient ----------------------------------------------------------------------
+        db = None
+        if bias is not None and ctx.needs_input_grad[2]:
+            db = torch.zeros(Cout, dtype=torch.float32, device=dy.device)
+            flat = dz5.reshape(-1, Coutp)
+            _lib.call('sg_colsum_bf16', _ptr(flat), flat.shape[0], Cout, Coutp, _ptr(db), _stream())
+        # ---- weight gradient ---------------------------------------------------------------------
+        dw = None
+        if ctx.needs_input_grad[1]:
+            g3 = torch.zeros_like(m3)
+            if spec.kind == 's1':
+                ops.wgrad_tc(dz5, x5, g3, Ho, Wo, convspec.wgrad_s1(spec.k, spec.pad), Cout, Cin)
+            elif spec.kind == 's2':
+                ops.wgrad_tc(dz5, x5, g3, Ho, Wo, convspec.wgrad_s2(spec.k, spec.pad), Cout, Cin)
+            else:
+                ops.wgrad_tc(dz5, x5, g3, x5.shape[2], x5.shape[3], convspec.wgrad_convT(spec.k, 1), Cout, Cin)
+            dw = grad_like_weight(g3, weight, spec.kind)
+        # ---- input gradient (in the operand's own format) ---------------------------------------
+        dx = None
+        if spec.need_dx and ctx.needs_input_grad[0]:
+            Cx = x5.shape[4]
+            c0, c1 = spec.dx_channels or (0, Cin)
+            partial = (c0, c1) != (0, Cin) or Cx != Cin
+            dx = (torch.zeros if partial else torch.empty)(x5.shape, dtype=BF, device=x5.device)
+            wsub = wt[c0:c1]
+            _, P, Hx, Wx, _ = x5.shape
+            base = dx.view(-1)[c0:]
+            if spec.kind == 's1':
+                ops.conv_tc(dz5, wsub, base, (Hx * Wx * Cx, Wx * Cx, Cx, 1), Hx, Wx, convspec.dgrad_s1(spec.k, spec.pad))
+            elif spec.kind == 's2':
+                taps, phases = convspec.dgrad_s2(spec.k, spec.pad)
+                for (tb, nt, a, b) in phases:
+                    plane = base[(a * 2 + b) * Hx * Wx * Cx:]
+                    ops.conv_tc(dz5, wsub, plane, (4 * Hx * Wx * Cx, Wx * Cx, Cx, 1), Hx, Wx, taps[tb:tb + nt])
+            else:
+                ops.conv_tc(dz5, wsub, base, (Hx * Wx * Cx, Wx * Cx, Cx, 1), Hx, Wx, convspec.dgrad_convT(spec.k, 1))
+        return dx, dw, db, None
+
+
+def conv(x5, weight, bias, spec):
+    y, stats = ConvFn.apply(x5, weight, bias, spec)
+    return (y, stats) if spec.stats else y
+
+
+class LinearFn(torch.autograd.Function):
+    """nn.Linear (+ fused ReLU) as a 1-tap tcgen05 GEMM (layers.py:215-231, graph.py:85,120)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act):
+        wk, _ = packed_weights(weight, 's1')
+        M, K = x.shape
+        Nout = weight.shape[0]
+        xb = cast_pad(x) if x.dtype != BF else x
+        y = torch.empty((M, Nout), dtype=torch.float32, device=x.device)
+        if M > 0:
+            ops.conv_tc(xb.view(1, 1, 1, M, xb.shape[1]), wk, y, (0, 0, Nout, 1), 1, M, [(0, 0, 0, 0)], bias=bias, act=act)
+        ctx.act = act
+        ctx.in_dtype = x.dtype
+        ctx.K = K
+        ctx.save_for_backward(xb, weight, y if act != _lib.ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, weight, y = ctx.saved_tensors
+        _, wt = packed_weights(weight, 's1')
+        M, Nout, K = dy.shape[0], weight.shape[0], ctx.K
+        Np = wt.shape[2]
+        dz = cast_pad(dy, Np, mask_y=y, slope=0.0)
+        dz5 = dz.view(1, 1, 1, M, Np)
+        dx = dw = db = None
+        if M == 0:
+            return (torch.zeros((0, K), device=dy.device) if ctx.needs_input_grad[0] else None,
+                    torch.zeros_like(weight), torch.zeros(Nout, device=dy.device), None)
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((M, K), dtype=torch.float32, device=dy.device)
+            ops.conv_tc(dz5, wt, dx, (0, 0, K, 1), 1, M, [(0, 0, 0, 0)])
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros((Nout, 1, K), dtype=torch.float32, device=dy.device)
+            ops.wgrad_tc(dz5, xb.view(1, 1, 1, M, xb.shape[1]), dw, 1, M, [(0, 0, 0, 0, 0, 0, 0)], Nout, K)
+            dw = dw.view(Nout, K)
+        if ctx.needs_input_grad[2]:
+            db = torch.zeros(Nout, dtype=torch.float32, device=dy.device)
+            _lib.call('sg_colsum_bf16', _ptr(dz), M, Nout, Np, _ptr(db), _stream())
+        return dx, dw, db, None
+
+
+def linear(x, weight, bias, act=_lib.ACT_NONE):
+    return LinearFn.apply(x, weight, bias, act)
+
+
+# ---------------------------------------------------------------------------------------------
+# normalisation + activation + padding operand writer
+# ---------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class NapSpec:
+    norm: str = None          # None | 'in' | 'bn'
+    eps: float = 1e-5
+    momentum: float = 0.1
+    act: int = _lib.ACT_NONE
+    slope: float = 0.0
+    up: int = 1
+    pad: int = 0
+    pad_mode: int = 0         # 0 zeros, 1 reflection
+    planes: bool = False
+    res_pad: int = 0          # the residual operand carries this much halo around the plain tensor
+
+
+class NapFn(torch.autograd.Function):
+    """InstanceNorm2d / BatchNorm2d(train) + ReLU/LeakyReLU + residual add + ReflectionPad2d / nearest
+    upsample / parity-plane split in one pass (layers.py:251-267,292-314, generators.py:20-23)."""
+
+    @staticmethod
+    def forward(ctx, src, stats, gamma, beta, residual, running, spec):
+        src = src.contiguous()
+        N, H, W, C = src.shape
+        dev = src.device
+        scale = shift = mean = rstd = None
+        if spec.norm is not None:
+            scale, shift, mean, rstd = (torch.empty(N * C, dtype=torch.float32, device=dev) for _ in range(4))
+            rm, rv = (running if running is not None else (None, None))
+            _lib.call('sg_norm_finalize', _ptr(stats), 0 if spec.norm == 'in' else 1, N, C, float(H * W), spec.eps,
+                      _ptr(gamma), _ptr(beta), _ptr(rm), _ptr(rv), spec.momentum, _ptr(scale), _ptr(shift), _ptr(mean),
+                      _ptr(rstd), _stream())
+        res_ptr, res_strides = None, (0, 0, 0)
+        if residual is not None:
+            _, _, Hr, Wr, Cr = residual.shape
+            p = spec.res_pad
+            assert residual.is_contiguous() and Cr == C and Hr == H + 2 * p and Wr == W + 2 * p
+            res_strides = (Hr * Wr * Cr, Wr * Cr, Cr)
+            res_ptr = residual.data_ptr() + 2 * (p * Wr * Cr + p * Cr)
+        out = nap_forward(src, scale, shift, spec.act, spec.slope, res_ptr, res_strides, spec.up, spec.pad, spec.pad_mode,
+                          spec.planes)
+        ctx.spec = spec
+        ctx.res_shape = None if residual is None else tuple(residual.shape)
+        ctx.res_strides = res_strides
+        ctx.save_for_backward(src, scale, shift, mean, rstd)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        spec = ctx.spec
+        src, scale, shift, mean, rstd = ctx.saved_tensors
+        N, H, W, C = src.shape
+        dev = src.device
+        g = g.contiguous()
+        d = _nap_desc(src, scale, shift, spec.act, spec.slope, None, ctx.res_strides, spec.up, spec.pad, spec.pad_mode,
+                      spec.planes)
+        dsrc = torch.empty((N, H, W, C), dtype=BF, device=dev)
+        dres = dres_ptr = None
+        if ctx.res_shape is not None and ctx.needs_input_grad[4]:
+            assert spec.act == _lib.ACT_NONE
+            dres = torch.zeros(ctx.res_shape, dtype=BF, device=dev)
+            p = spec.res_pad
+            dres_ptr = dres.data_ptr() + 2 * (p * ctx.res_shape[3] * C + p * C)
+        sums = None
+        bn = spec.norm == 'bn'
+        if spec.norm is not None:
+            sums = torch.empty((C if bn else N * C, 2), dtype=torch.float32, device=dev)
+        count = float(H * W * (N if bn else 1))
+        _lib.call('sg_norm_act_pad_bwd', ctypes.byref(d), _ptr(g), _ptr(mean), _ptr(rstd), int(bn), count, _ptr(sums), 0,
+                  _ptr(dsrc), dres_ptr, _stream())
+        dgamma = dbeta = None
+        if bn:
+            dgamma, dbeta = sums[:, 1].contiguous(), sums[:, 0].contiguous()
+        return dsrc, None, dgamma, dbeta, dres, None, None
+
+
+def nap(src, stats=None, gamma=None, beta=None, residual=None, running=None, spec=NapSpec()):
+    return NapFn.apply(src, stats, gamma, beta, residual, running, spec)
+
+
+def to_planes_fn(raw):
+    """differentiable plain NHWC -> parity planes"""
+    return nap(raw, spec=NapSpec(planes=True))
+
+
+def plain_fn(raw, pad=0):
+    """differentiable plain NHWC -> (N,1,H+2p,W+2p,C) zero-haloed operand (a free view when pad=0)"""
+    if pad == 0:
+        return raw.unsqueeze(1)
+    return nap(raw, spec=NapSpec(pad=pad))
+
+
+# ---------------------------------------------------------------------------------------------
+# layout / crop / graph
+# ---------------------------------------------------------------------------------------------
+class LayoutFn(torch.autograd.Function):
+    """masks_to_layout, train branch (layout.py:64-93,149-155).  nhwc_bf16=True returns the raw
+    channels-last bf16 buffer (N,H,W,Cp) that feeds the generator / discriminator operands; otherwise
+    the reference's (N,D,H,W) f32 tensor."""
+
+    @staticmethod
+    def forward(ctx, vecs, boxes, masks, ranges, H, W, align_corners, nhwc_bf16):
+        fmt = ops.NHWC_BF16 if nhwc_bf16 else ops.NCHW_F32
+        out = ops.masks_to_layout_fwd(vecs, boxes, masks, ranges, H, W, align_corners, fmt, raw=True)
+        ctx.save_for_backward(vecs, boxes, masks, ranges)
+        ctx.cfg = (H, W, align_corners)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        vecs, boxes, masks, ranges = ctx.saved_tensors
+        H, W, ac = ctx.cfg
+        need_dm = ctx.needs_input_grad[2] and masks.is_floating_point()
+        dv, dm = ops.masks_to_layout_bwd(vecs, boxes, masks, ranges, H, W, g.contiguous(), ac, need_dmasks=need_dm)
+        return dv, None, dm, None, None, None, None, None
+
+
+class CropFn(torch.autograd.Function):
+    """crop_bbox_batch (bilinear.py:26-130); output NHWC bf16 operand (Cp=8) or NCHW f32."""
+
+    @staticmethod
+    def forward(ctx, feats, boxes, box_to_feats, HH, WW, align_corners, nhwc_bf16):
+        fmt = ops.NHWC_BF16 if nhwc_bf16 else ops.NCHW_F32
+        out = ops.crop_bbox_fwd(feats, boxes, box_to_feats, HH, WW, align_corners, fmt)
+        ctx.save_for_backward(boxes, box_to_feats)
+        ctx.cfg = (tuple(feats.shape), align_corners, fmt)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        boxes, b2f = ctx.saved_tensors
+        shape, ac, fmt = ctx.cfg
+        return ops.crop_bbox_bwd(g.contiguous(), boxes, b2f, *shape, align_corners=ac, grad_format=fmt), None, None, None, None, None, None
+
+
+class GatherFn(torch.autograd.Function):
+    """[obj[s] | pred | obj[o]] row gather (graph.py:79-84), bf16 operand for net1's first GEMM."""
+
+    @staticmethod
+    def forward(ctx, obj_vecs, pred_vecs, edges, seg_ptr, seg_src, as_bf16):
+        O, Do = obj_vecs.shape
+        T, Dp = pred_vecs.shape
+        ld = round_up(2 * Do + Dp, 8) if as_bf16 else 2 * Do + Dp
+        out = ops.gconv_gather(obj_vecs.float(), pred_vecs.float(), edges, BF if as_bf16 else torch.float32, ld)
+        ctx.save_for_backward(seg_ptr, seg_src)
+        ctx.dims = (O, T, Do, Dp)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        seg_ptr, seg_src = ctx.saved_tensors
+        O, T, Do, Dp = ctx.dims
+        dobj, dpred = ops.gconv_gather_bwd(g.float(), seg_ptr, seg_src, O, T, Do, Dp)
+        return dobj, dpred, None, None, None, None
+
+
+class PoolFn(torch.autograd.Function):
+    """per-object average of the subject / object messages (graph.py:94-116) + pass-through of new_p."""
+
+    @staticmethod
+    def forward(ctx, new_t, edges, seg_ptr, seg_src, O, H, Dout, avg):
+        pooled = ops.gconv_pool(new_t, H + Dout, seg_ptr, seg_src, O, H, avg)
+        new_p = new_t[:, H:H + Dout].contiguous()
+        ctx.save_for_backward(edges, seg_ptr)
+        ctx.dims = (new_t.shape[0], H, Dout, avg)
+        return pooled, new_p
+
+    @staticmethod
+    def backward(ctx, dpooled, dnew_p):
+        edges, seg_ptr = ctx.saved_tensors
+        T, H, Dout, avg = ctx.dims
+        return ops.gconv_pool_bwd(dpooled, dnew_p, edges, seg_ptr, T, H, Dout, avg), None, None, None, None, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------
+# pooling / concat / format conversion
+# ---------------------------------------------------------------------------------------------
+class GapFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):           # bf16 (N,H,W,C) -> f32 (N,C)
+        N, H, W, C = x.shape
+        y = torch.empty((N, C), dtype=torch.float32, device=x.device)
+        _lib.call('sg_gap_fwd', _ptr(x.contiguous()), N, H * W, C, _ptr(y), _stream())
+        ctx.shape = (N, H, W, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        N, H, W, C = ctx.shape
+        gx = torch.empty(ctx.shape, dtype=BF, device=g.device)
+        _lib.call('sg_gap_bwd', _ptr(g.contiguous().float()), N, H * W, C, _ptr(gx), _stream())
+        return gx
+
+
+class AvgPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):           # bf16 (N,H,W,C)
+        N, H, W, C = x.shape
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        y = torch.empty((N, Ho, Wo, C), dtype=BF, device=x.device)
+        _lib.call('sg_avgpool3x3s2_fwd', _ptr(x.contiguous()), N, H, W, C, _ptr(y), _stream())
+        ctx.shape = (N, H, W, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        N, H, W, C = ctx.shape
+        gx = torch.empty(ctx.shape, dtype=BF, device=g.device)
+        _lib.call('sg_avgpool3x3s2_bwd', _ptr(g.contiguous()), N, H, W, C, _ptr(gx), _stream())
+        return gx
+
+
+class ConcatCondFn(torch.autograd.Function):
+    """concat of a broadcast one-hot class vector behind the feature channels (discriminators.py:107-109)."""
+
+    @staticmethod
+    def forward(ctx, x, cls, n_cls):   # x bf16 (N,H,W,Cs)
+        N, H, W, Cs = x.shape
+        Cd = round_up(Cs + n_cls, 8)
+        out = torch.empty((N, H, W, Cd), dtype=BF, device=x.device)
+        _lib.call('sg_concat_cond', _ptr(x.contiguous()), H * W, N, Cs, Cd, _ptr(cls), n_cls, _ptr(out), _stream())
+        ctx.dims = (N, H, W, Cs, Cd)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        N, H, W, Cs, Cd = ctx.dims
+        gx = torch.empty((N, H, W, Cs), dtype=BF, device=g.device)
+        _lib.call('sg_slice_channels', _ptr(g.contiguous()), N * H * W, Cd, Cs, _ptr(gx), _stream())
+        return gx, None, None
+
+
+class ImageSlotFn(torch.autograd.Function):
+    """cat((layout, img), dim=1) (trainer.py:246,250,328): writes the f32 NCHW image into channels
+    [c0, c0+3) of a COPY of the channels-last bf16 layout buffer.  Only the image gets a gradient —
+    the layout operand is detached at every call site whose gradient is used (trainer.py:249-250)."""
+
+    @staticmethod
+    def forward(ctx, layout_nhwc, img, c0):
+        N, H, W, Cp = layout_nhwc.shape
+        out = layout_nhwc.clone()
+        C = img.shape[1]
+        _lib.call('sg_nchw_to_nhwc', _ptr(img.contiguous().float()), 0, N, C, H, W, Cp, c0, _ptr(out), _stream())
+        ctx.dims = (N, C, H, W, Cp, c0)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        N, C, H, W, Cp, c0 = ctx.dims
+        gi = torch.empty((N, C, H, W), dtype=torch.float32, device=g.device)
+        _lib.call('sg_nhwc_to_nchw', _ptr(g.contiguous()), N, C, H, W, Cp, c0, _ptr(gi), _stream())
+        return None, gi, None
+
+
+class ToNhwcFn(torch.autograd.Function):
+    """f32 / i64 NCHW -> zero-padded bf16 NHWC (Cp) operand, gradient back to f32 NCHW."""
+
+    @staticmethod
+    def forward(ctx, x, Cp):
+        N, C, H, W = x.shape
+        out = torch.zeros((N, H, W, Cp), dtype=BF, device=x.device)
+        dt = 1 if x.dtype == torch.int64 else 0
+        xs = x.contiguous() if dt else x.contiguous().float()
+        _lib.call('sg_nchw_to_nhwc', _ptr(xs), dt, N, C, H, W, Cp, 0, _ptr(out), _stream())
+        ctx.dims = (N, C, H, W, Cp)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        N, C, H, W, Cp = ctx.dims
+        gi = torch.empty((N, C, H, W), dtype=torch.float32, device=g.device)
+        _lib.call('sg_nhwc_to_nchw', _ptr(g.contiguous()), N, C, H, W, Cp, 0, _ptr(gi), _stream())
+        return gi, None
+
+
+class FeatureViewFn(torch.autograd.Function):
+    """Logical NCHW view of a plain bf16 NHWC feature map (what the reference returns from its
+    discriminators); the gradient comes back channels-last and is made contiguous NHWC."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.permute(0, 2, 3, 1).contiguous().to(BF)

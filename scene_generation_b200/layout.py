@@ -1,0 +1,40 @@
+"""masks/boxes -> layout (mirror of scene_generation/layout.py; kernel: sg_masks_to_layout_*)."""
+import torch
+
+from . import functional as Fn
+from . import ops, synthetic
+
+
+def _ranges(obj_to_img, N=None):
+    """Per-image object ranges, computed once on the host (replaces the per-object .item() loop of
+    layout.py:143-155; the object->image map is host data produced by the collate function)."""
+    r = getattr(obj_to_img, '_sg_ranges', None)
+    if r is not None:
+        return r
+    return torch.from_numpy(synthetic.image_ranges(obj_to_img, N)).to(obj_to_img.device)
+
+
+def masks_to_layout(vecs, boxes, masks, obj_to_img, H, W=None, pooling='sum', test_mode=False, align_corners=False,
+                    nhwc_bf16=False, N=None):
+    """layout.py:64-93.  Returns (N,D,H,W); with nhwc_bf16 the result is a bf16 view of a channels-last
+    buffer (N,H,W,Cp) which is also attached as ``._sg_nhwc`` for the conv operands."""
+    if pooling != 'sum':
+        raise NotImplementedError('only pooling="sum" is used by the model')
+    W = H if W is None else W
+    ranges = _ranges(obj_to_img, N)
+    D = vecs.shape[1]
+    if test_mode:
+        with torch.no_grad():
+            fmt = ops.NHWC_BF16 if nhwc_bf16 else ops.NCHW_F32
+            raw = ops.masks_to_layout_fwd(vecs, boxes, masks, ranges, H, W, align_corners, fmt, test_mode=True, raw=True)
+    else:
+        raw = Fn.LayoutFn.apply(vecs, boxes, masks, ranges, H, W, align_corners, nhwc_bf16)
+    if not nhwc_bf16:
+        return raw
+    out = raw.permute(0, 3, 1, 2)[:, :D]
+    out._sg_nhwc = raw
+    return out
+
+
+def boxes_to_layout(*args, **kwargs):
+    raise NotImplementedError('boxes_to_layout is dead code in the reference (layout.py:59 raises TypeError)')

@@ -1,0 +1,120 @@
+"""Scene-graph -> image model (mirror of scene_generation/model.py: same constructor, same forward
+signature and return tuple, same state_dict keys; all tensor math on libsg_b200 kernels)."""
+import torch
+import torch.nn as nn
+
+from .bilinear import crop_bbox_batch
+from .generators import AppearanceEncoder, define_G, mask_net
+from .graph import GraphIndex, GraphTripleConv, GraphTripleConvNet
+from .layers import build_mlp
+from .layout import masks_to_layout
+from .utils import VectorPool
+
+
+class Model(nn.Module):
+    """model.py:12-124.  Extra keyword-only options (defaults keep the reference behaviour of the
+    in-container oracle): ``layout_dtype`` 'bf16' (channels-last operand, default) or 'f32' (reference
+    NCHW tensors), ``align_corners`` for the three grid_sample call sites."""
+
+    def __init__(self, vocab, image_size=(64, 64), embedding_dim=128, gconv_dim=128, gconv_hidden_dim=512,
+                 gconv_pooling='avg', gconv_num_layers=5, mask_size=32, mlp_normalization='none',
+                 appearance_normalization='', activation='', n_downsample_global=4, box_dim=128,
+                 use_attributes=False, box_noise_dim=64, mask_noise_dim=64, pool_size=100, rep_size=32,
+                 layout_dtype='bf16', align_corners=False):
+        super().__init__()
+        self.vocab = vocab
+        self.image_size = image_size
+        self.use_attributes = use_attributes
+        self.box_noise_dim = box_noise_dim
+        self.mask_noise_dim = mask_noise_dim
+        self.object_size = 64
+        self.fake_pool = VectorPool(pool_size)
+        self.layout_dtype = layout_dtype
+        self.align_corners = align_corners
+
+        self.num_objs = len(vocab['object_to_idx'])
+        self.num_preds = len(vocab['pred_idx_to_name'])
+        self.obj_embeddings = nn.Embedding(self.num_objs, embedding_dim)
+        self.pred_embeddings = nn.Embedding(self.num_preds, embedding_dim)
+        attributes_dim = vocab['num_attributes'] if use_attributes else 0
+        if gconv_num_layers == 0:
+            self.gconv = nn.Linear(embedding_dim, gconv_dim)
+        else:
+            self.gconv = GraphTripleConv(input_dim=embedding_dim, attributes_dim=attributes_dim, output_dim=gconv_dim,
+                                         hidden_dim=gconv_hidden_dim, pooling=gconv_pooling,
+                                         mlp_normalization=mlp_normalization)
+        self.gconv_net = None
+        if gconv_num_layers > 1:
+            self.gconv_net = GraphTripleConvNet(input_dim=gconv_dim, hidden_dim=gconv_hidden_dim, pooling=gconv_pooling,
+                                                num_layers=gconv_num_layers - 1, mlp_normalization=mlp_normalization)
+        self.box_dim = box_dim
+        self.box_net = build_mlp([box_dim, gconv_hidden_dim, 4], batch_norm=mlp_normalization)
+        self.g_mask_dim = gconv_dim + mask_noise_dim
+        self.mask_net = mask_net(self.g_mask_dim, mask_size)
+        self.repr_input = self.g_mask_dim
+        self.repr_net = build_mlp([self.repr_input, 64, rep_size], batch_norm=mlp_normalization)
+        self.image_encoder = AppearanceEncoder(vocab=vocab, arch='C4-64-2,C4-128-2,C4-256-2',
+                                               normalization=appearance_normalization, activation=activation,
+                                               padding='valid', vecs_size=self.g_mask_dim)
+        self.layout_to_image = define_G(self.num_objs + rep_size, 3, 64, n_downsample_global, 9, 'instance')
+
+    def forward(self, gt_imgs, objs, triples, obj_to_img, boxes_gt=None, masks_gt=None, attributes=None,
+                test_mode=False, use_gt_box=False, features=None):
+        O = objs.size(0)
+        obj_vecs, pred_vecs = self.scene_graph_to_vectors(objs, triples, attributes)
+        box_vecs, mask_vecs, scene_layout_vecs, wrong_layout_vecs = \
+            self.create_components_vecs(gt_imgs, boxes_gt, obj_to_img, objs, obj_vecs, features)
+        boxes_pred = self.box_net(box_vecs)
+        masks_pred = self.mask_net(mask_vecs, fused_sigmoid=True).squeeze(1)        # model.py:106-107
+        H, W = self.image_size
+        N = gt_imgs.size(0) if gt_imgs is not None else None
+        lay = dict(align_corners=self.align_corners, nhwc_bf16=self.layout_dtype == 'bf16', N=N)
+        if test_mode:
+            boxes = boxes_gt if use_gt_box else boxes_pred
+            masks = masks_gt if masks_gt is not None else masks_pred
+            pred_layout = masks_to_layout(scene_layout_vecs, boxes, masks, obj_to_img, H, W, test_mode=True, **lay)
+            return self.layout_to_image(pred_layout), boxes_pred, masks_pred, None, pred_layout, None
+        gt_layout = masks_to_layout(scene_layout_vecs, boxes_gt, masks_gt, obj_to_img, H, W, **lay)
+        pred_layout = masks_to_layout(scene_layout_vecs, boxes_gt, masks_pred, obj_to_img, H, W, **lay)
+        wrong_layout = masks_to_layout(wrong_layout_vecs, boxes_gt, masks_gt, obj_to_img, H, W, **lay)
+        imgs_pred = self.layout_to_image(gt_layout)
+        return imgs_pred, boxes_pred, masks_pred, gt_layout, pred_layout, wrong_layout
+
+    def scene_graph_to_vectors(self, objs, triples, attributes):
+        """model.py:126-143."""
+        s, p, o = triples[:, 0], triples[:, 1], triples[:, 2]
+        edges = torch.stack([s, o], dim=1)
+        obj_vecs = self.obj_embeddings(objs)
+        pred_vecs = self.pred_embeddings(p)
+        if self.use_attributes:
+            obj_vecs = torch.cat([obj_vecs, attributes], dim=1)
+        if isinstance(self.gconv, nn.Linear):
+            from . import functional as Fn
+            obj_vecs = Fn.linear(obj_vecs, self.gconv.weight, self.gconv.bias)
+        else:
+            index = GraphIndex(edges, objs.size(0))
+            obj_vecs, pred_vecs = self.gconv(obj_vecs, pred_vecs, edges, index)
+            if self.gconv_net is not None:
+                obj_vecs, pred_vecs = self.gconv_net(obj_vecs, pred_vecs, edges, index)
+        return obj_vecs, pred_vecs
+
+    def create_components_vecs(self, imgs, boxes, obj_to_img, objs, obj_vecs, features):
+        """model.py:145-172."""
+        O = objs.size(0)
+        layout_noise = torch.randn((1, self.mask_noise_dim), dtype=obj_vecs.dtype, device=obj_vecs.device).repeat((O, 1))
+        mask_vecs = torch.cat([obj_vecs, layout_noise], dim=1)
+        if features is None:
+            crops = crop_bbox_batch(imgs, boxes, obj_to_img, self.object_size, align_corners=self.align_corners, operand=True)
+            obj_repr = self.repr_net(self.image_encoder(crops))
+        else:
+            obj_repr = self.repr_net(mask_vecs)
+            rows = [i for i, f in enumerate(features) if f is not None]
+            if rows:
+                obj_repr = obj_repr.clone()
+                obj_repr[rows] = torch.stack([features[i].to(obj_repr) for i in rows])
+        one_hot_obj = torch.zeros((O, self.num_objs), dtype=obj_repr.dtype, device=obj_repr.device)
+        one_hot_obj = one_hot_obj.scatter_(1, objs.view(-1, 1).long(), 1.0)
+        layout_vecs = torch.cat([one_hot_obj, obj_repr], dim=1)
+        wrong_objs_rep = self.fake_pool.query(objs, obj_repr)
+        wrong_layout_vecs = torch.cat([one_hot_obj, wrong_objs_rep], dim=1)
+        return obj_vecs, mask_vecs, layout_vecs, wrong_layout_vecs

@@ -39,7 +39,8 @@ _MASK_DT = {torch.float32: 0, torch.int64: 1, torch.uint8: 2}
 # ---------------------------------------------------------------------------------------------
 # layout
 # ---------------------------------------------------------------------------------------------
-def masks_to_layout_fwd(vecs, boxes, masks, ranges, H, W, align_corners=False, out_format=NCHW_F32, test_mode=False):
+def masks_to_layout_fwd(vecs, boxes, masks, ranges, H, W, align_corners=False, out_format=NCHW_F32, test_mode=False,
+                        raw=False):
     """ranges: int32 (N,2) device tensor.  Returns (N,D,H,W) f32, or a (N,D,H,W) *view* of a
     channels-last bf16 buffer with Cp = round_up(D, 8) physical channels."""
     _need_cuda(vecs, boxes, masks, ranges)
@@ -59,7 +60,7 @@ def masks_to_layout_fwd(vecs, boxes, masks, ranges, H, W, align_corners=False, o
         _lib.call('sg_masks_to_layout_test', *args, _ptr(ws), _ptr(buf), _stream())
     else:
         _lib.call('sg_masks_to_layout_fwd', *args, _ptr(buf), _stream())
-    if out_format == NHWC_BF16:
+    if out_format == NHWC_BF16 and not raw:
         return buf.permute(0, 3, 1, 2)[:, :D]
     return buf
 
@@ -71,13 +72,12 @@ def masks_to_layout_bwd(vecs, boxes, masks, ranges, H, W, grad, align_corners=Fa
     N = ranges.shape[0]
     vecs, boxes, masks = vecs.contiguous().float(), boxes.contiguous().float(), masks.contiguous()
     if grad.dtype == torch.bfloat16:
-        g = grad.permute(0, 2, 3, 1)
-        Cp = g.stride(2)
-        if not (g.stride(3) == 1 and Cp % 8 == 0 and g.stride(1) == W * Cp and g.stride(0) == H * W * Cp):
-            Cp = round_up(D, 8)
-            gb = torch.zeros((N, H, W, Cp), dtype=torch.bfloat16, device=grad.device)
-            gb[..., :D] = g
-            g = gb
+        if grad.dim() == 4 and grad.shape[1] == H and grad.shape[2] == W and grad.is_contiguous():
+            g = grad                                   # raw (N,H,W,Cp) buffer
+        else:                                          # logical (N,D,H,W) view / tensor
+            g = torch.zeros((N, H, W, round_up(D, 8)), dtype=torch.bfloat16, device=grad.device)
+            g[..., :D] = grad.permute(0, 2, 3, 1)
+        Cp = g.shape[3]
         fmt = NHWC_BF16
     else:
         g = grad.contiguous().float()
@@ -190,7 +190,8 @@ def conv_tc(x5, w3, y, y_strides, Hout, Wout, taps, phases=None, oh_mul=1, ow_mu
     d.x, (d.x_N, d.x_P, d.x_H, d.x_W, d.x_C) = x5.data_ptr(), x5.shape
     d.w, (d.w_Cout, d.w_taps, d.w_C) = w3.data_ptr(), w3.shape
     d.y, d.y_dtype = y.data_ptr(), (BF16 if y.dtype == torch.bfloat16 else F32)
-    d.y_os_img, d.y_os_h, d.y_os_w = y_strides
+    d.y_os_img, d.y_os_h, d.y_os_w = y_strides[:3]
+    d.y_os_c = y_strides[3] if len(y_strides) > 3 else 1
     d.Hout, d.Wout, d.oh_mul, d.ow_mul, d.in_h0, d.in_w0 = Hout, Wout, oh_mul, ow_mul, in_h0, in_w0
     if phases is None:
         phases = [(0, len(taps), 0, 0)]

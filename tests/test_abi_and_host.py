@@ -1,0 +1,140 @@
+"""CPU: the C-ABI library loads and exports every symbol of include/sg_b200.h; host-side index logic
+(tap / phase tables, CSR, image ranges, synthetic batches) against plain PyTorch."""
+import ctypes
+import itertools
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from scene_generation_b200 import _lib, convspec, ops, synthetic
+
+
+def test_library_builds_and_exports_declared_symbols():
+    path = _lib.build()
+    h = ctypes.CDLL(path)
+    decl = _lib.declared_symbols()
+    assert len(decl) >= 30
+    missing = [s for s in decl if not hasattr(h, s)]
+    assert not missing, missing
+    bound = set(_lib._SIGS) | set(_lib._RESTYPES)
+    assert set(decl) == bound, (set(decl) ^ bound)
+    assert _lib.lib().sg_arch() == 100
+    assert b'sm_100a' in _lib.lib().sg_version()
+
+
+def test_struct_sizes_match_header_layout():
+    # sg_tap_t 8 B, sg_phase_t 16 B, sg_wtap_t 16 B: the descriptors are passed by pointer across the ABI
+    assert ctypes.sizeof(_lib.Tap) == 8 and ctypes.sizeof(_lib.Phase) == 16 and ctypes.sizeof(_lib.WTap) == 16
+    assert ctypes.sizeof(_lib.ConvDesc) % 8 == 0 and ctypes.sizeof(_lib.WgradDesc) % 8 == 0
+
+
+def test_ops_refuse_cpu_tensors():
+    with pytest.raises(RuntimeError):
+        ops.crop_bbox_fwd(torch.zeros(1, 3, 4, 4), torch.zeros(1, 4), torch.zeros(1, dtype=torch.long), 2, 2)
+
+
+# ---- emulate the documented semantics of sg_conv_tc / sg_wgrad_tc to validate the tap tables -----------
+def emulate_conv(x5, w3, Hout, Wout, taps, phases=None, oh_mul=1, ow_mul=1, in_h0=0, in_w0=0):
+    N, P, H, W, C = x5.shape
+    Cout = w3.shape[0]
+    phases = phases or [(0, len(taps), 0, 0)]
+    y = torch.zeros(N, Hout * oh_mul, Wout * ow_mul, Cout)
+    for (tb, nt, a, b) in phases:
+        for (dh, dw, pl, wt) in taps[tb:tb + nt]:
+            for h in range(Hout):
+                for w in range(Wout):
+                    hh, ww = h + dh + in_h0, w + dw + in_w0
+                    if 0 <= hh < H and 0 <= ww < W:
+                        y[:, h * oh_mul + a, w * ow_mul + b] += x5[:, pl, hh, ww] @ w3[:, wt].t()
+    return y
+
+
+def planes(x):     # (N,C,H,W) -> (N,4,ceil,ceil,C)
+    N, C, H, W = x.shape
+    out = torch.zeros(N, 4, (H + 1) // 2, (W + 1) // 2, C)
+    for ph, pw in itertools.product(range(2), range(2)):
+        s = x[:, :, ph::2, pw::2]
+        out[:, ph * 2 + pw, :s.shape[2], :s.shape[3]] = s.permute(0, 2, 3, 1)
+    return out
+
+
+def w3_of(w):      # (Cout,Cin,k,k) -> (Cout,k*k,Cin)
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1, w.shape[1])
+
+
+@pytest.mark.parametrize('H,k,p', [(7, 4, 2), (8, 3, 1), (6, 4, 0)])
+def test_tap_tables_stride2_and_adjoint(H, k, p):
+    torch.manual_seed(0)
+    x, w = torch.randn(2, 3, H, H), torch.randn(5, 3, k, k)
+    ref = F.conv2d(x, w, stride=2, padding=p)
+    Ho = ref.shape[2]
+    y = emulate_conv(planes(x), w3_of(w), Ho, Ho, convspec.conv_s2(k, p))
+    assert torch.allclose(y.permute(0, 3, 1, 2), ref, atol=1e-4)
+    # adjoint: phases write the parity planes of dx
+    dy = torch.randn_like(ref)
+    xr = x.clone().requires_grad_(True)
+    F.conv2d(xr, w, stride=2, padding=p).backward(dy)
+    taps, phases = convspec.dgrad_s2(k, p)
+    wT = w3_of(w.permute(1, 0, 2, 3))
+    Hh = (H + 1) // 2
+    dxp = torch.zeros(2, 4, Hh, Hh, 3)
+    for (tb, nt, a, b) in phases:
+        dxp[:, a * 2 + b] = emulate_conv(dy.permute(0, 2, 3, 1).unsqueeze(1), wT, Hh, Hh, taps[tb:tb + nt])
+    assert torch.allclose(dxp, planes(xr.grad), atol=1e-4) or torch.allclose(dxp[planes(torch.ones_like(x)) > 0], planes(xr.grad)[planes(torch.ones_like(x)) > 0], atol=1e-4)
+
+
+def test_tap_tables_transposed_conv_and_adjoint():
+    torch.manual_seed(1)
+    x, w = torch.randn(2, 4, 5, 5), torch.randn(4, 3, 3, 3)       # ConvT weight (Cin_t, Cout_t, k, k)
+    ref = F.conv_transpose2d(x, w, stride=2, padding=1, output_padding=1)
+    taps, phases = convspec.convT_s2(3, 1)
+    y = emulate_conv(x.permute(0, 2, 3, 1).unsqueeze(1), w3_of(w.permute(1, 0, 2, 3)), 5, 5, taps, phases, 2, 2)
+    assert torch.allclose(y.permute(0, 3, 1, 2), ref, atol=1e-4)
+    dy = torch.randn_like(ref)
+    xr = x.clone().requires_grad_(True)
+    F.conv_transpose2d(xr, w, stride=2, padding=1, output_padding=1).backward(dy)
+    dx = emulate_conv(planes(dy), w3_of(w), 5, 5, convspec.dgrad_convT(3, 1))   # B = [Cin_t][taps][Cout_t]
+    assert torch.allclose(dx.permute(0, 3, 1, 2), xr.grad, atol=1e-4)
+
+
+def test_tap_tables_stride1_and_dgrad():
+    torch.manual_seed(2)
+    x, w = torch.randn(1, 3, 6, 6), torch.randn(4, 3, 3, 3)
+    taps, off = convspec.conv_s1(3, 1)
+    y = emulate_conv(x.permute(0, 2, 3, 1).unsqueeze(1), w3_of(w), 6, 6, taps, in_h0=off, in_w0=off)
+    assert torch.allclose(y.permute(0, 3, 1, 2), F.conv2d(x, w, padding=1), atol=1e-4)
+    dy = torch.randn(1, 4, 6, 6)
+    xr = x.clone().requires_grad_(True)
+    F.conv2d(xr, w, padding=1).backward(dy)
+    dx = emulate_conv(dy.permute(0, 2, 3, 1).unsqueeze(1), w3_of(w.permute(1, 0, 2, 3)), 6, 6, convspec.dgrad_s1(3, 1))
+    assert torch.allclose(dx.permute(0, 3, 1, 2), xr.grad, atol=1e-4)
+
+
+def test_incidence_csr_order_matches_reference_scatter_order():
+    edges = np.array([[0, 2], [1, 2], [2, 0], [0, 1], [3, 3]])
+    ptr, src = ops.build_incidence_csr(edges, 5)
+    assert ptr.tolist() == [0, 3, 5, 8, 10, 10]
+    # object 0: subject of t0, t3 then object of t2
+    assert src[ptr[0]:ptr[1]].tolist() == [0, 6, 5]
+    assert src[ptr[2]:ptr[3]].tolist() == [4, 1, 3]
+    assert src[ptr[3]:ptr[4]].tolist() == [8, 9]
+    with pytest.raises(IndexError):
+        ops.build_incidence_csr(np.array([[0, 7]]), 3)
+
+
+def test_synthetic_batch_contract_and_ranges():
+    b = synthetic.make_batch(5, (32, 32), 20, 1, 6, seed=3)
+    imgs, objs, boxes, masks, triples, o2i, t2i, attrs = b
+    assert imgs.shape == (5, 3, 32, 32) and objs.dtype == torch.int64 and masks.dtype == torch.int64
+    r = synthetic.image_ranges(o2i)
+    assert r[0, 0] == 0 and r[-1, 1] == objs.numel() and (r[1:, 0] == r[:-1, 1]).all()
+    for i, (s, e) in enumerate(r):
+        assert objs[e - 1] == 0 and (o2i[s:e] == i).all()                    # __image__ last, contiguous
+        assert boxes[e - 1].tolist() == [0, 0, 1, 1] and masks[e - 1].min() == 1
+    assert ((triples[:, 0] >= 0) & (triples[:, 2] < objs.numel())).all()
+    same = synthetic.make_batch(5, (32, 32), 20, 1, 6, seed=3)
+    assert all(torch.equal(x, y) for x, y in zip(b, same))
+    with pytest.raises(ValueError):
+        synthetic.image_ranges(torch.tensor([0, 1, 0]))

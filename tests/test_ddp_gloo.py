@@ -1,0 +1,47 @@
+"""CPU, world_size 2, gloo: the data-parallel plumbing (flat gradient buffer all-reduce, parameter
+broadcast) gives every rank the mean gradient of the concatenated batch, also when a parameter got no
+gradient on a rank (the use_gt coin flip, train.py:195)."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from scene_generation_b200 import ddp
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(rank)          # different initial weights per rank: broadcast must fix that
+    net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2), torch.nn.Linear(2, 2))
+    ddp.broadcast_parameters(net)
+    red = ddp.FlatGradReducer(net)
+    full = torch.arange(32, dtype=torch.float32).view(8, 4) / 10
+    x = full[rank * 4:(rank + 1) * 4]
+    red.zero()
+    h = net[1](net[0](x))
+    loss = h.pow(2).mean()           # net[2] is unused -> its gradient slots stay zero
+    loss.backward()
+    red.allreduce()
+    ret[rank] = [p.grad.clone() for p in net.parameters()] + [p.detach().clone() for p in net.parameters()]
+    dist.destroy_process_group()
+
+
+def test_flat_grad_allreduce_equals_big_batch_gradient():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    g0, g1 = ret[0], ret[1]
+    for a, b in zip(g0, g1):
+        assert torch.equal(a, b)                     # identical grads and params on both ranks
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2), torch.nn.Linear(2, 2))
+    full = torch.arange(32, dtype=torch.float32).view(8, 4) / 10
+    net[1](net[0](full)).pow(2).mean().backward()
+    n = len(list(net.parameters()))
+    for p, g in zip(net.parameters(), g0[:n]):
+        ref = p.grad if p.grad is not None else torch.zeros_like(p)
+        assert torch.allclose(g, ref, atol=1e-6)
