@@ -37,6 +37,8 @@ def parse():
     ap.add_argument('--kmax', type=int, default=8)
     ap.add_argument('--cpu-batch', type=int, default=2, help='images per step of the CPU baseline sample')
     ap.add_argument('--cpu-steps', type=int, default=3)
+    ap.add_argument('--cpu-budget', type=int, default=90, help='seconds the CPU baseline may take')
+    ap.add_argument('--cpu-worker', action='store_true', help=argparse.SUPPRESS)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     return ap.parse_args()
@@ -71,13 +73,89 @@ def cpu_reference_rate(image_size, n_imgs, steps, warmup, kmin, kmax):
     return n_imgs / mean, mean, cores
 
 
+def log(msg):
+    print('[bench %.1fs] %s' % (time.perf_counter() - _T0, msg), file=sys.stderr, flush=True)
+
+
+_T0 = time.perf_counter()
+
+
+def host_threads():
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 64))      # torch CPU kernels stop scaling (and oversubscribe) far below the core count of a GPU host
+
+
+def cpu_worker(a):
+    """child process: prints one JSON line per finished step so the parent can stop it at its time budget"""
+    from oracle import restate as R
+    from scene_generation_b200 import synthetic
+    import random
+    cores = host_threads()
+    torch.set_num_threads(cores)
+    H = a.image_size
+    cfg = dict(image_size=(H, H), num_objs=NUM_OBJS, rep_size=32, mask_size=32, n_downsample_global=4,
+               gconv_num_layers=5, crop_size=32, ngf=64, n_blocks=9)
+    tr = R.OracleTrainer(R.make_state_dicts(cfg, seed=0), cfg)
+    random.seed(0)
+    print(json.dumps({'ready': True, 'cores': cores}), flush=True)
+    s = 0
+    while True:
+        batch = synthetic.make_batch(a.cpu_batch, (H, H), NUM_OBJS, a.kmin, a.kmax, seed=1000 + s)
+        t0 = time.perf_counter()
+        tr.step(batch, torch.randn((1, 64)), use_gt=(s % 2 == 0))
+        print(json.dumps({'step': s, 'sec': time.perf_counter() - t0}), flush=True)
+        s += 1
+
+
+def cpu_reference_bounded(a, steps, warmup, budget_s):
+    """Run the CPU worker for at most budget_s seconds; returns (images/s, s/step, cores, steps measured)."""
+    import select
+    cmd = [sys.executable, os.path.abspath(__file__), '--cpu-worker', '--cpu-batch', str(a.cpu_batch), '--image-size',
+           str(a.image_size), '--kmin', str(a.kmin), '--kmax', str(a.kmax)]
+    env = dict(os.environ)
+    env.pop('RANK', None)
+    p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env)
+    t_end = time.perf_counter() + budget_s
+    times, cores = [], host_threads()
+    try:
+        while len(times) < warmup + steps:
+            left = t_end - time.perf_counter()
+            if left <= 0:
+                break
+            r, _, _ = select.select([p.stdout], [], [], left)
+            if not r:
+                break
+            line = p.stdout.readline()
+            if not line:
+                break
+            d = json.loads(line)
+            if 'cores' in d:
+                cores = d['cores']
+            if 'sec' in d:
+                times.append(d['sec'])
+    finally:
+        p.kill()
+        p.wait()
+    meas = times[warmup:] if len(times) > warmup else times
+    if not meas:
+        return None, None, cores, 0
+    mean = sum(meas) / len(meas)
+    return a.cpu_batch / mean, mean, cores, len(meas)
+
+
 def run_reference_arm(a):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    rate, mean, cores = cpu_reference_rate(a.image_size, a.cpu_batch, a.steps, max(a.warmup, 1), a.kmin, a.kmax)
-    sample = '%d images/step x %d steps of the %dx%d, <=%d-object workload (fp32, %d host threads)' % (
-        a.cpu_batch, a.steps, a.image_size, a.image_size, a.kmax, cores)
+    rate, mean, cores, n = cpu_reference_bounded(a, a.steps, max(a.warmup, 1), a.cpu_budget)
+    if rate is None:
+        print(json.dumps({'impl': 'reference', 'unavailable': 'CPU reference produced no step within %d s' % a.cpu_budget}))
+        return
+    sample = '%d images/step x %d measured steps of the %dx%d, <=%d-object workload (fp32, %d host threads, <=%d s budget)' % (
+        a.cpu_batch, n, a.image_size, a.image_size, a.kmax, cores, a.cpu_budget)
     line = {
         'impl': 'reference', 'metric': 'images/sec (train step, %dx%d, bs32/GPU)' % (a.image_size, a.image_size),
         'value': rate, 'unit': 'images/s', 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': max(a.warmup, 1),
@@ -209,6 +287,8 @@ def load_peaks():
 # ------------------------------------------------------------------------------------------------
 def main():
     a = parse()
+    if a.cpu_worker:
+        return cpu_worker(a)
     if a.impl == 'reference':
         return run_reference_arm(a)
 
@@ -251,7 +331,7 @@ def main():
         hb = host_batches[i % n_distinct]
         batch = tuple(t.to(dev, non_blocking=True) for t in hb)
         tr.train_step(batch, use_gt=(i % 2 == 0))
-        return float(tr.generator_losses.total_loss)      # device -> host read of the step's result
+        return float(tr.generator_losses.total_loss.detach())      # device -> host read of the step's result
 
     def timed(fn, steps):
         barrier()
@@ -266,14 +346,18 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    log('model built; warm-up')
     for i in range(max(a.warmup, 3)):
         step_resident(i)
+        torch.cuda.synchronize()
+        log('warm-up step %d done' % i)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     _lib.reset_launch_count()
     ms_total = timed(step_resident, a.steps)
     launches = _lib.launch_count()
+    log('timed %d steps: %.1f ms/step' % (a.steps, ms_total / a.steps))
     clocks = sampler.stop() if rank == 0 else None
     images = a.batch * world * a.steps
     value = images / (ms_total / 1e3)
@@ -306,10 +390,11 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        rate, mean, cores = cpu_reference_rate(H, a.cpu_batch, a.cpu_steps, 1, a.kmin, a.kmax)
+        log('cpu baseline (<= %d s)' % a.cpu_budget)
+        rate, mean, cores, n = cpu_reference_bounded(a, a.cpu_steps, 1, a.cpu_budget)
         cpu = {'value': rate, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-               'sample': '%d images/step x %d steps (+1 warm-up) of the same workload, fp32, %d host threads, %.2f s/step'
-                         % (a.cpu_batch, a.cpu_steps, cores, mean)}
+               'sample': '%d images/step x %d measured steps (+1 warm-up) of the same workload, fp32, %d host threads, '
+                         '%s s/step, budget %d s' % (a.cpu_batch, n, cores, ('%.2f' % mean) if mean else 'n/a', a.cpu_budget)}
 
     if rank == 0:
         line = {

@@ -89,6 +89,7 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
 struct ConvKParams {
   int Hout, Wout, tiles_w, tiles_h, BW, BH, BI, n_img;
   int kblocks, Cout;
+  int a_bytes;      // bytes of one A box = 128 * BW*BH*BI (rows beyond the box keep stale smem and are masked)
   int in_h0, in_w0;
   long long os_img, os_h, os_w, os_c;
   int oh_mul, ow_mul;
@@ -161,7 +162,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&empty[s], par ^ 1);
         const int tap_i = it / p.kblocks, kb = it - tap_i * p.kblocks;
         const sg_tap_t tp = p.taps[ph.tap_begin + tap_i];
-        mbar_expect_tx(&full[s], A_BYTES + Cfg::B_BYTES);
+        mbar_expect_tx(&full[s], p.a_bytes + Cfg::B_BYTES);
         tma_load_5d(sA + s * A_BYTES, &tmA, &full[s], kb * 64, w0 + tp.dw + p.in_w0, h0 + tp.dh + p.in_h0, tp.plane, img0);
         tma_load_3d(sB + s * Cfg::B_STRIDE, &tmB, &full[s], kb * 64, tp.wtap, n0);
       }
@@ -188,7 +189,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int r = q * 32 + lane;
     const int ww = r % p.BW, hh = (r / p.BW) % p.BH, ii = r / (p.BW * p.BH);
     const int img = img0 + ii, h = h0 + hh, w = w0 + ww;
-    const bool valid = (img < p.n_img) && (h < p.Hout) && (w < p.Wout);
+    const bool valid = (ii < p.BI) && (img < p.n_img) && (h < p.Hout) && (w < p.Wout);
     const long long off = (long long)img * p.os_img + (long long)(h * p.oh_mul + ph.oh_off) * p.os_h +
                           (long long)(w * p.ow_mul + ph.ow_off) * p.os_w;
     const bool seg_full = (p.BI == 1) || ((p.BW * p.BH) % 32 == 0);
@@ -283,6 +284,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 struct WgradKParams {
   int tiles_w, tiles_h, BW, BH, BI;
   int ktiles_total, ktiles_per_split;
+  int atomic;       // 0: this CTA owns its dw tile (ksplit == 1) -> plain stores
   int Cout, Cin, w_taps, dw_C, n_ci_tiles;
   float* dw;
   sg_wtap_t taps[SG_MAX_TAPS];
@@ -385,9 +387,26 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tmem_ld_wait();
       if (co < p.Cout) {
         float* dst = p.dw + ((long long)co * p.w_taps + tp.wtap) * p.dw_C + ci0 + c0;
+        const bool vec = (ci0 + c0 + 32 <= p.Cin) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+        if (vec && !p.atomic) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (ci0 + c0 + j < p.Cin) atomicAdd(dst + j, __uint_as_float(raw[j]));
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]),
+                                                              __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3]));
+        } else if (vec) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(raw[j])),
+                         "f"(__uint_as_float(raw[j + 1])), "f"(__uint_as_float(raw[j + 2])), "f"(__uint_as_float(raw[j + 3]))
+                         : "memory");
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (ci0 + c0 + j < p.Cin) {
+              if (p.atomic) atomicAdd(dst + j, __uint_as_float(raw[j]));
+              else dst[j] = __uint_as_float(raw[j]);
+            }
+        }
       }
     }
   }
@@ -396,18 +415,27 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 1) tmem_dealloc<BN>(tmem);
 }
 
-// choose the 128-row (or `rows`-row) tile box (BW, BH, BI) minimising padded work
-void choose_tile(int rows, int H, int W, int N, int* BW, int* BH, int* BI) {
+// Choose the TMA box (BW, BH, BI) of one M tile.  exact=false (conv): any box with BW*BH*BI <= rows —
+// smem rows beyond the box stay stale and their accumulator rows are masked in the epilogue, so
+// odd extents (10x10, 65x65, 134x134) do not round up to powers of two.  exact=true (wgrad): the box
+// is the reduction dimension and must fill the stage exactly.  Minimises the number of tiles.
+void choose_tile(int rows, bool exact, int H, int W, int N, int* BW, int* BH, int* BI) {
   long best = -1;
-  for (int bw = 1; bw <= rows; bw <<= 1) {
-    for (int bh = 1; bw * bh <= rows; bh <<= 1) {
-      int bi = rows / (bw * bh);
-      if (bw > 256 || bh > 256 || bi > 256) continue;
-      if (bi > 1 && (bw < W || bh < H)) continue;   // several images per tile only if one image fits
-      if (bw * bh * bi != rows) continue;
+  int best_rows = 0;
+  for (int bw = 1; bw <= rows && bw <= 256; ++bw) {
+    if (!exact && bw > W) break;
+    for (int bh = 1; bw * bh <= rows && bh <= 256; ++bh) {
+      if (!exact && bh > H) break;
+      int bi = 1;
+      if (bw >= W && bh >= H) bi = rows / (bw * bh);       // several images per tile only if one image fits
+      if (bi > 256) bi = 256;
+      if (!exact && bi > N) bi = N;
+      if (exact && bw * bh * bi != rows) continue;
       long cost = (long)sg_cdiv(W, bw) * sg_cdiv(H, bh) * sg_cdiv(N, bi);
-      if (best < 0 || cost < best || (cost == best && bw > *BW)) {
+      int used = bw * bh * bi;
+      if (best < 0 || cost < best || (cost == best && (bw > *BW || (bw == *BW && used < best_rows)))) {
         best = cost;
+        best_rows = used;
         *BW = bw; *BH = bh; *BI = bi;
       }
     }
@@ -456,7 +484,8 @@ extern "C" int sg_conv_tc(const sg_conv_desc_t* d, sg_stream_t stream) {
                  "sg_conv_tc: phase %d tap range invalid", i);
   ConvKParams kp;
   memset(&kp, 0, sizeof(kp));
-  choose_tile(128, d->Hout, d->Wout, d->x_N, &kp.BW, &kp.BH, &kp.BI);
+  choose_tile(128, false, d->Hout, d->Wout, d->x_N, &kp.BW, &kp.BH, &kp.BI);
+  kp.a_bytes = 128 * kp.BW * kp.BH * kp.BI;
   kp.Hout = d->Hout; kp.Wout = d->Wout;
   kp.tiles_w = sg_cdiv(d->Wout, kp.BW); kp.tiles_h = sg_cdiv(d->Hout, kp.BH);
   const int img_tiles = sg_cdiv(d->x_N, kp.BI);
@@ -477,7 +506,18 @@ extern "C" int sg_conv_tc(const sg_conv_desc_t* d, sg_stream_t stream) {
   long long adims[5] = {d->x_C, d->x_W, d->x_H, d->x_P, d->x_N};
   int abox[5] = {64, kp.BW, kp.BH, 1, kp.BI};
   if (int e = make_tmap(&tmA, d->x, 5, adims, abox)) return e;
-  const int BN = d->w_Cout > 128 ? 256 : (d->w_Cout > 64 ? 128 : (d->w_Cout > 16 ? 64 : 16));
+  // N tile: the MMA time of a CTA grows with BN, the number of waves over the 148 SMs shrinks with it
+  int BN = 16;
+  if (d->w_Cout > 16) {
+    const long m_ctas = (long)kp.tiles_w * kp.tiles_h * img_tiles * d->nphases;
+    double best_t = 0;
+    for (int cand = 256; cand >= 64; cand >>= 1) {
+      if (cand > 64 && cand / 2 >= d->w_Cout) continue;             // do not tile far beyond Cout
+      long ctas = m_ctas * sg_cdiv(d->w_Cout, cand);
+      double t = (double)((ctas + 147) / 148) * (cand + 48);        // +48: per-CTA prologue/epilogue in units of N columns
+      if (best_t == 0 || t < best_t) { best_t = t; BN = cand; }
+    }
+  }
   long long bdims[3] = {d->w_C, d->w_taps, d->w_Cout};
   int bbox[3] = {64, 1, BN};
   if (int e = make_tmap(&tmB, d->w, 3, bdims, bbox)) return e;
@@ -497,7 +537,7 @@ extern "C" int sg_wgrad_tc(const sg_wgrad_desc_t* d, sg_stream_t stream) {
   SG_CHECK_ARG(d->Hred > 0 && d->Wred > 0 && d->N > 0 && d->Cout > 0 && d->Cin > 0, "sg_wgrad_tc: empty problem");
   WgradKParams kp;
   memset(&kp, 0, sizeof(kp));
-  choose_tile(64, d->Hred, d->Wred, d->N, &kp.BW, &kp.BH, &kp.BI);
+  choose_tile(64, true, d->Hred, d->Wred, d->N, &kp.BW, &kp.BH, &kp.BI);
   kp.tiles_w = sg_cdiv(d->Wred, kp.BW); kp.tiles_h = sg_cdiv(d->Hred, kp.BH);
   kp.ktiles_total = kp.tiles_w * kp.tiles_h * sg_cdiv(d->N, kp.BI);
   kp.Cout = d->Cout; kp.Cin = d->Cin; kp.w_taps = d->w_taps; kp.dw_C = d->dw_C; kp.dw = d->dw;
@@ -516,6 +556,7 @@ extern "C" int sg_wgrad_tc(const sg_wgrad_desc_t* d, sg_stream_t stream) {
   }
   kp.ktiles_per_split = sg_cdiv(kp.ktiles_total, ksplit);
   ksplit = sg_cdiv(kp.ktiles_total, kp.ktiles_per_split);
+  kp.atomic = ksplit > 1;
   CUtensorMap tmA, tmB;
   long long adims[5] = {d->dy_C, d->dy_W, d->dy_H, d->dy_P, d->N};
   long long bdims[5] = {d->x_C, d->x_W, d->x_H, d->x_P, d->N};

@@ -151,39 +151,39 @@ class Trainer:
             if args.l1_pixel_loss_weight > 0:
                 gl.add_loss(F.l1_loss(imgs_pred, imgs), 'L1_pixel_loss', args.l1_pixel_loss_weight)
             gl.add_loss(F.mse_loss(boxes_pred, boxes), 'bbox_pred', args.bbox_pred_loss_weight)
-        scores_fake, ac_loss, _ = self.obj_discriminator(imgs_pred, objs, boxes, obj_to_img)
-        gl.add_loss(ac_loss, 'ac_loss', args.ac_loss_weight)
-        gl.add_loss(self.gan_g_loss(scores_fake), 'g_gan_obj_loss', args.d_obj_weight)
-        if self.mask_discriminator is not None:
-            scores_fake = self.mask_discriminator(masks_pred.unsqueeze(1), objs)
-            gl.add_loss(self.criterionGAN(scores_fake, True), 'g_gan_mask_obj_loss', args.d_mask_weight)
-            if args.d_mask_features_weight > 0:
-                with torch.no_grad():
-                    scores_real = self.mask_discriminator(masks.unsqueeze(1), objs)
-                gl.add_loss(self.calculate_features_loss(scores_fake, scores_real), 'g_mask_features_loss',
-                            args.d_mask_features_weight)
-        if self.netD is not None:
-            with torch.no_grad():       # only used detached (trainer.py:246,339)
-                pred_real = self.netD.forward_pair(layout, imgs)
-            img_pred_fake = self.netD.forward_pair(layout, imgs_pred)
-            gl.add_loss(self.criterionGAN(img_pred_fake, True), 'g_gan_img_loss', args.d_img_weight)
-            if args.d_img_features_weight > 0:
-                gl.add_loss(self.calculate_features_loss(img_pred_fake, pred_real), 'g_gan_features_loss_img',
-                            args.d_img_features_weight)
-        gl._terms['total_loss'] = gl.total_loss.detach()
-        # the G step also deposits (unused) gradients in the discriminators (trainer.py:262); they are
-        # cleared by every D step's zero_grad before use, so they are dropped here instead
-        for net in (self.obj_discriminator, self.mask_discriminator, self.netD):
-            if net is not None:
-                for p in net.parameters():
-                    p.requires_grad_(False)
+        # The G step back-propagates THROUGH the discriminators; the gradients it would deposit in their
+        # parameters (trainer.py:262) are cleared by every D step's zero_grad before use, so the D weights are
+        # frozen for this graph and their wgrad kernels are skipped.
+        d_nets = [n for n in (self.obj_discriminator, self.mask_discriminator, self.netD) if n is not None]
+        for net in d_nets:
+            for p in net.parameters():
+                p.requires_grad_(False)
         try:
+            scores_fake, ac_loss, _ = self.obj_discriminator(imgs_pred, objs, boxes, obj_to_img)
+            gl.add_loss(ac_loss, 'ac_loss', args.ac_loss_weight)
+            gl.add_loss(self.gan_g_loss(scores_fake), 'g_gan_obj_loss', args.d_obj_weight)
+            if self.mask_discriminator is not None:
+                scores_fake = self.mask_discriminator(masks_pred.unsqueeze(1), objs)
+                gl.add_loss(self.criterionGAN(scores_fake, True), 'g_gan_mask_obj_loss', args.d_mask_weight)
+                if args.d_mask_features_weight > 0:
+                    with torch.no_grad():
+                        scores_real = self.mask_discriminator(masks.unsqueeze(1), objs)
+                    gl.add_loss(self.calculate_features_loss(scores_fake, scores_real), 'g_mask_features_loss',
+                                args.d_mask_features_weight)
+            if self.netD is not None:
+                with torch.no_grad():       # only used detached (trainer.py:246,339)
+                    pred_real = self.netD.forward_pair(layout, imgs)
+                img_pred_fake = self.netD.forward_pair(layout, imgs_pred)
+                gl.add_loss(self.criterionGAN(img_pred_fake, True), 'g_gan_img_loss', args.d_img_weight)
+                if args.d_img_features_weight > 0:
+                    gl.add_loss(self.calculate_features_loss(img_pred_fake, pred_real), 'g_gan_features_loss_img',
+                                args.d_img_features_weight)
+            gl._terms['total_loss'] = gl.total_loss.detach()
             self._step('g', self.optimizer, gl)
         finally:
-            for net in (self.obj_discriminator, self.mask_discriminator, self.netD):
-                if net is not None:
-                    for p in net.parameters():
-                        p.requires_grad_(True)
+            for net in d_nets:
+                for p in net.parameters():
+                    p.requires_grad_(True)
 
     def train_obj_discriminator(self, imgs, imgs_pred, objs, boxes, boxes_pred, obj_to_img):
         if self.obj_discriminator is None:
