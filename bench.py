@@ -253,11 +253,22 @@ class KernelProbe:
             e1.record()
             probe.records.append(('wgrad_tc', flops, e0, e1, (dy5.shape[0], Hred, Wred, Cout, Cin, len(taps), 1)))
             return r
-        ops.conv_tc, ops.wgrad_tc = conv_tc, wgrad_tc
+        self.orig_layout = ops.masks_to_layout_fwd
+
+        def layout_fwd(vecs, boxes, masks, ranges, H, W, align_corners=False, out_format=0, test_mode=False, raw=False):
+            N, D = ranges.shape[0], vecs.shape[1]
+            nbytes = float(N * H * W * (((D + 7) // 8 * 8) * 2 if out_format == 1 else D * 4))   # algorithmic: the output write
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = probe.orig_layout(vecs, boxes, masks, ranges, H, W, align_corners, out_format, test_mode, raw)
+            e1.record()
+            probe.records.append(('layout_fwd', nbytes, e0, e1, (N, H, W, D, 0, 0, 0)))
+            return r
+        ops.conv_tc, ops.wgrad_tc, ops.masks_to_layout_fwd = conv_tc, wgrad_tc, layout_fwd
         return self
 
     def __exit__(self, *exc):
-        self.ops.conv_tc, self.ops.wgrad_tc = self.orig_conv, self.orig_wgrad
+        self.ops.conv_tc, self.ops.wgrad_tc, self.ops.masks_to_layout_fwd = self.orig_conv, self.orig_wgrad, self.orig_layout
 
     def summary(self):
         torch.cuda.synchronize()
@@ -376,6 +387,7 @@ def main():
             step_resident(0)
             fam, top = probe.summary()
         peak_tf, peak_hbm, which = load_peaks()
+        lay = fam.pop('layout_fwd', None)
         dom = max(fam.items(), key=lambda kv: kv[1]['ms'])
         achieved = dom[1]['flops'] / (dom[1]['ms'] * 1e-3) / 1e12
         roofline = {'kernel': dom[0], 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
@@ -383,10 +395,19 @@ def main():
                     'launches_per_step': dom[1]['launches'], 'ms_per_step': dom[1]['ms']}
         kernels = {k: {'launches': v['launches'], 'ms': round(v['ms'], 3),
                        'tflops': round(v['flops'] / (v['ms'] * 1e-3) / 1e12, 1)} for k, v in fam.items()}
-        worst = sorted(top.items(), key=lambda kv: -kv[1]['ms'])[:6]
-        kernels['top_shapes'] = [{'kernel': k[0], 'N,H,W,Cout,Cin,taps,phases': list(k[1]), 'launches': v['launches'],
-                                  'ms': round(v['ms'], 3), 'tflops': round(v['flops'] / (v['ms'] * 1e-3) / 1e12, 1)}
-                                 for k, v in worst]
+        if lay is not None:       # HBM-bound layout scatter: algorithmic bytes = the output write
+            gbs = lay['flops'] / (lay['ms'] * 1e-3) / 1e9
+            kernels['layout_fwd'] = {'launches': lay['launches'], 'ms': round(lay['ms'], 3), 'bound': 'hbm',
+                                     'achieved_gbs': round(gbs, 1), 'peak_gbs': peak_hbm, 'frac': round(gbs / peak_hbm, 3)}
+        shapes = sorted(((k, v) for k, v in top.items() if k[0] != 'layout_fwd'), key=lambda kv: -kv[1]['ms'])
+        fmt = lambda k, v: {'kernel': k[0], 'N,H,W,Cout,Cin,taps,phases': list(k[1]), 'launches': v['launches'],
+                            'ms': round(v['ms'], 3), 'tflops': round(v['flops'] / (v['ms'] * 1e-3) / 1e12, 1)}
+        kernels['top_shapes'] = [fmt(k, v) for k, v in shapes[:6]]
+        try:
+            os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+            json.dump([fmt(k, v) for k, v in shapes], open(os.path.join(ROOT, 'gpurun_out', 'bench_shapes.json'), 'w'), indent=0)
+        except OSError:
+            pass
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

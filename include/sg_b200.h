@@ -113,8 +113,10 @@ int sg_conv_tc(const sg_conv_desc_t* desc, sg_stream_t stream);
 
 /* Weight gradient (cuDNN wgrad in the reference):
  *   dw[co, wtap, ci] += sum_{img,h,w} dy[img, pa, h+dha, w+dwa, co] * x[img, pb, h+dhb, w+dwb, ci]
- * for every entry of the tap table (a = dy side, b = x side).  dw is f32 [Cout][w_taps][dw_C]
- * and is ACCUMULATED into (split-K atomics) — the caller zeroes it. */
+ * for every entry of the tap table (a = dy side, b = x side).  dw is f32 [Cout][w_taps][dw_C] and is
+ * OVERWRITTEN (the call zeroes it itself when it splits the reduction and accumulates atomically).
+ * At least one side must have zero tap offsets and extents equal to (Hred, Wred), so that pixels
+ * outside the reduction extent read as zero through the TMA fill. */
 typedef struct {
   int16_t dha, dwa, pa, dhb, dwb, pb, wtap, pad;
 } sg_wtap_t;

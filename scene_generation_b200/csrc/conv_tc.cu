@@ -557,6 +557,7 @@ extern "C" int sg_wgrad_tc(const sg_wgrad_desc_t* d, sg_stream_t stream) {
   kp.ktiles_per_split = sg_cdiv(kp.ktiles_total, ksplit);
   ksplit = sg_cdiv(kp.ktiles_total, kp.ktiles_per_split);
   kp.atomic = ksplit > 1;
+  if (kp.atomic) cudaMemsetAsync(d->dw, 0, sizeof(float) * (size_t)d->Cout * d->w_taps * d->dw_C, stream);
   CUtensorMap tmA, tmB;
   long long adims[5] = {d->dy_C, d->dy_W, d->dy_H, d->dy_P, d->N};
   long long bdims[5] = {d->x_C, d->x_W, d->x_H, d->x_P, d->N};

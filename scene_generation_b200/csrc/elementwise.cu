@@ -78,6 +78,23 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int ta
   }
 }
 
+// transposed operand: wt[ci][t][co] = w[co][t][ci] through a 32x32 shared-memory tile (both sides coalesced)
+__global__ void pack_weight_t_kernel(const float* __restrict__ w, int Cout, int taps, int Cin, int Cout_p,
+                                     bf16* __restrict__ wt) {
+  __shared__ float tile[32][33];
+  const int t = blockIdx.z;
+  const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    int co = co0 + r, ci = ci0 + threadIdx.x;
+    tile[r][threadIdx.x] = (co < Cout && ci < Cin) ? w[((long)co * taps + t) * Cin + ci] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    int ci = ci0 + r, co = co0 + threadIdx.x;
+    if (ci < Cin && co < Cout_p) wt[((long)ci * taps + t) * Cout_p + co] = __float2bfloat16(tile[threadIdx.x][r]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // norm finalize: conv-epilogue sums -> per-(image,channel) scale/shift (+ saved mean/rstd)
 // ---------------------------------------------------------------------------------------------
@@ -476,13 +493,32 @@ __global__ void gap_bwd_kernel(const float* __restrict__ gy, int N, int HW, int 
   gx[idx] = __float2bfloat16(gy[(long)n * C + c] / (float)HW);
 }
 
-// column sums of a bf16 [rows][C] matrix into f32 [C] (bias gradient), accumulated atomically
+// column sums of a bf16 [rows][ld] matrix (ld % 8 == 0) into f32 [C] (bias gradient), accumulated atomically.
+// thread = (8-channel chunk, row lane); 16-byte loads; per-block partials reduced through shared memory.
 __global__ void colsum_kernel(const bf16* __restrict__ x, long rows, int C, int ld, int rows_per_block, float* __restrict__ out) {
-  long r0 = (long)blockIdx.x * rows_per_block;
-  long r1 = min(r0 + rows_per_block, rows);
+  extern __shared__ float red[];     // [lanes][nC*8]
+  const int nC = ld / 8;
+  const int lanes = blockDim.x / nC;
+  const int ch = threadIdx.x % nC, lane = threadIdx.x / nC;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  if (lane < lanes) {
+    long r0 = (long)blockIdx.x * rows_per_block;
+    long r1 = min(r0 + rows_per_block, rows);
+    for (long r = r0 + lane; r < r1; r += lanes) {
+      float t[8];
+      load8(x + r * ld + ch * 8, t);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += t[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[lane * nC * 8 + ch * 8 + k] = acc[k];
+  }
+  __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = 0.f;
-    for (long r = r0; r < r1; ++r) s += __bfloat162float(x[r * ld + c]);
+    for (int l = 0; l < lanes; ++l) s += red[l * nC * 8 + c];
     atomicAdd(out + c, s);
   }
 }
@@ -504,9 +540,14 @@ extern "C" int sg_pack_weight(const float* w, int Cout, int taps, int Cin, int C
                               sg_stream_t stream) {
   SG_CHECK_ARG(Cout > 0 && taps > 0 && Cin > 0 && Cin_p >= Cin && Cin_p % 8 == 0, "pack_weight: bad sizes");
   SG_CHECK_ARG(wt == nullptr || (Cout_p >= Cout && Cout_p % 8 == 0), "pack_weight: bad Cout_p");
-  long total = (long)Cout * taps * Cin_p + (wt ? (long)Cin * taps * Cout_p : 0);
-  LAUNCH_1D(pack_weight_kernel, total, stream, w, Cout, taps, Cin, Cin_p, Cout_p, (bf16*)wk, (bf16*)wt);
+  long total = (long)Cout * taps * Cin_p;
+  LAUNCH_1D(pack_weight_kernel, total, stream, w, Cout, taps, Cin, Cin_p, Cout_p, (bf16*)wk, (bf16*)nullptr);
   SG_CHECK_LAUNCH("sg_pack_weight");
+  if (wt) {
+    dim3 grid(sg_cdiv(Cout_p, 32), sg_cdiv(Cin, 32), taps);
+    pack_weight_t_kernel<<<grid, dim3(32, 8), 0, stream>>>(w, Cout, taps, Cin, Cout_p, (bf16*)wt);
+    SG_CHECK_LAUNCH("sg_pack_weight(transposed)");
+  }
   return SG_OK;
 }
 
@@ -568,7 +609,11 @@ extern "C" int sg_norm_act_pad_bwd(const sg_nap_desc_t* d, const void* grad, con
     int threads = nC >= 256 ? nC : 256;
     threads = (threads / nC) * nC;
     SG_CHECK_ARG(threads <= 1024, "norm_act_pad_bwd: too many channels");
-    int pix_per_block = 1024;
+    const int lanes = threads / nC;
+    long total_px = (long)d->N * d->H * d->W;
+    int pix_per_block = (int)((total_px + 1183) / 1184);           // ~8 CTAs per SM
+    if (pix_per_block < lanes) pix_per_block = lanes;
+    pix_per_block = ((pix_per_block + lanes - 1) / lanes) * lanes;
     dim3 grid(sg_cdiv((long)d->H * d->W, pix_per_block), d->N);
     nap_bwd_reduce_kernel<<<grid, threads, 0, stream>>>(b, pix_per_block);
     SG_CHECK_LAUNCH("sg_norm_act_pad_bwd(reduce)");
@@ -655,9 +700,15 @@ extern "C" int sg_gap_bwd(const float* gy, int N, int HW, int C, void* gx, sg_st
 
 extern "C" int sg_colsum_bf16(const void* x, long long rows, int C, int ld, float* out, sg_stream_t stream) {
   SG_CHECK_ARG(x && out && rows > 0 && C > 0 && ld >= C, "colsum: bad arguments");
-  int rpb = (int)((rows + 592 - 1) / 592);
-  if (rpb < 32) rpb = 32;
-  colsum_kernel<<<sg_cdiv(rows, rpb), 256, 0, stream>>>((const bf16*)x, rows, C, ld, rpb, out);
+  SG_CHECK_ARG(ld % 8 == 0 && ld <= 8192, "colsum: ld must be a multiple of 8 (<= 8192)");
+  const int nC = ld / 8;
+  int threads = nC >= 256 ? nC : (256 / nC) * nC;
+  SG_CHECK_ARG(threads <= 1024, "colsum: too many channels");
+  const int lanes = threads / nC;
+  int rpb = (int)((rows + 1183) / 1184);
+  if (rpb < lanes * 4) rpb = lanes * 4;
+  size_t smem = sizeof(float) * (size_t)lanes * nC * 8;
+  colsum_kernel<<<sg_cdiv(rows, rpb), threads, smem, stream>>>((const bf16*)x, rows, C, ld, rpb, out);
   SG_CHECK_LAUNCH("sg_colsum_bf16");
   return SG_OK;
 }

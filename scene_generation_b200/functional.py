@@ -234,7 +234,7 @@ class ConvFn(torch.autograd.Function):
         # ---- weight gradient ---------------------------------------------------------------------
         dw = None
         if ctx.needs_input_grad[1]:
-            g3 = torch.zeros_like(m3)
+            g3 = torch.empty_like(m3)
             if spec.kind == 's1':
                 ops.wgrad_tc(dz5, x5, g3, Ho, Wo, convspec.wgrad_s1(spec.k, spec.pad), Cout, Cin)
             elif spec.kind == 's2':
@@ -303,7 +303,7 @@ class LinearFn(torch.autograd.Function):
             dx = torch.empty((M, K), dtype=torch.float32, device=dy.device)
             ops.conv_tc(dz5, wt, dx, (0, 0, K, 1), 1, M, [(0, 0, 0, 0)])
         if ctx.needs_input_grad[1]:
-            dw = torch.zeros((Nout, 1, K), dtype=torch.float32, device=dy.device)
+            dw = torch.empty((Nout, 1, K), dtype=torch.float32, device=dy.device)
             ops.wgrad_tc(dz5, xb.view(1, 1, 1, M, xb.shape[1]), dw, 1, M, [(0, 0, 0, 0, 0, 0, 0)], Nout, K)
             dw = dw.view(Nout, K)
         if ctx.needs_input_grad[2]:

@@ -209,7 +209,7 @@ def conv_tc(x5, w3, y, y_strides, Hout, Wout, taps, phases=None, oh_mul=1, ow_mu
 
 
 def wgrad_tc(dy5, x5, dw, Hred, Wred, taps, Cout, Cin, ksplit=0):
-    """dy5: bf16 (N,P,H,W,Cd); x5: bf16 (N,P,H,W,Cx); dw: f32 (Cout, w_taps, dw_C) ACCUMULATED into.
+    """dy5: bf16 (N,P,H,W,Cd); x5: bf16 (N,P,H,W,Cx); dw: f32 (Cout, w_taps, dw_C), overwritten.
     taps: list of (dha, dwa, pa, dhb, dwb, pb, wtap)."""
     _need_cuda(dy5, x5, dw)
     assert dy5.dtype == torch.bfloat16 and x5.dtype == torch.bfloat16 and dw.dtype == torch.float32

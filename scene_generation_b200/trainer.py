@@ -57,7 +57,7 @@ class Trainer:
         self.criterionVGG = None
         self.criterionFeat = torch.nn.L1Loss()
         self.criterionGAN = GANLoss(use_lsgan=not args.no_lsgan)
-        self.optimizer = torch.optim.Adam(model.parameters(), lr=args.learning_rate, betas=(args.beta1, 0.999))
+        self.optimizer = torch.optim.Adam(model.parameters(), lr=args.learning_rate, betas=(args.beta1, 0.999), fused=True)
 
     def init_obj_discriminator(self, args, checkpoint):
         self.obj_discriminator, self.optimizer_d_obj = None, None
@@ -72,7 +72,7 @@ class Trainer:
             self.obj_discriminator.align_corners = getattr(args, 'align_corners', False)
             self.obj_discriminator.train()
             self.optimizer_d_obj = torch.optim.Adam(self.obj_discriminator.parameters(), lr=args.learning_rate,
-                                                    betas=(args.beta1, 0.999))
+                                                    betas=(args.beta1, 0.999), fused=True)
 
     def init_mask_discriminator(self, args, checkpoint):
         self.mask_discriminator, self.optimizer_d_mask = None, None
@@ -86,7 +86,7 @@ class Trainer:
             self.mask_discriminator = define_mask_D(**kw).to('cuda')
             self.mask_discriminator.train()
             self.optimizer_d_mask = torch.optim.Adam(self.mask_discriminator.parameters(), lr=args.mask_learning_rate,
-                                                     betas=(args.beta1, 0.999))
+                                                     betas=(args.beta1, 0.999), fused=True)
 
     def init_image_discriminator(self, args, checkpoint):
         if args.d_img_weight == 0:
@@ -101,7 +101,7 @@ class Trainer:
         self.netD = define_D(**kw).to('cuda')
         self.netD.train()
         self.optimizer_d_img = torch.optim.Adam(list(self.netD.parameters()), lr=args.learning_rate,
-                                                betas=(args.beta1, 0.999))
+                                                betas=(args.beta1, 0.999), fused=True)
 
     # ---- checkpoint (trainer.py:136-203) -------------------------------------------------------
     def restore_checkpoint(self, checkpoint):
@@ -134,7 +134,10 @@ class Trainer:
 
     # ---- the four sub-steps (trainer.py:205-325) -----------------------------------------------
     def _step(self, name, optimizer, losses):
-        optimizer.zero_grad(set_to_none=name not in self.reducers)
+        if name in self.reducers:
+            self.reducers[name].zero()            # .grad tensors are views of one flat buffer
+        else:
+            optimizer.zero_grad(set_to_none=True)
         losses.total_loss.backward()
         if name in self.reducers:
             self.reducers[name].allreduce()
