@@ -326,8 +326,10 @@ def main():
     for i in range(n_distinct):
         hb = synthetic.make_batch(a.batch, (H, H), NUM_OBJS, a.kmin, a.kmax, seed=7919 * rank + i)
         host_batches.append(tuple(t.pin_memory() for t in hb))
-    dev_batches = [tuple(t.to(dev, non_blocking=True) for t in hb) for hb in host_batches]
-    h2d_bytes = sum(t.numel() * t.element_size() for t in host_batches[0])
+    # index structures the loader derives from its host copy of the batch (object ranges, triple CSR, class list)
+    metas = [synthetic.HostMeta(hb) for hb in host_batches]
+    dev_batches = [m.attach(tuple(t.to(dev, non_blocking=True) for t in hb)) for m, hb in zip(metas, host_batches)]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host_batches[0]) + metas[0].nbytes()
 
     def barrier():
         torch.cuda.synchronize()
@@ -340,7 +342,7 @@ def main():
 
     def step_e2e(i):
         hb = host_batches[i % n_distinct]
-        batch = tuple(t.to(dev, non_blocking=True) for t in hb)
+        batch = metas[i % n_distinct].attach(tuple(t.to(dev, non_blocking=True) for t in hb))
         tr.train_step(batch, use_gt=(i % 2 == 0))
         return float(tr.generator_losses.total_loss.detach())      # device -> host read of the step's result
 

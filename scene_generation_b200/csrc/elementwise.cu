@@ -24,6 +24,11 @@ __device__ __forceinline__ void load8(const bf16* p, float* f) {
     f[2 * j + 1] = v.y;
   }
 }
+__device__ __forceinline__ void load8f(const float* p, float* f) {   // p 32-byte aligned
+  float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
 __device__ __forceinline__ void store8(bf16* p, const float* f) {
   __align__(16) __nv_bfloat162 pk[4];
 #pragma unroll
@@ -267,13 +272,26 @@ __device__ __forceinline__ void gprime(const NapBwdArgs& b, int n, int h, int w,
   fold_grad(a, b.g, n, h, w, ch, gp);
   float x[8];
   load8(a.src + (((long)n * a.H + h) * a.W + w) * a.C + ch * 8, x);
+  const long pc = (long)n * a.C + ch * 8;
+  if (a.scale && a.act != SG_ACT_NONE) {
+    float sc[8], sh[8];
+    load8f(a.scale + pc, sc);
+    load8f(a.shift + pc, sh);
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int c = ch * 8 + k;
-    float z = x[k];
-    if (a.scale) z = fmaf(x[k], a.scale[(long)n * a.C + c], a.shift[(long)n * a.C + c]);
-    gp[k] *= act_grad(z, a.act, a.slope);
-    xh[k] = b.save_mean ? (x[k] - b.save_mean[(long)n * a.C + c]) * b.save_rstd[(long)n * a.C + c] : 0.f;
+    for (int k = 0; k < 8; ++k) gp[k] *= act_grad(fmaf(x[k], sc[k], sh[k]), a.act, a.slope);
+  } else if (a.act != SG_ACT_NONE) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) gp[k] *= act_grad(x[k], a.act, a.slope);
+  }
+  if (b.save_mean) {
+    float mu[8], rs[8];
+    load8f(b.save_mean + pc, mu);
+    load8f(b.save_rstd + pc, rs);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) xh[k] = (x[k] - mu[k]) * rs[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) xh[k] = 0.f;
   }
 }
 
@@ -326,17 +344,28 @@ __global__ void nap_bwd_apply_kernel(NapBwdArgs b) {
   }
   gprime(b, n, h, w, ch, gp, xh);
   float o[8];
+  const long pc = (long)n * a.C + ch * 8;
+  if (b.save_mean) {
+    float sc[8], s01[8], s23[8];
+    load8f(a.scale + pc, sc);                                          // scale = rstd (* gamma)
+    const float* sm = b.sums + ((b.bn ? 0 : (long)n * a.C) + ch * 8) * 2;   // (S1,S2) pairs of 8 channels
+    load8f(sm, s01);
+    load8f(sm + 8, s23);
+    const float inv = 1.f / b.count;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int c = ch * 8 + k;
-    if (b.save_mean) {
-      const float* sm = b.sums + ((b.bn ? 0 : (long)n * a.C) + c) * 2;
-      float m1 = sm[0] / b.count, m2 = sm[1] / b.count;
-      o[k] = a.scale[(long)n * a.C + c] * (gp[k] - m1 - xh[k] * m2);   // scale = rstd (* gamma)
-    } else {
-      float sc = a.scale ? a.scale[(long)n * a.C + c] : 1.f;
-      o[k] = gp[k] * sc;
+    for (int k = 0; k < 8; ++k) {
+      float m1 = (k < 4 ? s01[2 * k] : s23[2 * k - 8]) * inv;
+      float m2 = (k < 4 ? s01[2 * k + 1] : s23[2 * k - 7]) * inv;
+      o[k] = sc[k] * (gp[k] - m1 - xh[k] * m2);
     }
+  } else if (a.scale) {
+    float sc[8];
+    load8f(a.scale + pc, sc);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = gp[k] * sc[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = gp[k];
   }
   long off;
   if (b.out_planes) {

@@ -156,6 +156,126 @@ __global__ void __launch_bounds__(THREADS) layout_fwd_kernel(LayoutArgs a, void*
 }
 
 // ------------------------------------------------------------------------------------------------
+// forward, NHWC bf16, bandwidth-oriented variant.  Per 64-pixel tile only the objects whose (slightly
+// dilated) box intersects the tile are sampled and accumulated — typically 2-3 of the image's 4-9 —
+// the compacted list keeps the reference's object order (deterministic summation), every thread owns
+// one (pixel, 8-channel) item at a time (8 accumulators, high occupancy) and writes one 16-byte store.
+// ------------------------------------------------------------------------------------------------
+constexpr int MAXA = 16;      // active objects per pass
+
+__device__ __forceinline__ bool box_touches_tile(const LayoutArgs& a, const float* bx, int p0, int p1) {
+  // pixel rows / columns covered by pixels [p0, p1]
+  const int h_lo = p0 / a.W, h_hi = p1 / a.W;
+  int w_lo = 0, w_hi = a.W - 1;
+  if (h_lo == h_hi) { w_lo = p0 % a.W; w_hi = p1 % a.W; }
+  float x0 = bx[0], y0 = bx[1], x1 = bx[2], y1 = bx[3];
+  float ww = x1 - x0, hh = y1 - y0;
+  if (!(isfinite(ww) && isfinite(hh) && isfinite(x0) && isfinite(y0))) return true;   // let the sampler decide
+  if (ww == 0.f || hh == 0.f) return false;           // inf / NaN grid -> grid_sample yields 0 everywhere
+  // bilinear taps reach one mask texel beyond the box: dilate by |extent|/(M-1) (covers both align_corners modes)
+  float mx = fabsf(ww) / (float)max(a.M - 1, 1), my = fabsf(hh) / (float)max(a.M - 1, 1);
+  float xa = fminf(x0, x1) - mx, xb = fmaxf(x0, x1) + mx, ya = fminf(y0, y1) - my, yb = fmaxf(y0, y1) + my;
+  float sx = (float)max(a.W - 1, 1), sy = (float)max(a.H - 1, 1);
+  float wl = xa * sx - 1.f, wh = xb * sx + 1.f, hl = ya * sy - 1.f, hu = yb * sy + 1.f;
+  return !((float)w_hi < wl || (float)w_lo > wh || (float)h_hi < hl || (float)h_lo > hu);
+}
+
+__global__ void __launch_bounds__(THREADS) layout_fwd_nhwc_kernel(LayoutArgs a, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float smem[];
+  float* sS = smem;                       // [MAXA][TP]
+  float* sV = smem + MAXA * TP;           // [MAXA][Cp]
+  __shared__ int sAct[MAXA];
+  __shared__ int sNact, sNext;
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * TP;
+  const int HW = a.H * a.W;
+  const int p1 = min(p0 + TP, HW) - 1;
+  const int o_begin = a.ranges[2 * n], o_end = a.ranges[2 * n + 1];
+  const int chunks = a.Cp / 8;
+  const int items = TP * chunks;
+  int scan = o_begin;        // next object to test
+  bool first_pass = true;
+  for (;;) {
+    // ---- warp 0 compacts the next <= MAXA active objects in object order --------------------------
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int nact = 0, pos = scan;
+      while (pos < o_end && nact < MAXA) {
+        int o = pos + threadIdx.x;
+        bool act = (o < o_end) && box_touches_tile(a, a.boxes + 4 * o, p0, p1);
+        unsigned m = __ballot_sync(0xffffffffu, act);
+        int before = __popc(m & ((1u << threadIdx.x) - 1));
+        int room = MAXA - nact;
+        if (act && before < room) sAct[nact + before] = o;
+        int total = __popc(m);
+        if (total > room) {
+          // stop right after the last object that fitted
+          int last = -1, cnt = 0;
+          for (int b = 0; b < 32; ++b)
+            if (m & (1u << b)) { if (cnt < room) last = b; ++cnt; }
+          nact = MAXA;
+          pos += last + 1;
+          break;
+        }
+        nact += total;
+        pos += 32;
+      }
+      if (threadIdx.x == 0) { sNact = nact; sNext = min(pos, o_end); }
+    }
+    __syncthreads();
+    const int nact = sNact;
+    scan = sNext;
+    if (nact == 0 && !first_pass) break;
+    // ---- sample the active objects over the tile, stage their vectors ---------------------------------
+    for (int i = threadIdx.x; i < nact * TP; i += THREADS) {
+      int k = i / TP, px = i - k * TP;
+      int p = p0 + px;
+      float s = 0.f;
+      if (p < HW) s = sample_mask(a, sAct[k], p / a.W, p % a.W, a.boxes + 4 * sAct[k]);
+      sS[i] = s;
+    }
+    for (int i = threadIdx.x; i < nact * a.Cp; i += THREADS) {
+      int k = i / a.Cp, c = i - k * a.Cp;
+      sV[i] = (c < a.D) ? a.vecs[(long)sAct[k] * a.D + c] : 0.f;
+    }
+    __syncthreads();
+    // ---- one (pixel, 8-channel) item per thread ----------------------------------------------------------
+    for (int it = threadIdx.x; it < items; it += THREADS) {
+      int px = it / chunks, ch = it - px * chunks;
+      int p = p0 + px;
+      if (p >= HW) continue;
+      __nv_bfloat16* dst = out + ((long)n * HW + p) * a.Cp + ch * 8;
+      float acc[8];
+      if (first_pass) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      } else {   // > MAXA objects overlap this tile: continue from the stored partial sum
+        uint4 raw = *reinterpret_cast<const uint4*>(dst);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h2[j]); acc[2 * j] = f.x; acc[2 * j + 1] = f.y; }
+      }
+      for (int k = 0; k < nact; ++k) {
+        float s = sS[k * TP + px];
+        if (s == 0.f) continue;
+        const float4* v = reinterpret_cast<const float4*>(sV + k * a.Cp + ch * 8);
+        float4 v0 = v[0], v1 = v[1];
+        acc[0] = __fmaf_rn(v0.x, s, acc[0]); acc[1] = __fmaf_rn(v0.y, s, acc[1]);
+        acc[2] = __fmaf_rn(v0.z, s, acc[2]); acc[3] = __fmaf_rn(v0.w, s, acc[3]);
+        acc[4] = __fmaf_rn(v1.x, s, acc[4]); acc[5] = __fmaf_rn(v1.y, s, acc[5]);
+        acc[6] = __fmaf_rn(v1.z, s, acc[6]); acc[7] = __fmaf_rn(v1.w, s, acc[7]);
+      }
+      __align__(16) __nv_bfloat162 pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pk[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(pk);
+    }
+    first_pass = false;
+    if (scan >= o_end) break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // backward (train branch): dvecs[o,c] = sum_p S_o(p) g[n,c,p];  dmask via the 4 bilinear corners.
 // ------------------------------------------------------------------------------------------------
 template <bool NHWC_BF16>
@@ -354,8 +474,8 @@ extern "C" int sg_masks_to_layout_fwd(const float* vecs, const float* boxes, con
   dim3 grid(sg_cdiv((long)H * W, TP), N);
   size_t smem = sizeof(float) * (MAXO * TP + MAXO * Cp);
   if (out_format == 1) {
-    cudaFuncSetAttribute(layout_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    layout_fwd_kernel<true><<<grid, THREADS, smem, stream>>>(a, out);
+    size_t smem2 = sizeof(float) * (MAXA * TP + MAXA * Cp);
+    layout_fwd_nhwc_kernel<<<grid, THREADS, smem2, stream>>>(a, (__nv_bfloat16*)out);
   } else {
     cudaFuncSetAttribute(layout_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     layout_fwd_kernel<false><<<grid, THREADS, smem, stream>>>(a, out);

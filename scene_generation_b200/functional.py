@@ -16,6 +16,8 @@ from ._lib import NapDesc
 from .ops import _ptr, _stream, round_up
 
 BF = torch.bfloat16
+ONE_TAP = ((0, 0, 0, 0),)
+ONE_WTAP = ((0, 0, 0, 0, 0, 0, 0),)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -255,10 +257,9 @@ class ConvFn(torch.autograd.Function):
             if spec.kind == 's1':
                 ops.conv_tc(dz5, wsub, base, (Hx * Wx * Cx, Wx * Cx, Cx, 1), Hx, Wx, convspec.dgrad_s1(spec.k, spec.pad))
             elif spec.kind == 's2':
-                taps, phases = convspec.dgrad_s2(spec.k, spec.pad)
-                for (tb, nt, a, b) in phases:
+                for (a, b, ptaps) in convspec.dgrad_s2_phase_taps(spec.k, spec.pad):
                     plane = base[(a * 2 + b) * Hx * Wx * Cx:]
-                    ops.conv_tc(dz5, wsub, plane, (4 * Hx * Wx * Cx, Wx * Cx, Cx, 1), Hx, Wx, taps[tb:tb + nt])
+                    ops.conv_tc(dz5, wsub, plane, (4 * Hx * Wx * Cx, Wx * Cx, Cx, 1), Hx, Wx, ptaps)
             else:
                 ops.conv_tc(dz5, wsub, base, (Hx * Wx * Cx, Wx * Cx, Cx, 1), Hx, Wx, convspec.dgrad_convT(spec.k, 1))
         return dx, dw, db, None
@@ -280,7 +281,7 @@ class LinearFn(torch.autograd.Function):
         xb = cast_pad(x) if x.dtype != BF else x
         y = torch.empty((M, Nout), dtype=torch.float32, device=x.device)
         if M > 0:
-            ops.conv_tc(xb.view(1, 1, 1, M, xb.shape[1]), wk, y, (0, 0, Nout, 1), 1, M, [(0, 0, 0, 0)], bias=bias, act=act)
+            ops.conv_tc(xb.view(1, 1, 1, M, xb.shape[1]), wk, y, (0, 0, Nout, 1), 1, M, ONE_TAP, bias=bias, act=act)
         ctx.act = act
         ctx.in_dtype = x.dtype
         ctx.K = K
@@ -301,10 +302,10 @@ class LinearFn(torch.autograd.Function):
                     torch.zeros_like(weight), torch.zeros(Nout, device=dy.device), None)
         if ctx.needs_input_grad[0]:
             dx = torch.empty((M, K), dtype=torch.float32, device=dy.device)
-            ops.conv_tc(dz5, wt, dx, (0, 0, K, 1), 1, M, [(0, 0, 0, 0)])
+            ops.conv_tc(dz5, wt, dx, (0, 0, K, 1), 1, M, ONE_TAP)
         if ctx.needs_input_grad[1]:
             dw = torch.empty((Nout, 1, K), dtype=torch.float32, device=dy.device)
-            ops.wgrad_tc(dz5, xb.view(1, 1, 1, M, xb.shape[1]), dw, 1, M, [(0, 0, 0, 0, 0, 0, 0)], Nout, K)
+            ops.wgrad_tc(dz5, xb.view(1, 1, 1, M, xb.shape[1]), dw, 1, M, ONE_WTAP, Nout, K)
             dw = dw.view(Nout, K)
         if ctx.needs_input_grad[2]:
             db = torch.zeros(Nout, dtype=torch.float32, device=dy.device)

@@ -24,6 +24,13 @@ class GraphIndex:
         self.seg_src = torch.from_numpy(src).to(edges.device)
         self.O = num_objs
 
+    @classmethod
+    def from_host(cls, edges, seg_ptr, seg_src, num_objs):
+        """edges / CSR tensors already on the device (built by the loader from host data)."""
+        self = cls.__new__(cls)
+        self.edges, self.seg_ptr, self.seg_src, self.O = edges.contiguous(), seg_ptr, seg_src, num_objs
+        return self
+
 
 class GraphTripleConv(nn.Module):
     """graph.py:33-122: gather [s,p,o] -> net1 -> split -> per-object average -> net2."""

@@ -92,7 +92,9 @@ class Model(nn.Module):
             from . import functional as Fn
             obj_vecs = Fn.linear(obj_vecs, self.gconv.weight, self.gconv.bias)
         else:
-            index = GraphIndex(edges, objs.size(0))
+            meta = getattr(triples, '_sg_csr', None)      # (seg_ptr, seg_src) attached by the loader
+            index = GraphIndex.from_host(edges, meta[0], meta[1], objs.size(0)) if meta is not None else \
+                GraphIndex(edges, objs.size(0))
             obj_vecs, pred_vecs = self.gconv(obj_vecs, pred_vecs, edges, index)
             if self.gconv_net is not None:
                 obj_vecs, pred_vecs = self.gconv_net(obj_vecs, pred_vecs, edges, index)

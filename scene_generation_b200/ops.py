@@ -178,50 +178,68 @@ def crop_bbox_bwd(grad, boxes, box_to_feats, N, C, H, W, align_corners=False, gr
 # ---------------------------------------------------------------------------------------------
 # tensor-core conv / gemm
 # ---------------------------------------------------------------------------------------------
+_desc_cache = {}
+
+
 def conv_tc(x5, w3, y, y_strides, Hout, Wout, taps, phases=None, oh_mul=1, ow_mul=1, in_h0=0, in_w0=0,
             bias=None, act=_lib.ACT_NONE, slope=0.0, stats=None):
     """x5: bf16 (N,P,H,W,C) contiguous; w3: bf16 (Cout,taps,C) contiguous; y: f32/bf16 output storage
-    addressed as img*os_img + (h*oh_mul+oh_off)*os_h + (w*ow_mul+ow_off)*os_w + co with
-    y_strides=(os_img, os_h, os_w) in elements.  taps: list of (dh, dw, plane, wtap).
-    phases: list of (tap_begin, ntaps, oh_off, ow_off) or None for a single phase."""
-    _need_cuda(x5, w3, y)
-    assert x5.dtype == torch.bfloat16 and w3.dtype == torch.bfloat16 and x5.is_contiguous() and w3.is_contiguous()
-    d = ConvDesc()
-    d.x, (d.x_N, d.x_P, d.x_H, d.x_W, d.x_C) = x5.data_ptr(), x5.shape
-    d.w, (d.w_Cout, d.w_taps, d.w_C) = w3.data_ptr(), w3.shape
-    d.y, d.y_dtype = y.data_ptr(), (BF16 if y.dtype == torch.bfloat16 else F32)
-    d.y_os_img, d.y_os_h, d.y_os_w = y_strides[:3]
-    d.y_os_c = y_strides[3] if len(y_strides) > 3 else 1
-    d.Hout, d.Wout, d.oh_mul, d.ow_mul, d.in_h0, d.in_w0 = Hout, Wout, oh_mul, ow_mul, in_h0, in_w0
-    if phases is None:
-        phases = [(0, len(taps), 0, 0)]
-    d.nphases = len(phases)
-    for i, ph in enumerate(phases):
-        d.phases[i] = Phase(*ph)
-    d.ntaps = len(taps)
-    for i, tp in enumerate(taps):
-        d.taps[i] = Tap(*tp)
+    addressed as img*os_img + (h*oh_mul+oh_off)*os_h + (w*ow_mul+ow_off)*os_w + co*os_c with
+    y_strides=(os_img, os_h, os_w[, os_c]) in elements.  taps: sequence of (dh, dw, plane, wtap).
+    phases: sequence of (tap_begin, ntaps, oh_off, ow_off) or None for a single phase.
+    The filled descriptor is cached per call-site geometry; only the pointers change per call."""
+    key = ('c', x5.shape, w3.shape, y.dtype, tuple(y_strides), Hout, Wout, id(taps), id(phases), oh_mul, ow_mul,
+           in_h0, in_w0, act, slope)
+    ent = _desc_cache.get(key)
+    if ent is None or ent[1] is not taps or ent[2] is not phases:
+        _need_cuda(x5, w3, y)
+        assert x5.dtype == torch.bfloat16 and w3.dtype == torch.bfloat16 and x5.is_contiguous() and w3.is_contiguous()
+        d = ConvDesc()
+        d.x_N, d.x_P, d.x_H, d.x_W, d.x_C = x5.shape
+        d.w_Cout, d.w_taps, d.w_C = w3.shape
+        d.y_dtype = BF16 if y.dtype == torch.bfloat16 else F32
+        d.y_os_img, d.y_os_h, d.y_os_w = y_strides[:3]
+        d.y_os_c = y_strides[3] if len(y_strides) > 3 else 1
+        d.Hout, d.Wout, d.oh_mul, d.ow_mul, d.in_h0, d.in_w0 = Hout, Wout, oh_mul, ow_mul, in_h0, in_w0
+        ph = phases if phases is not None else [(0, len(taps), 0, 0)]
+        d.nphases = len(ph)
+        for i, p in enumerate(ph):
+            d.phases[i] = Phase(*p)
+        d.ntaps = len(taps)
+        for i, tp in enumerate(taps):
+            d.taps[i] = Tap(*tp)
+        d.act, d.slope = act, slope
+        ent = (d, taps, phases, ctypes.byref(d))
+        _desc_cache[key] = ent
+    d = ent[0]
+    d.x, d.w, d.y = x5.data_ptr(), w3.data_ptr(), y.data_ptr()
     d.bias = None if bias is None else bias.data_ptr()
-    d.act, d.slope = act, slope
     d.stats = None if stats is None else stats.data_ptr()
-    _lib.call('sg_conv_tc', ctypes.byref(d), _stream())
+    _lib.call('sg_conv_tc', ent[3], _stream())
     return y
 
 
 def wgrad_tc(dy5, x5, dw, Hred, Wred, taps, Cout, Cin, ksplit=0):
     """dy5: bf16 (N,P,H,W,Cd); x5: bf16 (N,P,H,W,Cx); dw: f32 (Cout, w_taps, dw_C), overwritten.
-    taps: list of (dha, dwa, pa, dhb, dwb, pb, wtap)."""
-    _need_cuda(dy5, x5, dw)
-    assert dy5.dtype == torch.bfloat16 and x5.dtype == torch.bfloat16 and dw.dtype == torch.float32
-    assert dy5.is_contiguous() and x5.is_contiguous() and dw.is_contiguous()
-    d = WgradDesc()
-    d.dy, (d.N, d.dy_P, d.dy_H, d.dy_W, d.dy_C) = dy5.data_ptr(), dy5.shape
-    d.x, (_, d.x_P, d.x_H, d.x_W, d.x_C) = x5.data_ptr(), x5.shape
-    d.Hred, d.Wred = Hred, Wred
-    d.dw, d.Cout, d.Cin, d.w_taps, d.dw_C = dw.data_ptr(), Cout, Cin, dw.shape[1], dw.shape[2]
-    d.ntaps = len(taps)
-    for i, tp in enumerate(taps):
-        d.taps[i] = WTap(*tp, 0)
-    d.ksplit = ksplit
-    _lib.call('sg_wgrad_tc', ctypes.byref(d), _stream())
+    taps: sequence of (dha, dwa, pa, dhb, dwb, pb, wtap)."""
+    key = ('w', dy5.shape, x5.shape, dw.shape, Hred, Wred, id(taps), Cout, Cin, ksplit)
+    ent = _desc_cache.get(key)
+    if ent is None or ent[1] is not taps:
+        _need_cuda(dy5, x5, dw)
+        assert dy5.dtype == torch.bfloat16 and x5.dtype == torch.bfloat16 and dw.dtype == torch.float32
+        assert dy5.is_contiguous() and x5.is_contiguous() and dw.is_contiguous()
+        d = WgradDesc()
+        d.N, d.dy_P, d.dy_H, d.dy_W, d.dy_C = dy5.shape
+        _, d.x_P, d.x_H, d.x_W, d.x_C = x5.shape
+        d.Hred, d.Wred = Hred, Wred
+        d.Cout, d.Cin, d.w_taps, d.dw_C = Cout, Cin, dw.shape[1], dw.shape[2]
+        d.ntaps = len(taps)
+        for i, tp in enumerate(taps):
+            d.taps[i] = WTap(*tp, 0)
+        d.ksplit = ksplit
+        ent = (d, taps, None, ctypes.byref(d))
+        _desc_cache[key] = ent
+    d = ent[0]
+    d.dy, d.x, d.dw = dy5.data_ptr(), x5.data_ptr(), dw.data_ptr()
+    _lib.call('sg_wgrad_tc', ent[3], _stream())
     return dw

@@ -105,3 +105,32 @@ def image_ranges(obj_to_img, n_imgs=None):
         raise ValueError('objects of one image must be contiguous and images in order '
                          '(layout.py:152-155)')
     return np.stack([starts, ends], axis=1).astype(np.int32)
+
+
+class HostMeta:
+    """Host-side index structures of one collated batch, computed from the CPU tensors the loader already
+    holds (object ranges per image, CSR of triple incidences per object, the class list).  attach() tags the
+    device copies of the batch with them so that Model.forward needs no device->host synchronisation
+    (the reference syncs per object: layout.py:143-155, utils.py:71)."""
+
+    def __init__(self, batch_cpu):
+        from . import ops
+        imgs, objs, boxes, masks, triples, obj_to_img, triple_to_img, attributes = batch_cpu
+        self.n_imgs = imgs.shape[0]
+        self.ranges = torch.from_numpy(image_ranges(obj_to_img, self.n_imgs))
+        ptr, src = ops.build_incidence_csr(triples[:, [0, 2]].numpy(), objs.numel())
+        self.seg_ptr, self.seg_src = torch.from_numpy(ptr), torch.from_numpy(src)
+        self.objs = objs.tolist()
+        if torch.cuda.is_available():
+            self.ranges, self.seg_ptr, self.seg_src = (t.pin_memory() for t in (self.ranges, self.seg_ptr, self.seg_src))
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in (self.ranges, self.seg_ptr, self.seg_src))
+
+    def attach(self, batch_dev):
+        imgs, objs, boxes, masks, triples, obj_to_img, triple_to_img, attributes = batch_dev
+        dev = objs.device
+        obj_to_img._sg_ranges = self.ranges.to(dev, non_blocking=True)
+        triples._sg_csr = (self.seg_ptr.to(dev, non_blocking=True), self.seg_src.to(dev, non_blocking=True))
+        objs._sg_host = self.objs
+        return batch_dev

@@ -47,30 +47,60 @@ class LossManager(object):
 
 
 class VectorPool:
-    """utils.py:62-90: per-class pool of appearance vectors (host side, python `random`)."""
+    """utils.py:62-90: per-class pool of appearance vectors with the reference's replacement policy and
+    the same python `random` draws in the same order.  The policy only depends on the class ids and on
+    how full each class pool is — never on the vector values — so the bookkeeping runs on the host from the
+    (host-side) object list while the vectors themselves stay in one device tensor: no device->host copy,
+    no pipeline drain (the reference moves every vector to the CPU and back, utils.py:71-89)."""
 
     def __init__(self, pool_size):
         self.pool_size = pool_size
-        self.vectors = {}
+        self.slots = {}          # class id -> list of global row ids
+        self.store = None        # (capacity, R) device tensor
+        self.used = 0
+
+    def _grow(self, need, like):
+        cap = 0 if self.store is None else self.store.shape[0]
+        if self.used + need <= cap:
+            return
+        new_cap = max(1024, 2 * cap, self.used + need)
+        store = torch.zeros((new_cap, like.shape[1]), dtype=like.dtype, device=like.device)
+        if self.store is not None:
+            store[:cap] = self.store
+        self.store = store
 
     def query(self, objs, vectors):
         if self.pool_size == 0:
             return vectors
-        objs_l = objs.tolist()
-        vecs = vectors.detach().float().cpu()
-        out = []
-        for obj, vec in zip(objs_l, vecs):
-            vec = vec.clone()
-            pool = self.vectors.setdefault(obj, [])
-            if len(pool) == 0:
-                out.append(vec)
-                pool.append(vec)
-            elif len(pool) < self.pool_size:
-                rid = random.randint(0, len(pool) - 1)
-                pool.append(vec)
-                out.append(pool[rid])
+        objs_l = getattr(objs, '_sg_host', None)
+        if objs_l is None:
+            objs_l = objs.tolist()
+        vecs = vectors.detach()
+        self._grow(len(objs_l), vecs)
+        cap = self.store.shape[0]
+        content = {}             # row id -> index of the batch vector written into it during this call
+        src = []
+        for i, obj in enumerate(objs_l):
+            ids = self.slots.setdefault(obj, [])
+            n = len(ids)
+            if n == 0:
+                src.append(cap + i)
+                ids.append(self.used)
+                content[self.used] = i
+                self.used += 1
+            elif n < self.pool_size:
+                g = ids[random.randint(0, n - 1)]
+                ids.append(self.used)
+                content[self.used] = i
+                self.used += 1
+                src.append(cap + content[g] if g in content else g)
             else:
-                rid = random.randint(0, len(pool) - 1)
-                out.append(pool[rid])
-                pool[rid] = vec
-        return torch.stack(out).to(vectors.device)
+                g = ids[random.randint(0, n - 1)]
+                src.append(cap + content[g] if g in content else g)
+                content[g] = i
+        idx = torch.tensor(src, dtype=torch.long, device=vecs.device)
+        out = torch.cat([self.store, vecs], dim=0).index_select(0, idx)
+        rows = torch.tensor(list(content.keys()), dtype=torch.long, device=vecs.device)
+        vals = torch.tensor(list(content.values()), dtype=torch.long, device=vecs.device)
+        self.store.index_copy_(0, rows, vecs.index_select(0, vals))
+        return out

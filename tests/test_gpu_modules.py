@@ -59,8 +59,8 @@ def test_generator_small_forward_backward():
     report = [('input', cosine(xg.grad, xo.grad), 1.0)]
     for name, p in G.named_parameters():
         ref = sd['layout_to_image.' + name].grad
-        if name.endswith('.bias') and ref.abs().max() < 1e-4:
-            continue      # biases in front of InstanceNorm have zero true gradient
+        if name.endswith('.bias') and not name.startswith('model.31'):
+            continue      # biases in front of InstanceNorm have zero true gradient (pure rounding noise on both sides)
         report.append((name, cosine(p.grad, ref), float(p.grad.float().norm().cpu() / ref.norm())))
     print('\n'.join('%-40s cos %.4f  |g|/|ref| %.3f' % r for r in report))
     # 64x64 input -> 4x4 maps in the resblocks: InstanceNorm backward over 16 bf16 values is the noisiest spot
