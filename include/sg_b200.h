@@ -171,8 +171,8 @@ typedef struct {
 int sg_norm_act_pad_fwd(const sg_nap_desc_t* d, void* out, sg_stream_t stream);
 /* adjoint: grad has the layout of the forward output.  With save_mean != NULL the norm backward
  * dsrc = scale * (g' - mean(g') - xhat * mean(g' xhat)) is applied (bn=1: statistics over all images);
- * sums is (N*C*2) [bn=0] / (C*2) [bn=1] f32 scratch that returns S1 = sum g', S2 = sum g' xhat
- * (= d beta, d gamma for BatchNorm).  dsrc is plain bf16 NHWC or (out_planes=1) parity planes.
+ * sums is f32 scratch of N*C*2 floats (per-image S1 = sum g', S2 = sum g' xhat) plus, for bn=1, C*2 more
+ * floats behind them that return the batch totals (= d beta, d gamma for BatchNorm).  dsrc is plain bf16 NHWC or (out_planes=1) parity planes.
  * dres (optional, bf16, addressed with the residual's res_os_* strides) receives the folded
  * gradient of the residual input. */
 int sg_norm_act_pad_bwd(const sg_nap_desc_t* d, const void* grad, const float* save_mean, const float* save_rstd,

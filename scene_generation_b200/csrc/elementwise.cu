@@ -296,6 +296,7 @@ __device__ __forceinline__ void gprime(const NapBwdArgs& b, int n, int h, int w,
 }
 
 __global__ void nap_bwd_reduce_kernel(NapBwdArgs b, int pix_per_block) {
+  extern __shared__ float red[];                // [lanes][nC*16]: (S1,S2) pairs per channel
   const NapArgs& a = b.f;
   const int nC = a.C / 8;
   const int lanes = blockDim.x / nC;            // pixel lanes per block
@@ -304,7 +305,6 @@ __global__ void nap_bwd_reduce_kernel(NapBwdArgs b, int pix_per_block) {
   const int HW = a.H * a.W;
   const int p_begin = blockIdx.x * pix_per_block;
   const int p_end = min(p_begin + pix_per_block, HW);
-  if (lane >= lanes) return;
   float s1[8], s2[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
@@ -317,12 +317,30 @@ __global__ void nap_bwd_reduce_kernel(NapBwdArgs b, int pix_per_block) {
       s2[k] += gp[k] * xh[k];
     }
   }
-  float* dst = b.sums + ((b.bn ? 0 : (long)n * a.C) + ch * 8) * 2;
+  float* mine = red + (lane * nC + ch) * 16;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    atomicAdd(dst + 2 * k, s1[k]);
-    atomicAdd(dst + 2 * k + 1, s2[k]);
+    mine[2 * k] = s1[k];
+    mine[2 * k + 1] = s2[k];
   }
+  __syncthreads();
+  // one atomic per (block, channel, sum); always into the image's own slots (BatchNorm totals are formed by
+  // bn_total_kernel afterwards) so that same-address contention stays at blocks-per-image
+  float* dst = b.sums + (long)n * a.C * 2;
+  for (int t = threadIdx.x; t < nC * 16; t += blockDim.x) {
+    float v = 0.f;
+    for (int l = 0; l < lanes; ++l) v += red[l * nC * 16 + t];
+    atomicAdd(dst + t, v);
+  }
+}
+
+// BatchNorm: totals[c*2+j] = sum over images of the per-image partials; stored behind them at sums[N*C*2 ...]
+__global__ void bn_total_kernel(float* sums, int N, int C) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= C * 2) return;
+  float v = 0.f;
+  for (int n = 0; n < N; ++n) v += sums[(long)n * C * 2 + t];
+  sums[(long)N * C * 2 + t] = v;
 }
 
 __global__ void nap_bwd_apply_kernel(NapBwdArgs b) {
@@ -348,7 +366,7 @@ __global__ void nap_bwd_apply_kernel(NapBwdArgs b) {
   if (b.save_mean) {
     float sc[8], s01[8], s23[8];
     load8f(a.scale + pc, sc);                                          // scale = rstd (* gamma)
-    const float* sm = b.sums + ((b.bn ? 0 : (long)n * a.C) + ch * 8) * 2;   // (S1,S2) pairs of 8 channels
+    const float* sm = b.sums + ((long)(b.bn ? a.N : n) * a.C + ch * 8) * 2;   // (S1,S2) pairs of 8 channels
     load8f(sm, s01);
     load8f(sm + 8, s23);
     const float inv = 1.f / b.count;
@@ -634,18 +652,22 @@ extern "C" int sg_norm_act_pad_bwd(const sg_nap_desc_t* d, const void* grad, con
   b.out_planes = out_planes; b.dsrc = (bf16*)dsrc; b.dres = (bf16*)dres;
   const int nC = d->C / 8;
   if (save_mean) {
-    cudaMemsetAsync(sums, 0, sizeof(float) * 2 * (size_t)(bn ? d->C : (size_t)d->N * d->C), stream);
+    cudaMemsetAsync(sums, 0, sizeof(float) * 2 * (size_t)d->N * d->C, stream);
     int threads = nC >= 256 ? nC : 256;
     threads = (threads / nC) * nC;
     SG_CHECK_ARG(threads <= 1024, "norm_act_pad_bwd: too many channels");
     const int lanes = threads / nC;
     long total_px = (long)d->N * d->H * d->W;
-    int pix_per_block = (int)((total_px + 1183) / 1184);           // ~8 CTAs per SM
-    if (pix_per_block < lanes) pix_per_block = lanes;
+    int pix_per_block = (int)((total_px + 1183) / 1184);           // ~8 CTAs per SM ...
+    if (pix_per_block < lanes * 8) pix_per_block = lanes * 8;      // ... but at least 8 pixels per thread
     pix_per_block = ((pix_per_block + lanes - 1) / lanes) * lanes;
     dim3 grid(sg_cdiv((long)d->H * d->W, pix_per_block), d->N);
-    nap_bwd_reduce_kernel<<<grid, threads, 0, stream>>>(b, pix_per_block);
+    nap_bwd_reduce_kernel<<<grid, threads, sizeof(float) * 16 * threads, stream>>>(b, pix_per_block);
     SG_CHECK_LAUNCH("sg_norm_act_pad_bwd(reduce)");
+    if (bn) {
+      bn_total_kernel<<<sg_cdiv(2 * d->C, 256), 256, 0, stream>>>(sums, d->N, d->C);
+      SG_CHECK_LAUNCH("sg_norm_act_pad_bwd(bn totals)");
+    }
   }
   long total = (long)d->N * d->H * d->W * nC;
   if (out_planes) {

@@ -384,13 +384,13 @@ class NapFn(torch.autograd.Function):
         sums = None
         bn = spec.norm == 'bn'
         if spec.norm is not None:
-            sums = torch.empty((C if bn else N * C, 2), dtype=torch.float32, device=dev)
+            sums = torch.empty(((N + 1) * C if bn else N * C, 2), dtype=torch.float32, device=dev)
         count = float(H * W * (N if bn else 1))
         _lib.call('sg_norm_act_pad_bwd', ctypes.byref(d), _ptr(g), _ptr(mean), _ptr(rstd), int(bn), count, _ptr(sums), 0,
                   _ptr(dsrc), dres_ptr, _stream())
         dgamma = dbeta = None
         if bn:
-            dgamma, dbeta = sums[:, 1].contiguous(), sums[:, 0].contiguous()
+            dgamma, dbeta = sums[N * C:, 1].contiguous(), sums[N * C:, 0].contiguous()
         return dsrc, None, dgamma, dbeta, dres, None, None
 
 

@@ -3,7 +3,7 @@ comparison with the CPU oracle."""
 import random
 import sys
 import torch
-sys.path.insert(0, '.')
+sys.path.insert(0, '.'); sys.path.insert(0, '..')
 from oracle import cases, restate as R
 from scene_generation_b200 import args as sgargs, synthetic
 from scene_generation_b200.trainer import Trainer
