@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(THREADS) layout_fwd_nhwc_kernel(LayoutArgs a, 
   float* sS = smem;                       // [MAXA][TP]
   float* sV = smem + MAXA * TP;           // [MAXA][Cp]
   __shared__ int sAct[MAXA];
+  __shared__ unsigned sNz[MAXA];
   __shared__ int sNact, sNext;
   const int n = blockIdx.y;
   const int p0 = blockIdx.x * TP;
@@ -192,7 +193,6 @@ __global__ void __launch_bounds__(THREADS) layout_fwd_nhwc_kernel(LayoutArgs a, 
   const int p1 = min(p0 + TP, HW) - 1;
   const int o_begin = a.ranges[2 * n], o_end = a.ranges[2 * n + 1];
   const int chunks = a.Cp / 8;
-  const int items = TP * chunks;
   int scan = o_begin;        // next object to test
   bool first_pass = true;
   for (;;) {
@@ -234,41 +234,50 @@ __global__ void __launch_bounds__(THREADS) layout_fwd_nhwc_kernel(LayoutArgs a, 
       if (p < HW) s = sample_mask(a, sAct[k], p / a.W, p % a.W, a.boxes + 4 * sAct[k]);
       sS[i] = s;
     }
+    if (threadIdx.x < MAXA) sNz[threadIdx.x] = 0u;
+    __syncthreads();
     for (int i = threadIdx.x; i < nact * a.Cp; i += THREADS) {
       int k = i / a.Cp, c = i - k * a.Cp;
-      sV[i] = (c < a.D) ? a.vecs[(long)sAct[k] * a.D + c] : 0.f;
+      float v = (c < a.D) ? a.vecs[(long)sAct[k] * a.D + c] : 0.f;
+      sV[i] = v;
+      if (v != 0.f) atomicOr(&sNz[k], 1u << (c >> 3));     // which 8-channel chunks of this object are non-zero
     }
     __syncthreads();
-    // ---- one (pixel, 8-channel) item per thread ----------------------------------------------------------
-    for (int it = threadIdx.x; it < items; it += THREADS) {
-      int px = it / chunks, ch = it - px * chunks;
-      int p = p0 + px;
-      if (p >= HW) continue;
-      __nv_bfloat16* dst = out + ((long)n * HW + p) * a.Cp + ch * 8;
-      float acc[8];
-      if (first_pass) {
+    // ---- thread (tx = 8-channel chunk, ty = pixel lane): no div/mod, one 416-byte contiguous row per warp ---------
+    // The class part of a layout vector is one-hot: per object only ~5 of the 26 chunks are non-zero, the rest
+    // of the (object, chunk) pairs is skipped through the bit mask.
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    if (tx < chunks) {
+      for (int px = ty; px < TP; px += THREADS / 32) {
+        int p = p0 + px;
+        if (p >= HW) break;
+        __nv_bfloat16* dst = out + ((long)n * HW + p) * a.Cp + tx * 8;
+        float acc[8];
+        if (first_pass) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-      } else {   // > MAXA objects overlap this tile: continue from the stored partial sum
-        uint4 raw = *reinterpret_cast<const uint4*>(dst);
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+          for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        } else {   // > MAXA objects overlap this tile: continue from the stored partial sum
+          uint4 raw = *reinterpret_cast<const uint4*>(dst);
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h2[j]); acc[2 * j] = f.x; acc[2 * j + 1] = f.y; }
+          for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h2[j]); acc[2 * j] = f.x; acc[2 * j + 1] = f.y; }
+        }
+        for (int k = 0; k < nact; ++k) {
+          if (!((sNz[k] >> tx) & 1u)) continue;
+          float s = sS[k * TP + px];
+          if (s == 0.f) continue;
+          const float4* v = reinterpret_cast<const float4*>(sV + k * a.Cp + tx * 8);
+          float4 v0 = v[0], v1 = v[1];
+          acc[0] = __fmaf_rn(v0.x, s, acc[0]); acc[1] = __fmaf_rn(v0.y, s, acc[1]);
+          acc[2] = __fmaf_rn(v0.z, s, acc[2]); acc[3] = __fmaf_rn(v0.w, s, acc[3]);
+          acc[4] = __fmaf_rn(v1.x, s, acc[4]); acc[5] = __fmaf_rn(v1.y, s, acc[5]);
+          acc[6] = __fmaf_rn(v1.z, s, acc[6]); acc[7] = __fmaf_rn(v1.w, s, acc[7]);
+        }
+        __align__(16) __nv_bfloat162 pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pk[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(pk);
       }
-      for (int k = 0; k < nact; ++k) {
-        float s = sS[k * TP + px];
-        if (s == 0.f) continue;
-        const float4* v = reinterpret_cast<const float4*>(sV + k * a.Cp + ch * 8);
-        float4 v0 = v[0], v1 = v[1];
-        acc[0] = __fmaf_rn(v0.x, s, acc[0]); acc[1] = __fmaf_rn(v0.y, s, acc[1]);
-        acc[2] = __fmaf_rn(v0.z, s, acc[2]); acc[3] = __fmaf_rn(v0.w, s, acc[3]);
-        acc[4] = __fmaf_rn(v1.x, s, acc[4]); acc[5] = __fmaf_rn(v1.y, s, acc[5]);
-        acc[6] = __fmaf_rn(v1.z, s, acc[6]); acc[7] = __fmaf_rn(v1.w, s, acc[7]);
-      }
-      __align__(16) __nv_bfloat162 pk[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) pk[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
-      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(pk);
     }
     first_pass = false;
     if (scan >= o_end) break;

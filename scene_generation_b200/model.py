@@ -60,6 +60,8 @@ class Model(nn.Module):
 
     def forward(self, gt_imgs, objs, triples, obj_to_img, boxes_gt=None, masks_gt=None, attributes=None,
                 test_mode=False, use_gt_box=False, features=None):
+        from . import ops
+        ops.refresh_stream()
         O = objs.size(0)
         obj_vecs, pred_vecs = self.scene_graph_to_vectors(objs, triples, attributes)
         box_vecs, mask_vecs, scene_layout_vecs, wrong_layout_vecs = \

@@ -15,8 +15,21 @@ F32, BF16 = 0, 1
 NCHW_F32, NHWC_BF16 = 0, 1
 
 
+_stream_cache = [None]
+
+
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """cudaStream_t of torch's current stream.  torch.cuda.current_stream() costs several microseconds, which
+    adds up over ~1100 launches per step: the handle is cached until refresh_stream() is called (Model.forward
+    and every Trainer sub-step call it on entry, i.e. after any `with torch.cuda.stream(...)` switch)."""
+    s = _stream_cache[0]
+    if s is None:
+        s = _stream_cache[0] = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return s
+
+
+def refresh_stream():
+    _stream_cache[0] = None
 
 
 def _ptr(t):

@@ -134,6 +134,8 @@ class Trainer:
 
     # ---- the four sub-steps (trainer.py:205-325) -----------------------------------------------
     def _step(self, name, optimizer, losses):
+        from . import ops
+        ops.refresh_stream()
         if name in self.reducers:
             self.reducers[name].zero()            # .grad tensors are views of one flat buffer
         else:

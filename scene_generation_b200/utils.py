@@ -80,27 +80,31 @@ class VectorPool:
         cap = self.store.shape[0]
         content = {}             # row id -> index of the batch vector written into it during this call
         src = []
+        slots, pool_size, randint, used = self.slots, self.pool_size, random.randint, self.used
         for i, obj in enumerate(objs_l):
-            ids = self.slots.setdefault(obj, [])
+            ids = slots.get(obj)
+            if ids is None:
+                ids = slots[obj] = []
             n = len(ids)
             if n == 0:
                 src.append(cap + i)
-                ids.append(self.used)
-                content[self.used] = i
-                self.used += 1
-            elif n < self.pool_size:
-                g = ids[random.randint(0, n - 1)]
-                ids.append(self.used)
-                content[self.used] = i
-                self.used += 1
+                ids.append(used)
+                content[used] = i
+                used += 1
+            elif n < pool_size:
+                g = ids[randint(0, n - 1)]
+                ids.append(used)
+                content[used] = i
+                used += 1
                 src.append(cap + content[g] if g in content else g)
             else:
-                g = ids[random.randint(0, n - 1)]
+                g = ids[randint(0, n - 1)]
                 src.append(cap + content[g] if g in content else g)
                 content[g] = i
-        idx = torch.tensor(src, dtype=torch.long, device=vecs.device)
-        out = torch.cat([self.store, vecs], dim=0).index_select(0, idx)
-        rows = torch.tensor(list(content.keys()), dtype=torch.long, device=vecs.device)
-        vals = torch.tensor(list(content.values()), dtype=torch.long, device=vecs.device)
-        self.store.index_copy_(0, rows, vecs.index_select(0, vals))
+        self.used = used
+        no = len(src)
+        allidx = torch.tensor(src + list(content.keys()) + list(content.values()), dtype=torch.long).to(vecs.device, non_blocking=True)
+        nw = len(content)
+        out = torch.cat([self.store, vecs], dim=0).index_select(0, allidx[:no])
+        self.store.index_copy_(0, allidx[no:no + nw], vecs.index_select(0, allidx[no + nw:]))
         return out

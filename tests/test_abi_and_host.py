@@ -138,3 +138,22 @@ def test_synthetic_batch_contract_and_ranges():
     assert all(torch.equal(x, y) for x, y in zip(b, same))
     with pytest.raises(ValueError):
         synthetic.image_ranges(torch.tensor([0, 1, 0]))
+
+
+def test_vector_pool_matches_reference_policy_and_rng_order():
+    """device-resident VectorPool (host index logic) == the reference's CPU pool (utils.py:62-90, restated in the
+    oracle) for the same python `random` stream, incl. reads of vectors written earlier in the same batch."""
+    import random
+    from oracle.restate import VectorPool as RefPool
+    from scene_generation_b200.utils import VectorPool
+    a, b = VectorPool(3), RefPool(3)
+    for step in range(50):
+        n = random.Random(step).randint(1, 12)
+        objs = torch.tensor([random.Random(step * 31 + i).randint(0, 4) for i in range(n)])
+        vecs = torch.randn(n, 5)
+        random.seed(step)
+        ra = a.query(objs, vecs)
+        random.seed(step)
+        rb = b.query(objs, vecs)
+        assert torch.equal(ra, rb)
+    assert VectorPool(0).query(objs, vecs) is vecs
