@@ -14,11 +14,20 @@ def rank():
     return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
 
 
+def flat_view(t):
+    """1-D view of the memory of a dense (possibly permuted, e.g. channels-last) tensor — collectives need
+    contiguous tensors, the conv weights are stored [Cout][kh][kw][Cin] under their logical (Cout,Cin,kh,kw) shape."""
+    if t.is_contiguous():
+        return t.view(-1)
+    return t.as_strided((t.numel(),), (1,), t.storage_offset())
+
+
 def broadcast_parameters(module, src=0):
     """identical replicas at start (and BN buffers from rank 0, PyTorch-DDP style)."""
     with torch.no_grad():
         for t in list(module.parameters()) + list(module.buffers()):
-            dist.broadcast(t.data, src)
+            if t.numel():
+                dist.broadcast(flat_view(t.data), src)
 
 
 class FlatGradReducer:

@@ -15,6 +15,10 @@ def _worker(rank, world, port, ret):
     dist.init_process_group('gloo', rank=rank, world_size=world)
     torch.manual_seed(rank)          # different initial weights per rank: broadcast must fix that
     net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2), torch.nn.Linear(2, 2))
+    conv = torch.nn.Conv2d(3, 5, 3)
+    conv.weight = torch.nn.Parameter(conv.weight.data.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2))   # channels-last master
+    ddp.broadcast_parameters(conv)
+    ret['conv%d' % rank] = conv.weight.detach().clone()
     ddp.broadcast_parameters(net)
     red = ddp.FlatGradReducer(net)
     full = torch.arange(32, dtype=torch.float32).view(8, 4) / 10
@@ -35,6 +39,7 @@ def test_flat_grad_allreduce_equals_big_batch_gradient():
     port = 29500 + os.getpid() % 2000
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     g0, g1 = ret[0], ret[1]
+    assert torch.equal(ret['conv0'], ret['conv1']) and ret['conv0'].stride() == ret['conv1'].stride()
     for a, b in zip(g0, g1):
         assert torch.equal(a, b)                     # identical grads and params on both ranks
     torch.manual_seed(0)
