@@ -249,6 +249,7 @@ class ConvFn(torch.autograd.Function):
         if spec.need_dx and ctx.needs_input_grad[0]:
             Cx = x5.shape[4]
             c0, c1 = spec.dx_channels or (0, Cin)
+            c0 = c0 // 8 * 8          # keep the output pointer 16-byte aligned for the vector-store epilogue
             partial = (c0, c1) != (0, Cin) or Cx != Cin
             dx = (torch.zeros if partial else torch.empty)(x5.shape, dtype=BF, device=x5.device)
             wsub = wt[c0:c1]
@@ -344,7 +345,11 @@ class NapFn(torch.autograd.Function):
         N, H, W, C = src.shape
         dev = src.device
         scale = shift = mean = rstd = None
-        if spec.norm is not None:
+        if spec.norm == 'bn_eval':      # BatchNorm2d in eval mode: fixed affine from the running statistics
+            rm, rv = running
+            sc = gamma.detach() * torch.rsqrt(rv + spec.eps)
+            scale, shift = sc.repeat(N).contiguous(), (beta.detach() - rm * sc).repeat(N).contiguous()
+        elif spec.norm is not None:
             scale, shift, mean, rstd = (torch.empty(N * C, dtype=torch.float32, device=dev) for _ in range(4))
             rm, rv = (running if running is not None else (None, None))
             _lib.call('sg_norm_finalize', _ptr(stats), 0 if spec.norm == 'in' else 1, N, C, float(H * W), spec.eps,
@@ -383,7 +388,7 @@ class NapFn(torch.autograd.Function):
             dres_ptr = dres.data_ptr() + 2 * (p * ctx.res_shape[3] * C + p * C)
         sums = None
         bn = spec.norm == 'bn'
-        if spec.norm is not None:
+        if spec.norm in ('in', 'bn'):
             sums = torch.empty(((N + 1) * C if bn else N * C, 2), dtype=torch.float32, device=dev)
         count = float(H * W * (N if bn else 1))
         _lib.call('sg_norm_act_pad_bwd', ctypes.byref(d), _ptr(g), _ptr(mean), _ptr(rstd), int(bn), count, _ptr(sums), 0,

@@ -46,15 +46,15 @@ class MaskNet(nn.Sequential):
             if bn is None:
                 op = Fn.nap(x, spec=NapSpec(up=2))
             else:
-                op = Fn.nap(x, stats, bn.weight, bn.bias, None, (bn.running_mean, bn.running_var) if self.training else None,
-                            NapSpec(norm='bn', eps=bn.eps, momentum=bn.momentum, act=_lib.ACT_RELU, up=2))
+                op = Fn.nap(x, stats, bn.weight, bn.bias, None, (bn.running_mean, bn.running_var),
+                            NapSpec(norm='bn' if self.training else 'bn_eval', eps=bn.eps, momentum=bn.momentum, act=_lib.ACT_RELU, up=2))
                 if self.training:
                     bn.num_batches_tracked += 1
             x, stats = Fn.conv(op, conv.weight, conv.bias, ConvSpec('s1', 3, 1, stats=True))
             bn = nbn
             i += 4
-        op = Fn.nap(x, stats, bn.weight, bn.bias, None, (bn.running_mean, bn.running_var) if self.training else None,
-                    NapSpec(norm='bn', eps=bn.eps, momentum=bn.momentum, act=_lib.ACT_RELU))
+        op = Fn.nap(x, stats, bn.weight, bn.bias, None, (bn.running_mean, bn.running_var),
+                    NapSpec(norm='bn' if self.training else 'bn_eval', eps=bn.eps, momentum=bn.momentum, act=_lib.ACT_RELU))
         if self.training:
             bn.num_batches_tracked += 1
         last = mods[i]
@@ -137,7 +137,10 @@ class GlobalGenerator(nn.Module):
         IN_RELU = dict(norm='in', act=_lib.ACT_RELU)
         x = as_nhwc_operand(input)                                           # (N,H,W,Cp) bf16
         op = Fn.nap(x, spec=NapSpec(pad=3, pad_mode=1))
-        y, st = Fn.conv(op, m[1].weight, m[1].bias, ConvSpec('s1', 7, 0, stats=True))
+        # Model tags the layout with the channel range that carries a gradient (the appearance part; the
+        # one-hot class channels are constants, model.py:165-168): the first conv's dgrad is restricted to it
+        y, st = Fn.conv(op, m[1].weight, m[1].bias,
+                        ConvSpec('s1', 7, 0, stats=True, dx_channels=getattr(input, '_sg_grad_channels', None)))
         i = 4
         for d in range(self.n_downsampling):
             hw = tuple(y.shape[1:3])

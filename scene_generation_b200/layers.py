@@ -128,8 +128,8 @@ class CropCNN(nn.Sequential):
             else:
                 stats, bn, slope = pend
                 op = Fn.nap(x, stats, bn.weight, bn.bias, None,
-                            (bn.running_mean, bn.running_var) if self.training else None,
-                            NapSpec(norm='bn', eps=bn.eps, momentum=bn.momentum, act=_lib.ACT_LEAKY, slope=slope, planes=True))
+                            (bn.running_mean, bn.running_var),
+                            NapSpec(norm='bn' if self.training else 'bn_eval', eps=bn.eps, momentum=bn.momentum, act=_lib.ACT_LEAKY, slope=slope, planes=True))
                 if self.training:
                     bn.num_batches_tracked += 1
             nxt = next((j for j in range(i + 1, len(mods)) if isinstance(mods[j], nn.Conv2d)), None)

@@ -77,6 +77,9 @@ class Model(nn.Module):
             pred_layout = masks_to_layout(scene_layout_vecs, boxes, masks, obj_to_img, H, W, test_mode=True, **lay)
             return self.layout_to_image(pred_layout), boxes_pred, masks_pred, None, pred_layout, None
         gt_layout = masks_to_layout(scene_layout_vecs, boxes_gt, masks_gt, obj_to_img, H, W, **lay)
+        if self.layout_dtype == 'bf16':
+            # only the appearance channels of layout_vecs carry a gradient (one_hot_obj is a constant)
+            gt_layout._sg_grad_channels = (self.num_objs, scene_layout_vecs.shape[1])
         pred_layout = masks_to_layout(scene_layout_vecs, boxes_gt, masks_pred, obj_to_img, H, W, **lay)
         wrong_layout = masks_to_layout(wrong_layout_vecs, boxes_gt, masks_gt, obj_to_img, H, W, **lay)
         imgs_pred = self.layout_to_image(gt_layout)

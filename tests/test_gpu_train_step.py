@@ -124,3 +124,56 @@ def test_generator_step_gradients_vs_oracle_autograd():
     bad = [r for r in ws if r[1] < 0.6]
     assert not bad, bad
     assert sum(r[1] for r in ws) / len(ws) > 0.85
+
+
+def test_inference_path_test_mode_eval_bn_vs_oracle():
+    """scripts/sample_images.py path: model.eval(), test_mode=True compositing (layout.py:157-169), BatchNorm on
+    running statistics, GT boxes/masks — vs the oracle in eval mode."""
+    cfg = cases.CFG1
+    sds = R.make_state_dicts(cfg, seed=5)
+    # non-trivial running statistics
+    g = torch.Generator().manual_seed(3)
+    for k in list(sds['g']):
+        if k.endswith('running_mean'):
+            sds['g'][k] = torch.randn(sds['g'][k].shape, generator=g) * 0.1
+        if k.endswith('running_var'):
+            sds['g'][k] = torch.rand(sds['g'][k].shape, generator=g) + 0.5
+    tr = make_trainer(cfg, sds)
+    m = tr.model.eval()
+    batch_cpu = cases.cfg1_batch()
+    imgs, objs, boxes, masks, triples, o2i, t2i, attrs = [t.to(DEV) for t in batch_cpu]
+    noise = cases.noise_for(5)
+    orig = torch.randn
+    torch.randn = lambda *a, **k: noise.to(DEV).clone()
+    try:
+        with torch.no_grad():
+            out = m(imgs, objs, triples, o2i, boxes_gt=boxes, masks_gt=masks, attributes=attrs, test_mode=True, use_gt_box=True)
+    finally:
+        torch.randn = orig
+    ref = R.model_forward(sds['g'], cfg, batch_cpu, noise, pool=None, test_mode=True, use_gt_box=True, train=False)
+    assert out[3] is None and out[5] is None
+    d = (out[4].float().cpu() - ref[4]).abs()
+    assert d.max() <= 2e-2 * ref[4].abs().max(), 'test-mode layout'
+    assert (out[2].cpu() - ref[2]).abs().max() <= 3e-2, 'masks_pred (eval BN)'
+    assert (out[0].cpu() - ref[0]).abs().mean() <= 3e-2, 'imgs_pred'
+    bn = m.mask_net[2]
+    assert torch.equal(bn.running_mean.cpu(), sds['g']['mask_net.2.running_mean'])     # eval mode must not touch them
+
+
+@pytest.mark.parametrize('size,kmin,kmax', [(256, 8, 15), (128, 29, 29)])
+def test_cfg4_cfg5_shapes_run(size, kmin, kmax):
+    """BASELINE configs[3] (256x256, <=16 objects) and configs[4] (30-object graphs): shapes, tiles and the
+    layout kernel's multi-object paths at a small batch."""
+    a = sgargs.default_args(image_size=(size, size), num_objs=172)
+    torch.manual_seed(0)
+    tr = Trainer(a, synthetic.make_vocab(172), {})
+    batch = synthetic.make_batch(2, (size, size), 172, kmin=kmin, kmax=kmax, seed=11, device=DEV)
+    out = tr.train_step(batch, use_gt=True)
+    assert out[0].shape == (2, 3, size, size) and torch.isfinite(out[0]).all()
+    ref = R.masks_to_layout(torch.cat([R.one_hot(batch[1].cpu(), 172), torch.zeros(batch[1].numel(), 32)], 1),
+                            batch[2].cpu(), batch[3].cpu(), batch[5].cpu(), size)
+    got = out[3].float().cpu()[:, :172]
+    assert (got - ref[:, :172]).abs().max() <= 2e-2 * ref.abs().max()        # class channels of the layout vs the oracle
+    for lm in (tr.generator_losses, tr.d_img_losses):
+        for name, v in lm.items():
+            assert v == v and abs(v) < 1e4, (name, v)
