@@ -41,6 +41,8 @@ def parse():
     ap.add_argument('--cpu-worker', action='store_true', help=argparse.SUPPRESS)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--profile-step', action='store_true',
+                    help='after warm-up run ONE step between cudaProfilerStart/Stop and exit (use with ncu --profile-from-start off)')
     return ap.parse_args()
 
 
@@ -184,7 +186,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.FIELDS,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -364,6 +366,13 @@ def main():
         step_resident(i)
         torch.cuda.synchronize()
         log('warm-up step %d done' % i)
+    if a.profile_step:
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        step_resident(0)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -384,6 +393,9 @@ def main():
 
     # one instrumented (untimed) step: per-launch device time + algorithmic FLOPs of the tensor-core kernels
     roofline, kernels = None, None
+    if rank != 0:
+        step_resident(0)          # the probe step contains the gradient all-reduces: every rank must take part
+        torch.cuda.synchronize()
     if rank == 0:
         with KernelProbe() as probe:
             # let the host run ahead of the device so that event intervals of small launches measure the kernel,

@@ -12,6 +12,7 @@
 //     (tcgen05.ld -> bias -> InstanceNorm/BatchNorm partial sums -> activation -> vector stores).
 //   wgrad_tc_kernel : D[128 couts, BN cins] = sum over 64-pixel boxes dy[pix, co]^T x[pix(+tap), ci]
 //     both operands MN-major (pixel = K is the strided smem dimension), split-K with fp32 atomics.
+#include <stdlib.h>
 #include "common.cuh"
 #include "ptx.cuh"
 #include "../../include/sg_b200.h"
@@ -115,7 +116,10 @@ struct ConvCfg {
   static constexpr int B_STRIDE = (B_BYTES < 1024 ? 1024 : B_BYTES);
 };
 
-template <int BN>
+// MC = true: launched as clusters of 2 CTAs along M that work on the same weight tile; each CTA fetches
+// half of B and multicasts it to both, which removes a third of the L2 -> SM operand traffic of a
+// 128 x BN tile (the limiter of the 1024-channel resblock GEMMs with single-CTA tiles).
+template <int BN, bool MC>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ ConvKParams p) {
@@ -141,7 +145,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], MC ? 2 : 1);      // MC: the slot is free when BOTH CTAs' MMAs have consumed it
     }
     mbar_init(accum_full, 1);
     fence_barrier_init();
@@ -151,8 +155,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) tmem_alloc<Cfg::TM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync();                    // peer barriers must be initialised before any remote arrive / TMA
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const uint32_t crank = MC ? cluster_ctarank() : 0;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -164,7 +170,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const sg_tap_t tp = p.taps[ph.tap_begin + tap_i];
         mbar_expect_tx(&full[s], p.a_bytes + Cfg::B_BYTES);
         tma_load_5d(sA + s * A_BYTES, &tmA, &full[s], kb * 64, w0 + tp.dw + p.in_w0, h0 + tp.dh + p.in_h0, tp.plane, img0);
-        tma_load_3d(sB + s * Cfg::B_STRIDE, &tmB, &full[s], kb * 64, tp.wtap, n0);
+        if (MC)
+          tma_load_3d_mc(sB + s * Cfg::B_STRIDE + crank * (Cfg::B_BYTES / 2), &tmB, &full[s], kb * 64, tp.wtap,
+                         n0 + (int)crank * (BN / 2), (uint16_t)3);
+        else
+          tma_load_3d(sB + s * Cfg::B_STRIDE, &tmB, &full[s], kb * 64, tp.wtap, n0);
       }
     }
   } else if (warp == 1) {
@@ -179,7 +189,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint64_t bd = umma_desc_sw128(smem_u32(sB + s * Cfg::B_STRIDE), 16, 1024);
 #pragma unroll
         for (int k = 0; k < 4; ++k) mma_bf16(tmem, ad + 2 * k, bd + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
-        mma_commit(&empty[s]);   // frees the smem slot once these MMAs have read it
+        if (MC) mma_commit_mc(&empty[s], (uint16_t)3);
+        else mma_commit(&empty[s]);   // frees the smem slot once these MMAs have read it
       }
       mma_commit(accum_full);
     }
@@ -277,6 +288,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync();                    // the peer may still multicast into / arrive on this CTA's smem
   if (warp == 1) tmem_dealloc<Cfg::TM_COLS>(tmem);
 }
 
@@ -442,17 +454,53 @@ void choose_tile(int rows, bool exact, int H, int W, int N, int* BW, int* BH, in
   }
 }
 
-template <int BN>
-int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKParams& kp, dim3 grid, cudaStream_t stream) {
+template <int BN, bool MC>
+int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKParams& kp, dim3 grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN>::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN>::SMEM);
     if (e != cudaSuccess) return sg_fail(SG_ERR_CUDA, "conv_tc smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  conv_tc_kernel<BN><<<grid, 192, ConvCfg<BN>::SMEM, stream>>>(tmA, tmB, kp);
+  if (MC) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = ConvCfg<BN>::SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, MC>, tmA, tmB, kp);
+    if (e != cudaSuccess) return sg_fail(SG_ERR_CUDA, "sg_conv_tc (cluster launch): %s", cudaGetErrorString(e));
+  } else {
+    conv_tc_kernel<BN, MC><<<grid, 192, ConvCfg<BN>::SMEM, stream>>>(tmA, tmB, kp);
+  }
   SG_CHECK_LAUNCH("sg_conv_tc");
   return SG_OK;
+}
+
+template <int BN>
+int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKParams& kp, dim3 grid, bool mc, cudaStream_t stream) {
+  if (mc) {
+    if constexpr (BN >= 128) return launch_conv_t<BN, true>(tmA, tmB, kp, grid, stream);
+  }
+  return launch_conv_t<BN, false>(tmA, tmB, kp, grid, stream);
+}
+
+// SG_CONV_MULTICAST=1 enables the 2-CTA-cluster weight-multicast variant for long-K, wide-N launches
+bool multicast_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SG_CONV_MULTICAST");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
 }
 
 template <int BN>
@@ -519,14 +567,18 @@ extern "C" int sg_conv_tc(const sg_conv_desc_t* d, sg_stream_t stream) {
     }
   }
   long long bdims[3] = {d->w_C, d->w_taps, d->w_Cout};
-  int bbox[3] = {64, 1, BN};
+  int m_tiles = kp.tiles_w * kp.tiles_h * img_tiles;
+  // weight multicast pays when the K loop is long (L2-bound operand streaming) and there are CTA pairs to form
+  const bool mc = multicast_enabled() && BN >= 128 && m_tiles >= 2 && (long)d->ntaps * kp.kblocks >= 32;
+  if (mc) m_tiles = (m_tiles + 1) & ~1;           // an odd tail tile gets a fully masked partner
+  int bbox[3] = {64, 1, mc ? BN / 2 : BN};
   if (int e = make_tmap(&tmB, d->w, 3, bdims, bbox)) return e;
-  dim3 grid(kp.tiles_w * kp.tiles_h * img_tiles, sg_cdiv(d->w_Cout, BN), d->nphases);
+  dim3 grid(m_tiles, sg_cdiv(d->w_Cout, BN), d->nphases);
   switch (BN) {
-    case 256: return launch_conv<256>(tmA, tmB, kp, grid, stream);
-    case 128: return launch_conv<128>(tmA, tmB, kp, grid, stream);
-    case 64: return launch_conv<64>(tmA, tmB, kp, grid, stream);
-    default: return launch_conv<16>(tmA, tmB, kp, grid, stream);
+    case 256: return launch_conv<256>(tmA, tmB, kp, grid, mc, stream);
+    case 128: return launch_conv<128>(tmA, tmB, kp, grid, mc, stream);
+    case 64: return launch_conv<64>(tmA, tmB, kp, grid, false, stream);
+    default: return launch_conv<16>(tmA, tmB, kp, grid, false, stream);
   }
 }
 
