@@ -49,32 +49,6 @@ def parse():
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference's train step on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_rate(image_size, n_imgs, steps, warmup, kmin, kmax):
-    """images/sec of the reference algorithm (oracle/restate.py OracleTrainer: fp32, torch CPU kernels for the
-    dense contractions) on all host threads, on a bounded sample of the bench workload."""
-    from oracle import restate as R
-    from scene_generation_b200 import synthetic
-    import random
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    cfg = dict(image_size=(image_size, image_size), num_objs=NUM_OBJS, rep_size=32, mask_size=32, n_downsample_global=4,
-               gconv_num_layers=5, crop_size=32, ngf=64, n_blocks=9)
-    sds = R.make_state_dicts(cfg, seed=0)
-    tr = R.OracleTrainer(sds, cfg)
-    random.seed(0)
-    times = []
-    for s in range(warmup + steps):
-        batch = synthetic.make_batch(n_imgs, (image_size, image_size), NUM_OBJS, kmin, kmax, seed=1000 + s)
-        noise = torch.randn((1, 64))
-        t0 = time.perf_counter()
-        tr.step(batch, noise, use_gt=(s % 2 == 0))
-        dt = time.perf_counter() - t0
-        if s >= warmup:
-            times.append(dt)
-    mean = sum(times) / len(times)
-    return n_imgs / mean, mean, cores
-
-
 def log(msg):
     print('[bench %.1fs] %s' % (time.perf_counter() - _T0, msg), file=sys.stderr, flush=True)
 

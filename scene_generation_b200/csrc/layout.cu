@@ -49,6 +49,21 @@ __device__ __forceinline__ float sample_mask(const LayoutArgs& a, int o, int h, 
   return s;
 }
 
+// same with the y axis of the tap precomputed (identical arithmetic, hoisted out of the pixel loop)
+__device__ __forceinline__ float sample_mask_x(const LayoutArgs& a, int o, int w, const float* bx, const SgBilin& ay) {
+  float x0 = bx[0];
+  float ww = __fsub_rn(bx[2], x0);
+  float gx = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(sg_linspace01(w, a.W), x0), ww), 2.f), 1.f);
+  SgBilin ax = sg_axis(gx, a.M, a.align_corners);
+  const long base = (long)o * a.M * a.M;
+  float s = 0.f;
+  if (ay.ok0 && ax.ok0) s = __fmaf_rn(__fmul_rn(ax.w0, ay.w0), load_mask(a.masks, a.mask_dtype, base + (long)ay.i0 * a.M + ax.i0), s);
+  if (ay.ok0 && ax.ok1) s = __fmaf_rn(__fmul_rn(ax.w1, ay.w0), load_mask(a.masks, a.mask_dtype, base + (long)ay.i0 * a.M + ax.i0 + 1), s);
+  if (ay.ok1 && ax.ok0) s = __fmaf_rn(__fmul_rn(ax.w0, ay.w1), load_mask(a.masks, a.mask_dtype, base + (long)(ay.i0 + 1) * a.M + ax.i0), s);
+  if (ay.ok1 && ax.ok1) s = __fmaf_rn(__fmul_rn(ax.w1, ay.w1), load_mask(a.masks, a.mask_dtype, base + (long)(ay.i0 + 1) * a.M + ax.i0 + 1), s);
+  return s;
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward, train branch (layout.py:149-155): NHWC bf16 (Cp channels, zero padded) or NCHW fp32
 // ------------------------------------------------------------------------------------------------
@@ -186,6 +201,7 @@ __global__ void __launch_bounds__(THREADS) layout_fwd_nhwc_kernel(LayoutArgs a, 
   float* sV = smem + MAXA * TP;           // [MAXA][Cp]
   __shared__ int sAct[MAXA];
   __shared__ unsigned sNz[MAXA];
+  __shared__ SgBilin sAy[MAXA * 2];
   __shared__ int sNact, sNext;
   const int n = blockIdx.y;
   const int p0 = blockIdx.x * TP;
@@ -227,11 +243,24 @@ __global__ void __launch_bounds__(THREADS) layout_fwd_nhwc_kernel(LayoutArgs a, 
     scan = sNext;
     if (nact == 0 && !first_pass) break;
     // ---- sample the active objects over the tile, stage their vectors ---------------------------------
+    const int h_lo = p0 / a.W;
+    if (threadIdx.x < nact * 2) {      // a 64-pixel tile touches at most two image rows (W >= 32)
+      const int k = threadIdx.x >> 1, r = threadIdx.x & 1;
+      const float* bx = a.boxes + 4 * sAct[k];
+      float y0 = bx[1], hh = __fsub_rn(bx[3], y0);
+      float gy = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(sg_linspace01(min(h_lo + r, a.H - 1), a.H), y0), hh), 2.f), 1.f);
+      sAy[k * 2 + r] = sg_axis(gy, a.M, a.align_corners);
+    }
+    __syncthreads();
     for (int i = threadIdx.x; i < nact * TP; i += THREADS) {
       int k = i / TP, px = i - k * TP;
       int p = p0 + px;
       float s = 0.f;
-      if (p < HW) s = sample_mask(a, sAct[k], p / a.W, p % a.W, a.boxes + 4 * sAct[k]);
+      if (p < HW) {
+        const int h = p / a.W, w = p - h * a.W;
+        if (h - h_lo < 2) s = sample_mask_x(a, sAct[k], w, a.boxes + 4 * sAct[k], sAy[k * 2 + (h - h_lo)]);
+        else s = sample_mask(a, sAct[k], h, w, a.boxes + 4 * sAct[k]);     // W < 32: more than two rows per tile
+      }
       sS[i] = s;
     }
     if (threadIdx.x < MAXA) sNz[threadIdx.x] = 0u;
@@ -248,6 +277,8 @@ __global__ void __launch_bounds__(THREADS) layout_fwd_nhwc_kernel(LayoutArgs a, 
     // of the (object, chunk) pairs is skipped through the bit mask.
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     if (tx < chunks) {
+      unsigned mine = 0u;            // objects of this pass whose chunk tx is non-zero (pixel invariant)
+      for (int k = 0; k < nact; ++k) mine |= ((sNz[k] >> tx) & 1u) << k;
       for (int px = ty; px < TP; px += THREADS / 32) {
         int p = p0 + px;
         if (p >= HW) break;
@@ -262,8 +293,8 @@ __global__ void __launch_bounds__(THREADS) layout_fwd_nhwc_kernel(LayoutArgs a, 
 #pragma unroll
           for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h2[j]); acc[2 * j] = f.x; acc[2 * j + 1] = f.y; }
         }
-        for (int k = 0; k < nact; ++k) {
-          if (!((sNz[k] >> tx) & 1u)) continue;
+        for (unsigned m = mine; m != 0u; m &= m - 1u) {
+          const int k = __ffs(m) - 1;
           float s = sS[k * TP + px];
           if (s == 0.f) continue;
           const float4* v = reinterpret_cast<const float4*>(sV + k * a.Cp + tx * 8);

@@ -157,3 +157,47 @@ def test_vector_pool_matches_reference_policy_and_rng_order():
         rb = b.query(objs, vecs)
         assert torch.equal(ra, rb)
     assert VectorPool(0).query(objs, vecs) is vecs
+
+
+def emulate_wgrad(dy5, x5, Hred, Wred, taps, Cout, Cin, w_taps):
+    """documented semantics of sg_wgrad_tc: dw[co, wtap, ci] = sum dy[img, pa, h+dha, w+dwa, co] * x[img, pb, h+dhb, w+dwb, ci]"""
+    dw = torch.zeros(Cout, w_taps, Cin)
+    for (dha, dwa, pa, dhb, dwb, pb, wt) in taps:
+        for h in range(Hred):
+            for w in range(Wred):
+                ha, wa, hb, wb = h + dha, w + dwa, h + dhb, w + dwb
+                if 0 <= ha < dy5.shape[2] and 0 <= wa < dy5.shape[3] and 0 <= hb < x5.shape[2] and 0 <= wb < x5.shape[3]:
+                    dw[:, wt] += torch.einsum('nc,nd->cd', dy5[:, pa, ha, wa, :Cout], x5[:, pb, hb, wb, :Cin])
+    return dw
+
+
+def test_wgrad_tap_tables():
+    torch.manual_seed(3)
+    # stride-1 (pad 1), stride-2 (k4 p2, odd size) and transposed conv
+    x, w = torch.randn(2, 3, 6, 6), torch.randn(4, 3, 3, 3, requires_grad=True)
+    out = F.conv2d(x, w, padding=1)
+    dy = torch.randn_like(out)
+    out.backward(dy)
+    got = emulate_wgrad(dy.permute(0, 2, 3, 1).unsqueeze(1), x.permute(0, 2, 3, 1).unsqueeze(1), 6, 6, convspec.wgrad_s1(3, 1), 4, 3, 9)
+    assert torch.allclose(got, w.grad.permute(0, 2, 3, 1).reshape(4, 9, 3), atol=1e-4)
+    x, w = torch.randn(2, 3, 7, 7), torch.randn(4, 3, 4, 4, requires_grad=True)
+    out = F.conv2d(x, w, stride=2, padding=2)
+    dy = torch.randn_like(out)
+    out.backward(dy)
+    got = emulate_wgrad(dy.permute(0, 2, 3, 1).unsqueeze(1), planes(x), out.shape[2], out.shape[3], convspec.wgrad_s2(4, 2), 4, 3, 16)
+    assert torch.allclose(got, w.grad.permute(0, 2, 3, 1).reshape(4, 16, 3), atol=1e-4)
+    x, w = torch.randn(2, 4, 5, 5), torch.randn(4, 3, 3, 3, requires_grad=True)      # ConvT weight (Cin_t, Cout_t, k, k)
+    out = F.conv_transpose2d(x, w, stride=2, padding=1, output_padding=1)
+    dy = torch.randn_like(out)
+    out.backward(dy)
+    got = emulate_wgrad(planes(dy), x.permute(0, 2, 3, 1).unsqueeze(1), 5, 5, convspec.wgrad_convT(3, 1), 3, 4, 9)
+    assert torch.allclose(got, w.grad.permute(1, 2, 3, 0).reshape(3, 9, 4), atol=1e-4)
+
+
+def test_host_meta_matches_device_free_derivation():
+    b = synthetic.make_batch(4, (32, 32), 20, 1, 5, seed=8)
+    m = synthetic.HostMeta(b)
+    assert torch.equal(m.ranges, torch.from_numpy(synthetic.image_ranges(b[5])))
+    ptr, src = ops.build_incidence_csr(b[4][:, [0, 2]].numpy(), b[1].numel())
+    assert m.seg_ptr.tolist() == ptr.tolist() and m.seg_src.tolist() == src.tolist() and m.objs == b[1].tolist()
+    assert m.nbytes() == 4 * (m.ranges.numel() + m.seg_ptr.numel() + m.seg_src.numel())

@@ -20,9 +20,10 @@ def main(path, out):
     rows = [(r['Kernel Name'], r['Grid Size'], float(r['Metric Value'].replace(',', ''))) for r in csv.DictReader(lines)]
     idx = [i for i, (n, _, _) in enumerate(rows) if 'layout_fwd' in n]
     starts = [i for k, i in enumerate(idx) if k == 0 or i - idx[k - 1] > 3]
-    if len(starts) < 2:
-        raise SystemExit('need at least one complete step in the capture')
-    a, b = starts[-2], starts[-1]
+    if len(starts) >= 2:
+        a, b = starts[-2], starts[-1]
+    else:                      # capture taken with bench.py --profile-step: the file IS one step
+        a, b = 0, len(rows)
     step = rows[a:b]
     tot = sum(t for _, _, t in step)
     agg = collections.defaultdict(lambda: [0, 0.0])
@@ -45,7 +46,7 @@ def main(path, out):
         f.write('\n## tensor-core launches by grid\n\n| kernel | grid | launches | ms | us/launch |\n|---|---|---:|---:|---:|\n')
         g2 = collections.defaultdict(lambda: [0, 0.0])
         for n, g, t in step:
-            m = re.search(r'(conv_tc_kernel|wgrad_tc_kernel)<(\d+)>', n)
+            m = re.search(r'(conv_tc_kernel|wgrad_tc_kernel)<([0-9, ]+)>', n)
             if m:
                 g2[('%s<%s>' % m.groups(), g)][0] += 1
                 g2[('%s<%s>' % m.groups(), g)][1] += t
