@@ -134,6 +134,14 @@ typedef struct {
 } sg_wgrad_desc_t;
 int sg_wgrad_tc(const sg_wgrad_desc_t* desc, sg_stream_t stream);
 
+/* Input gradient of a stride-1 "valid" convolution with a tiny output-channel count (the generator's last
+ * 7x7 conv 64 -> 3, generators.py:87) as a direct CUDA-core convolution:
+ *   dx[n,u,v,ci] = sum_{kh,kw,co} dz[n,u-kh,v-kw,co] * w[co,kh,kw,ci],  u < H+k-1, v < W+k-1
+ * dz: bf16 [N][H][W][dzC] (first Cout channels used), w: the f32 master [Cout][k*k][Cin], dx: bf16
+ * [N][H+k-1][W+k-1][Cin].  Cout <= 4, k <= 7, Cin in {32, 64}. */
+int sg_dgrad_small_cout(const void* dz, int dzC, const float* w, int Cout, int k, int Cin, int N, int H, int W,
+                        void* dx, sg_stream_t stream);
+
 /* ---- operand preparation ------------------------------------------------------------------ */
 /* f32 (rows, cols) with row pitch ld_src -> bf16 (rows, ld_dst); columns >= cols are zero.  With
  * mask_y != NULL the value is multiplied by relu'/leaky' derived from the layer OUTPUT mask_y

@@ -10,7 +10,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
 LIB_PATH = os.path.join(_HERE, 'libsg_b200.so')
-SOURCES = ['runtime.cu', 'layout.cu', 'graph.cu', 'crop.cu', 'conv_tc.cu', 'elementwise.cu']
+SOURCES = ['runtime.cu', 'layout.cu', 'graph.cu', 'crop.cu', 'conv_tc.cu', 'elementwise.cu', 'smallconv.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
 
@@ -120,6 +120,7 @@ _SIGS = {
     'sg_gap_bwd': [_P, c_int, c_int, c_int, _P, _P],
     'sg_colsum_bf16': [_P, c_long, c_int, c_int, _P, _P],
     'sg_wgrad_tc': [ctypes.POINTER(WgradDesc), _P],
+    'sg_dgrad_small_cout': [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
 }
 _RESTYPES = {'sg_last_error': ctypes.c_char_p, 'sg_version': ctypes.c_char_p, 'sg_arch': c_int,
              'sg_launch_count': ctypes.c_ulonglong, 'sg_reset_launch_count': None}

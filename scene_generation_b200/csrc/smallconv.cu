@@ -1,0 +1,91 @@
+// Direct (CUDA-core) adjoints for convolutions with a tiny output-channel count (the generator's last
+// 7x7 conv, 64 -> 3, generators.py:87).  On the tensor-core path their GEMMs have N (dgrad: K) = 3 and waste
+// > 90 % of every MMA; as direct convolutions they are FMA / bandwidth bound (SURVEY.md §7 "last conv").
+//
+//   dgrad :  dx[n, u, v, ci] = sum_{kh,kw} sum_{co} dz[n, u-kh, v-kw, co] * w[co, kh, kw, ci]     (u < H+k-1)
+//            i.e. the gradient w.r.t. the PRE-PADDED operand of a stride-1 "valid" convolution.
+#include "common.cuh"
+#include "../../include/sg_b200.h"
+
+namespace {
+
+constexpr int TILE = 16;          // output pixels per block edge
+constexpr int MAXK = 7;
+constexpr int MAXCO = 4;
+
+template <int CIN>
+__global__ void __launch_bounds__(TILE * TILE)
+dgrad_small_cout_kernel(const __nv_bfloat16* __restrict__ dz, int dzC, const float* __restrict__ w, int Cout, int k, int N,
+                        int H, int W, __nv_bfloat16* __restrict__ dx) {
+  extern __shared__ float smem[];
+  const int taps = k * k;
+  float* sW = smem;                                   // [Cout][taps][CIN]
+  float* sZ = smem + Cout * taps * CIN;               // [Cout][TILE+k-1][TILE+k-1]
+  const int P = TILE + k - 1;
+  const int Hp = H + k - 1, Wp = W + k - 1;
+  const int n = blockIdx.z, u0 = blockIdx.y * TILE, v0 = blockIdx.x * TILE;
+  for (int i = threadIdx.x; i < Cout * taps * CIN; i += blockDim.x) sW[i] = w[i];
+  for (int i = threadIdx.x; i < Cout * P * P; i += blockDim.x) {
+    int co = i / (P * P), r = (i / P) % P, c = i % P;
+    int h = u0 - (k - 1) + r, x = v0 - (k - 1) + c;       // dz row/col feeding output (u0.., v0..)
+    float v = 0.f;
+    if (h >= 0 && h < H && x >= 0 && x < W) v = __bfloat162float(dz[(((long)n * H + h) * W + x) * dzC + co]);
+    sZ[i] = v;
+  }
+  __syncthreads();
+  const int tu = threadIdx.x / TILE, tv = threadIdx.x % TILE;
+  const int u = u0 + tu, v = v0 + tv;
+  float acc[CIN];
+#pragma unroll
+  for (int c = 0; c < CIN; ++c) acc[c] = 0.f;
+  for (int kh = 0; kh < k; ++kh)
+    for (int kw = 0; kw < k; ++kw)
+      for (int co = 0; co < Cout; ++co) {
+        // dz[u-kh, v-kw] sits at sZ[co][tu + (k-1) - kh][tv + (k-1) - kw]
+        float z = sZ[(co * P + tu + (k - 1) - kh) * P + tv + (k - 1) - kw];
+        if (z == 0.f) continue;
+        const float4* wr = reinterpret_cast<const float4*>(sW + (co * taps + kh * k + kw) * CIN);
+#pragma unroll
+        for (int c4 = 0; c4 < CIN / 4; ++c4) {
+          float4 q = wr[c4];
+          acc[4 * c4] = fmaf(z, q.x, acc[4 * c4]);
+          acc[4 * c4 + 1] = fmaf(z, q.y, acc[4 * c4 + 1]);
+          acc[4 * c4 + 2] = fmaf(z, q.z, acc[4 * c4 + 2]);
+          acc[4 * c4 + 3] = fmaf(z, q.w, acc[4 * c4 + 3]);
+        }
+      }
+  if (u < Hp && v < Wp) {
+    __nv_bfloat16* dst = dx + (((long)n * Hp + u) * Wp + v) * CIN;
+#pragma unroll
+    for (int c8 = 0; c8 < CIN / 8; ++c8) {
+      __align__(16) __nv_bfloat162 pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pk[j] = __floats2bfloat162_rn(acc[8 * c8 + 2 * j], acc[8 * c8 + 2 * j + 1]);
+      *reinterpret_cast<uint4*>(dst + 8 * c8) = *reinterpret_cast<uint4*>(pk);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int sg_dgrad_small_cout(const void* dz, int dzC, const float* w, int Cout, int k, int Cin, int N, int H, int W,
+                                   void* dx, sg_stream_t stream) {
+  SG_CHECK_ARG(dz && w && dx, "dgrad_small_cout: null pointer");
+  SG_CHECK_ARG(Cout >= 1 && Cout <= MAXCO && k >= 1 && k <= MAXK && dzC >= Cout, "dgrad_small_cout: Cout must be <= 4, k <= 7");
+  SG_CHECK_ARG(Cin == 64 || Cin == 32, "dgrad_small_cout: Cin must be 32 or 64 (got %d)", Cin);
+  SG_CHECK_ARG(N > 0 && H > 0 && W > 0, "dgrad_small_cout: empty problem");
+  const int P = TILE + k - 1;
+  dim3 grid(sg_cdiv(W + k - 1, TILE), sg_cdiv(H + k - 1, TILE), N);
+  size_t smem = sizeof(float) * ((size_t)Cout * k * k * Cin + (size_t)Cout * P * P);
+  if (Cin == 64) {
+    cudaFuncSetAttribute(dgrad_small_cout_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dgrad_small_cout_kernel<64><<<grid, TILE * TILE, smem, stream>>>((const __nv_bfloat16*)dz, dzC, w, Cout, k, N, H, W,
+                                                                      (__nv_bfloat16*)dx);
+  } else {
+    cudaFuncSetAttribute(dgrad_small_cout_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dgrad_small_cout_kernel<32><<<grid, TILE * TILE, smem, stream>>>((const __nv_bfloat16*)dz, dzC, w, Cout, k, N, H, W,
+                                                                      (__nv_bfloat16*)dx);
+  }
+  SG_CHECK_LAUNCH("sg_dgrad_small_cout");
+  return SG_OK;
+}

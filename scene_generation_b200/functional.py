@@ -255,7 +255,12 @@ class ConvFn(torch.autograd.Function):
             wsub = wt[c0:c1]
             _, P, Hx, Wx, _ = x5.shape
             base = dx.view(-1)[c0:]
-            if spec.kind == 's1':
+            if spec.kind == 's1' and spec.pad == 0 and Cout <= 4 and Cin in (32, 64) and Cx == Cin and not partial \
+                    and dz5.shape[1] == 1:
+                # tiny Cout (the 64 -> 3 output conv): direct CUDA-core dgrad instead of a K=3 tensor-core GEMM
+                _lib.call('sg_dgrad_small_cout', _ptr(dz5), dz5.shape[4], _ptr(m3), Cout, spec.k, Cin, N, Ho, Wo, _ptr(dx),
+                          _stream())
+            elif spec.kind == 's1':
                 ops.conv_tc(dz5, wsub, base, (Hx * Wx * Cx, Wx * Cx, Cx, 1), Hx, Wx, convspec.dgrad_s1(spec.k, spec.pad))
             elif spec.kind == 's2':
                 for (a, b, ptaps) in convspec.dgrad_s2_phase_taps(spec.k, spec.pad):

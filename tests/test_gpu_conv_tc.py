@@ -177,3 +177,28 @@ def test_wgrad_s2_and_convT():
     dwt = torch.zeros(C, k * k, Co, device=DEV)       # [Cout_t][taps][Cin_t]
     ops.wgrad_tc(to_planes(dy), to_nhwc5(xt), dwt, 8, 8, convspec.wgrad_convT(k, 1), C, Co)
     check(dwt, wtr.grad.permute(1, 2, 3, 0).reshape(C, k * k, Co))
+
+
+@pytest.mark.parametrize('H,W', [(16, 16), (21, 35)])
+def test_output_conv_64_to_3_tanh_forward_and_all_adjoints(H, W):
+    """The generator's last layer (reflpad3 + conv7 64->3 + tanh, generators.py:87) through ConvFn: fused tanh epilogue
+    with f32 NCHW output, direct small-Cout dgrad kernel, tensor-core wgrad, bias column sums."""
+    from scene_generation_b200 import functional as Fn
+    from scene_generation_b200.functional import ConvSpec
+    N, C, Co, k = 2, 64, 3, 7
+    x, w, b = rnd(N, C, H, W, seed=30), rnd(Co, C, k, k, seed=31, scale=0.05), rnd(Co, seed=32)
+    xp = F.pad(r32(x), (3, 3, 3, 3), mode='reflect')
+    xr = xp.clone().requires_grad_(True)
+    wr, br = r32(w).requires_grad_(True), b.clone().requires_grad_(True)
+    ref = torch.tanh(F.conv2d(xr, wr, br))
+    g = rnd(*ref.shape, seed=33)
+    ref.backward(g)
+    wd = torch.nn.Parameter(w.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2).to(DEV))     # channels-last master
+    bd = torch.nn.Parameter(b.to(DEV))
+    op = to_nhwc5(xp).requires_grad_(True)
+    y = Fn.conv(op, wd, bd, ConvSpec('s1', 7, 0, act=3, out='f32_nchw'))
+    check(y, ref.detach(), 1e-2)
+    y.backward(g.to(DEV))
+    check(op.grad[:, 0].permute(0, 3, 1, 2), xr.grad, 2e-2)
+    check(wd.grad, wr.grad, 2e-2)
+    check(bd.grad, br.grad, 2e-2)
