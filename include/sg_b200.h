@@ -142,6 +142,12 @@ int sg_wgrad_tc(const sg_wgrad_desc_t* desc, sg_stream_t stream);
 int sg_dgrad_small_cout(const void* dz, int dzC, const float* w, int Cout, int k, int Cin, int N, int H, int W,
                         void* dx, sg_stream_t stream);
 
+/* Weight gradient of the same layer (tiny Cout): dw[co,kh*k+kw,ci] = sum dz[n,h,w,co] * xop[n,h+kh,w+kw,ci]
+ * with the pre-padded bf16 operand xop [N][H+k-1][W+k-1][64]; dw f32 [Cout][k*k][64] is overwritten.
+ * Cout <= 3, Cin == 64, k in {3, 7}. */
+int sg_wgrad_small_cout(const void* dz, int dzC, const void* xop, int Cout, int k, int Cin, int N, int H, int W,
+                        float* dw, sg_stream_t stream);
+
 /* ---- operand preparation ------------------------------------------------------------------ */
 /* f32 (rows, cols) with row pitch ld_src -> bf16 (rows, ld_dst); columns >= cols are zero.  With
  * mask_y != NULL the value is multiplied by relu'/leaky' derived from the layer OUTPUT mask_y

@@ -121,6 +121,7 @@ _SIGS = {
     'sg_colsum_bf16': [_P, c_long, c_int, c_int, _P, _P],
     'sg_wgrad_tc': [ctypes.POINTER(WgradDesc), _P],
     'sg_dgrad_small_cout': [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
+    'sg_wgrad_small_cout': [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
 }
 _RESTYPES = {'sg_last_error': ctypes.c_char_p, 'sg_version': ctypes.c_char_p, 'sg_arch': c_int,
              'sg_launch_count': ctypes.c_ulonglong, 'sg_reset_launch_count': None}

@@ -66,7 +66,94 @@ dgrad_small_cout_kernel(const __nv_bfloat16* __restrict__ dz, int dzC, const flo
   }
 }
 
+// wgrad: dw[co, kh*k+kw, ci] = sum_{n,h,w} dz[n,h,w,co] * xop[n, h+kh, w+kw, ci]   (xop pre-padded: (H+k-1, W+k-1))
+// Persistent blocks walk over 8x32-pixel tiles; the bf16 input patch (tile + halo, 64 channels) is staged in
+// shared memory once and reused by all k*k taps; thread = (channel, tap group) keeps its 3 x 13 partial sums in
+// registers across tiles and flushes them with one atomic per output at the end.
+constexpr int WT_H = 8, WT_W = 32;
+template <int K>
+__global__ void __launch_bounds__(256)
+wgrad_small_cout_kernel(const __nv_bfloat16* __restrict__ dz, int dzC, const __nv_bfloat16* __restrict__ xop, int Cout, int N,
+                        int H, int W, float* __restrict__ dw) {
+  constexpr int CIN = 64, TAPS = K * K, PH = WT_H + K - 1, PW = WT_W + K - 1, TPG = (TAPS + 3) / 4;
+  extern __shared__ __nv_bfloat16 sm16[];
+  __nv_bfloat16* sX = sm16;                                                  // [PH][PW][CIN]
+  float* sZ = reinterpret_cast<float*>(sm16 + PH * PW * CIN);                // [WT_H*WT_W][MAXCO]
+  const int ci = threadIdx.x & 63, tq = threadIdx.x >> 6;
+  const int Hp = H + K - 1, Wp = W + K - 1;
+  const int tiles_w = (W + WT_W - 1) / WT_W, tiles_h = (H + WT_H - 1) / WT_H;
+  const int n_tiles = N * tiles_h * tiles_w;
+  float acc[TPG][MAXCO - 1];
+#pragma unroll
+  for (int t = 0; t < TPG; ++t)
+#pragma unroll
+    for (int c = 0; c < MAXCO - 1; ++c) acc[t][c] = 0.f;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
+    const int h0 = th * WT_H, w0 = tw * WT_W;
+    __syncthreads();
+    for (int i = threadIdx.x; i < PH * PW * (CIN / 8); i += 256) {           // 16-byte copies of the patch
+      int c8 = i % (CIN / 8), pc = (i / (CIN / 8)) % PW, pr = i / ((CIN / 8) * PW);
+      int hh = h0 + pr, wc = w0 + pc;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (hh < Hp && wc < Wp) v = *reinterpret_cast<const uint4*>(xop + (((long)n * Hp + hh) * Wp + wc) * CIN + c8 * 8);
+      *reinterpret_cast<uint4*>(sX + (pr * PW + pc) * CIN + c8 * 8) = v;
+    }
+    for (int i = threadIdx.x; i < WT_H * WT_W * (MAXCO - 1); i += 256) {
+      int co = i % (MAXCO - 1), px = i / (MAXCO - 1);
+      int hh = h0 + px / WT_W, wc = w0 + px % WT_W;
+      float v = 0.f;
+      if (co < Cout && hh < H && wc < W) v = __bfloat162float(dz[(((long)n * H + hh) * W + wc) * dzC + co]);
+      sZ[px * (MAXCO - 1) + co] = v;
+    }
+    __syncthreads();
+    for (int px = 0; px < WT_H * WT_W; ++px) {
+      const float z0 = sZ[px * 3], z1 = sZ[px * 3 + 1], z2 = sZ[px * 3 + 2];
+      if (z0 == 0.f && z1 == 0.f && z2 == 0.f) continue;
+      const int pr = px / WT_W, pc = px % WT_W;
+#pragma unroll
+      for (int t = 0; t < TPG; ++t) {
+        const int tap = tq + 4 * t;
+        if (tap < TAPS) {
+          const int kh = tap / K, kw = tap % K;
+          float x = __bfloat162float(sX[((pr + kh) * PW + pc + kw) * CIN + ci]);
+          acc[t][0] = fmaf(z0, x, acc[t][0]);
+          acc[t][1] = fmaf(z1, x, acc[t][1]);
+          acc[t][2] = fmaf(z2, x, acc[t][2]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < TPG; ++t) {
+    const int tap = tq + 4 * t;
+    if (tap < TAPS)
+      for (int co = 0; co < Cout && co < MAXCO - 1; ++co) atomicAdd(dw + ((long)co * TAPS + tap) * CIN + ci, acc[t][co]);
+  }
+}
+
 }  // namespace
+
+extern "C" int sg_wgrad_small_cout(const void* dz, int dzC, const void* xop, int Cout, int k, int Cin, int N, int H, int W,
+                                   float* dw, sg_stream_t stream) {
+  SG_CHECK_ARG(dz && xop && dw, "wgrad_small_cout: null pointer");
+  SG_CHECK_ARG(Cout >= 1 && Cout <= 3 && dzC >= Cout && Cin == 64 && (k == 7 || k == 3), "wgrad_small_cout: needs Cout <= 3, Cin == 64, k in {3, 7}");
+  SG_CHECK_ARG(N > 0 && H > 0 && W > 0, "wgrad_small_cout: empty problem");
+  cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * k * k * Cin, stream);
+  const int tiles = N * sg_cdiv(H, WT_H) * sg_cdiv(W, WT_W);
+  const int grid = tiles < 296 ? tiles : 296;
+  const int PH = WT_H + k - 1, PW = WT_W + k - 1;
+  size_t smem = sizeof(__nv_bfloat16) * (size_t)PH * PW * 64 + sizeof(float) * WT_H * WT_W * 3;
+  if (k == 7) {
+    cudaFuncSetAttribute(wgrad_small_cout_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    wgrad_small_cout_kernel<7><<<grid, 256, smem, stream>>>((const __nv_bfloat16*)dz, dzC, (const __nv_bfloat16*)xop, Cout, N, H, W, dw);
+  } else {
+    cudaFuncSetAttribute(wgrad_small_cout_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    wgrad_small_cout_kernel<3><<<grid, 256, smem, stream>>>((const __nv_bfloat16*)dz, dzC, (const __nv_bfloat16*)xop, Cout, N, H, W, dw);
+  }
+  SG_CHECK_LAUNCH("sg_wgrad_small_cout");
+  return SG_OK;
+}
 
 extern "C" int sg_dgrad_small_cout(const void* dz, int dzC, const float* w, int Cout, int k, int Cin, int N, int H, int W,
                                    void* dx, sg_stream_t stream) {

@@ -237,7 +237,11 @@ class ConvFn(torch.autograd.Function):
         dw = None
         if ctx.needs_input_grad[1]:
             g3 = torch.empty_like(m3)
-            if spec.kind == 's1':
+            if spec.kind == 's1' and spec.pad == 0 and Cout <= 3 and Cin == 64 and x5.shape[4] == 64 and spec.k in (3, 7) \
+                    and dz5.shape[1] == 1:
+                _lib.call('sg_wgrad_small_cout', _ptr(dz5), dz5.shape[4], _ptr(x5), Cout, spec.k, Cin, N, Ho, Wo, _ptr(g3),
+                          _stream())
+            elif spec.kind == 's1':
                 ops.wgrad_tc(dz5, x5, g3, Ho, Wo, convspec.wgrad_s1(spec.k, spec.pad), Cout, Cin)
             elif spec.kind == 's2':
                 ops.wgrad_tc(dz5, x5, g3, Ho, Wo, convspec.wgrad_s2(spec.k, spec.pad), Cout, Cin)
