@@ -89,7 +89,7 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
 // ------------------------------------------------------------------------------------------------
 struct ConvKParams {
   int Hout, Wout, tiles_w, tiles_h, BW, BH, BI, n_img;
-  int kblocks, Cout;
+  int kblocks, Cout, stages;
   int a_bytes;      // bytes of one A box = 128 * BW*BH*BI (rows beyond the box keep stale smem and are masked)
   int in_h0, in_w0;
   long long os_img, os_h, os_w, os_c;
@@ -109,22 +109,26 @@ constexpr int A_BYTES = 128 * 128;   // 128 rows x 64 bf16
 
 template <int BN>
 struct ConvCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  // Pipeline depth is a launch parameter.  Default ("shallow"): two CTAs share an SM (<= 113 KB each), so the
+  // prologue / TMEM drain / store epilogue of one tile overlaps the MMA main loop of the other; "deep"
+  // (SG_CONV_DEEP=1): one CTA per SM with the whole shared memory as its ring.
+  static constexpr int STAGES_DEEP = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES_SHALLOW = (BN == 256) ? 2 : (BN == 128 ? 3 : (BN == 64 ? 4 : 6));
   static constexpr int B_BYTES = BN * 128;
   static constexpr int TM_COLS = BN < 32 ? 32 : BN;
-  static constexpr int SMEM = STAGES * (A_BYTES + (B_BYTES < 1024 ? 1024 : B_BYTES)) + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int B_STRIDE = (B_BYTES < 1024 ? 1024 : B_BYTES);
+  static constexpr int smem_bytes(int stages) { return stages * (A_BYTES + B_STRIDE) + 1024 /*align slack*/ + 256 /*barriers*/; }
 };
 
 // MC = true: launched as clusters of 2 CTAs along M that work on the same weight tile; each CTA fetches
 // half of B and multicasts it to both, which removes a third of the L2 -> SM operand traffic of a
 // 128 x BN tile (the limiter of the 1024-channel resblock GEMMs with single-CTA tiles).
 template <int BN, bool MC>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ ConvKParams p) {
   using Cfg = ConvCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
+  const int STAGES = p.stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -162,9 +166,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t par = (it / STAGES) & 1;
+      int s = 0;
+      uint32_t par = 0;
+      for (int it = 0; it < iters; ++it, ++s) {
+        if (s == STAGES) { s = 0; par ^= 1; }
         mbar_wait(&empty[s], par ^ 1);
         const int tap_i = it / p.kblocks, kb = it - tap_i * p.kblocks;
         const sg_tap_t tp = p.taps[ph.tap_begin + tap_i];
@@ -180,9 +185,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t par = (it / STAGES) & 1;
+      int s = 0;
+      uint32_t par = 0;
+      for (int it = 0; it < iters; ++it, ++s) {
+        if (s == STAGES) { s = 0; par ^= 1; }
         mbar_wait(&full[s], par);
         tc_fence_after();
         const uint64_t ad = umma_desc_sw128(smem_u32(sA + s * A_BYTES), 16, 1024);
@@ -297,7 +303,7 @@ struct WgradKParams {
   int tiles_w, tiles_h, BW, BH, BI;
   int ktiles_total, ktiles_per_split;
   int atomic;       // 0: this CTA owns its dw tile (ksplit == 1) -> plain stores
-  int Cout, Cin, w_taps, dw_C, n_ci_tiles;
+  int Cout, Cin, w_taps, dw_C, n_ci_tiles, stages;
   float* dw;
   sg_wtap_t taps[SG_MAX_TAPS];
 };
@@ -308,16 +314,17 @@ template <int BN>
 struct WgradCfg {
   static constexpr int NB = BN / 64;
   static constexpr int STAGE_BYTES = (2 + NB) * WG_BOX_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int STAGES_DEEP = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES_SHALLOW = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);      // <= 113 KB: two CTAs per SM
+  static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 + 256; }
 };
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, 2)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ WgradKParams p) {
   using Cfg = WgradCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
+  const int STAGES = p.stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
@@ -351,9 +358,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t par = (it / STAGES) & 1;
+      int s = 0;
+      uint32_t par = 0;
+      for (int it = 0; it < iters; ++it, ++s) {
+        if (s == STAGES) { s = 0; par ^= 1; }
         mbar_wait(&empty[s], par ^ 1);
         const int kt = kt_begin + it;
         const int tw = kt % p.tiles_w, th = (kt / p.tiles_w) % p.tiles_h, ti = kt / (p.tiles_w * p.tiles_h);
@@ -370,9 +378,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp == 1) {
     if (lane == 0 && iters > 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t par = (it / STAGES) & 1;
+      int s = 0;
+      uint32_t par = 0;
+      for (int it = 0; it < iters; ++it, ++s) {
+        if (s == STAGES) { s = 0; par ^= 1; }
         mbar_wait(&full[s], par);
         tc_fence_after();
         uint8_t* st = smem + s * Cfg::STAGE_BYTES;
@@ -454,20 +463,35 @@ void choose_tile(int rows, bool exact, int H, int W, int N, int* BW, int* BH, in
   }
 }
 
+// SG_CONV_DEEP=1: one CTA per SM with a deep ring (the round-1 baseline configuration, kept for A/B runs)
+bool deep_pipeline() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SG_CONV_DEEP");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 template <int BN, bool MC>
-int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKParams& kp, dim3 grid, cudaStream_t stream) {
+int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKParams& kp, dim3 grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN>::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ConvCfg<BN>::smem_bytes(ConvCfg<BN>::STAGES_DEEP));
     if (e != cudaSuccess) return sg_fail(SG_ERR_CUDA, "conv_tc smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
+  // a grid that does not even fill the SMs once gains nothing from co-residency: give each CTA the deep ring
+  const bool one_wave = (long)grid.x * grid.y * grid.z <= 148;
+  kp.stages = (deep_pipeline() || MC || one_wave) ? ConvCfg<BN>::STAGES_DEEP : ConvCfg<BN>::STAGES_SHALLOW;
+  const int smem_bytes = ConvCfg<BN>::smem_bytes(kp.stages);
   if (MC) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = grid;
     cfg.blockDim = dim3(192);
-    cfg.dynamicSmemBytes = ConvCfg<BN>::SMEM;
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -479,14 +503,14 @@ int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKPar
     cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, MC>, tmA, tmB, kp);
     if (e != cudaSuccess) return sg_fail(SG_ERR_CUDA, "sg_conv_tc (cluster launch): %s", cudaGetErrorString(e));
   } else {
-    conv_tc_kernel<BN, MC><<<grid, 192, ConvCfg<BN>::SMEM, stream>>>(tmA, tmB, kp);
+    conv_tc_kernel<BN, MC><<<grid, 192, smem_bytes, stream>>>(tmA, tmB, kp);
   }
   SG_CHECK_LAUNCH("sg_conv_tc");
   return SG_OK;
 }
 
 template <int BN>
-int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKParams& kp, dim3 grid, bool mc, cudaStream_t stream) {
+int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKParams& kp, dim3 grid, bool mc, cudaStream_t stream) {
   if (mc) {
     if constexpr (BN >= 128) return launch_conv_t<BN, true>(tmA, tmB, kp, grid, stream);
   }
@@ -504,14 +528,17 @@ bool multicast_enabled() {
 }
 
 template <int BN>
-int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const WgradKParams& kp, dim3 grid, cudaStream_t stream) {
+int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, WgradKParams& kp, dim3 grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradCfg<BN>::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         WgradCfg<BN>::smem_bytes(WgradCfg<BN>::STAGES_DEEP));
     if (e != cudaSuccess) return sg_fail(SG_ERR_CUDA, "wgrad_tc smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  wgrad_tc_kernel<BN><<<grid, 192, WgradCfg<BN>::SMEM, stream>>>(tmA, tmB, kp);
+  const bool one_wave = (long)grid.x * grid.y * grid.z <= 148;
+  kp.stages = (deep_pipeline() || one_wave) ? WgradCfg<BN>::STAGES_DEEP : WgradCfg<BN>::STAGES_SHALLOW;
+  wgrad_tc_kernel<BN><<<grid, 192, WgradCfg<BN>::smem_bytes(kp.stages), stream>>>(tmA, tmB, kp);
   SG_CHECK_LAUNCH("sg_wgrad_tc");
   return SG_OK;
 }
