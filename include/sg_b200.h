@@ -108,6 +108,9 @@ typedef struct {
   float slope;
   float* stats;           /* (x_N, Cout, 2) f32 sum / sum-of-squares of the pre-activation output, or NULL
                              (caller zeroes it); feeds InstanceNorm / BatchNorm */
+  int w_img_rows;         /* 0: one weight tensor for all images.  > 0: per-image weights, w is
+                             [x_N * w_img_rows][w_taps][w_C] and image i uses rows [i * w_img_rows, + w_Cout)
+                             (channel-compacted layouts, see sg_pack_weight_cmap); needs Hout*Wout >= 128 */
 } sg_conv_desc_t;
 int sg_conv_tc(const sg_conv_desc_t* desc, sg_stream_t stream);
 
@@ -131,6 +134,8 @@ typedef struct {
   int ntaps;
   sg_wtap_t taps[SG_MAX_TAPS];
   int ksplit;             /* 0 = auto */
+  int per_image;          /* 1: dw is f32 [N][Cout][w_taps][dw_C], one slab per image (no reduction over
+                             images; the per-image weight gradients of a channel-compacted operand) */
 } sg_wgrad_desc_t;
 int sg_wgrad_tc(const sg_wgrad_desc_t* desc, sg_stream_t stream);
 
@@ -159,6 +164,21 @@ int sg_cast_pad_bf16(const float* src, long long rows, int cols, long long ld_sr
  * operand) and, when wt != NULL, the transposed bf16 [Cin][taps][Cout_p] used by dgrad. */
 int sg_pack_weight(const float* w, int Cout, int taps, int Cin, int Cin_p, int Cout_p, void* wk, void* wt,
                    sg_stream_t stream);
+
+/* ---- channel-compacted layouts ----------------------------------------------------------------
+ * model.py:165-168 builds layout vectors cat(one_hot(class), appearance): per image only the classes that
+ * occur in it give non-zero layout channels.  A compacted layout keeps Cc (= 64) channels per image and a
+ * channel map cmap int32 (N, Cc): dense channel of compact channel j of image n, or -1.  The consumer's
+ * first convolution (generators.py:69, discriminators.py:211) then runs with per-image weights
+ *   wk[n][co][tap][j]  = w[co][tap][cmap[n][j]]          (bf16, fprop / sg_conv_desc_t.w_img_rows = Cout)
+ *   wt[n][j][tap][co]  = w[co][tap][cmap[n][j]]          (bf16 [N][Cc][taps][Cout_p], dgrad, w_img_rows = Cc)
+ * (zero where cmap is -1 or >= Cin); either output may be NULL. */
+int sg_pack_weight_cmap(const float* w, int Cout, int taps, int Cin, const int* cmap, int N, int Cc, int Cout_p,
+                        void* wk, void* wt, sg_stream_t stream);
+/* adjoint: per-image weight gradients dwc f32 [N][Cout][taps][Cc] (sg_wgrad_desc_t.per_image) summed into the
+ * dense dw f32 [Cout][taps][Cin], which is overwritten. */
+int sg_wgrad_cmap_scatter(const float* dwc, const int* cmap, int N, int Cout, int taps, int Cc, int Cin, float* dw,
+                          sg_stream_t stream);
 
 /* ---- layers.py:292-301 InstanceNorm2d / BatchNorm2d, ReLU / LeakyReLU, ReflectionPad2d,
  *      Interpolate(nearest x2), fused into one operand-writer pass (and its adjoint) ----------- */

@@ -10,7 +10,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
 LIB_PATH = os.path.join(_HERE, 'libsg_b200.so')
-SOURCES = ['runtime.cu', 'layout.cu', 'graph.cu', 'crop.cu', 'conv_tc.cu', 'elementwise.cu', 'smallconv.cu']
+SOURCES = ['runtime.cu', 'layout.cu', 'graph.cu', 'crop.cu', 'conv_tc.cu', 'elementwise.cu', 'smallconv.cu', 'compact.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
 
@@ -39,6 +39,7 @@ class ConvDesc(ctypes.Structure):
         ('nphases', c_int), ('phases', Phase * 4),
         ('ntaps', c_int), ('taps', Tap * SG_MAX_TAPS),
         ('bias', c_void_p), ('act', c_int), ('slope', c_float), ('stats', c_void_p),
+        ('w_img_rows', c_int),
     ]
 
 
@@ -64,7 +65,7 @@ class WgradDesc(ctypes.Structure):
         ('Hred', c_int), ('Wred', c_int),
         ('dw', c_void_p), ('Cout', c_int), ('Cin', c_int), ('w_taps', c_int), ('dw_C', c_int),
         ('ntaps', c_int), ('taps', WTap * SG_MAX_TAPS),
-        ('ksplit', c_int),
+        ('ksplit', c_int), ('per_image', c_int),
     ]
 
 
@@ -106,6 +107,8 @@ _SIGS = {
     'sg_conv_tc': [ctypes.POINTER(ConvDesc), _P],
     'sg_cast_pad_bf16': [_P, c_long, c_int, c_long, c_int, _P, c_float, _P, _P],
     'sg_pack_weight': [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P],
+    'sg_pack_weight_cmap': [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P, _P, _P],
+    'sg_wgrad_cmap_scatter': [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P],
     'sg_norm_finalize': [_P, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, c_float, _P, _P, _P, _P, _P],
     'sg_norm_act_pad_fwd': [ctypes.POINTER(NapDesc), _P, _P],
     'sg_norm_act_pad_bwd': [ctypes.POINTER(NapDesc), _P, _P, _P, c_int, c_float, _P, c_int, _P, _P, _P],

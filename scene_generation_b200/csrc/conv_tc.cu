@@ -90,6 +90,7 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
 struct ConvKParams {
   int Hout, Wout, tiles_w, tiles_h, BW, BH, BI, n_img;
   int kblocks, Cout, stages;
+  int w_img_rows;   // > 0: per-image weights, image i uses rows [i * w_img_rows, ...) of the weight tensor
   int a_bytes;      // bytes of one A box = 128 * BW*BH*BI (rows beyond the box keep stale smem and are masked)
   int in_h0, in_w0;
   long long os_img, os_h, os_w, os_c;
@@ -143,6 +144,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, ti = mt / (p.tiles_w * p.tiles_h);
   const int w0 = tw * p.BW, h0 = th * p.BH, img0 = ti * p.BI;
   const int n0 = blockIdx.y * BN;
+  const int wrow0 = n0 + img0 * p.w_img_rows;        // weight-tensor row of this tile's first output channel
   const sg_phase_t ph = p.phases[blockIdx.z];
   const int iters = ph.ntaps * p.kblocks;
 
@@ -177,9 +179,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_load_5d(sA + s * A_BYTES, &tmA, &full[s], kb * 64, w0 + tp.dw + p.in_w0, h0 + tp.dh + p.in_h0, tp.plane, img0);
         if (MC)
           tma_load_3d_mc(sB + s * Cfg::B_STRIDE + crank * (Cfg::B_BYTES / 2), &tmB, &full[s], kb * 64, tp.wtap,
-                         n0 + (int)crank * (BN / 2), (uint16_t)3);
+                         wrow0 + (int)crank * (BN / 2), (uint16_t)3);
         else
-          tma_load_3d(sB + s * Cfg::B_STRIDE, &tmB, &full[s], kb * 64, tp.wtap, n0);
+          tma_load_3d(sB + s * Cfg::B_STRIDE, &tmB, &full[s], kb * 64, tp.wtap, wrow0);
       }
     }
   } else if (warp == 1) {
@@ -304,6 +306,7 @@ struct WgradKParams {
   int ktiles_total, ktiles_per_split;
   int atomic;       // 0: this CTA owns its dw tile (ksplit == 1) -> plain stores
   int Cout, Cin, w_taps, dw_C, n_ci_tiles, stages;
+  long long dw_split_stride;   // per_image: floats between the dw slabs of consecutive k-splits (= images)
   float* dw;
   sg_wtap_t taps[SG_MAX_TAPS];
 };
@@ -407,7 +410,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, raw);
       tmem_ld_wait();
       if (co < p.Cout) {
-        float* dst = p.dw + ((long long)co * p.w_taps + tp.wtap) * p.dw_C + ci0 + c0;
+        float* dst = p.dw + (long long)blockIdx.z * p.dw_split_stride + ((long long)co * p.w_taps + tp.wtap) * p.dw_C + ci0 + c0;
         const bool vec = (ci0 + c0 + 32 <= p.Cin) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
         if (vec && !p.atomic) {
 #pragma unroll
@@ -567,6 +570,9 @@ extern "C" int sg_conv_tc(const sg_conv_desc_t* d, sg_stream_t stream) {
   kp.n_img = d->x_N;
   kp.kblocks = sg_cdiv(d->x_C < d->w_C ? d->x_C : d->w_C, 64);
   kp.Cout = d->w_Cout;
+  SG_CHECK_ARG(d->w_img_rows >= 0, "sg_conv_tc: w_img_rows must be >= 0");
+  SG_CHECK_ARG(d->w_img_rows == 0 || kp.BI == 1, "sg_conv_tc: per-image weights need tiles within one image (H*W >= 128)");
+  kp.w_img_rows = d->w_img_rows;
   kp.in_h0 = d->in_h0; kp.in_w0 = d->in_w0;
   kp.os_img = d->y_os_img; kp.os_h = d->y_os_h; kp.os_w = d->y_os_w; kp.os_c = d->y_os_c;
   kp.oh_mul = d->oh_mul; kp.ow_mul = d->ow_mul;
@@ -593,10 +599,10 @@ extern "C" int sg_conv_tc(const sg_conv_desc_t* d, sg_stream_t stream) {
       if (best_t == 0 || t < best_t) { best_t = t; BN = cand; }
     }
   }
-  long long bdims[3] = {d->w_C, d->w_taps, d->w_Cout};
+  long long bdims[3] = {d->w_C, d->w_taps, d->w_img_rows > 0 ? (long long)d->w_img_rows * d->x_N : (long long)d->w_Cout};
   int m_tiles = kp.tiles_w * kp.tiles_h * img_tiles;
   // weight multicast pays when the K loop is long (L2-bound operand streaming) and there are CTA pairs to form
-  const bool mc = multicast_enabled() && BN >= 128 && m_tiles >= 2 && (long)d->ntaps * kp.kblocks >= 32;
+  const bool mc = multicast_enabled() && d->w_img_rows == 0 && BN >= 128 && m_tiles >= 2 && (long)d->ntaps * kp.kblocks >= 32;
   if (mc) m_tiles = (m_tiles + 1) & ~1;           // an odd tail tile gets a fully masked partner
   int bbox[3] = {64, 1, mc ? BN / 2 : BN};
   if (int e = make_tmap(&tmB, d->w, 3, bdims, bbox)) return e;
@@ -625,7 +631,12 @@ extern "C" int sg_wgrad_tc(const sg_wgrad_desc_t* d, sg_stream_t stream) {
   kp.n_ci_tiles = sg_cdiv(d->Cin, BN);
   const int co_tiles = sg_cdiv(d->Cout, 128);
   int ksplit = d->ksplit;
-  if (ksplit <= 0) {
+  if (d->per_image) {
+    // one k-split per image: dw is [N][Cout][w_taps][dw_C], every slab is owned by the CTAs of one image
+    SG_CHECK_ARG(kp.BI == 1, "sg_wgrad_tc: per_image needs reduction tiles within one image (Hred*Wred >= 64)");
+    ksplit = d->N;
+    kp.dw_split_stride = (long long)d->Cout * d->w_taps * d->dw_C;
+  } else if (ksplit <= 0) {
     long base_ctas = (long)co_tiles * kp.n_ci_tiles * d->ntaps;
     ksplit = (int)((2 * 148 + base_ctas - 1) / base_ctas);
     if (ksplit > kp.ktiles_total) ksplit = kp.ktiles_total;
@@ -635,7 +646,7 @@ extern "C" int sg_wgrad_tc(const sg_wgrad_desc_t* d, sg_stream_t stream) {
   }
   kp.ktiles_per_split = sg_cdiv(kp.ktiles_total, ksplit);
   ksplit = sg_cdiv(kp.ktiles_total, kp.ktiles_per_split);
-  kp.atomic = ksplit > 1;
+  kp.atomic = ksplit > 1 && !d->per_image;
   if (kp.atomic) cudaMemsetAsync(d->dw, 0, sizeof(float) * (size_t)d->Cout * d->w_taps * d->dw_C, stream);
   CUtensorMap tmA, tmB;
   long long adims[5] = {d->dy_C, d->dy_W, d->dy_H, d->dy_P, d->N};

@@ -63,6 +63,24 @@ def packed_weights(weight, kind):
     return wk, wt
 
 
+def packed_weights_cmap(weight, kind, cmap):
+    """Per-image bf16 operands of a channel-compacted input (csrc/compact.cu): wk (N,Cout,taps,Cc) and
+    wt (N,Cc,taps,Cout_p) with channel j of image n taken from dense input channel cmap[n,j].  One entry
+    per weight: the layouts of one step share their channel map."""
+    key = (id(weight), 'cmap')
+    ent = _pack_cache.get(key)
+    if ent is not None and ent[0] == weight._version and ent[3] is weight and ent[4] is cmap:
+        return ent[1], ent[2]
+    m3 = master3(weight.detach(), kind)
+    Cout, taps, Cin = m3.shape
+    N, Cc = cmap.shape
+    wk = torch.empty((N, Cout, taps, Cc), dtype=BF, device=weight.device)
+    wt = torch.empty((N, Cc, taps, round_up(Cout, 8)), dtype=BF, device=weight.device)
+    _lib.call('sg_pack_weight_cmap', _ptr(m3), Cout, taps, Cin, _ptr(cmap), N, Cc, wt.shape[3], _ptr(wk), _ptr(wt), _stream())
+    _pack_cache[key] = (weight._version, wk, wt, weight, cmap)
+    return wk, wt
+
+
 def clear_weight_cache():
     _pack_cache.clear()
 
@@ -184,11 +202,19 @@ class ConvFn(torch.autograd.Function):
     layers.py:251,266, discriminators.py:134-156,211-233)."""
 
     @staticmethod
-    def forward(ctx, x5, weight, bias, spec):
-        wk, _ = packed_weights(weight, spec.kind)
-        Cout = wk.shape[0]
+    def forward(ctx, x5, weight, bias, spec, cmap=None):
+        """cmap: int32 (N, Cc) channel map of a channel-compacted operand (x5's Cc channels of image n are the
+        dense input channels cmap[n]); the convolution then runs with per-image gathered weights."""
+        if cmap is None:
+            wk, _ = packed_weights(weight, spec.kind)
+        else:
+            assert spec.kind in ('s1', 's2') and cmap.dtype == torch.int32 and cmap.is_contiguous()
+            assert cmap.shape == (x5.shape[0], x5.shape[4])
+            wk, _ = packed_weights_cmap(weight, spec.kind, cmap)
+        Cout = wk.shape[-3]
         y, stats = _conv_forward(x5, wk, bias, spec, Cout)
         ctx.spec = spec
+        ctx.cmap = cmap
         ctx.save_for_backward(x5, weight, bias, y if spec.act != _lib.ACT_NONE else None)
         if stats is None:
             stats = torch.empty(0, device=x5.device)
@@ -199,8 +225,12 @@ class ConvFn(torch.autograd.Function):
     def backward(ctx, dy, _dstats):
         spec = ctx.spec
         x5, weight, bias, y = ctx.saved_tensors
-        _, wt = packed_weights(weight, spec.kind)
-        Cin, taps_n, Coutp = wt.shape
+        cmap = ctx.cmap
+        if cmap is None:
+            _, wt = packed_weights(weight, spec.kind)
+        else:
+            _, wt = packed_weights_cmap(weight, spec.kind, cmap)
+        Cin, taps_n, Coutp = wt.shape[-3:]          # Cin: channels of the operand (compacted: Cc)
         m3 = master3(weight, spec.kind)
         Cout = m3.shape[0]
         N = x5.shape[0]
@@ -237,6 +267,9 @@ class ConvFn(torch.autograd.Function):
         dw = None
         if ctx.needs_input_grad[1]:
             g3 = torch.empty_like(m3)
+            g3_dense = g3
+            if cmap is not None:    # per-image gradients of the gathered weights, scattered back below
+                g3 = torch.empty((N, Cout, taps_n, Cin), dtype=torch.float32, device=dy.device)
             if spec.kind == 's1' and spec.pad == 0 and Cout <= 3 and Cin == 64 and x5.shape[4] == 64 and spec.k in (3, 7) \
                     and dz5.shape[1] == 1:
                 _lib.call('sg_wgrad_small_cout', _ptr(dz5), dz5.shape[4], _ptr(x5), Cout, spec.k, Cin, N, Ho, Wo, _ptr(g3),
@@ -247,6 +280,10 @@ class ConvFn(torch.autograd.Function):
                 ops.wgrad_tc(dz5, x5, g3, Ho, Wo, convspec.wgrad_s2(spec.k, spec.pad), Cout, Cin)
             else:
                 ops.wgrad_tc(dz5, x5, g3, x5.shape[2], x5.shape[3], convspec.wgrad_convT(spec.k, 1), Cout, Cin)
+            if cmap is not None:
+                _lib.call('sg_wgrad_cmap_scatter', _ptr(g3), _ptr(cmap), N, Cout, taps_n, Cin, m3.shape[2], _ptr(g3_dense),
+                          _stream())
+                g3 = g3_dense
             dw = grad_like_weight(g3, weight, spec.kind)
         # ---- input gradient (in the operand's own format) ---------------------------------------
         dx = None
@@ -256,7 +293,7 @@ class ConvFn(torch.autograd.Function):
             c0 = c0 // 8 * 8          # keep the output pointer 16-byte aligned for the vector-store epilogue
             partial = (c0, c1) != (0, Cin) or Cx != Cin
             dx = (torch.zeros if partial else torch.empty)(x5.shape, dtype=BF, device=x5.device)
-            wsub = wt[c0:c1]
+            wsub, wr = (wt[c0:c1], None) if cmap is None else (wt, (c0, c1))
             _, P, Hx, Wx, _ = x5.shape
             base = dx.view(-1)[c0:]
             if spec.kind == 's1' and spec.pad == 0 and Cout <= 4 and Cin in (32, 64) and Cx == Cin and not partial \
@@ -265,18 +302,18 @@ class ConvFn(torch.autograd.Function):
                 _lib.call('sg_dgrad_small_cout', _ptr(dz5), dz5.shape[4], _ptr(m3), Cout, spec.k, Cin, N, Ho, Wo, _ptr(dx),
                           _stream())
             elif spec.kind == 's1':
-                ops.conv_tc(dz5, wsub, base, (Hx * Wx * Cx, Wx * Cx, Cx, 1), Hx, Wx, convspec.dgrad_s1(spec.k, spec.pad))
+                ops.conv_tc(dz5, wsub, base, (Hx * Wx * Cx, Wx * Cx, Cx, 1), Hx, Wx, convspec.dgrad_s1(spec.k, spec.pad), w_rows=wr)
             elif spec.kind == 's2':
                 for (a, b, ptaps) in convspec.dgrad_s2_phase_taps(spec.k, spec.pad):
                     plane = base[(a * 2 + b) * Hx * Wx * Cx:]
-                    ops.conv_tc(dz5, wsub, plane, (4 * Hx * Wx * Cx, Wx * Cx, Cx, 1), Hx, Wx, ptaps)
+                    ops.conv_tc(dz5, wsub, plane, (4 * Hx * Wx * Cx, Wx * Cx, Cx, 1), Hx, Wx, ptaps, w_rows=wr)
             else:
                 ops.conv_tc(dz5, wsub, base, (Hx * Wx * Cx, Wx * Cx, Cx, 1), Hx, Wx, convspec.dgrad_convT(spec.k, 1))
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
-def conv(x5, weight, bias, spec):
-    y, stats = ConvFn.apply(x5, weight, bias, spec)
+def conv(x5, weight, bias, spec, cmap=None):
+    y, stats = ConvFn.apply(x5, weight, bias, spec, cmap)
     return (y, stats) if spec.stats else y
 
 

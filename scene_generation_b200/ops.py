@@ -195,21 +195,30 @@ _desc_cache = {}
 
 
 def conv_tc(x5, w3, y, y_strides, Hout, Wout, taps, phases=None, oh_mul=1, ow_mul=1, in_h0=0, in_w0=0,
-            bias=None, act=_lib.ACT_NONE, slope=0.0, stats=None):
-    """x5: bf16 (N,P,H,W,C) contiguous; w3: bf16 (Cout,taps,C) contiguous; y: f32/bf16 output storage
+            bias=None, act=_lib.ACT_NONE, slope=0.0, stats=None, w_rows=None):
+    """x5: bf16 (N,P,H,W,C) contiguous; w3: bf16 (Cout,taps,C) contiguous — or (N,R,taps,C) per-image weights
+    (channel-compacted operands), of which rows [w_rows[0], w_rows[1]) of every image are the output channels;
+    y: f32/bf16 output storage
     addressed as img*os_img + (h*oh_mul+oh_off)*os_h + (w*ow_mul+ow_off)*os_w + co*os_c with
     y_strides=(os_img, os_h, os_w[, os_c]) in elements.  taps: sequence of (dh, dw, plane, wtap).
     phases: sequence of (tap_begin, ntaps, oh_off, ow_off) or None for a single phase.
     The filled descriptor is cached per call-site geometry; only the pointers change per call."""
     key = ('c', x5.shape, w3.shape, y.dtype, tuple(y_strides), Hout, Wout, id(taps), id(phases), oh_mul, ow_mul,
-           in_h0, in_w0, act, slope)
+           in_h0, in_w0, act, slope, w_rows)
     ent = _desc_cache.get(key)
     if ent is None or ent[1] is not taps or ent[2] is not phases:
         _need_cuda(x5, w3, y)
         assert x5.dtype == torch.bfloat16 and w3.dtype == torch.bfloat16 and x5.is_contiguous() and w3.is_contiguous()
         d = ConvDesc()
         d.x_N, d.x_P, d.x_H, d.x_W, d.x_C = x5.shape
-        d.w_Cout, d.w_taps, d.w_C = w3.shape
+        if w3.dim() == 4:
+            assert w3.shape[0] == x5.shape[0]
+            _, d.w_img_rows, d.w_taps, d.w_C = w3.shape
+            r0, r1 = w_rows or (0, w3.shape[1])
+            d.w_Cout = r1 - r0
+        else:
+            d.w_Cout, d.w_taps, d.w_C = w3.shape
+            d.w_img_rows = 0
         d.y_dtype = BF16 if y.dtype == torch.bfloat16 else F32
         d.y_os_img, d.y_os_h, d.y_os_w = y_strides[:3]
         d.y_os_c = y_strides[3] if len(y_strides) > 3 else 1
@@ -226,6 +235,8 @@ def conv_tc(x5, w3, y, y_strides, Hout, Wout, taps, phases=None, oh_mul=1, ow_mu
         _desc_cache[key] = ent
     d = ent[0]
     d.x, d.w, d.y = x5.data_ptr(), w3.data_ptr(), y.data_ptr()
+    if w_rows is not None:
+        d.w += w_rows[0] * w3.shape[-2] * w3.shape[-1] * 2
     d.bias = None if bias is None else bias.data_ptr()
     d.stats = None if stats is None else stats.data_ptr()
     _lib.call('sg_conv_tc', ent[3], _stream())
@@ -233,7 +244,8 @@ def conv_tc(x5, w3, y, y_strides, Hout, Wout, taps, phases=None, oh_mul=1, ow_mu
 
 
 def wgrad_tc(dy5, x5, dw, Hred, Wred, taps, Cout, Cin, ksplit=0):
-    """dy5: bf16 (N,P,H,W,Cd); x5: bf16 (N,P,H,W,Cx); dw: f32 (Cout, w_taps, dw_C), overwritten.
+    """dy5: bf16 (N,P,H,W,Cd); x5: bf16 (N,P,H,W,Cx); dw: f32 (Cout, w_taps, dw_C), overwritten — or
+    (N, Cout, w_taps, dw_C): per-image weight gradients (no reduction over images).
     taps: sequence of (dha, dwa, pa, dhb, dwb, pb, wtap)."""
     key = ('w', dy5.shape, x5.shape, dw.shape, Hred, Wred, id(taps), Cout, Cin, ksplit)
     ent = _desc_cache.get(key)
@@ -245,7 +257,9 @@ def wgrad_tc(dy5, x5, dw, Hred, Wred, taps, Cout, Cin, ksplit=0):
         d.N, d.dy_P, d.dy_H, d.dy_W, d.dy_C = dy5.shape
         _, d.x_P, d.x_H, d.x_W, d.x_C = x5.shape
         d.Hred, d.Wred = Hred, Wred
-        d.Cout, d.Cin, d.w_taps, d.dw_C = Cout, Cin, dw.shape[1], dw.shape[2]
+        d.Cout, d.Cin, d.w_taps, d.dw_C = Cout, Cin, dw.shape[-2], dw.shape[-1]
+        d.per_image = int(dw.dim() == 4)
+        assert dw.dim() == 3 or dw.shape[0] == dy5.shape[0]
         d.ntaps = len(taps)
         for i, tp in enumerate(taps):
             d.taps[i] = WTap(*tp, 0)
