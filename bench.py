@@ -210,7 +210,10 @@ class KernelProbe:
         probe = self
 
         def conv_tc(x5, w3, y, y_strides, Hout, Wout, taps, phases=None, **kw):
-            N, Cout, Cin = x5.shape[0], w3.shape[0], min(x5.shape[4], w3.shape[2])
+            # per-image weights (channel-compacted operands) are (N, rows, taps, C): the K the tensor core runs
+            wr = kw.get('w_rows')
+            N, Cin = x5.shape[0], min(x5.shape[4], w3.shape[-1])
+            Cout = (wr[1] - wr[0]) if wr else w3.shape[-3]
             nph = len(phases) if phases else 1
             ntap = sum(p[1] for p in phases) if phases else len(taps)
             flops = 2.0 * N * Hout * Wout * Cout * Cin * ntap
@@ -231,12 +234,14 @@ class KernelProbe:
             return r
         self.orig_layout = ops.masks_to_layout_fwd
 
-        def layout_fwd(vecs, boxes, masks, ranges, H, W, align_corners=False, out_format=0, test_mode=False, raw=False):
+        def layout_fwd(vecs, boxes, masks, ranges, H, W, align_corners=False, out_format=0, test_mode=False, raw=False,
+                       Cp=None):
             N, D = ranges.shape[0], vecs.shape[1]
-            nbytes = float(N * H * W * (((D + 7) // 8 * 8) * 2 if out_format == 1 else D * 4))   # algorithmic: the output write
+            cp = Cp or (D + 7) // 8 * 8
+            nbytes = float(N * H * W * (cp * 2 if out_format == 1 else D * 4))   # algorithmic: the output write
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            r = probe.orig_layout(vecs, boxes, masks, ranges, H, W, align_corners, out_format, test_mode, raw)
+            r = probe.orig_layout(vecs, boxes, masks, ranges, H, W, align_corners, out_format, test_mode, raw, Cp)
             e1.record()
             probe.records.append(('layout_fwd', nbytes, e0, e1, (N, H, W, D, 0, 0, 0)))
             return r
@@ -269,6 +274,33 @@ def load_peaks():
         d = json.load(open(p))
         return d.get('bf16_tflops_sustained', 1441.7), d.get('hbm_gbs', 6572.9), 'measured (MEASURED_PEAKS.json, sustained)'
     return 1400.0, 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def time_dense_layout(model, batch, H, peak_hbm, reps=10):
+    """masks_to_layout (layout.py:64-93) with the reference's dense layout vectors cat(one_hot, appearance), bf16
+    NHWC output, timed alone with CUDA events; a 256 MB memset between launches evicts L2."""
+    from scene_generation_b200 import ops
+    imgs, objs, boxes, masks, triples, o2i = batch[:6]
+    O = objs.numel()
+    vecs = torch.zeros((O, model.num_objs + model.rep_size), device=objs.device)
+    vecs.scatter_(1, objs.view(-1, 1), 1.0)
+    vecs[:, model.num_objs:] = torch.randn(O, model.rep_size, device=objs.device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=objs.device)
+    times = []
+    for r in range(reps + 2):
+        flush.zero_()
+        torch.cuda._sleep(400000)          # let the host run ahead so the interval is the kernel, not the launch gap
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = ops.masks_to_layout_fwd(vecs, boxes, masks, o2i._sg_ranges, H, H, False, ops.NHWC_BF16, raw=True)
+        e1.record()
+        torch.cuda.synchronize()
+        if r >= 2:
+            times.append(e0.elapsed_time(e1))
+    ms = sorted(times)[len(times) // 2]
+    gbs = out.numel() * 2 / (ms * 1e-3) / 1e9
+    return {'launches': 1, 'ms': round(ms, 4), 'bound': 'hbm', 'bytes': out.numel() * 2, 'achieved_gbs': round(gbs, 1),
+            'peak_gbs': peak_hbm, 'frac': round(gbs / peak_hbm, 3)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -394,6 +426,9 @@ def main():
         fmt = lambda k, v: {'kernel': k[0], 'N,H,W,Cout,Cin,taps,phases': list(k[1]), 'launches': v['launches'],
                             'ms': round(v['ms'], 3), 'tflops': round(v['flops'] / (v['ms'] * 1e-3) / 1e12, 1)}
         kernels['top_shapes'] = [fmt(k, v) for k, v in shapes[:6]]
+        # the train step runs the channel-compacted (64-channel) variant of the scatter; the reference-shaped one
+        # (every vocabulary channel, layout.py:64-93 — the inference path) is timed on its own
+        kernels['layout_fwd_dense'] = time_dense_layout(tr.model, dev_batches[0], H, peak_hbm)
         try:
             os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
             json.dump([fmt(k, v) for k, v in shapes], open(os.path.join(ROOT, 'gpurun_out', 'bench_shapes.json'), 'w'), indent=0)

@@ -111,6 +111,8 @@ typedef struct {
   int w_img_rows;         /* 0: one weight tensor for all images.  > 0: per-image weights, w is
                              [x_N * w_img_rows][w_taps][w_C] and image i uses rows [i * w_img_rows, + w_Cout)
                              (channel-compacted layouts, see sg_pack_weight_cmap); needs Hout*Wout >= 128 */
+  int w_row0;             /* per-image weights only: first row (output channel) within an image's block, so that
+                             a restricted dgrad covers rows [w_row0, w_row0 + w_Cout); 0 otherwise */
 } sg_conv_desc_t;
 int sg_conv_tc(const sg_conv_desc_t* desc, sg_stream_t stream);
 

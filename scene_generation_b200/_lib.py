@@ -39,7 +39,7 @@ class ConvDesc(ctypes.Structure):
         ('nphases', c_int), ('phases', Phase * 4),
         ('ntaps', c_int), ('taps', Tap * SG_MAX_TAPS),
         ('bias', c_void_p), ('act', c_int), ('slope', c_float), ('stats', c_void_p),
-        ('w_img_rows', c_int),
+        ('w_img_rows', c_int), ('w_row0', c_int),
     ]
 
 

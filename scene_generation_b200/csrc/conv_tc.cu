@@ -90,7 +90,8 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
 struct ConvKParams {
   int Hout, Wout, tiles_w, tiles_h, BW, BH, BI, n_img;
   int kblocks, Cout, stages;
-  int w_img_rows;   // > 0: per-image weights, image i uses rows [i * w_img_rows, ...) of the weight tensor
+  int w_img_rows;   // > 0: per-image weights, image i uses rows [i * w_img_rows + w_row0, ...) of the weight tensor
+  int w_row0;
   int a_bytes;      // bytes of one A box = 128 * BW*BH*BI (rows beyond the box keep stale smem and are masked)
   int in_h0, in_w0;
   long long os_img, os_h, os_w, os_c;
@@ -144,7 +145,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, ti = mt / (p.tiles_w * p.tiles_h);
   const int w0 = tw * p.BW, h0 = th * p.BH, img0 = ti * p.BI;
   const int n0 = blockIdx.y * BN;
-  const int wrow0 = n0 + img0 * p.w_img_rows;        // weight-tensor row of this tile's first output channel
+  const int wrow0 = n0 + img0 * p.w_img_rows + p.w_row0;        // weight-tensor row of this tile's first output channel
   const sg_phase_t ph = p.phases[blockIdx.z];
   const int iters = ph.ntaps * p.kblocks;
 
@@ -573,6 +574,9 @@ extern "C" int sg_conv_tc(const sg_conv_desc_t* d, sg_stream_t stream) {
   SG_CHECK_ARG(d->w_img_rows >= 0, "sg_conv_tc: w_img_rows must be >= 0");
   SG_CHECK_ARG(d->w_img_rows == 0 || kp.BI == 1, "sg_conv_tc: per-image weights need tiles within one image (H*W >= 128)");
   kp.w_img_rows = d->w_img_rows;
+  SG_CHECK_ARG(d->w_row0 >= 0 && (d->w_img_rows == 0 ? d->w_row0 == 0 : d->w_row0 + d->w_Cout <= d->w_img_rows),
+               "sg_conv_tc: w_row0 / w_Cout outside the per-image weight rows");
+  kp.w_row0 = d->w_row0;
   kp.in_h0 = d->in_h0; kp.in_w0 = d->in_w0;
   kp.os_img = d->y_os_img; kp.os_h = d->y_os_h; kp.os_w = d->y_os_w; kp.os_c = d->y_os_c;
   kp.oh_mul = d->oh_mul; kp.ow_mul = d->ow_mul;

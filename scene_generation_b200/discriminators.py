@@ -99,7 +99,7 @@ def _patch_layers(input_nc, ndf, n_layers, norm_layer, kw, extra_in=0):
     return seq
 
 
-def _run_patch_d(layers, x_plain, cond=None, n_cls=0, need_dx=True, dx_channels=None):
+def _run_patch_d(layers, x_plain, cond=None, n_cls=0, need_dx=True, dx_channels=None, cmap=None):
     """One PatchGAN column.  layers: list of nn.Sequential ([conv, (IN), (LeakyReLU)]).  x_plain: bf16 NHWC.
     Returns the list of feature maps (logical NCHW views; the last one f32)."""
     feats = []
@@ -121,15 +121,17 @@ def _run_patch_d(layers, x_plain, cond=None, n_cls=0, need_dx=True, dx_channels=
             spec = dict(kind='s1', k=k, pad=pad)
         if first:
             spec.update(need_dx=need_dx, dx_channels=dx_channels)
+        cm = cmap if first else None          # channel-compacted input: per-image gathered weights in layer 0
         if last:
-            y = Fn.conv(op, conv.weight, conv.bias, ConvSpec(out='f32_nchw', **spec))
+            y = Fn.conv(op, conv.weight, conv.bias, ConvSpec(out='f32_nchw', **spec), cm)
             feats.append(y)
             break
         if has_norm:
-            y, st = Fn.conv(op, conv.weight, conv.bias, ConvSpec(stats=True, **spec))
+            y, st = Fn.conv(op, conv.weight, conv.bias, ConvSpec(stats=True, **spec), cm)
             x = Fn.nap(y, st, spec=NapSpec(norm='in', act=_lib.ACT_LEAKY, slope=0.2)).squeeze(1)
         else:
-            x = Fn.conv(op, conv.weight, conv.bias, ConvSpec(act=_lib.ACT_LEAKY if has_act else _lib.ACT_NONE, slope=0.2, **spec))
+            x = Fn.conv(op, conv.weight, conv.bias,
+                        ConvSpec(act=_lib.ACT_LEAKY if has_act else _lib.ACT_NONE, slope=0.2, **spec), cm)
         feats.append(Fn.FeatureViewFn.apply(x))
     return feats
 
@@ -173,11 +175,11 @@ class MultiscaleDiscriminator(nn.Module):
         self.downsample = nn.AvgPool2d(3, stride=2, padding=[1, 1], count_include_pad=False)
         channels_last_(self)
 
-    def _columns(self, x_plain, need_dx, dx_channels):
+    def _columns(self, x_plain, need_dx, dx_channels, cmap=None):
         result, cur = [], x_plain
         for i in range(self.num_D):
             layers = [getattr(self, 'scale' + str(self.num_D - 1 - i) + '_layer' + str(j)) for j in range(self.n_layers + 2)]
-            result.append(_run_patch_d(layers, cur, need_dx=need_dx, dx_channels=dx_channels))
+            result.append(_run_patch_d(layers, cur, need_dx=need_dx, dx_channels=dx_channels, cmap=cmap))
             if i != self.num_D - 1:
                 cur = Fn.AvgPoolFn.apply(cur)
         return result
@@ -191,11 +193,13 @@ class MultiscaleDiscriminator(nn.Module):
         constant, exactly like every gradient-carrying call site of the reference (trainer.py:249-250,
         309-319 pass detached layouts); img: f32 (N,3,H,W)."""
         raw = getattr(layout, '_sg_nhwc', None)
-        D = layout.shape[1]
+        cmap = getattr(layout, '_sg_cmap', None)      # channel-compacted layout: D = slots + appearance channels,
+        D = layout.shape[1]                           # cmap already maps channels [D, D+3) to the image inputs
         if raw is None or raw.shape[3] < D + img.shape[1]:
+            assert cmap is None
             return self.forward(torch.cat((layout.float(), img), dim=1))
         x = Fn.ImageSlotFn.apply(raw.detach(), img, D)
-        return self._columns(x, img.requires_grad, (D, D + img.shape[1]))
+        return self._columns(x, img.requires_grad, (D, D + img.shape[1]), cmap)
 
 
 class MultiscaleMaskDiscriminator(nn.Module):

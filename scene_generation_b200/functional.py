@@ -470,9 +470,9 @@ class LayoutFn(torch.autograd.Function):
     the reference's (N,D,H,W) f32 tensor."""
 
     @staticmethod
-    def forward(ctx, vecs, boxes, masks, ranges, H, W, align_corners, nhwc_bf16):
+    def forward(ctx, vecs, boxes, masks, ranges, H, W, align_corners, nhwc_bf16, Cp=None):
         fmt = ops.NHWC_BF16 if nhwc_bf16 else ops.NCHW_F32
-        out = ops.masks_to_layout_fwd(vecs, boxes, masks, ranges, H, W, align_corners, fmt, raw=True)
+        out = ops.masks_to_layout_fwd(vecs, boxes, masks, ranges, H, W, align_corners, fmt, raw=True, Cp=Cp)
         ctx.save_for_backward(vecs, boxes, masks, ranges)
         ctx.cfg = (H, W, align_corners)
         return out
@@ -483,7 +483,7 @@ class LayoutFn(torch.autograd.Function):
         H, W, ac = ctx.cfg
         need_dm = ctx.needs_input_grad[2] and masks.is_floating_point()
         dv, dm = ops.masks_to_layout_bwd(vecs, boxes, masks, ranges, H, W, g.contiguous(), ac, need_dmasks=need_dm)
-        return dv, None, dm, None, None, None, None, None
+        return dv, None, dm, None, None, None, None, None, None
 
 
 class CropFn(torch.autograd.Function):

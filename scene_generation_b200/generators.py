@@ -140,7 +140,8 @@ class GlobalGenerator(nn.Module):
         # Model tags the layout with the channel range that carries a gradient (the appearance part; the
         # one-hot class channels are constants, model.py:165-168): the first conv's dgrad is restricted to it
         y, st = Fn.conv(op, m[1].weight, m[1].bias,
-                        ConvSpec('s1', 7, 0, stats=True, dx_channels=getattr(input, '_sg_grad_channels', None)))
+                        ConvSpec('s1', 7, 0, stats=True, dx_channels=getattr(input, '_sg_grad_channels', None)),
+                        getattr(input, '_sg_cmap', None))      # channel-compacted layout: per-image gathered weights
         i = 4
         for d in range(self.n_downsampling):
             hw = tuple(y.shape[1:3])

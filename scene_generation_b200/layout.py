@@ -4,6 +4,8 @@ import torch
 from . import functional as Fn
 from . import ops, synthetic
 
+COMPACT_CC = 64     # channels of a channel-compacted layout (one 64-wide K block of the tensor-core convolutions)
+
 
 def _ranges(obj_to_img, N=None):
     """Per-image object ranges, computed once on the host (replaces the per-object .item() loop of
@@ -15,9 +17,13 @@ def _ranges(obj_to_img, N=None):
 
 
 def masks_to_layout(vecs, boxes, masks, obj_to_img, H, W=None, pooling='sum', test_mode=False, align_corners=False,
-                    nhwc_bf16=False, N=None):
+                    nhwc_bf16=False, N=None, cmap=None):
     """layout.py:64-93.  Returns (N,D,H,W); with nhwc_bf16 the result is a bf16 view of a channels-last
-    buffer (N,H,W,Cp) which is also attached as ``._sg_nhwc`` for the conv operands."""
+    buffer (N,H,W,Cp) which is also attached as ``._sg_nhwc`` for the conv operands.
+
+    cmap (int32 (N, COMPACT_CC), nhwc_bf16 only): ``vecs`` are channel-compacted layout vectors (class slots of
+    the image instead of the vocabulary, see Model._compact_plan); the result then has D = vecs.shape[1]
+    compact channels, carries the map as ``._sg_cmap`` and is expanded by expand_layout()."""
     if pooling != 'sum':
         raise NotImplementedError('only pooling="sum" is used by the model')
     W = H if W is None else W
@@ -28,12 +34,31 @@ def masks_to_layout(vecs, boxes, masks, obj_to_img, H, W=None, pooling='sum', te
             fmt = ops.NHWC_BF16 if nhwc_bf16 else ops.NCHW_F32
             raw = ops.masks_to_layout_fwd(vecs, boxes, masks, ranges, H, W, align_corners, fmt, test_mode=True, raw=True)
     else:
-        raw = Fn.LayoutFn.apply(vecs, boxes, masks, ranges, H, W, align_corners, nhwc_bf16)
+        raw = Fn.LayoutFn.apply(vecs, boxes, masks, ranges, H, W, align_corners, nhwc_bf16,
+                                COMPACT_CC if cmap is not None else None)
     if not nhwc_bf16:
         return raw
     out = raw.permute(0, 3, 1, 2)[:, :D]
     out._sg_nhwc = raw
+    if cmap is not None:
+        assert not test_mode and cmap.shape == (raw.shape[0], COMPACT_CC)
+        out._sg_cmap = cmap
     return out
+
+
+def expand_layout(layout, num_channels):
+    """Dense (N, num_channels, H, W) f32 tensor of a channel-compacted layout (the tensor the reference's
+    masks_to_layout returns); dense layouts pass through."""
+    cmap = getattr(layout, '_sg_cmap', None)
+    if cmap is None:
+        return layout
+    N, Dc, H, W = layout.shape
+    idx = cmap[:, :Dc].long()
+    ok = (idx >= 0) & (idx < num_channels)
+    dense = torch.zeros((N, num_channels + 1, H, W), dtype=torch.float32, device=layout.device)
+    tgt = torch.where(ok, idx, torch.full_like(idx, num_channels))          # unused slots land in a scratch channel
+    dense.scatter_add_(1, tgt.view(N, Dc, 1, 1).expand(N, Dc, H, W), layout.float())
+    return dense[:, :num_channels]
 
 
 def boxes_to_layout(*args, **kwargs):

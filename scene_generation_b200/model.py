@@ -1,5 +1,7 @@
 """Scene-graph -> image model (mirror of scene_generation/model.py: same constructor, same forward
 signature and return tuple, same state_dict keys; all tensor math on libsg_b200 kernels)."""
+import os
+
 import torch
 import torch.nn as nn
 
@@ -7,7 +9,7 @@ from .bilinear import crop_bbox_batch
 from .generators import AppearanceEncoder, define_G, mask_net
 from .graph import GraphIndex, GraphTripleConv, GraphTripleConvNet
 from .layers import build_mlp
-from .layout import masks_to_layout
+from .layout import COMPACT_CC, masks_to_layout
 from .utils import VectorPool
 
 
@@ -57,6 +59,11 @@ class Model(nn.Module):
                                                normalization=appearance_normalization, activation=activation,
                                                padding='valid', vecs_size=self.g_mask_dim)
         self.layout_to_image = define_G(self.num_objs + rep_size, 3, 64, n_downsample_global, 9, 'instance')
+        # Channel-compacted layouts (csrc/compact.cu): Cc = 64 channels per image = S class slots + the
+        # appearance vector + 3 spare channels for the discriminator's image slot.
+        self.rep_size = rep_size
+        self.compact_slots = (COMPACT_CC - 3 - rep_size) // 8 * 8
+        self.compact_layout = os.environ.get('SG_LAYOUT_COMPACT', '1') != '0'
 
     def forward(self, gt_imgs, objs, triples, obj_to_img, boxes_gt=None, masks_gt=None, attributes=None,
                 test_mode=False, use_gt_box=False, features=None):
@@ -64,13 +71,15 @@ class Model(nn.Module):
         ops.refresh_stream()
         O = objs.size(0)
         obj_vecs, pred_vecs = self.scene_graph_to_vectors(objs, triples, attributes)
+        N = gt_imgs.size(0) if gt_imgs is not None else None
+        plan = None if test_mode else self._compact_plan(objs, N)
         box_vecs, mask_vecs, scene_layout_vecs, wrong_layout_vecs = \
-            self.create_components_vecs(gt_imgs, boxes_gt, obj_to_img, objs, obj_vecs, features)
+            self.create_components_vecs(gt_imgs, boxes_gt, obj_to_img, objs, obj_vecs, features, plan)
         boxes_pred = self.box_net(box_vecs)
         masks_pred = self.mask_net(mask_vecs, fused_sigmoid=True).squeeze(1)        # model.py:106-107
         H, W = self.image_size
-        N = gt_imgs.size(0) if gt_imgs is not None else None
-        lay = dict(align_corners=self.align_corners, nhwc_bf16=self.layout_dtype == 'bf16', N=N)
+        lay = dict(align_corners=self.align_corners, nhwc_bf16=self.layout_dtype == 'bf16', N=N,
+                   cmap=None if plan is None else plan[1])
         if test_mode:
             boxes = boxes_gt if use_gt_box else boxes_pred
             masks = masks_gt if masks_gt is not None else masks_pred
@@ -79,7 +88,8 @@ class Model(nn.Module):
         gt_layout = masks_to_layout(scene_layout_vecs, boxes_gt, masks_gt, obj_to_img, H, W, **lay)
         if self.layout_dtype == 'bf16':
             # only the appearance channels of layout_vecs carry a gradient (one_hot_obj is a constant)
-            gt_layout._sg_grad_channels = (self.num_objs, scene_layout_vecs.shape[1])
+            c0 = self.num_objs if plan is None else self.compact_slots
+            gt_layout._sg_grad_channels = (c0, scene_layout_vecs.shape[1])
         pred_layout = masks_to_layout(scene_layout_vecs, boxes_gt, masks_pred, obj_to_img, H, W, **lay)
         wrong_layout = masks_to_layout(wrong_layout_vecs, boxes_gt, masks_gt, obj_to_img, H, W, **lay)
         imgs_pred = self.layout_to_image(gt_layout)
@@ -105,8 +115,29 @@ class Model(nn.Module):
                 obj_vecs, pred_vecs = self.gconv_net(obj_vecs, pred_vecs, edges, index)
         return obj_vecs, pred_vecs
 
-    def create_components_vecs(self, imgs, boxes, obj_to_img, objs, obj_vecs, features):
-        """model.py:145-172."""
+    def _compact_plan(self, objs, N):
+        """(obj_slot (O,) int64, cmap (N, 64) int32) of the channel-compacted layouts, from the class-slot
+        table the loader attached to ``objs`` (synthetic.HostMeta); None -> dense layouts."""
+        meta = getattr(objs, '_sg_compact', None)
+        S = self.compact_slots
+        if meta is None or not self.compact_layout or self.layout_dtype != 'bf16' or S < 8 or N is None \
+                or min(self.image_size) < 64:
+            return None
+        obj_slot, slot_cls, used = meta
+        if used > S or slot_cls.shape[0] != N:
+            return None
+        tail = getattr(self, '_cmap_tail', None)
+        if tail is None or tail.device != slot_cls.device:
+            D, A = self.num_objs + self.rep_size, self.rep_size
+            t = [self.num_objs + a for a in range(A)] + [D, D + 1, D + 2]      # appearance, then the image slot
+            t += [-1] * (COMPACT_CC - S - len(t))
+            tail = self._cmap_tail = torch.tensor(t, dtype=torch.int32, device=slot_cls.device)
+        cmap = torch.cat([slot_cls[:, :S], tail.unsqueeze(0).expand(N, -1)], dim=1).contiguous()
+        return obj_slot, cmap
+
+    def create_components_vecs(self, imgs, boxes, obj_to_img, objs, obj_vecs, features, plan=None):
+        """model.py:145-172.  With a compact plan the one-hot part of the layout vectors indexes the image's
+        class slots instead of the vocabulary."""
         O = objs.size(0)
         layout_noise = torch.randn((1, self.mask_noise_dim), dtype=obj_vecs.dtype, device=obj_vecs.device).repeat((O, 1))
         mask_vecs = torch.cat([obj_vecs, layout_noise], dim=1)
@@ -119,8 +150,12 @@ class Model(nn.Module):
             if rows:
                 obj_repr = obj_repr.clone()
                 obj_repr[rows] = torch.stack([features[i].to(obj_repr) for i in rows])
-        one_hot_obj = torch.zeros((O, self.num_objs), dtype=obj_repr.dtype, device=obj_repr.device)
-        one_hot_obj = one_hot_obj.scatter_(1, objs.view(-1, 1).long(), 1.0)
+        if plan is None:
+            one_hot_obj = torch.zeros((O, self.num_objs), dtype=obj_repr.dtype, device=obj_repr.device)
+            one_hot_obj = one_hot_obj.scatter_(1, objs.view(-1, 1).long(), 1.0)
+        else:
+            one_hot_obj = torch.zeros((O, self.compact_slots), dtype=obj_repr.dtype, device=obj_repr.device)
+            one_hot_obj = one_hot_obj.scatter_(1, plan[0].view(-1, 1), 1.0)
         layout_vecs = torch.cat([one_hot_obj, obj_repr], dim=1)
         wrong_objs_rep = self.fake_pool.query(objs, obj_repr)
         wrong_layout_vecs = torch.cat([one_hot_obj, wrong_objs_rep], dim=1)

@@ -53,7 +53,7 @@ _MASK_DT = {torch.float32: 0, torch.int64: 1, torch.uint8: 2}
 # layout
 # ---------------------------------------------------------------------------------------------
 def masks_to_layout_fwd(vecs, boxes, masks, ranges, H, W, align_corners=False, out_format=NCHW_F32, test_mode=False,
-                        raw=False):
+                        raw=False, Cp=None):
     """ranges: int32 (N,2) device tensor.  Returns (N,D,H,W) f32, or a (N,D,H,W) *view* of a
     channels-last bf16 buffer with Cp = round_up(D, 8) physical channels."""
     _need_cuda(vecs, boxes, masks, ranges)
@@ -61,7 +61,8 @@ def masks_to_layout_fwd(vecs, boxes, masks, ranges, H, W, align_corners=False, o
     M = masks.shape[1]
     N = ranges.shape[0]
     vecs, boxes, masks = vecs.contiguous().float(), boxes.contiguous().float(), masks.contiguous()
-    Cp = round_up(D, 8)
+    Cp = Cp or round_up(D, 8)
+    assert Cp >= D and Cp % 8 == 0
     if out_format == NHWC_BF16:
         buf = torch.empty((N, H, W, Cp), dtype=torch.bfloat16, device=vecs.device)
     else:
@@ -215,10 +216,11 @@ def conv_tc(x5, w3, y, y_strides, Hout, Wout, taps, phases=None, oh_mul=1, ow_mu
             assert w3.shape[0] == x5.shape[0]
             _, d.w_img_rows, d.w_taps, d.w_C = w3.shape
             r0, r1 = w_rows or (0, w3.shape[1])
-            d.w_Cout = r1 - r0
+            d.w_Cout, d.w_row0 = r1 - r0, r0
         else:
+            assert w_rows is None
             d.w_Cout, d.w_taps, d.w_C = w3.shape
-            d.w_img_rows = 0
+            d.w_img_rows = d.w_row0 = 0
         d.y_dtype = BF16 if y.dtype == torch.bfloat16 else F32
         d.y_os_img, d.y_os_h, d.y_os_w = y_strides[:3]
         d.y_os_c = y_strides[3] if len(y_strides) > 3 else 1
@@ -235,8 +237,6 @@ def conv_tc(x5, w3, y, y_strides, Hout, Wout, taps, phases=None, oh_mul=1, ow_mu
         _desc_cache[key] = ent
     d = ent[0]
     d.x, d.w, d.y = x5.data_ptr(), w3.data_ptr(), y.data_ptr()
-    if w_rows is not None:
-        d.w += w_rows[0] * w3.shape[-2] * w3.shape[-1] * 2
     d.bias = None if bias is None else bias.data_ptr()
     d.stats = None if stats is None else stats.data_ptr()
     _lib.call('sg_conv_tc', ent[3], _stream())

@@ -107,6 +107,30 @@ def image_ranges(obj_to_img, n_imgs=None):
     return np.stack([starts, ends], axis=1).astype(np.int32)
 
 
+MAX_CLASS_SLOTS = 32
+
+
+def class_slots(objs, obj_to_img, n_imgs):
+    """Per-image class slots for channel-compacted layouts (csrc/compact.cu): the distinct classes of an image
+    in order of first appearance.  Returns (obj_slot int64 (O,), slot_cls int32 (N, MAX_CLASS_SLOTS) padded
+    with -1, the largest number of slots any image uses).  An image with more than MAX_CLASS_SLOTS classes
+    reports its true count (the model then falls back to dense layouts) and its overflow objects get slot 0."""
+    tables = [dict() for _ in range(n_imgs)]
+    obj_slot = []
+    for c, n in zip(objs, obj_to_img):
+        t = tables[n]
+        if c not in t:
+            t[c] = len(t)
+        obj_slot.append(t[c] if t[c] < MAX_CLASS_SLOTS else 0)
+    slot_cls = np.full((n_imgs, MAX_CLASS_SLOTS), -1, dtype=np.int32)
+    for n, t in enumerate(tables):
+        for c, k in t.items():
+            if k < MAX_CLASS_SLOTS:
+                slot_cls[n, k] = c
+    used = max((len(t) for t in tables), default=0)
+    return torch.tensor(obj_slot, dtype=torch.int64), torch.from_numpy(slot_cls), used
+
+
 class HostMeta:
     """Host-side index structures of one collated batch, computed from the CPU tensors the loader already
     holds (object ranges per image, CSR of triple incidences per object, the class list).  attach() tags the
@@ -121,11 +145,13 @@ class HostMeta:
         ptr, src = ops.build_incidence_csr(triples[:, [0, 2]].numpy(), objs.numel())
         self.seg_ptr, self.seg_src = torch.from_numpy(ptr), torch.from_numpy(src)
         self.objs = objs.tolist()
+        self.obj_slot, self.slot_cls, self.slots_used = class_slots(self.objs, obj_to_img.tolist(), self.n_imgs)
         if torch.cuda.is_available():
-            self.ranges, self.seg_ptr, self.seg_src = (t.pin_memory() for t in (self.ranges, self.seg_ptr, self.seg_src))
+            self.ranges, self.seg_ptr, self.seg_src, self.obj_slot, self.slot_cls = (
+                t.pin_memory() for t in (self.ranges, self.seg_ptr, self.seg_src, self.obj_slot, self.slot_cls))
 
     def nbytes(self):
-        return sum(t.numel() * t.element_size() for t in (self.ranges, self.seg_ptr, self.seg_src))
+        return sum(t.numel() * t.element_size() for t in (self.ranges, self.seg_ptr, self.seg_src, self.obj_slot, self.slot_cls))
 
     def attach(self, batch_dev):
         imgs, objs, boxes, masks, triples, obj_to_img, triple_to_img, attributes = batch_dev
@@ -133,4 +159,5 @@ class HostMeta:
         obj_to_img._sg_ranges = self.ranges.to(dev, non_blocking=True)
         triples._sg_csr = (self.seg_ptr.to(dev, non_blocking=True), self.seg_src.to(dev, non_blocking=True))
         objs._sg_host = self.objs
+        objs._sg_compact = (self.obj_slot.to(dev, non_blocking=True), self.slot_cls.to(dev, non_blocking=True), self.slots_used)
         return batch_dev

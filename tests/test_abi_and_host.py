@@ -200,4 +200,34 @@ def test_host_meta_matches_device_free_derivation():
     assert torch.equal(m.ranges, torch.from_numpy(synthetic.image_ranges(b[5])))
     ptr, src = ops.build_incidence_csr(b[4][:, [0, 2]].numpy(), b[1].numel())
     assert m.seg_ptr.tolist() == ptr.tolist() and m.seg_src.tolist() == src.tolist() and m.objs == b[1].tolist()
-    assert m.nbytes() == 4 * (m.ranges.numel() + m.seg_ptr.numel() + m.seg_src.numel())
+    assert m.nbytes() == 4 * (m.ranges.numel() + m.seg_ptr.numel() + m.seg_src.numel() + m.slot_cls.numel()) + 8 * m.obj_slot.numel()
+    # class slots of the channel-compacted layouts: slot_cls[img, obj_slot[o]] is the object's class
+    o2i, objs = b[5].tolist(), b[1].tolist()
+    for o, (n, c) in enumerate(zip(o2i, objs)):
+        assert int(m.slot_cls[n, int(m.obj_slot[o])]) == c
+    for n in range(4):
+        row = [c for c in m.slot_cls[n].tolist() if c >= 0]
+        assert sorted(row) == sorted(set(objs[o] for o in range(len(objs)) if o2i[o] == n))
+    assert m.slots_used == max(len(set(objs[o] for o in range(len(objs)) if o2i[o] == n)) for n in range(4))
+
+
+def test_class_slots_overflow_and_expand_layout_cpu():
+    """More classes than slots -> slots_used reports it (the model then keeps dense layouts); expand_layout
+    scatters compact channels back to the vocabulary."""
+    from scene_generation_b200 import layout as L
+    objs = list(range(40)) + [3, 3]
+    o2i = [0] * 40 + [1, 1]
+    slot, table, used = synthetic.class_slots(objs, o2i, 2)
+    assert used == 40 and table.shape == (2, synthetic.MAX_CLASS_SLOTS) and int(slot.max()) < synthetic.MAX_CLASS_SLOTS
+    assert table[1].tolist()[:2] == [3, -1] and slot[-2:].tolist() == [0, 0]
+    cmap = torch.full((1, 64), -1, dtype=torch.int32)
+    cmap[0, :2] = torch.tensor([4, 1], dtype=torch.int32)
+    cmap[0, 24:27] = torch.tensor([6, 7, 8], dtype=torch.int32)
+    lay = torch.zeros(1, 27, 2, 2)
+    lay[0, 0], lay[0, 1], lay[0, 24:27] = 1.0, 2.0, 3.0
+    lay._sg_cmap = cmap
+    dense = L.expand_layout(lay, 9)
+    assert dense.shape == (1, 9, 2, 2)
+    assert dense[0, :, 0, 0].tolist() == [0, 2, 0, 0, 1, 0, 3, 3, 3]
+    plain = torch.ones(1, 9, 2, 2)
+    assert L.expand_layout(plain, 9) is plain
