@@ -171,10 +171,9 @@ __global__ void __launch_bounds__(THREADS) layout_fwd_kernel(LayoutArgs a, void*
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward, NHWC bf16, bandwidth-oriented variant.  Per 64-pixel tile only the objects whose (slightly
-// dilated) box intersects the tile are sampled and accumulated — typically 2-3 of the image's 4-9 —
-// the compacted list keeps the reference's object order (deterministic summation), every thread owns
-// one (pixel, 8-channel) item at a time (8 accumulators, high occupancy) and writes one 16-byte store.
+// forward, NHWC bf16, bandwidth-oriented variant.  Per 128-pixel tile only the objects whose (slightly
+// dilated) box intersects the tile are sampled and accumulated — typically 2-4 of the image's 4-9 —
+// and the compacted list keeps the reference's object order (deterministic summation).
 // ------------------------------------------------------------------------------------------------
 constexpr int MAXA = 16;      // active objects per pass
 
@@ -195,38 +194,51 @@ __device__ __forceinline__ bool box_touches_tile(const LayoutArgs& a, const floa
   return !((float)w_hi < wl || (float)w_lo > wh || (float)h_hi < hl || (float)h_lo > hu);
 }
 
-__global__ void __launch_bounds__(THREADS) layout_fwd_nhwc_kernel(LayoutArgs a, __nv_bfloat16* __restrict__ out) {
-  extern __shared__ float smem[];
-  float* sS = smem;                       // [MAXA][TP]
-  float* sV = smem + MAXA * TP;           // [MAXA][Cp]
+constexpr int TPX = 128;     // pixels per tile of the NHWC kernel: TPX * Cp * 2 contiguous output bytes
+
+// Tile kernel.  The output tile of TPX consecutive pixels is one contiguous run of TPX * Cp * 2 bytes in
+// the NHWC tensor: it is composed in shared memory and leaves with a single bulk (TMA) store, so the
+// FMA phase issues no global stores and no per-pixel address arithmetic.  A layout vector is
+// cat(one_hot(class), appearance) (model.py:165-168): per object only ~5 of the Cp/8 eight-channel chunks
+// are non-zero.  The tile is zero-filled once and only the UNION of non-zero chunks of the active objects
+// is accumulated, one (pixel, chunk) item per thread, objects in the reference's order.
+__global__ void __launch_bounds__(THREADS) layout_fwd_tile_kernel(LayoutArgs a, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(smem_raw);                   // [TPX][Cp]
+  float* sS = reinterpret_cast<float*>(smem_raw + (size_t)TPX * a.Cp * 2);            // [MAXA][TPX]
+  float* sV = sS + MAXA * TPX;                                                        // [MAXA][Cp]
   __shared__ int sAct[MAXA];
   __shared__ unsigned sNz[MAXA];
   __shared__ SgBilin sAy[MAXA * 2];
-  __shared__ int sNact, sNext;
+  __shared__ int sNact, sNext, sNuni;
+  __shared__ int sUni[32];
+  __shared__ unsigned sUmask[32];
   const int n = blockIdx.y;
-  const int p0 = blockIdx.x * TP;
+  const int p0 = blockIdx.x * TPX;
   const int HW = a.H * a.W;
-  const int p1 = min(p0 + TP, HW) - 1;
+  const int npx = min(TPX, HW - p0);
+  const int p1 = p0 + npx - 1;
   const int o_begin = a.ranges[2 * n], o_end = a.ranges[2 * n + 1];
   const int chunks = a.Cp / 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h_lo = p0 / a.W;
   int scan = o_begin;        // next object to test
   bool first_pass = true;
   for (;;) {
-    // ---- warp 0 compacts the next <= MAXA active objects in object order --------------------------
-    __syncthreads();
-    if (threadIdx.x < 32) {
+    __syncthreads();         // the previous pass has consumed sAct / sS / sV
+    if (warp == 0) {
+      // ---- warp 0 compacts the next <= MAXA objects whose (dilated) box touches the tile, in object order ----
       int nact = 0, pos = scan;
       while (pos < o_end && nact < MAXA) {
-        int o = pos + threadIdx.x;
+        int o = pos + lane;
         bool act = (o < o_end) && box_touches_tile(a, a.boxes + 4 * o, p0, p1);
         unsigned m = __ballot_sync(0xffffffffu, act);
-        int before = __popc(m & ((1u << threadIdx.x) - 1));
+        int before = __popc(m & ((1u << lane) - 1));
         int room = MAXA - nact;
         if (act && before < room) sAct[nact + before] = o;
         int total = __popc(m);
         if (total > room) {
-          // stop right after the last object that fitted
-          int last = -1, cnt = 0;
+          int last = -1, cnt = 0;          // stop right after the last object that fitted
           for (int b = 0; b < 32; ++b)
             if (m & (1u << b)) { if (cnt < room) last = b; ++cnt; }
           nact = MAXA;
@@ -236,35 +248,27 @@ __global__ void __launch_bounds__(THREADS) layout_fwd_nhwc_kernel(LayoutArgs a, 
         nact += total;
         pos += 32;
       }
-      if (threadIdx.x == 0) { sNact = nact; sNext = min(pos, o_end); }
+      if (lane == 0) { sNact = nact; sNext = min(pos, o_end); }
+    } else {
+      if (first_pass) {      // ---- meanwhile the other warps clear the tile ----
+        uint4* t4 = reinterpret_cast<uint4*>(tile);
+        const int n16 = npx * a.Cp / 8;
+        for (int i = threadIdx.x - 32; i < n16; i += THREADS - 32) t4[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      if (threadIdx.x - 32 < MAXA) sNz[threadIdx.x - 32] = 0u;
     }
     __syncthreads();
     const int nact = sNact;
     scan = sNext;
-    if (nact == 0 && !first_pass) break;
-    // ---- sample the active objects over the tile, stage their vectors ---------------------------------
-    const int h_lo = p0 / a.W;
-    if (threadIdx.x < nact * 2) {      // a 64-pixel tile touches at most two image rows (W >= 32)
+    if (nact == 0) break;
+    // ---- y-axis taps per (object, tile row) and the objects' vectors -------------------------------------
+    if (threadIdx.x < nact * 2) {
       const int k = threadIdx.x >> 1, r = threadIdx.x & 1;
       const float* bx = a.boxes + 4 * sAct[k];
       float y0 = bx[1], hh = __fsub_rn(bx[3], y0);
       float gy = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(sg_linspace01(min(h_lo + r, a.H - 1), a.H), y0), hh), 2.f), 1.f);
       sAy[k * 2 + r] = sg_axis(gy, a.M, a.align_corners);
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < nact * TP; i += THREADS) {
-      int k = i / TP, px = i - k * TP;
-      int p = p0 + px;
-      float s = 0.f;
-      if (p < HW) {
-        const int h = p / a.W, w = p - h * a.W;
-        if (h - h_lo < 2) s = sample_mask_x(a, sAct[k], w, a.boxes + 4 * sAct[k], sAy[k * 2 + (h - h_lo)]);
-        else s = sample_mask(a, sAct[k], h, w, a.boxes + 4 * sAct[k]);     // W < 32: more than two rows per tile
-      }
-      sS[i] = s;
-    }
-    if (threadIdx.x < MAXA) sNz[threadIdx.x] = 0u;
-    __syncthreads();
     for (int i = threadIdx.x; i < nact * a.Cp; i += THREADS) {
       int k = i / a.Cp, c = i - k * a.Cp;
       float v = (c < a.D) ? a.vecs[(long)sAct[k] * a.D + c] : 0.f;
@@ -272,46 +276,77 @@ __global__ void __launch_bounds__(THREADS) layout_fwd_nhwc_kernel(LayoutArgs a, 
       if (v != 0.f) atomicOr(&sNz[k], 1u << (c >> 3));     // which 8-channel chunks of this object are non-zero
     }
     __syncthreads();
-    // ---- thread (tx = 8-channel chunk, ty = pixel lane): no div/mod, one 416-byte contiguous row per warp ---------
-    // The class part of a layout vector is one-hot: per object only ~5 of the 26 chunks are non-zero, the rest
-    // of the (object, chunk) pairs is skipped through the bit mask.
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    if (tx < chunks) {
-      unsigned mine = 0u;            // objects of this pass whose chunk tx is non-zero (pixel invariant)
-      for (int k = 0; k < nact; ++k) mine |= ((sNz[k] >> tx) & 1u) << k;
-      for (int px = ty; px < TP; px += THREADS / 32) {
-        int p = p0 + px;
-        if (p >= HW) break;
-        __nv_bfloat16* dst = out + ((long)n * HW + p) * a.Cp + tx * 8;
-        float acc[8];
-        if (first_pass) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-        } else {   // > MAXA objects overlap this tile: continue from the stored partial sum
-          uint4 raw = *reinterpret_cast<const uint4*>(dst);
-          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h2[j]); acc[2 * j] = f.x; acc[2 * j + 1] = f.y; }
-        }
-        for (unsigned m = mine; m != 0u; m &= m - 1u) {
-          const int k = __ffs(m) - 1;
-          float s = sS[k * TP + px];
-          if (s == 0.f) continue;
-          const float4* v = reinterpret_cast<const float4*>(sV + k * a.Cp + tx * 8);
-          float4 v0 = v[0], v1 = v[1];
-          acc[0] = __fmaf_rn(v0.x, s, acc[0]); acc[1] = __fmaf_rn(v0.y, s, acc[1]);
-          acc[2] = __fmaf_rn(v0.z, s, acc[2]); acc[3] = __fmaf_rn(v0.w, s, acc[3]);
-          acc[4] = __fmaf_rn(v1.x, s, acc[4]); acc[5] = __fmaf_rn(v1.y, s, acc[5]);
-          acc[6] = __fmaf_rn(v1.z, s, acc[6]); acc[7] = __fmaf_rn(v1.w, s, acc[7]);
-        }
-        __align__(16) __nv_bfloat162 pk[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) pk[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
-        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(pk);
+    // ---- warp 0: union of non-zero chunks (+ per chunk the objects that have it); all: sample the masks -----
+    if (warp == 0) {
+      unsigned m = 0u;
+      if (lane < chunks)
+        for (int k = 0; k < nact; ++k) m |= ((sNz[k] >> lane) & 1u) << k;
+      unsigned b = __ballot_sync(0xffffffffu, m != 0u);
+      if (m != 0u) {
+        int pos = __popc(b & ((1u << lane) - 1));
+        sUni[pos] = lane;
+        sUmask[pos] = m;
       }
+      if (lane == 0) sNuni = __popc(b);
+    }
+    for (int i = threadIdx.x; i < nact * TPX; i += THREADS) {
+      const int k = i / TPX, px = i - k * TPX;
+      float s = 0.f;
+      if (px < npx) {
+        const int p = p0 + px;
+        const int h = p / a.W, w = p - h * a.W;
+        if (h - h_lo < 2) s = sample_mask_x(a, sAct[k], w, a.boxes + 4 * sAct[k], sAy[k * 2 + (h - h_lo)]);
+        else s = sample_mask(a, sAct[k], h, w, a.boxes + 4 * sAct[k]);     // narrow images: more than two rows per tile
+      }
+      sS[i] = s;
+    }
+    __syncthreads();
+    // ---- one (pixel, non-zero chunk) item per thread: lanes = consecutive pixels, the chunk is warp-uniform ----
+    const int nuni = sNuni;
+    for (int i = threadIdx.x; i < nuni * TPX; i += THREADS) {
+      const int ui = i / TPX, px = i - ui * TPX;
+      if (px >= npx) continue;
+      const int chunk = sUni[ui];
+      __nv_bfloat16* dst = tile + (size_t)px * a.Cp + chunk * 8;
+      float acc[8];
+      if (first_pass) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      } else {   // > MAXA objects overlap this tile: continue from the partial sum
+        uint4 raw = *reinterpret_cast<const uint4*>(dst);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h2[j]); acc[2 * j] = f.x; acc[2 * j + 1] = f.y; }
+      }
+      for (unsigned m = sUmask[ui]; m != 0u; m &= m - 1u) {
+        const int k = __ffs(m) - 1;
+        const float s = sS[k * TPX + px];
+        if (s == 0.f) continue;
+        const float4* v = reinterpret_cast<const float4*>(sV + k * a.Cp + chunk * 8);
+        const float4 v0 = v[0], v1 = v[1];
+        acc[0] = __fmaf_rn(v0.x, s, acc[0]); acc[1] = __fmaf_rn(v0.y, s, acc[1]);
+        acc[2] = __fmaf_rn(v0.z, s, acc[2]); acc[3] = __fmaf_rn(v0.w, s, acc[3]);
+        acc[4] = __fmaf_rn(v1.x, s, acc[4]); acc[5] = __fmaf_rn(v1.y, s, acc[5]);
+        acc[6] = __fmaf_rn(v1.z, s, acc[6]); acc[7] = __fmaf_rn(v1.w, s, acc[7]);
+      }
+      __align__(16) __nv_bfloat162 pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pk[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(pk);
     }
     first_pass = false;
     if (scan >= o_end) break;
+  }
+  // ---- the finished tile leaves in one bulk store -----------------------------------------------------------
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the async proxy
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long gdst = reinterpret_cast<unsigned long long>(out + ((size_t)n * HW + p0) * a.Cp);
+    const unsigned ssrc = (unsigned)__cvta_generic_to_shared(tile);
+    const unsigned bytes = (unsigned)npx * a.Cp * 2;
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must stay valid until it has been read
   }
 }
 
@@ -514,8 +549,15 @@ extern "C" int sg_masks_to_layout_fwd(const float* vecs, const float* boxes, con
   dim3 grid(sg_cdiv((long)H * W, TP), N);
   size_t smem = sizeof(float) * (MAXO * TP + MAXO * Cp);
   if (out_format == 1) {
-    size_t smem2 = sizeof(float) * (MAXA * TP + MAXA * Cp);
-    layout_fwd_nhwc_kernel<<<grid, THREADS, smem2, stream>>>(a, (__nv_bfloat16*)out);
+    SG_CHECK_ARG(((uintptr_t)out & 15) == 0, "masks_to_layout: NHWC output must be 16-byte aligned");
+    size_t smem2 = (size_t)TPX * Cp * 2 + sizeof(float) * (MAXA * TPX + MAXA * Cp);
+    static size_t smem_set = 0;
+    if (smem2 > smem_set) {
+      cudaFuncSetAttribute(layout_fwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+      smem_set = smem2;
+    }
+    dim3 grid2(sg_cdiv((long)H * W, TPX), N);
+    layout_fwd_tile_kernel<<<grid2, THREADS, smem2, stream>>>(a, (__nv_bfloat16*)out);
   } else {
     cudaFuncSetAttribute(layout_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     layout_fwd_kernel<false><<<grid, THREADS, smem, stream>>>(a, out);
