@@ -118,28 +118,53 @@ __global__ void norm_finalize_kernel(const float* __restrict__ stats, int mode, 
     shift[idx] = -mean * rstd;
     save_mean[idx] = mean;
     save_rstd[idx] = rstd;
-  } else {           // BatchNorm2d (train): statistics over all images
-    if (idx >= C) return;
-    float s = 0.f, ss = 0.f;
-    for (int n = 0; n < n_img; ++n) {
-      s += stats[2 * (n * C + idx)];
-      ss += stats[2 * (n * C + idx) + 1];
-    }
+  }
+}
+
+// BatchNorm2d (train): statistics over all images.  One block per channel: the per-image partial sums are
+// reduced across the block, then the (identical) per-image scale / shift rows are written in parallel.
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, int n_img, int C, float count, float eps,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* running_mean, float* running_var, float momentum,
+                                   float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ save_mean, float* __restrict__ save_rstd) {
+  __shared__ float red[2][32];
+  __shared__ float res[4];
+  const int c = blockIdx.x;
+  float s = 0.f, ss = 0.f;
+  for (int n = threadIdx.x; n < n_img; n += blockDim.x) {
+    s += stats[2 * ((long)n * C + c)];
+    ss += stats[2 * ((long)n * C + c) + 1];
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = ss; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s = ss = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { s += red[0][w]; ss += red[1][w]; }
     float tot = count * n_img;
     float mean = s / tot;
     float var = fmaxf(ss / tot - mean * mean, 0.f);
     float rstd = rsqrtf(var + eps);
-    float g = gamma ? gamma[idx] : 1.f, b = beta ? beta[idx] : 0.f;
+    float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
     if (running_mean) {
-      running_mean[idx] = (1.f - momentum) * running_mean[idx] + momentum * mean;
-      running_var[idx] = (1.f - momentum) * running_var[idx] + momentum * var * (tot / fmaxf(tot - 1.f, 1.f));
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * (tot / fmaxf(tot - 1.f, 1.f));
     }
-    for (int n = 0; n < n_img; ++n) {
-      scale[n * C + idx] = g * rstd;
-      shift[n * C + idx] = b - mean * g * rstd;
-      save_mean[n * C + idx] = mean;
-      save_rstd[n * C + idx] = rstd;
-    }
+    res[0] = g * rstd; res[1] = b - mean * g * rstd; res[2] = mean; res[3] = rstd;
+  }
+  __syncthreads();
+  const float sc = res[0], sh = res[1], mu = res[2], rs = res[3];
+  for (int n = threadIdx.x; n < n_img; n += blockDim.x) {
+    const long i = (long)n * C + c;
+    scale[i] = sc;
+    shift[i] = sh;
+    save_mean[i] = mu;
+    save_rstd[i] = rs;
   }
 }
 
@@ -165,21 +190,22 @@ __device__ __forceinline__ int src_coord(int hp, int pad, int pad_mode, int Hu) 
   return hu;
 }
 
+// grid.x = output row (n, plane, i), grid.y * blockDim.x covers the (j, channel-chunk) items of a row: the row
+// decomposition is block-uniform and the only per-thread division is by the chunk count
 __global__ void nap_fwd_kernel(NapArgs a, bf16* __restrict__ out) {
   const int nC = a.C / 8;
   const int Hu = a.H * a.up, Wu = a.W * a.up;
   const int Hp = Hu + 2 * a.pad, Wp = Wu + 2 * a.pad;
   const int Ho = a.planes ? (Hp + 1) / 2 : Hp, Wo = a.planes ? (Wp + 1) / 2 : Wp;
   const int P = a.planes ? 4 : 1;
-  long total = (long)a.N * P * Ho * Wo * nC;
-  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  int ch = idx % nC;
-  long r = idx / nC;
-  int j = r % Wo; r /= Wo;
-  int i = r % Ho; r /= Ho;
-  int pl = r % P;
-  int n = r / P;
+  const unsigned item = blockIdx.y * blockDim.x + threadIdx.x;
+  if (item >= (unsigned)(Wo * nC)) return;
+  const int j = item / (unsigned)nC, ch = item - j * nC;
+  const unsigned row = blockIdx.x;
+  const int i = row % (unsigned)Ho;
+  const unsigned rp = row / (unsigned)Ho;
+  const int pl = rp % (unsigned)P, n = rp / (unsigned)P;
+  const long idx = (long)row * (Wo * nC) + item;
   int hp = a.planes ? 2 * i + (pl >> 1) : i;
   int wp = a.planes ? 2 * j + (pl & 1) : j;
   float f[8];
@@ -343,17 +369,15 @@ __global__ void bn_total_kernel(float* sums, int N, int C) {
   sums[(long)N * C * 2 + t] = v;
 }
 
+// grid.x = source row (n, h), grid.y * blockDim.x covers its (w, channel-chunk) items
 __global__ void nap_bwd_apply_kernel(NapBwdArgs b) {
   const NapArgs& a = b.f;
   const int nC = a.C / 8;
-  long total = (long)a.N * a.H * a.W * nC;
-  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  int ch = idx % nC;
-  long r = idx / nC;
-  int w = r % a.W; r /= a.W;
-  int h = r % a.H;
-  int n = r / a.H;
+  const unsigned item = blockIdx.y * blockDim.x + threadIdx.x;
+  if (item >= (unsigned)(a.W * nC)) return;
+  const int w = item / (unsigned)nC, ch = item - w * nC;
+  const int h = blockIdx.x % (unsigned)a.H, n = blockIdx.x / (unsigned)a.H;
+  const long idx = (long)blockIdx.x * (a.W * nC) + item;
   float gp[8], xh[8];
   if (b.dres) {
     float fg[8];
@@ -603,9 +627,14 @@ extern "C" int sg_norm_finalize(const float* stats, int mode, int n_img, int C, 
                                 float* shift, float* save_mean, float* save_rstd, sg_stream_t stream) {
   SG_CHECK_ARG(stats && scale && shift && save_mean && save_rstd, "norm_finalize: null pointer");
   SG_CHECK_ARG((mode == 0 || mode == 1) && n_img > 0 && C > 0 && count > 0, "norm_finalize: bad arguments");
-  int total = mode == 0 ? n_img * C : C;
-  LAUNCH_1D(norm_finalize_kernel, total, stream, stats, mode, n_img, C, count, eps, gamma, beta, running_mean, running_var,
-            momentum, scale, shift, save_mean, save_rstd);
+  if (mode == 0) {
+    LAUNCH_1D(norm_finalize_kernel, n_img * C, stream, stats, mode, n_img, C, count, eps, gamma, beta, running_mean, running_var,
+              momentum, scale, shift, save_mean, save_rstd);
+  } else {
+    const int threads = n_img >= 128 ? 128 : (n_img > 32 ? 64 : 32);
+    bn_finalize_kernel<<<C, threads, 0, stream>>>(stats, n_img, C, count, eps, gamma, beta, running_mean, running_var, momentum,
+                                                  scale, shift, save_mean, save_rstd);
+  }
   SG_CHECK_LAUNCH("sg_norm_finalize");
   return SG_OK;
 }
@@ -634,8 +663,12 @@ extern "C" int sg_norm_act_pad_fwd(const sg_nap_desc_t* d, void* out, sg_stream_
   NapArgs a = nap_args(d);
   const int Hp = d->H * d->up + 2 * d->pad, Wp = d->W * d->up + 2 * d->pad;
   const long per_img = d->planes ? 4L * ((Hp + 1) / 2) * ((Wp + 1) / 2) : (long)Hp * Wp;
-  long total = (long)d->N * per_img * (d->C / 8);
-  LAUNCH_1D(nap_fwd_kernel, total, stream, a, (bf16*)out);
+  const long rows = d->N * (d->planes ? 4L * ((Hp + 1) / 2) : (long)Hp);
+  const int row_items = (d->planes ? (Wp + 1) / 2 : Wp) * (d->C / 8);
+  (void)per_img;
+  SG_CHECK_ARG(rows < (1L << 31), "norm_act_pad_fwd: too many rows");
+  const int threads = row_items >= 256 ? 256 : ((row_items + 31) / 32) * 32;
+  nap_fwd_kernel<<<dim3((unsigned)rows, sg_cdiv(row_items, threads)), threads, 0, stream>>>(a, (bf16*)out);
   SG_CHECK_LAUNCH("sg_norm_act_pad_fwd");
   return SG_OK;
 }
@@ -669,13 +702,16 @@ extern "C" int sg_norm_act_pad_bwd(const sg_nap_desc_t* d, const void* grad, con
       SG_CHECK_LAUNCH("sg_norm_act_pad_bwd(bn totals)");
     }
   }
-  long total = (long)d->N * d->H * d->W * nC;
   if (out_planes) {
     // odd sizes leave unwritten slots in the parity planes: zero them first
     if ((d->H & 1) || (d->W & 1))
       cudaMemsetAsync(dsrc, 0, sizeof(bf16) * 4 * (size_t)d->N * ((d->H + 1) / 2) * ((d->W + 1) / 2) * d->C, stream);
   }
-  LAUNCH_1D(nap_bwd_apply_kernel, total, stream, b);
+  {
+    const int row_items = d->W * nC;
+    const int threads = row_items >= 256 ? 256 : ((row_items + 31) / 32) * 32;
+    nap_bwd_apply_kernel<<<dim3((unsigned)(d->N * d->H), sg_cdiv(row_items, threads)), threads, 0, stream>>>(b);
+  }
   SG_CHECK_LAUNCH("sg_norm_act_pad_bwd(apply)");
   return SG_OK;
 }

@@ -85,6 +85,45 @@ def clear_weight_cache():
     _pack_cache.clear()
 
 
+class ZeroArena:
+    """f32 scratch that reads as zero when handed out.  The conv epilogue statistics, bias gradients and similar
+    accumulators of one training step (several hundred small buffers) come from here: Trainer.train_step calls
+    begin_step(), which clears what the previous step used with ONE fill instead of one fill kernel per buffer.
+    Buffers are only valid until the next begin_step(); outside a training step (or when the arena is full)
+    zeros() falls back to torch.zeros."""
+
+    def __init__(self, nbytes=48 << 20):
+        self.capacity = nbytes // 4
+        self.buf = None
+        self.off = 0
+        self.active = False
+
+    def begin_step(self, device):
+        if self.buf is None or self.buf.device != device:
+            self.buf = torch.zeros(self.capacity, dtype=torch.float32, device=device)
+        elif self.off:
+            self.buf[:self.off].zero_()
+        self.off = 0
+        self.active = True
+
+    def end(self):
+        self.active = False
+
+    def zeros(self, shape, device):
+        n = 1
+        for s in shape:
+            n *= s
+        n_al = (n + 63) // 64 * 64                   # 256-byte granules keep every buffer vector-aligned
+        if not self.active or self.buf.device != device or self.off + n_al > self.capacity:
+            return torch.zeros(shape, dtype=torch.float32, device=device)
+        t = self.buf[self.off:self.off + n].view(shape)
+        self.off += n_al
+        return t
+
+
+ARENA = ZeroArena()
+
+
 # ---------------------------------------------------------------------------------------------
 # small kernel wrappers
 # ---------------------------------------------------------------------------------------------
@@ -184,7 +223,7 @@ def _conv_forward(x5, wk, bias, spec, Cout):
     else:
         y = torch.empty((N, Cout, Ho, Wo), dtype=torch.float32, device=dev)
         strides = (Cout * Ho * Wo, Wo, 1, Ho * Wo)
-    stats = torch.zeros((N, Cout, 2), dtype=torch.float32, device=dev) if spec.stats else None
+    stats = ARENA.zeros((N, Cout, 2), dev) if spec.stats else None
     kw = dict(bias=bias, act=spec.act, slope=spec.slope, stats=stats)
     if spec.kind == 's1':
         taps, off = convspec.conv_s1(spec.k, spec.pad)
@@ -260,7 +299,7 @@ class ConvFn(torch.autograd.Function):
         # ---- bias gradient ----------------------------------------------------------------------
         db = None
         if bias is not None and ctx.needs_input_grad[2]:
-            db = torch.zeros(Cout, dtype=torch.float32, device=dy.device)
+            db = ARENA.zeros((Cout,), dy.device)
             flat = dz5.reshape(-1, Coutp)
             _lib.call('sg_colsum_bf16', _ptr(flat), flat.shape[0], Cout, Coutp, _ptr(db), _stream())
         # ---- weight gradient ---------------------------------------------------------------------
