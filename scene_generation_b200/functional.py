@@ -394,7 +394,7 @@ class LinearFn(torch.autograd.Function):
             ops.wgrad_tc(dz5, xb.view(1, 1, 1, M, xb.shape[1]), dw, 1, M, ONE_WTAP, Nout, K)
             dw = dw.view(Nout, K)
         if ctx.needs_input_grad[2]:
-            db = torch.zeros(Nout, dtype=torch.float32, device=dy.device)
+            db = ARENA.zeros((Nout,), dy.device)
             _lib.call('sg_colsum_bf16', _ptr(dz), M, Nout, Np, _ptr(db), _stream())
         return dx, dw, db, None
 

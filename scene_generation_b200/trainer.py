@@ -9,6 +9,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ddp
+from . import functional as Fn
 from .discriminators import AcCropDiscriminator, define_D, define_mask_D
 from .losses import GANLoss, get_gan_losses
 from .model import Model
@@ -238,6 +239,7 @@ class Trainer:
         imgs, objs, boxes, masks, triples, obj_to_img, triple_to_img, attributes = batch
         if not use_gt:
             attributes = torch.zeros_like(attributes)
+        Fn.ARENA.begin_step(imgs.device)        # zero-initialised scratch of this iteration (one fill per step)
         out = self.model(imgs, objs, triples, obj_to_img, boxes_gt=boxes, masks_gt=masks, attributes=attributes)
         imgs_pred, boxes_pred, masks_pred, layout, layout_pred, layout_wrong = out
         self.train_generator(imgs, imgs_pred, masks, masks_pred, layout, objs, boxes, boxes_pred, obj_to_img, use_gt)
