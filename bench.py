@@ -354,12 +354,16 @@ def main():
         tr.train_step(batch, use_gt=(i % 2 == 0))
         return float(tr.generator_losses.total_loss.detach())      # device -> host read of the step's result
 
+    host_ms = [0.0]
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
         for i in range(steps):
             fn(i)
+        host_ms[0] = (time.perf_counter() - t0) * 1e3 / steps      # host time to ENQUEUE a step (no sync inside)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -385,6 +389,7 @@ def main():
     _lib.reset_launch_count()
     ms_total = timed(step_resident, a.steps)
     launches = _lib.launch_count()
+    host_enqueue_ms = host_ms[0]
     log('timed %d steps: %.1f ms/step' % (a.steps, ms_total / a.steps))
     clocks = sampler.stop() if rank == 0 else None
     images = a.batch * world * a.steps
@@ -457,7 +462,8 @@ def main():
                              % n_distinct,
                        'algorithmic_gflop_per_image': FLOPS_PER_IMAGE_STEP / 1e9},
             'model_tflops': value * FLOPS_PER_IMAGE_STEP / 1e12,
-            'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'kernels': kernels,
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'host_enqueue_ms_per_step': round(host_enqueue_ms, 2),
+            'roofline': roofline, 'kernels': kernels,
             'cpu_baseline': cpu,
         }
         print(json.dumps(line))

@@ -7,6 +7,7 @@ arithmetic.  Activations between tensor-core convolutions live in two bf16 forma
                 P=4 parity planes for stride-2 access).
 """
 import ctypes
+import os
 from dataclasses import dataclass
 
 import torch
@@ -99,6 +100,8 @@ class ZeroArena:
         self.active = False
 
     def begin_step(self, device):
+        if os.environ.get('SG_ZERO_ARENA', '1') == '0':
+            return
         if self.buf is None or self.buf.device != device:
             self.buf = torch.zeros(self.capacity, dtype=torch.float32, device=device)
         elif self.off:
