@@ -41,6 +41,8 @@ def parse():
     ap.add_argument('--cpu-worker', action='store_true', help=argparse.SUPPRESS)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--host-profile', action='store_true',
+                    help='cProfile 5 steps of the host side (launch path) into gpurun_out/host_profile_*.txt and exit')
     ap.add_argument('--profile-step', action='store_true',
                     help='after warm-up run ONE step between cudaProfilerStart/Stop and exit (use with ncu --profile-from-start off)')
     return ap.parse_args()
@@ -376,6 +378,23 @@ def main():
         step_resident(i)
         torch.cuda.synchronize()
         log('warm-up step %d done' % i)
+    if a.host_profile:
+        import cProfile
+        import io
+        import pstats
+        torch.cuda.synchronize()
+        pr = cProfile.Profile()
+        pr.enable()
+        for i in range(5):
+            step_resident(i)
+        pr.disable()
+        torch.cuda.synchronize()
+        for key in ('tottime', 'cumtime'):
+            buf = io.StringIO()
+            pstats.Stats(pr, stream=buf).sort_stats(key).print_stats(70)
+            os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+            open(os.path.join(ROOT, 'gpurun_out', 'host_profile_%s.txt' % key), 'w').write(buf.getvalue())
+        return
     if a.profile_step:
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStart()

@@ -210,7 +210,9 @@ __global__ void __launch_bounds__(THREADS) layout_fwd_tile_kernel(LayoutArgs a, 
   __shared__ int sAct[MAXA];
   __shared__ unsigned sNz[MAXA];
   __shared__ SgBilin sAy[MAXA * 2];
-  __shared__ int sNact, sNext;
+  __shared__ int sNact, sNext, sNuni;
+  __shared__ int sUni[32];
+  __shared__ unsigned sUmask[32];
   const int n = blockIdx.y;
   const int p0 = blockIdx.x * TPX;
   const int HW = a.H * a.W;
@@ -247,16 +249,6 @@ __global__ void __launch_bounds__(THREADS) layout_fwd_tile_kernel(LayoutArgs a, 
         pos += 32;
       }
       if (lane == 0) { sNact = nact; sNext = min(pos, o_end); }
-      __syncwarp();
-      // y-axis taps per (object, tile row): a tile of consecutive pixels touches at most two rows when W >= TPX / 2
-      nact = min(nact, MAXA);
-      if (lane < nact * 2) {
-        const int k = lane >> 1, r = lane & 1;
-        const float* bx = a.boxes + 4 * sAct[k];
-        float y0 = bx[1], hh = __fsub_rn(bx[3], y0);
-        float gy = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(sg_linspace01(min(h_lo + r, a.H - 1), a.H), y0), hh), 2.f), 1.f);
-        sAy[k * 2 + r] = sg_axis(gy, a.M, a.align_corners);
-      }
     } else {
       if (first_pass) {      // ---- meanwhile the other warps clear the tile ----
         uint4* t4 = reinterpret_cast<uint4*>(tile);
@@ -269,12 +261,33 @@ __global__ void __launch_bounds__(THREADS) layout_fwd_tile_kernel(LayoutArgs a, 
     const int nact = sNact;
     scan = sNext;
     if (nact == 0) break;
-    // ---- stage the objects' vectors (+ which 8-channel chunks are non-zero) and sample their masks ------------
+    // ---- y-axis taps per (object, tile row) and the objects' vectors -------------------------------------
+    if (threadIdx.x < nact * 2) {
+      const int k = threadIdx.x >> 1, r = threadIdx.x & 1;
+      const float* bx = a.boxes + 4 * sAct[k];
+      float y0 = bx[1], hh = __fsub_rn(bx[3], y0);
+      float gy = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(sg_linspace01(min(h_lo + r, a.H - 1), a.H), y0), hh), 2.f), 1.f);
+      sAy[k * 2 + r] = sg_axis(gy, a.M, a.align_corners);
+    }
     for (int i = threadIdx.x; i < nact * a.Cp; i += THREADS) {
       int k = i / a.Cp, c = i - k * a.Cp;
       float v = (c < a.D) ? a.vecs[(long)sAct[k] * a.D + c] : 0.f;
       sV[i] = v;
-      if (v != 0.f) atomicOr(&sNz[k], 1u << (c >> 3));
+      if (v != 0.f) atomicOr(&sNz[k], 1u << (c >> 3));     // which 8-channel chunks of this object are non-zero
+    }
+    __syncthreads();
+    // ---- warp 0: union of non-zero chunks (+ per chunk the objects that have it); all: sample the masks -----
+    if (warp == 0) {
+      unsigned m = 0u;
+      if (lane < chunks)
+        for (int k = 0; k < nact; ++k) m |= ((sNz[k] >> lane) & 1u) << k;
+      unsigned b = __ballot_sync(0xffffffffu, m != 0u);
+      if (m != 0u) {
+        int pos = __popc(b & ((1u << lane) - 1));
+        sUni[pos] = lane;
+        sUmask[pos] = m;
+      }
+      if (lane == 0) sNuni = __popc(b);
     }
     for (int i = threadIdx.x; i < nact * TPX; i += THREADS) {
       const int k = i / TPX, px = i - k * TPX;
@@ -288,18 +301,12 @@ __global__ void __launch_bounds__(THREADS) layout_fwd_tile_kernel(LayoutArgs a, 
       sS[i] = s;
     }
     __syncthreads();
-    // ---- every warp derives the union of non-zero chunks (and, per chunk, the objects that have it) itself ------
-    unsigned my_mask = 0u;
-    if (lane < chunks)
-      for (int k = 0; k < nact; ++k) my_mask |= ((sNz[k] >> lane) & 1u) << k;
-    const unsigned uni_bits = __ballot_sync(0xffffffffu, my_mask != 0u);
-    const int nuni = __popc(uni_bits);
     // ---- one (pixel, non-zero chunk) item per thread: lanes = consecutive pixels, the chunk is warp-uniform ----
-    for (int i0 = warp * 32; i0 < nuni * TPX; i0 += THREADS) {     // warp-uniform trip count (shuffles inside)
-      const int ui = i0 / TPX, px = i0 - ui * TPX + lane;
-      const int chunk = __fns(uni_bits, 0, ui + 1);                // the ui-th non-zero chunk
-      const unsigned umask = __shfl_sync(0xffffffffu, my_mask, chunk);
+    const int nuni = sNuni;
+    for (int i = threadIdx.x; i < nuni * TPX; i += THREADS) {
+      const int ui = i / TPX, px = i - ui * TPX;
       if (px >= npx) continue;
+      const int chunk = sUni[ui];
       __nv_bfloat16* dst = tile + (size_t)px * a.Cp + chunk * 8;
       float acc[8];
       if (first_pass) {
@@ -311,7 +318,7 @@ __global__ void __launch_bounds__(THREADS) layout_fwd_tile_kernel(LayoutArgs a, 
 #pragma unroll
         for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h2[j]); acc[2 * j] = f.x; acc[2 * j + 1] = f.y; }
       }
-      for (unsigned m = umask; m != 0u; m &= m - 1u) {
+      for (unsigned m = sUmask[ui]; m != 0u; m &= m - 1u) {
         const int k = __ffs(m) - 1;
         const float s = sS[k * TPX + px];
         if (s == 0.f) continue;

@@ -201,6 +201,36 @@ class MultiscaleDiscriminator(nn.Module):
         x = Fn.ImageSlotFn.apply(raw.detach(), img, D)
         return self._columns(x, img.requires_grad, (D, D + img.shape[1]), cmap)
 
+    def forward_pairs(self, pairs):
+        """[(layout, img), ...] -> one result per pair from ONE batched pass.  Exact: every layer of a PatchGAN column
+        (conv, InstanceNorm2d, LeakyReLU, AvgPool2d) acts per sample, so stacking the reference's separate
+        discriminate() calls of a D step (trainer.py:309-319) along the batch changes no value; it divides the
+        launch count of the step by the number of pairs and fills the small late-layer GEMMs.  Images must not
+        require a gradient (the D step passes detached images)."""
+        return _forward_pairs(self, pairs)
+
+
+def _forward_pairs(netD, pairs):
+    """MultiscaleDiscriminator.forward_pairs: see there."""
+    from . import ops
+    raws = [getattr(l, '_sg_nhwc', None) for l, _ in pairs]
+    cmaps = [getattr(l, '_sg_cmap', None) for l, _ in pairs]
+    D, C = pairs[0][0].shape[1], pairs[0][1].shape[1]
+    same = all(r is not None and r.shape == raws[0].shape for r in raws) and all(l.shape[1] == D for l, _ in pairs)
+    if not same or raws[0].shape[3] < D + C or any(img.requires_grad for _, img in pairs) \
+            or len(set(c is None for c in cmaps)) != 1:
+        return [netD.forward_pair(l, img) for l, img in pairs]
+    N, H, W, Cp = raws[0].shape
+    x = torch.empty((len(pairs) * N, H, W, Cp), dtype=torch.bfloat16, device=raws[0].device)
+    for k, (raw, (_, img)) in enumerate(zip(raws, pairs)):
+        xs = x[k * N:(k + 1) * N]
+        xs.copy_(raw.detach())
+        _lib.call('sg_nchw_to_nhwc', img.detach().contiguous().float().data_ptr(), 0, N, C, H, W, Cp, D, xs.data_ptr(),
+                  ops._stream())
+    cmap = None if cmaps[0] is None else torch.cat(cmaps, dim=0).contiguous()
+    cols = netD._columns(x, False, None, cmap)
+    return [[[f[k * N:(k + 1) * N] for f in col] for col in cols] for k in range(len(pairs))]
+
 
 class MultiscaleMaskDiscriminator(nn.Module):
     """discriminators.py:87-125: the one-hot class vector is concatenated (broadcast over space) in front

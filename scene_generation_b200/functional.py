@@ -113,13 +113,16 @@ class ZeroArena:
         self.active = False
 
     def zeros(self, shape, device):
-        n = 1
-        for s in shape:
+        if not self.active:
+            return torch.zeros(shape, dtype=torch.float32, device=device)
+        strides, n = [], 1
+        for s in reversed(shape):
+            strides.append(n)
             n *= s
         n_al = (n + 63) // 64 * 64                   # 256-byte granules keep every buffer vector-aligned
-        if not self.active or self.buf.device != device or self.off + n_al > self.capacity:
+        if self.off + n_al > self.capacity or self.buf.device != device:
             return torch.zeros(shape, dtype=torch.float32, device=device)
-        t = self.buf[self.off:self.off + n].view(shape)
+        t = self.buf.as_strided(shape, strides[::-1], self.off)      # one view op per buffer
         self.off += n_al
         return t
 

@@ -206,8 +206,16 @@ class Trainer:
         if self.mask_discriminator is None:
             return
         self.d_mask_losses = dl = LossManager()
-        scores_fake = self.mask_discriminator(masks_pred.unsqueeze(1), objs)
-        scores_real = self.mask_discriminator(masks.unsqueeze(1), objs)
+        if self.args.norm_D_mask == 'instance' and not masks_pred.requires_grad:
+            # fake and real masks in one batched pass: every layer acts per sample (conv, InstanceNorm, LeakyReLU)
+            O = objs.numel()
+            both = self.mask_discriminator(torch.cat([masks_pred.unsqueeze(1).float(), masks.unsqueeze(1).float()]),
+                                           torch.cat([objs, objs]))
+            scores_fake = [[f[:O] for f in col] for col in both]
+            scores_real = [[f[O:] for f in col] for col in both]
+        else:
+            scores_fake = self.mask_discriminator(masks_pred.unsqueeze(1), objs)
+            scores_real = self.mask_discriminator(masks.unsqueeze(1), objs)
         dl.add_loss(self.criterionGAN(scores_fake, False), 'fake_loss', 0.5)
         dl.add_loss(self.criterionGAN(scores_real, True), 'real_loss', 0.5)
         self._step('mask', self.optimizer_d_mask, dl)
@@ -217,9 +225,15 @@ class Trainer:
             return
         self.d_img_losses = dl = LossManager()
         alpha = 0.25
-        dl.add_loss(self.criterionGAN(self.discriminate(layout, imgs_pred), False), 'fake_image_loss', alpha)
-        dl.add_loss(self.criterionGAN(self.discriminate(layout_wrong, imgs), False), 'wrong_texture_loss', alpha)
-        dl.add_loss(self.criterionGAN(self.discriminate(layout, imgs), True), 'd_img_gan_real_loss', 0.5)
+        # the three discriminate() calls of trainer.py:309-319 as one batched pass (per-sample layers: exact)
+        pairs = [(layout, imgs_pred.detach()), (layout_wrong, imgs), (layout, imgs)]
+        if self.args.norm_D == 'instance':
+            fake, wrong, real = self.netD.forward_pairs(pairs)
+        else:
+            fake, wrong, real = (self.discriminate(l, i) for l, i in pairs)
+        dl.add_loss(self.criterionGAN(fake, False), 'fake_image_loss', alpha)
+        dl.add_loss(self.criterionGAN(wrong, False), 'wrong_texture_loss', alpha)
+        dl.add_loss(self.criterionGAN(real, True), 'd_img_gan_real_loss', 0.5)
         self._step('img', self.optimizer_d_img, dl)
 
     def discriminate(self, input_label, test_image):
