@@ -49,21 +49,6 @@ __device__ __forceinline__ float sample_mask(const LayoutArgs& a, int o, int h, 
   return s;
 }
 
-// same with the y axis of the tap precomputed (identical arithmetic, hoisted out of the pixel loop)
-__device__ __forceinline__ float sample_mask_x(const LayoutArgs& a, int o, int w, const float* bx, const SgBilin& ay) {
-  float x0 = bx[0];
-  float ww = __fsub_rn(bx[2], x0);
-  float gx = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(sg_linspace01(w, a.W), x0), ww), 2.f), 1.f);
-  SgBilin ax = sg_axis(gx, a.M, a.align_corners);
-  const long base = (long)o * a.M * a.M;
-  float s = 0.f;
-  if (ay.ok0 && ax.ok0) s = __fmaf_rn(__fmul_rn(ax.w0, ay.w0), load_mask(a.masks, a.mask_dtype, base + (long)ay.i0 * a.M + ax.i0), s);
-  if (ay.ok0 && ax.ok1) s = __fmaf_rn(__fmul_rn(ax.w1, ay.w0), load_mask(a.masks, a.mask_dtype, base + (long)ay.i0 * a.M + ax.i0 + 1), s);
-  if (ay.ok1 && ax.ok0) s = __fmaf_rn(__fmul_rn(ax.w0, ay.w1), load_mask(a.masks, a.mask_dtype, base + (long)(ay.i0 + 1) * a.M + ax.i0), s);
-  if (ay.ok1 && ax.ok1) s = __fmaf_rn(__fmul_rn(ax.w1, ay.w1), load_mask(a.masks, a.mask_dtype, base + (long)(ay.i0 + 1) * a.M + ax.i0 + 1), s);
-  return s;
-}
-
 // ------------------------------------------------------------------------------------------------
 // forward, train branch (layout.py:149-155): NHWC bf16 (Cp channels, zero padded) or NCHW fp32
 // ------------------------------------------------------------------------------------------------
@@ -171,17 +156,16 @@ __global__ void __launch_bounds__(THREADS) layout_fwd_kernel(LayoutArgs a, void*
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward, NHWC bf16, bandwidth-oriented variant.  Per 128-pixel tile only the objects whose (slightly
-// dilated) box intersects the tile are sampled and accumulated — typically 2-4 of the image's 4-9 —
+// forward, NHWC bf16, bandwidth-oriented variant.  Per 16x8-pixel tile only the objects whose (slightly
+// dilated) box intersects the tile are sampled and accumulated — typically 2-3 of the image's 4-9 —
 // and the compacted list keeps the reference's object order (deterministic summation).
 // ------------------------------------------------------------------------------------------------
-constexpr int MAXA = 16;      // active objects per pass
+constexpr int MAXA = 12;      // active objects per pass (12: three CTAs of the Cp = 208 layout per SM)
 
-__device__ __forceinline__ bool box_touches_tile(const LayoutArgs& a, const float* bx, int p0, int p1) {
-  // pixel rows / columns covered by pixels [p0, p1]
-  const int h_lo = p0 / a.W, h_hi = p1 / a.W;
-  int w_lo = 0, w_hi = a.W - 1;
-  if (h_lo == h_hi) { w_lo = p0 % a.W; w_hi = p1 % a.W; }
+constexpr int TW = 16, TH = 8;       // pixel tile of the NHWC kernel: TH row segments of TW * Cp * 2 contiguous bytes
+constexpr int TPX = TW * TH;
+
+__device__ __forceinline__ bool box_touches_rect(const LayoutArgs& a, const float* bx, int h_lo, int h_hi, int w_lo, int w_hi) {
   float x0 = bx[0], y0 = bx[1], x1 = bx[2], y1 = bx[3];
   float ww = x1 - x0, hh = y1 - y0;
   if (!(isfinite(ww) && isfinite(hh) && isfinite(x0) && isfinite(y0))) return true;   // let the sampler decide
@@ -194,34 +178,41 @@ __device__ __forceinline__ bool box_touches_tile(const LayoutArgs& a, const floa
   return !((float)w_hi < wl || (float)w_lo > wh || (float)h_hi < hl || (float)h_lo > hu);
 }
 
-constexpr int TPX = 128;     // pixels per tile of the NHWC kernel: TPX * Cp * 2 contiguous output bytes
+// one axis of the sampling grid of layout.py:96-128 for pixel coordinate `i` of `n` (same operations, same order
+// as sample_mask)
+__device__ __forceinline__ SgBilin grid_axis(const LayoutArgs& a, int i, int n, float b0, float b1) {
+  float ext = __fsub_rn(b1, b0);
+  float g = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(sg_linspace01(i, n), b0), ext), 2.f), 1.f);
+  return sg_axis(g, a.M, a.align_corners);
+}
 
-// Tile kernel.  The output tile of TPX consecutive pixels is one contiguous run of TPX * Cp * 2 bytes in
-// the NHWC tensor: it is composed in shared memory and leaves with a single bulk (TMA) store, so the
-// FMA phase issues no global stores and no per-pixel address arithmetic.  A layout vector is
-// cat(one_hot(class), appearance) (model.py:165-168): per object only ~5 of the Cp/8 eight-channel chunks
-// are non-zero.  The tile is zero-filled once and only the UNION of non-zero chunks of the active objects
-// is accumulated, one (pixel, chunk) item per thread, objects in the reference's order.
-__global__ void __launch_bounds__(THREADS) layout_fwd_tile_kernel(LayoutArgs a, __nv_bfloat16* __restrict__ out) {
+// Tile kernel.  A TW x TH pixel tile of the NHWC output is TH contiguous row segments of TW * Cp * 2 bytes: it is
+// composed in shared memory and leaves with TH bulk (TMA) stores, so the FMA phase issues no global stores and no
+// per-pixel address arithmetic.  The bilinear sampling grid is separable: the x taps of an object are shared by
+// the TH rows of the tile and the y taps by its TW columns, so the (IEEE) divisions of the grid are evaluated
+// TW + TH times per object and tile instead of once per sample.  A layout vector is cat(one_hot(class),
+// appearance) (model.py:165-168): per object only ~5 of the Cp/8 eight-channel chunks are non-zero.  The tile is
+// zero-filled once and only the UNION of non-zero chunks of the active objects is accumulated, one
+// (pixel, chunk) item per thread, objects in the reference's order.
+__global__ void __launch_bounds__(THREADS) layout_fwd_tile_kernel(LayoutArgs a, __nv_bfloat16* __restrict__ out, int tiles_w) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(smem_raw);                   // [TPX][Cp]
+  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(smem_raw);                   // [TH][TW][Cp]
   float* sS = reinterpret_cast<float*>(smem_raw + (size_t)TPX * a.Cp * 2);            // [MAXA][TPX]
   float* sV = sS + MAXA * TPX;                                                        // [MAXA][Cp]
   __shared__ int sAct[MAXA];
   __shared__ unsigned sNz[MAXA];
-  __shared__ SgBilin sAy[MAXA * 2];
+  __shared__ SgBilin sAx[MAXA * TW];
+  __shared__ SgBilin sAy[MAXA * TH];
   __shared__ int sNact, sNext, sNuni;
   __shared__ int sUni[32];
   __shared__ unsigned sUmask[32];
   const int n = blockIdx.y;
-  const int p0 = blockIdx.x * TPX;
-  const int HW = a.H * a.W;
-  const int npx = min(TPX, HW - p0);
-  const int p1 = p0 + npx - 1;
+  const int tw = blockIdx.x % tiles_w, th = blockIdx.x / tiles_w;
+  const int w0 = tw * TW, h0 = th * TH;
+  const int nw = min(TW, a.W - w0), nh = min(TH, a.H - h0);
   const int o_begin = a.ranges[2 * n], o_end = a.ranges[2 * n + 1];
   const int chunks = a.Cp / 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h_lo = p0 / a.W;
   int scan = o_begin;        // next object to test
   bool first_pass = true;
   for (;;) {
@@ -231,7 +222,7 @@ __global__ void __launch_bounds__(THREADS) layout_fwd_tile_kernel(LayoutArgs a, 
       int nact = 0, pos = scan;
       while (pos < o_end && nact < MAXA) {
         int o = pos + lane;
-        bool act = (o < o_end) && box_touches_tile(a, a.boxes + 4 * o, p0, p1);
+        bool act = (o < o_end) && box_touches_rect(a, a.boxes + 4 * o, h0, h0 + nh - 1, w0, w0 + nw - 1);
         unsigned m = __ballot_sync(0xffffffffu, act);
         int before = __popc(m & ((1u << lane) - 1));
         int room = MAXA - nact;
@@ -252,7 +243,7 @@ __global__ void __launch_bounds__(THREADS) layout_fwd_tile_kernel(LayoutArgs a, 
     } else {
       if (first_pass) {      // ---- meanwhile the other warps clear the tile ----
         uint4* t4 = reinterpret_cast<uint4*>(tile);
-        const int n16 = npx * a.Cp / 8;
+        const int n16 = TPX * a.Cp / 8;
         for (int i = threadIdx.x - 32; i < n16; i += THREADS - 32) t4[i] = make_uint4(0u, 0u, 0u, 0u);
       }
       if (threadIdx.x - 32 < MAXA) sNz[threadIdx.x - 32] = 0u;
@@ -261,13 +252,12 @@ __global__ void __launch_bounds__(THREADS) layout_fwd_tile_kernel(LayoutArgs a, 
     const int nact = sNact;
     scan = sNext;
     if (nact == 0) break;
-    // ---- y-axis taps per (object, tile row) and the objects' vectors -------------------------------------
-    if (threadIdx.x < nact * 2) {
-      const int k = threadIdx.x >> 1, r = threadIdx.x & 1;
+    // ---- grid taps per (object, tile column) and (object, tile row); the objects' vectors -------------------
+    for (int i = threadIdx.x; i < nact * (TW + TH); i += THREADS) {
+      const int k = i / (TW + TH), j = i - k * (TW + TH);
       const float* bx = a.boxes + 4 * sAct[k];
-      float y0 = bx[1], hh = __fsub_rn(bx[3], y0);
-      float gy = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(sg_linspace01(min(h_lo + r, a.H - 1), a.H), y0), hh), 2.f), 1.f);
-      sAy[k * 2 + r] = sg_axis(gy, a.M, a.align_corners);
+      if (j < TW) sAx[k * TW + j] = grid_axis(a, min(w0 + j, a.W - 1), a.W, bx[0], bx[2]);
+      else sAy[k * TH + (j - TW)] = grid_axis(a, min(h0 + j - TW, a.H - 1), a.H, bx[1], bx[3]);
     }
     for (int i = threadIdx.x; i < nact * a.Cp; i += THREADS) {
       int k = i / a.Cp, c = i - k * a.Cp;
@@ -291,12 +281,15 @@ __global__ void __launch_bounds__(THREADS) layout_fwd_tile_kernel(LayoutArgs a, 
     }
     for (int i = threadIdx.x; i < nact * TPX; i += THREADS) {
       const int k = i / TPX, px = i - k * TPX;
+      const int r = px / TW, c = px - r * TW;
       float s = 0.f;
-      if (px < npx) {
-        const int p = p0 + px;
-        const int h = p / a.W, w = p - h * a.W;
-        if (h - h_lo < 2) s = sample_mask_x(a, sAct[k], w, a.boxes + 4 * sAct[k], sAy[k * 2 + (h - h_lo)]);
-        else s = sample_mask(a, sAct[k], h, w, a.boxes + 4 * sAct[k]);     // narrow images: more than two rows per tile
+      if (r < nh && c < nw) {
+        const SgBilin ax = sAx[k * TW + c], ay = sAy[k * TH + r];
+        const long base = (long)sAct[k] * a.M * a.M;
+        if (ay.ok0 && ax.ok0) s = __fmaf_rn(__fmul_rn(ax.w0, ay.w0), load_mask(a.masks, a.mask_dtype, base + (long)ay.i0 * a.M + ax.i0), s);
+        if (ay.ok0 && ax.ok1) s = __fmaf_rn(__fmul_rn(ax.w1, ay.w0), load_mask(a.masks, a.mask_dtype, base + (long)ay.i0 * a.M + ax.i0 + 1), s);
+        if (ay.ok1 && ax.ok0) s = __fmaf_rn(__fmul_rn(ax.w0, ay.w1), load_mask(a.masks, a.mask_dtype, base + (long)(ay.i0 + 1) * a.M + ax.i0), s);
+        if (ay.ok1 && ax.ok1) s = __fmaf_rn(__fmul_rn(ax.w1, ay.w1), load_mask(a.masks, a.mask_dtype, base + (long)(ay.i0 + 1) * a.M + ax.i0 + 1), s);
       }
       sS[i] = s;
     }
@@ -305,7 +298,6 @@ __global__ void __launch_bounds__(THREADS) layout_fwd_tile_kernel(LayoutArgs a, 
     const int nuni = sNuni;
     for (int i = threadIdx.x; i < nuni * TPX; i += THREADS) {
       const int ui = i / TPX, px = i - ui * TPX;
-      if (px >= npx) continue;
       const int chunk = sUni[ui];
       __nv_bfloat16* dst = tile + (size_t)px * a.Cp + chunk * 8;
       float acc[8];
@@ -337,13 +329,15 @@ __global__ void __launch_bounds__(THREADS) layout_fwd_tile_kernel(LayoutArgs a, 
     first_pass = false;
     if (scan >= o_end) break;
   }
-  // ---- the finished tile leaves in one bulk store -----------------------------------------------------------
+  // ---- the finished tile leaves as TH bulk stores, one per row segment ---------------------------------------
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the async proxy
   __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned long long gdst = reinterpret_cast<unsigned long long>(out + ((size_t)n * HW + p0) * a.Cp);
-    const unsigned ssrc = (unsigned)__cvta_generic_to_shared(tile);
-    const unsigned bytes = (unsigned)npx * a.Cp * 2;
+  if ((int)threadIdx.x < nh) {
+    const int r = threadIdx.x;
+    const unsigned long long gdst =
+        reinterpret_cast<unsigned long long>(out + (((size_t)n * a.H + h0 + r) * a.W + w0) * a.Cp);
+    const unsigned ssrc = (unsigned)__cvta_generic_to_shared(tile + (size_t)r * TW * a.Cp);
+    const unsigned bytes = (unsigned)nw * a.Cp * 2;
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must stay valid until it has been read
@@ -556,8 +550,9 @@ extern "C" int sg_masks_to_layout_fwd(const float* vecs, const float* boxes, con
       cudaFuncSetAttribute(layout_fwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
       smem_set = smem2;
     }
-    dim3 grid2(sg_cdiv((long)H * W, TPX), N);
-    layout_fwd_tile_kernel<<<grid2, THREADS, smem2, stream>>>(a, (__nv_bfloat16*)out);
+    const int tiles_w = sg_cdiv(W, TW), tiles_h = sg_cdiv(H, TH);
+    dim3 grid2(tiles_w * tiles_h, N);
+    layout_fwd_tile_kernel<<<grid2, THREADS, smem2, stream>>>(a, (__nv_bfloat16*)out, tiles_w);
   } else {
     cudaFuncSetAttribute(layout_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     layout_fwd_kernel<false><<<grid, THREADS, smem, stream>>>(a, out);

@@ -100,7 +100,10 @@ class ZeroArena:
         self.active = False
 
     def begin_step(self, device):
-        if os.environ.get('SG_ZERO_ARENA', '1') == '0':
+        # Off by default: the step is host-bound on the launch path (bench.py: host_enqueue_ms_per_step) and a view
+        # per buffer costs the host slightly more than torch.zeros, although it saves ~300 fill kernels per step on
+        # the GPU.  SG_ZERO_ARENA=1 enables it (measured: -0.7 ms GPU, +0.8 ms host per step).
+        if os.environ.get('SG_ZERO_ARENA', '0') != '1':
             return
         if self.buf is None or self.buf.device != device:
             self.buf = torch.zeros(self.capacity, dtype=torch.float32, device=device)
@@ -441,7 +444,7 @@ class NapFn(torch.autograd.Function):
             sc = gamma.detach() * torch.rsqrt(rv + spec.eps)
             scale, shift = sc.repeat(N).contiguous(), (beta.detach() - rm * sc).repeat(N).contiguous()
         elif spec.norm is not None:
-            scale, shift, mean, rstd = (torch.empty(N * C, dtype=torch.float32, device=dev) for _ in range(4))
+            scale, shift, mean, rstd = torch.empty((4, N * C), dtype=torch.float32, device=dev).unbind(0)   # one allocation
             rm, rv = (running if running is not None else (None, None))
             _lib.call('sg_norm_finalize', _ptr(stats), 0 if spec.norm == 'in' else 1, N, C, float(H * W), spec.eps,
                       _ptr(gamma), _ptr(beta), _ptr(rm), _ptr(rv), spec.momentum, _ptr(scale), _ptr(shift), _ptr(mean),

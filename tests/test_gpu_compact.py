@@ -170,7 +170,9 @@ def test_generator_and_image_d_step_compact_vs_dense():
         is_compact = getattr(out[3], '_sg_cmap', None) is not None
         assert is_compact == compact
         if key == 'dense2':     # a second dense run: the run-to-run spread of the dense path itself (fp32 atomics)
-            runs[key] = dict(imgs=out[0].detach().float(), gl=dict(tr.generator_losses.all_losses))
+            runs[key] = dict(imgs=out[0].detach().float(), gl=dict(tr.generator_losses.all_losses),
+                             g={n: p.grad.detach().float().clone() for n, p in tr.model.named_parameters() if p.grad is not None},
+                             d={n: p.grad.detach().float().clone() for n, p in tr.netD.named_parameters() if p.grad is not None})
             continue
         dense_dim = tr.model.num_objs + tr.model.rep_size
         runs[compact] = dict(
@@ -199,20 +201,26 @@ def test_generator_and_image_d_step_compact_vs_dense():
         assert abs(v - b['gl'][name]) <= max(1e-2 * abs(v) + 1e-3, 4 * spread), (name, v, b['gl'][name], spread)
     for name, v in a['dl'].items():
         assert abs(v - b['dl'][name]) <= 3e-2 * abs(v) + 1e-3, (name, v, b['dl'][name])
+    def cosine(x, y):
+        return float(torch.dot(x.reshape(-1), y.reshape(-1)) / (x.norm() * y.norm() + 1e-30))
+
+    # gradients: cfg-1 is chaotic enough that two DENSE runs only agree to cos ~0.85-1.0 per layer; the compact path
+    # must agree with a dense run as well as a second dense run does (the per-image-weight kernels themselves are
+    # checked exactly in test_conv_per_image_weights_matches_dense)
     rows = []
     for grads in ('g', 'd'):
         assert a[grads].keys() == b[grads].keys()
         for name, ga in a[grads].items():
-            gb = b[grads][name]
-            if ga.abs().max() < 1e-7:
+            if ga.abs().max() < 1e-7 or name.endswith('.bias'):
                 continue
-            cos = float(torch.dot(ga.reshape(-1), gb.reshape(-1)) / (ga.norm() * gb.norm() + 1e-30))
-            rows.append((grads + '.' + name, cos, float(gb.norm() / ga.norm())))
-    print('\n'.join('%-60s cos %.4f ratio %.3f' % r for r in rows))
+            rows.append((grads + '.' + name, cosine(ga, b[grads][name]), cosine(ga, runs['dense2'][grads][name]),
+                         float(b[grads][name].norm() / ga.norm())))
+    print('\n'.join('%-60s cos(dense,compact) %.4f cos(dense,dense) %.4f ratio %.3f' % r for r in rows))
     first = [r for r in rows if r[0] in ('g.layout_to_image.model.1.weight', 'd.scale0_layer0.0.weight', 'd.scale1_layer0.0.weight')]
     assert len(first) == 3
-    for r in first:                       # the layers that run with per-image gathered weights
-        assert r[1] > 0.98 and abs(r[2] - 1) < 0.05, r
-    ws = [r for r in rows if not r[0].endswith('.bias')]
-    assert sum(r[1] for r in ws) / len(ws) > 0.95
-    assert min(r[1] for r in ws) > 0.7, min(ws, key=lambda r: r[1])
+    for r in rows:
+        assert r[1] >= r[2] - 0.08, r
+        assert abs(r[3] - 1) < 0.15, r
+    mean_c = sum(r[1] for r in rows) / len(rows)
+    mean_d = sum(r[2] for r in rows) / len(rows)
+    assert mean_c >= mean_d - 0.02, (mean_c, mean_d)
