@@ -351,9 +351,10 @@ def main():
         tr.train_step(dev_batches[i % n_distinct], use_gt=(i % 2 == 0))
 
     def step_e2e(i):
-        hb = host_batches[i % n_distinct]
-        batch = metas[i % n_distinct].attach(tuple(t.to(dev, non_blocking=True) for t in hb))
-        tr.train_step(batch, use_gt=(i % 2 == 0))
+        # the public call with HOST buffers: pinned batch + loader metadata in, total generator loss out.  With
+        # captured iterations the batch is copied straight into the graph's input buffers, otherwise to fresh tensors.
+        hb = metas[i % n_distinct].attach(host_batches[i % n_distinct])
+        tr.train_step(hb, use_gt=(i % 2 == 0))
         return float(tr.generator_losses.total_loss.detach())      # device -> host read of the step's result
 
     host_ms = [0.0]
@@ -378,7 +379,15 @@ def main():
         step_resident(i)
         torch.cuda.synchronize()
         log('warm-up step %d done' % i)
+    if tr.use_graphs and not a.host_profile:
+        # every (batch geometry, use_gt) pair of the timed loop: one more eager sighting at most, then the capture
+        for i in range(2 * n_distinct):
+            step_resident(i)
+        torch.cuda.synchronize()
+        log('captured %d iteration graphs (cuda graphs %s)' % (
+            sum(1 for v in tr._graphs.values() if not isinstance(v, str)), 'on' if tr.use_graphs else 'FELL BACK to eager'))
     if a.host_profile:
+        tr.use_graphs = False
         import cProfile
         import io
         import pstats
@@ -398,7 +407,7 @@ def main():
     if a.profile_step:
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStart()
-        step_resident(0)
+        step_resident(0)          # a graph replay when graphs are on: ncu lists the kernels of the graph one by one
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
         return
@@ -423,15 +432,18 @@ def main():
 
     # one instrumented (untimed) step: per-launch device time + algorithmic FLOPs of the tensor-core kernels
     roofline, kernels = None, None
+    def step_eager(i):
+        tr.train_step(dev_batches[i % n_distinct], use_gt=(i % 2 == 0), graph=False)
+
     if rank != 0:
-        step_resident(0)          # the probe step contains the gradient all-reduces: every rank must take part
+        step_eager(0)             # the probe step contains the gradient all-reduces: every rank must take part
         torch.cuda.synchronize()
     if rank == 0:
         with KernelProbe() as probe:
             # let the host run ahead of the device so that event intervals of small launches measure the kernel,
             # not the host's launch gap: park the stream on a ~100 ms spin first
             torch.cuda._sleep(int(2e8))
-            step_resident(0)
+            step_eager(0)         # launched eagerly: the probe wraps the Python entry points
             fam, top = probe.summary()
         peak_tf, peak_hbm, which = load_peaks()
         lay = fam.pop('layout_fwd', None)
@@ -482,6 +494,8 @@ def main():
                        'algorithmic_gflop_per_image': FLOPS_PER_IMAGE_STEP / 1e9},
             'model_tflops': value * FLOPS_PER_IMAGE_STEP / 1e12,
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'host_enqueue_ms_per_step': round(host_enqueue_ms, 2),
+            'cuda_graphs': {'enabled': bool(tr.use_graphs),
+                            'captured': sum(1 for v in tr._graphs.values() if not isinstance(v, str))},
             'roofline': roofline, 'kernels': kernels,
             'cpu_baseline': cpu,
         }

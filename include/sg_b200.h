@@ -28,6 +28,7 @@ const char* sg_version(void);
 int sg_arch(void);                       /* 100 = built for sm_100a */
 unsigned long long sg_launch_count(void);/* kernels launched by this library in this process */
 void sg_reset_launch_count(void);
+void sg_add_launch_count(unsigned long long n); /* account launches replayed from a captured CUDA graph */
 
 /* ---- layout.py:64-184  masks_to_layout / _boxes_to_grid / _pool_samples ---------------------- */
 /* mask_dtype: 0 f32, 1 i64, 2 u8.  img_ranges: int32 (N,2) object range [start,end) per image

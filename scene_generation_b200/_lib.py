@@ -127,7 +127,7 @@ _SIGS = {
     'sg_wgrad_small_cout': [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
 }
 _RESTYPES = {'sg_last_error': ctypes.c_char_p, 'sg_version': ctypes.c_char_p, 'sg_arch': c_int,
-             'sg_launch_count': ctypes.c_ulonglong, 'sg_reset_launch_count': None}
+             'sg_launch_count': ctypes.c_ulonglong, 'sg_reset_launch_count': None, 'sg_add_launch_count': None}
 
 
 def declared_symbols():
@@ -148,7 +148,7 @@ def lib():
         h = ctypes.CDLL(LIB_PATH)
         for name, rt in _RESTYPES.items():
             getattr(h, name).restype = rt
-            getattr(h, name).argtypes = []
+            getattr(h, name).argtypes = [ctypes.c_ulonglong] if name == 'sg_add_launch_count' else []
         for name, args in _SIGS.items():
             fn = getattr(h, name)
             fn.restype = c_int
@@ -180,3 +180,8 @@ def launch_count():
 
 def reset_launch_count():
     lib().sg_reset_launch_count()
+
+
+def add_launch_count(n):
+    """account launches that a CUDA graph replay performed without passing through the entry points"""
+    lib().sg_add_launch_count(int(n))

@@ -22,3 +22,5 @@ extern "C" const char* sg_version(void) { return "sg_b200 0.1.0 (sm_100a)"; }
 extern "C" int sg_arch(void) { return 100; }
 extern "C" unsigned long long sg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" void sg_reset_launch_count(void) { g_launches.store(0, std::memory_order_relaxed); }
+// launches replayed from a captured CUDA graph (the host enqueued them once, at capture): the caller accounts them
+extern "C" void sg_add_launch_count(unsigned long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }

@@ -86,6 +86,15 @@ def clear_weight_cache():
     _pack_cache.clear()
 
 
+def invalidate_packed(params):
+    """Drop the bf16 operands of these masters.  The version counter alone is not enough: fused optimizers
+    (torch._fused_adam_) update parameters WITHOUT bumping Tensor._version, so every optimizer step has to say
+    which weights it changed (Trainer._step does)."""
+    for p in params:
+        _pack_cache.pop(id(p), None)
+        _pack_cache.pop((id(p), 'cmap'), None)
+
+
 class ZeroArena:
     """f32 scratch that reads as zero when handed out.  The conv epilogue statistics, bias gradients and similar
     accumulators of one training step (several hundred small buffers) come from here: Trainer.train_step calls
@@ -99,14 +108,23 @@ class ZeroArena:
         self.off = 0
         self.active = False
 
-    def begin_step(self, device):
-        # Off by default: the step is host-bound on the launch path (bench.py: host_enqueue_ms_per_step) and a view
-        # per buffer costs the host slightly more than torch.zeros, although it saves ~300 fill kernels per step on
-        # the GPU.  SG_ZERO_ARENA=1 enables it (measured: -0.7 ms GPU, +0.8 ms host per step).
-        if os.environ.get('SG_ZERO_ARENA', '0') != '1':
-            return
+    def ensure(self, device):
+        """allocate the backing buffer (must happen outside a CUDA graph capture)"""
         if self.buf is None or self.buf.device != device:
             self.buf = torch.zeros(self.capacity, dtype=torch.float32, device=device)
+            self.off = 0
+
+    def begin_step(self, device, force=False):
+        # Off by default for eagerly launched steps: they are host-bound on the launch path (bench.py:
+        # host_enqueue_ms_per_step) and a view per buffer costs the host slightly more than torch.zeros, although it
+        # saves ~300 fill kernels per step on the GPU (measured: -0.7 ms GPU, +0.8 ms host per step).  SG_ZERO_ARENA=1
+        # enables it; captured steps (Trainer.train_step with CUDA graphs) always use it (force=True).
+        if not force and os.environ.get('SG_ZERO_ARENA', '0') != '1':
+            self.active = False
+            return
+        self.ensure(device)
+        if torch.cuda.is_current_stream_capturing():
+            self.buf.zero_()         # the replayed graph cannot know what the step before it used: clear everything
         elif self.off:
             self.buf[:self.off].zero_()
         self.off = 0

@@ -30,11 +30,13 @@ class Model(nn.Module):
         self.box_noise_dim = box_noise_dim
         self.mask_noise_dim = mask_noise_dim
         self.object_size = 64
-        self.fake_pool = VectorPool(pool_size)
+        self.fake_pool = None        # built below, once the vocabulary size is known
+        self.pool_plan = None        # device index vector of VectorPool.plan() when the host half ran outside (graph replay)
         self.layout_dtype = layout_dtype
         self.align_corners = align_corners
 
         self.num_objs = len(vocab['object_to_idx'])
+        self.fake_pool = VectorPool(pool_size, max_rows=self.num_objs * pool_size)
         self.num_preds = len(vocab['pred_idx_to_name'])
         self.obj_embeddings = nn.Embedding(self.num_objs, embedding_dim)
         self.pred_embeddings = nn.Embedding(self.num_preds, embedding_dim)
@@ -157,6 +159,6 @@ class Model(nn.Module):
             one_hot_obj = torch.zeros((O, self.compact_slots), dtype=obj_repr.dtype, device=obj_repr.device)
             one_hot_obj = one_hot_obj.scatter_(1, plan[0].view(-1, 1), 1.0)
         layout_vecs = torch.cat([one_hot_obj, obj_repr], dim=1)
-        wrong_objs_rep = self.fake_pool.query(objs, obj_repr)
+        wrong_objs_rep = self.fake_pool.query(objs, obj_repr, planned=self.pool_plan)
         wrong_layout_vecs = torch.cat([one_hot_obj, wrong_objs_rep], dim=1)
         return obj_vecs, mask_vecs, layout_vecs, wrong_layout_vecs

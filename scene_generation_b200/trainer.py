@@ -2,8 +2,16 @@
 constructor, same train_* methods and checkpoint keys).  Differences, all outside the arithmetic:
 loss terms stay on the device (no per-term .item()), the image discriminator takes (layout, image)
 pairs instead of a materialised concat, and with torch.distributed initialised every optimizer step
-is preceded by a flat-buffer NCCL all-reduce of that network's gradients (DDP semantics)."""
+is preceded by a flat-buffer NCCL all-reduce of that network's gradients (DDP semantics).
+
+train_step() launches the ~1900 kernels of one iteration either eagerly (host-bound: ~31 ms of Python/launch
+time per step against ~25 ms of GPU time) or — default — as ONE captured CUDA graph per batch geometry
+(number of objects / triples, the use_gt coin): the first step of a geometry runs eagerly, the second is
+captured, later ones are replayed after copying the batch into the graph's static input buffers.  The only
+per-step host work that survives is the VectorPool replacement policy (python `random`, utils.py:62-90), whose
+index vector is an input of the graph."""
 import os
+import warnings
 
 import torch
 import torch.nn.functional as F
@@ -21,6 +29,73 @@ except Exception:                              # pragma: no cover
     SummaryWriter = None
 
 
+class _BatchMeta:
+    """The loader's host-side index structures of a batch (synthetic.HostMeta.attach tags the tensors with them)."""
+
+    def __init__(self, ranges, seg_ptr, seg_src, obj_slot, slot_cls, slots_used, objs_host):
+        self.ranges, self.seg_ptr, self.seg_src, self.obj_slot, self.slot_cls = ranges, seg_ptr, seg_src, obj_slot, slot_cls
+        self.slots_used, self.objs_host = slots_used, objs_host
+
+    @classmethod
+    def of(cls, batch):
+        objs, triples, obj_to_img = batch[1], batch[4], batch[5]
+        ranges, csr = getattr(obj_to_img, '_sg_ranges', None), getattr(triples, '_sg_csr', None)
+        compact, objs_host = getattr(objs, '_sg_compact', None), getattr(objs, '_sg_host', None)
+        if ranges is None or csr is None or compact is None or objs_host is None:
+            return None
+        return cls(ranges, csr[0], csr[1], compact[0], compact[1], compact[2], objs_host)
+
+    def tensors(self):
+        return (self.ranges, self.seg_ptr, self.seg_src, self.obj_slot, self.slot_cls)
+
+    def geometry(self):
+        return tuple(tuple(t.shape) for t in self.tensors())
+
+    def attach(self, batch, tensors):
+        ranges, seg_ptr, seg_src, obj_slot, slot_cls = tensors
+        batch[5]._sg_ranges = ranges
+        batch[4]._sg_csr = (seg_ptr, seg_src)
+        batch[1]._sg_host = self.objs_host
+        batch[1]._sg_compact = (obj_slot, slot_cls, self.slots_used)
+        return batch
+
+
+def _batch_to_device(batch, device):
+    """device copies of a host batch, metadata tags included (no-op for a batch already on the device)"""
+    if all(t.is_cuda for t in batch):
+        return batch
+    meta = _BatchMeta.of(batch)
+    out = tuple(t.to(device, non_blocking=True) for t in batch)
+    if meta is not None:
+        meta.attach(out, tuple(t.to(device, non_blocking=True) for t in meta.tensors()))
+    return out
+
+
+class _StepGraph:
+    """One captured training iteration: static input buffers (batch, index metadata, VectorPool plan), the CUDA
+    graph, and the tensors it leaves behind (outputs of Model.forward, the four LossManagers)."""
+
+    def __init__(self, batch, meta, plan):
+        dev = torch.device('cuda', torch.cuda.current_device())
+        self.batch = tuple(torch.empty(t.shape, dtype=t.dtype, device=dev) for t in batch)
+        self.meta_tensors = tuple(torch.empty(t.shape, dtype=t.dtype, device=dev) for t in meta.tensors())
+        self.pool_idx = None if plan is None else torch.empty(plan.shape, dtype=plan.dtype, device=dev)
+        self.slots_used = meta.slots_used
+        self.graph = self.out = self.losses = None
+        self.launches = 0
+
+    def load(self, batch, meta, plan):
+        for dst, src in zip(self.batch + self.meta_tensors, tuple(batch) + meta.tensors()):
+            dst.copy_(src, non_blocking=True)
+        if plan is not None:
+            # pinned staging block from torch's caching host allocator (it is not handed out again before this copy
+            # has run), so the host does not wait for the previous iteration here
+            self.pool_idx.copy_(plan.pin_memory(), non_blocking=True)
+        # same compaction decision as at capture (part of the geometry key); the host class list feeds nothing in a replay
+        meta_static = _BatchMeta(*self.meta_tensors, self.slots_used, meta.objs_host)
+        meta_static.attach(self.batch, self.meta_tensors)
+
+
 class Trainer:
     def __init__(self, args, vocab, checkpoint):
         self.vocab = vocab
@@ -32,6 +107,11 @@ class Trainer:
         self.init_image_discriminator(args, checkpoint)
         self.init_obj_discriminator(args, checkpoint)
         self.init_mask_discriminator(args, checkpoint)
+        # CUDA-graph replay of whole iterations (SG_CUDA_GRAPH=0 or args.cuda_graphs=False: eager launches)
+        self.use_graphs = bool(getattr(args, 'cuda_graphs', True)) and os.environ.get('SG_CUDA_GRAPH', '1') != '0'
+        self._graphs = {}             # batch geometry -> 'warm' (seen once, ran eagerly) | _StepGraph
+        self._graph_pool = None       # one private memory pool shared by all captured iterations (replayed one at a time)
+        self.generator_losses = self.d_mask_losses = self.d_obj_losses = self.d_img_losses = None
         self.reducers = {}
         if ddp.world_size() > 1:
             for name, net in (('g', self.model), ('img', self.netD), ('obj', self.obj_discriminator),
@@ -58,7 +138,7 @@ class Trainer:
         self.criterionVGG = None
         self.criterionFeat = torch.nn.L1Loss()
         self.criterionGAN = GANLoss(use_lsgan=not args.no_lsgan)
-        self.optimizer = torch.optim.Adam(model.parameters(), lr=args.learning_rate, betas=(args.beta1, 0.999), fused=True)
+        self.optimizer = torch.optim.Adam(model.parameters(), lr=args.learning_rate, betas=(args.beta1, 0.999), fused=True, capturable=True)
 
     def init_obj_discriminator(self, args, checkpoint):
         self.obj_discriminator, self.optimizer_d_obj = None, None
@@ -73,7 +153,7 @@ class Trainer:
             self.obj_discriminator.align_corners = getattr(args, 'align_corners', False)
             self.obj_discriminator.train()
             self.optimizer_d_obj = torch.optim.Adam(self.obj_discriminator.parameters(), lr=args.learning_rate,
-                                                    betas=(args.beta1, 0.999), fused=True)
+                                                    betas=(args.beta1, 0.999), fused=True, capturable=True)
 
     def init_mask_discriminator(self, args, checkpoint):
         self.mask_discriminator, self.optimizer_d_mask = None, None
@@ -87,7 +167,7 @@ class Trainer:
             self.mask_discriminator = define_mask_D(**kw).to('cuda')
             self.mask_discriminator.train()
             self.optimizer_d_mask = torch.optim.Adam(self.mask_discriminator.parameters(), lr=args.mask_learning_rate,
-                                                     betas=(args.beta1, 0.999), fused=True)
+                                                     betas=(args.beta1, 0.999), fused=True, capturable=True)
 
     def init_image_discriminator(self, args, checkpoint):
         if args.d_img_weight == 0:
@@ -102,7 +182,7 @@ class Trainer:
         self.netD = define_D(**kw).to('cuda')
         self.netD.train()
         self.optimizer_d_img = torch.optim.Adam(list(self.netD.parameters()), lr=args.learning_rate,
-                                                betas=(args.beta1, 0.999), fused=True)
+                                                betas=(args.beta1, 0.999), fused=True, capturable=True)
 
     # ---- checkpoint (trainer.py:136-203) -------------------------------------------------------
     def restore_checkpoint(self, checkpoint):
@@ -142,9 +222,14 @@ class Trainer:
         else:
             optimizer.zero_grad(set_to_none=True)
         losses.total_loss.backward()
+        # drop the autograd graph now: a loss kept for logging would keep this iteration's AccumulateGrad nodes (bound
+        # to the stream they were created on) alive into the next iteration — fatal for a CUDA graph capture
+        losses.total_loss = losses.total_loss.detach()
         if name in self.reducers:
             self.reducers[name].allreduce()
         optimizer.step()
+        # fused Adam does not bump Tensor._version: tell the bf16 operand cache which masters changed
+        Fn.invalidate_packed(p for group in optimizer.param_groups for p in group['params'])
 
     def _one_hot(self, objs, like):
         oh = torch.zeros((objs.numel(), self.num_obj), dtype=like.dtype, device=like.device)
@@ -248,19 +333,116 @@ class Trainer:
                 loss = loss + dw * fw * self.criterionFeat(pred_fake[i][j].float(), pred_real[i][j].detach().float())
         return loss
 
-    def train_step(self, batch, use_gt=True):
-        """One iteration of train.py:190-215 on a collated batch (tensors already on the device)."""
+    def train_step(self, batch, use_gt=True, graph=None):
+        """One iteration of train.py:190-215 on a collated batch.  The batch tensors may live on the device or
+        (graph replay) in pinned host memory — they are copied into the captured iteration's input buffers.
+        graph: None -> self.use_graphs."""
+        use_graph = self.use_graphs if graph is None else graph
+        if use_graph and torch.is_grad_enabled():
+            return self._train_step_graphed(batch, use_gt)
+        return self._train_step_eager(batch, use_gt)
+
+    def _train_step_eager(self, batch, use_gt, arena=False):
+        batch = _batch_to_device(batch, 'cuda')
         imgs, objs, boxes, masks, triples, obj_to_img, triple_to_img, attributes = batch
         if not use_gt:
             attributes = torch.zeros_like(attributes)
-        Fn.ARENA.begin_step(imgs.device)        # zero-initialised scratch of this iteration (one fill per step)
+        Fn.ARENA.begin_step(imgs.device, force=arena)        # zero-initialised scratch of this iteration (one fill per step)
         out = self.model(imgs, objs, triples, obj_to_img, boxes_gt=boxes, masks_gt=masks, attributes=attributes)
         imgs_pred, boxes_pred, masks_pred, layout, layout_pred, layout_wrong = out
         self.train_generator(imgs, imgs_pred, masks, masks_pred, layout, objs, boxes, boxes_pred, obj_to_img, use_gt)
         self.train_mask_discriminator(masks, masks_pred.detach(), objs)
         self.train_obj_discriminator(imgs, imgs_pred.detach(), objs, boxes, boxes.detach(), obj_to_img)
         self.train_image_discriminator(imgs, imgs_pred.detach(), layout, layout_wrong)
+        Fn.ARENA.end()
         return out
+
+    # ---- captured iterations ---------------------------------------------------------------------
+    def _train_step_graphed(self, batch, use_gt):
+        from . import _lib, ops
+        meta = _BatchMeta.of(batch)
+        if meta is None:              # no loader metadata: Model.forward would have to sync for it -> not capturable
+            return self._train_step_eager(batch, use_gt)
+        compact = meta.slots_used <= self.model.compact_slots
+        key = (bool(use_gt), compact, tuple((tuple(t.shape), t.dtype) for t in batch)) + meta.geometry()
+        ent = self._graphs.get(key)
+        if ent is None:               # first sight of this geometry: eager (also warms every lazy initialisation)
+            self._graphs[key] = 'warm'
+            # detached like the outputs of a replay: a caller holding on to this iteration's autograd graph would
+            # keep its AccumulateGrad nodes (bound to the eager stream) alive into the capture
+            return tuple(o.detach() if torch.is_tensor(o) else o for o in self._train_step_eager(batch, use_gt))
+        pool = self.model.fake_pool
+        plan = None
+        if pool.pool_size > 0:        # host half of the VectorPool, exactly once per iteration
+            if pool.store is None:
+                return self._train_step_eager(batch, use_gt)
+            plan = pool.plan(meta.objs_host)
+        if ent == 'warm':
+            ent = _StepGraph(batch, meta, plan)
+            ent.load(batch, meta, plan)
+            try:
+                self._capture(ent, use_gt)
+            except Exception as e:          # capture executes nothing on the device: the eager path can still run this step
+                warnings.warn('CUDA graph capture of the training step failed (%s: %s); continuing with eager launches'
+                              % (type(e).__name__, e))
+                self.use_graphs = False
+                self._graphs.clear()
+                ops.refresh_stream()
+                Fn.clear_weight_cache()
+                self.model.pool_plan = None if plan is None else ent.pool_idx
+                try:
+                    return self._train_step_eager(ent.batch, use_gt)
+                finally:
+                    self.model.pool_plan = None
+            self._graphs[key] = ent
+        else:
+            ent.load(batch, meta, plan)
+        ent.graph.replay()
+        _lib.add_launch_count(ent.launches)
+        Fn.clear_weight_cache()       # the replay updated the weights behind the version counters of the bf16 operand cache
+        self.generator_losses, self.d_mask_losses, self.d_obj_losses, self.d_img_losses = ent.losses
+        return ent.out
+
+    def _materialize_optimizer_state(self):
+        """Adam creates a parameter's moments lazily at its first gradient (torch/optim/adam.py, _init_group).  Inside a
+        capture that creation would be recorded — and the moments re-zeroed by every replay — so parameters that have
+        not had a gradient yet (box_net when every eager iteration so far had use_gt=False) get their state here."""
+        for opt in (self.optimizer, self.optimizer_d_obj, self.optimizer_d_mask, self.optimizer_d_img):
+            if opt is None:
+                continue
+            for group in opt.param_groups:
+                for p in group['params']:
+                    if p.requires_grad and len(opt.state[p]) == 0:
+                        st = opt.state[p]
+                        st['step'] = torch.zeros((), dtype=torch.float32, device=p.device)
+                        st['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                        st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+
+    def _capture(self, ent, use_gt):
+        from . import _lib, ops
+        dev = ent.batch[0].device
+        self._materialize_optimizer_state()
+        Fn.clear_weight_cache()       # every weight is re-packed at its first use inside the graph
+        Fn.ARENA.ensure(dev)
+        self.model.pool_plan = ent.pool_idx
+        mode = os.environ.get('SG_GRAPH_CAPTURE_MODE', 'global')
+        g = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        try:
+            with torch.cuda.graph(g, pool=self._graph_pool, capture_error_mode=mode):
+                out = self._train_step_eager(ent.batch, use_gt, arena=True)
+                ent.out = tuple(o.detach() if torch.is_tensor(o) else o for o in out)
+                del out
+        finally:
+            self.model.pool_plan = None
+            Fn.ARENA.end()
+            ops.refresh_stream()      # the cached stream handle is the capture stream
+            Fn.clear_weight_cache()
+        ent.launches = _lib.launch_count() - n0
+        ent.losses = (self.generator_losses, self.d_mask_losses, self.d_obj_losses, self.d_img_losses)
+        ent.graph = g
+        if self._graph_pool is None:
+            self._graph_pool = g.pool()
 
     def write_losses(self, checkpoint, t):
         print('t = %d / %d' % (t, self.args.num_iterations))

@@ -88,8 +88,13 @@ def test_generator_shallow_gradients_tight():
     report = [('input', cosine(xg.grad, xo.grad))]
     for name, p in G.named_parameters():
         ref = sd['layout_to_image.' + name].grad
-        if name.endswith('.bias') and ref.abs().max() < 1e-4:
-            continue
+        if name.endswith('.bias'):
+            # a bias in front of InstanceNorm has an exactly-zero gradient; the oracle's value is fp32 rounding noise
+            # (its direction is meaningless): skip when it is negligible next to the same layer's weight gradient
+            wref = sd['layout_to_image.' + name[:-4] + 'weight'].grad
+            if ref.abs().max() < 1e-3 * wref.abs().max():
+                assert p.grad.abs().max() < 1e-2 * wref.abs().max(), name
+                continue
         report.append((name, cosine(p.grad, ref)))
     print('\n'.join('%-40s cos %.4f' % r for r in report))
     # bf16 storage noise flips a few ReLU gates per layer (and the L1/ReLU kinks amplify it going backward):
