@@ -114,6 +114,11 @@ typedef struct {
                              (channel-compacted layouts, see sg_pack_weight_cmap); needs Hout*Wout >= 128 */
   int w_row0;             /* per-image weights only: first row (output channel) within an image's block, so that
                              a restricted dgrad covers rows [w_row0, w_row0 + w_Cout); 0 otherwise */
+  int w_mn;               /* 1: "transposed" use of an fprop weight tensor (the dgrad of a convolution reads the same
+                             bf16 copy as its fprop): w is [w_rows][w_taps][w_C], the contraction runs over the ROWS
+                             (and x's channels) and output channel n is column w_col0 + n:
+                               y[.., n] = sum_tap sum_k x[.., k] * w[k, wtap, w_col0 + n],  n < w_Cout */
+  int w_rows, w_col0;     /* w_mn only; w_col0 % 8 == 0, w_col0 + w_Cout <= w_C */
 } sg_conv_desc_t;
 int sg_conv_tc(const sg_conv_desc_t* desc, sg_stream_t stream);
 

@@ -40,6 +40,7 @@ class ConvDesc(ctypes.Structure):
         ('ntaps', c_int), ('taps', Tap * SG_MAX_TAPS),
         ('bias', c_void_p), ('act', c_int), ('slope', c_float), ('stats', c_void_p),
         ('w_img_rows', c_int), ('w_row0', c_int),
+        ('w_mn', c_int), ('w_rows', c_int), ('w_col0', c_int),
     ]
 
 

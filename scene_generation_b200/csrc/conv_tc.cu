@@ -92,6 +92,7 @@ struct ConvKParams {
   int kblocks, Cout, stages;
   int w_img_rows;   // > 0: per-image weights, image i uses rows [i * w_img_rows + w_row0, ...) of the weight tensor
   int w_row0;
+  int w_col0;       // BMN kernels: first weight column (= output channel offset inside the fprop weight tensor)
   int a_bytes;      // bytes of one A box = 128 * BW*BH*BI (rows beyond the box keep stale smem and are masked)
   int in_h0, in_w0;
   long long os_img, os_h, os_w, os_c;
@@ -114,10 +115,10 @@ struct ConvCfg {
   // Pipeline depth is a launch parameter.  Default ("shallow"): two CTAs share an SM (<= 113 KB each), so the
   // prologue / TMEM drain / store epilogue of one tile overlaps the MMA main loop of the other; "deep"
   // (SG_CONV_DEEP=1): one CTA per SM with the whole shared memory as its ring.
-  static constexpr int STAGES_DEEP = (BN == 256) ? 4 : 6;
-  static constexpr int STAGES_SHALLOW = (BN == 256) ? 2 : (BN == 128 ? 3 : (BN == 64 ? 4 : 6));
+  static constexpr int STAGES_DEEP = (BN == 256) ? 4 : (BN == 192 ? 5 : 6);
+  static constexpr int STAGES_SHALLOW = (BN >= 192) ? 2 : (BN == 128 ? 3 : (BN == 64 ? 4 : 6));
   static constexpr int B_BYTES = BN * 128;
-  static constexpr int TM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int TM_COLS = BN < 32 ? 32 : (BN == 192 ? 256 : BN);   // TMEM allocations are powers of two
   static constexpr int B_STRIDE = (B_BYTES < 1024 ? 1024 : B_BYTES);
   static constexpr int smem_bytes(int stages) { return stages * (A_BYTES + B_STRIDE) + 1024 /*align slack*/ + 256 /*barriers*/; }
 };
@@ -125,7 +126,10 @@ struct ConvCfg {
 // MC = true: launched as clusters of 2 CTAs along M that work on the same weight tile; each CTA fetches
 // half of B and multicasts it to both, which removes a third of the L2 -> SM operand traffic of a
 // 128 x BN tile (the limiter of the 1024-channel resblock GEMMs with single-CTA tiles).
-template <int BN, bool MC>
+// BMN = true: the weight operand is read "transposed" from the fprop tensor [K rows][taps][N cols] (dgrad of a
+// convolution uses the SAME bf16 copy of the weights as its fprop): 64 x 64 TMA boxes with the output channel as
+// the contiguous dimension, i.e. an MN-major B operand (the layout wgrad_tc_kernel uses for both operands).
+template <int BN, bool MC, bool BMN>
 __global__ void __launch_bounds__(192, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ ConvKParams p) {
@@ -178,7 +182,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const sg_tap_t tp = p.taps[ph.tap_begin + tap_i];
         mbar_expect_tx(&full[s], p.a_bytes + Cfg::B_BYTES);
         tma_load_5d(sA + s * A_BYTES, &tmA, &full[s], kb * 64, w0 + tp.dw + p.in_w0, h0 + tp.dh + p.in_h0, tp.plane, img0);
-        if (MC)
+        if (BMN) {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_3d(sB + s * Cfg::B_STRIDE + j * 8192, &tmB, &full[s], p.w_col0 + n0 + 64 * j, tp.wtap, kb * 64);
+        } else if (MC)
           tma_load_3d_mc(sB + s * Cfg::B_STRIDE + crank * (Cfg::B_BYTES / 2), &tmB, &full[s], kb * 64, tp.wtap,
                          wrow0 + (int)crank * (BN / 2), (uint16_t)3);
         else
@@ -187,7 +195,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, BMN ? 1 : 0);
       int s = 0;
       uint32_t par = 0;
       for (int it = 0; it < iters; ++it, ++s) {
@@ -195,9 +203,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&full[s], par);
         tc_fence_after();
         const uint64_t ad = umma_desc_sw128(smem_u32(sA + s * A_BYTES), 16, 1024);
-        const uint64_t bd = umma_desc_sw128(smem_u32(sB + s * Cfg::B_STRIDE), 16, 1024);
+        // K-major B: 16-element K steps are 32 B apart inside the 128 B rows.  MN-major B: 64 N-elements per 128 B
+        // row, 8 K-rows per 1024 B group (SBO), next 64-column block one 8 KB box further (LBO); a K step of 16 rows
+        // is 2048 B.
+        const uint64_t bd = BMN ? umma_desc_sw128(smem_u32(sB + s * Cfg::B_STRIDE), 8192, 1024)
+                                : umma_desc_sw128(smem_u32(sB + s * Cfg::B_STRIDE), 16, 1024);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) mma_bf16(tmem, ad + 2 * k, bd + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k)
+          mma_bf16(tmem, ad + 2 * k, bd + (BMN ? 128 : 2) * k, idesc, (it | k) != 0 ? 1u : 0u);
         if (MC) mma_commit_mc(&empty[s], (uint16_t)3);
         else mma_commit(&empty[s]);   // frees the smem slot once these MMAs have read it
       }
@@ -318,8 +331,9 @@ template <int BN>
 struct WgradCfg {
   static constexpr int NB = BN / 64;
   static constexpr int STAGE_BYTES = (2 + NB) * WG_BOX_BYTES;
-  static constexpr int STAGES_DEEP = (BN == 256) ? 4 : 6;
-  static constexpr int STAGES_SHALLOW = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);      // <= 113 KB: two CTAs per SM
+  static constexpr int STAGES_DEEP = (BN == 256) ? 4 : (BN == 192 ? 5 : 6);
+  static constexpr int STAGES_SHALLOW = (BN >= 192) ? 2 : (BN == 128 ? 3 : 4);      // <= 113 KB: two CTAs per SM
+  static constexpr int TM_COLS = BN == 192 ? 256 : BN;
   static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 + 256; }
 };
 
@@ -354,7 +368,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
   }
-  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  if (warp == 1) tmem_alloc<Cfg::TM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -437,7 +451,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<BN>(tmem);
+  if (warp == 1) tmem_dealloc<Cfg::TM_COLS>(tmem);
 }
 
 // Choose the TMA box (BW, BH, BI) of one M tile.  exact=false (conv): any box with BW*BH*BI <= rows —
@@ -477,11 +491,11 @@ bool deep_pipeline() {
   return v == 1;
 }
 
-template <int BN, bool MC>
+template <int BN, bool MC, bool BMN>
 int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKParams& kp, dim3 grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, MC, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          ConvCfg<BN>::smem_bytes(ConvCfg<BN>::STAGES_DEEP));
     if (e != cudaSuccess) return sg_fail(SG_ERR_CUDA, "conv_tc smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
@@ -504,21 +518,35 @@ int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKParams& k
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, MC>, tmA, tmB, kp);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, MC, BMN>, tmA, tmB, kp);
     if (e != cudaSuccess) return sg_fail(SG_ERR_CUDA, "sg_conv_tc (cluster launch): %s", cudaGetErrorString(e));
   } else {
-    conv_tc_kernel<BN, MC><<<grid, 192, smem_bytes, stream>>>(tmA, tmB, kp);
+    conv_tc_kernel<BN, MC, BMN><<<grid, 192, smem_bytes, stream>>>(tmA, tmB, kp);
   }
   SG_CHECK_LAUNCH("sg_conv_tc");
   return SG_OK;
 }
 
 template <int BN>
-int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKParams& kp, dim3 grid, bool mc, cudaStream_t stream) {
-  if (mc) {
-    if constexpr (BN >= 128) return launch_conv_t<BN, true>(tmA, tmB, kp, grid, stream);
+int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKParams& kp, dim3 grid, bool mc, bool bmn,
+                cudaStream_t stream) {
+  if (bmn) {
+    if constexpr (BN >= 64) return launch_conv_t<BN, false, true>(tmA, tmB, kp, grid, stream);
   }
-  return launch_conv_t<BN, false>(tmA, tmB, kp, grid, stream);
+  if (mc) {
+    if constexpr (BN == 128 || BN == 256) return launch_conv_t<BN, true, false>(tmA, tmB, kp, grid, stream);
+  }
+  return launch_conv_t<BN, false, false>(tmA, tmB, kp, grid, stream);
+}
+
+// SG_CONV_NO192=1 keeps the N tiles at powers of two (A/B switch for the 192-wide tile)
+bool no192() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SG_CONV_NO192");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
 }
 
 // SG_CONV_MULTICAST=1 enables the 2-CTA-cluster weight-multicast variant for long-K, wide-N launches
@@ -569,7 +597,13 @@ extern "C" int sg_conv_tc(const sg_conv_desc_t* d, sg_stream_t stream) {
   kp.tiles_w = sg_cdiv(d->Wout, kp.BW); kp.tiles_h = sg_cdiv(d->Hout, kp.BH);
   const int img_tiles = sg_cdiv(d->x_N, kp.BI);
   kp.n_img = d->x_N;
-  kp.kblocks = sg_cdiv(d->x_C < d->w_C ? d->x_C : d->w_C, 64);
+  const bool bmn = d->w_mn != 0;
+  SG_CHECK_ARG(!bmn || (d->w_img_rows == 0 && d->w_rows > 0 && d->w_col0 >= 0 && d->w_col0 % 8 == 0 &&
+                        d->w_col0 + d->w_Cout <= d->w_C),
+               "sg_conv_tc: w_mn needs one weight tensor, w_rows > 0 and columns [w_col0, w_col0 + w_Cout) inside w_C");
+  const int k_extent = bmn ? d->w_rows : d->w_C;      // extent of the contraction inside the weight tensor
+  kp.kblocks = sg_cdiv(d->x_C < k_extent ? d->x_C : k_extent, 64);
+  kp.w_col0 = bmn ? d->w_col0 : 0;
   kp.Cout = d->w_Cout;
   SG_CHECK_ARG(d->w_img_rows >= 0, "sg_conv_tc: w_img_rows must be >= 0");
   SG_CHECK_ARG(d->w_img_rows == 0 || kp.BI == 1, "sg_conv_tc: per-image weights need tiles within one image (H*W >= 128)");
@@ -592,30 +626,38 @@ extern "C" int sg_conv_tc(const sg_conv_desc_t* d, sg_stream_t stream) {
   int abox[5] = {64, kp.BW, kp.BH, 1, kp.BI};
   if (int e = make_tmap(&tmA, d->x, 5, adims, abox)) return e;
   // N tile: the MMA time of a CTA grows with BN, the number of waves over the 148 SMs shrinks with it
-  int BN = 16;
+  int BN = bmn ? 64 : 16;
   if (d->w_Cout > 16) {
     const long m_ctas = (long)kp.tiles_w * kp.tiles_h * img_tiles * d->nphases;
     double best_t = 0;
-    for (int cand = 256; cand >= 64; cand >>= 1) {
+    const int cands[4] = {256, 192, 128, 64};
+    for (int ci = 0; ci < 4; ++ci) {
+      const int cand = cands[ci];
       if (cand > 64 && cand / 2 >= d->w_Cout) continue;             // do not tile far beyond Cout
+      // 192 only where it wastes less of the last tile than the powers of two (192-channel mask_net, 3 x 64 ...)
+      if (cand == 192 && (sg_cdiv(d->w_Cout, 192) * 192 - d->w_Cout >= 64 || no192())) continue;
       long ctas = m_ctas * sg_cdiv(d->w_Cout, cand);
       double t = (double)((ctas + 147) / 148) * (cand + 48);        // +48: per-CTA prologue/epilogue in units of N columns
       if (best_t == 0 || t < best_t) { best_t = t; BN = cand; }
     }
   }
-  long long bdims[3] = {d->w_C, d->w_taps, d->w_img_rows > 0 ? (long long)d->w_img_rows * d->x_N : (long long)d->w_Cout};
+  long long bdims[3] = {d->w_C, d->w_taps,
+                        bmn ? (long long)d->w_rows
+                            : (d->w_img_rows > 0 ? (long long)d->w_img_rows * d->x_N : (long long)d->w_Cout)};
   int m_tiles = kp.tiles_w * kp.tiles_h * img_tiles;
   // weight multicast pays when the K loop is long (L2-bound operand streaming) and there are CTA pairs to form
-  const bool mc = multicast_enabled() && d->w_img_rows == 0 && BN >= 128 && m_tiles >= 2 && (long)d->ntaps * kp.kblocks >= 32;
+  const bool mc = multicast_enabled() && !bmn && d->w_img_rows == 0 && (BN == 128 || BN == 256) && m_tiles >= 2 &&
+                  (long)d->ntaps * kp.kblocks >= 32;
   if (mc) m_tiles = (m_tiles + 1) & ~1;           // an odd tail tile gets a fully masked partner
-  int bbox[3] = {64, 1, mc ? BN / 2 : BN};
+  int bbox[3] = {64, 1, bmn ? 64 : (mc ? BN / 2 : BN)};
   if (int e = make_tmap(&tmB, d->w, 3, bdims, bbox)) return e;
   dim3 grid(m_tiles, sg_cdiv(d->w_Cout, BN), d->nphases);
   switch (BN) {
-    case 256: return launch_conv<256>(tmA, tmB, kp, grid, mc, stream);
-    case 128: return launch_conv<128>(tmA, tmB, kp, grid, mc, stream);
-    case 64: return launch_conv<64>(tmA, tmB, kp, grid, false, stream);
-    default: return launch_conv<16>(tmA, tmB, kp, grid, false, stream);
+    case 256: return launch_conv<256>(tmA, tmB, kp, grid, mc, bmn, stream);
+    case 192: return launch_conv<192>(tmA, tmB, kp, grid, false, bmn, stream);
+    case 128: return launch_conv<128>(tmA, tmB, kp, grid, mc, bmn, stream);
+    case 64: return launch_conv<64>(tmA, tmB, kp, grid, false, bmn, stream);
+    default: return launch_conv<16>(tmA, tmB, kp, grid, false, false, stream);
   }
 }
 
@@ -631,7 +673,7 @@ extern "C" int sg_wgrad_tc(const sg_wgrad_desc_t* d, sg_stream_t stream) {
   kp.ktiles_total = kp.tiles_w * kp.tiles_h * sg_cdiv(d->N, kp.BI);
   kp.Cout = d->Cout; kp.Cin = d->Cin; kp.w_taps = d->w_taps; kp.dw_C = d->dw_C; kp.dw = d->dw;
   for (int i = 0; i < d->ntaps; ++i) kp.taps[i] = d->taps[i];
-  const int BN = d->Cin > 128 ? 256 : (d->Cin > 64 ? 128 : 64);
+  const int BN = (d->Cin > 128 && d->Cin <= 192 && !no192()) ? 192 : (d->Cin > 128 ? 256 : (d->Cin > 64 ? 128 : 64));
   kp.n_ci_tiles = sg_cdiv(d->Cin, BN);
   const int co_tiles = sg_cdiv(d->Cout, 128);
   int ksplit = d->ksplit;
@@ -661,6 +703,7 @@ extern "C" int sg_wgrad_tc(const sg_wgrad_desc_t* d, sg_stream_t stream) {
   dim3 grid(co_tiles * kp.n_ci_tiles, d->ntaps, ksplit);
   switch (BN) {
     case 256: return launch_wgrad<256>(tmA, tmB, kp, grid, stream);
+    case 192: return launch_wgrad<192>(tmA, tmB, kp, grid, stream);
     case 128: return launch_wgrad<128>(tmA, tmB, kp, grid, stream);
     default: return launch_wgrad<64>(tmA, tmB, kp, grid, stream);
   }

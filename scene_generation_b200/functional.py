@@ -50,16 +50,25 @@ def grad_like_weight(g3, weight, kind):
     return v.permute(3, 0, 1, 2) if kind == 'T' else v.permute(0, 3, 1, 2)
 
 
-def packed_weights(weight, kind):
+# SG_DGRAD_WT=1: dgrad reads a second, transposed bf16 copy [Cin][taps][Cout] (K-major B operand) instead of the
+# fprop copy through the MN-major-B kernel variant (A/B switch; costs one more pack kernel per weight and step)
+DGRAD_WT = os.environ.get('SG_DGRAD_WT', '0') == '1'
+
+
+def packed_weights(weight, kind, need_t=False):
+    """bf16 operand(s) of a master weight: wk (Cout, taps, Cin_p) — read K-major by fprop and MN-major by dgrad —
+    and, only on request, the transposed copy wt (Cin, taps, Cout_p).  Re-packed when the master's version counter
+    moved or after invalidate_packed()."""
     key = id(weight)
     ent = _pack_cache.get(key)
-    if ent is not None and ent[0] == weight._version and ent[3] is weight:
+    if ent is not None and ent[0] == weight._version and ent[3] is weight and (ent[2] is not None or not need_t):
         return ent[1], ent[2]
     m3 = master3(weight.detach(), kind)
     Cout, taps, Cin = m3.shape
     wk = torch.empty((Cout, taps, round_up(Cin, 8)), dtype=BF, device=weight.device)
-    wt = torch.empty((Cin, taps, round_up(Cout, 8)), dtype=BF, device=weight.device)
-    _lib.call('sg_pack_weight', _ptr(m3), Cout, taps, Cin, wk.shape[2], wt.shape[2], _ptr(wk), _ptr(wt), _stream())
+    wt = torch.empty((Cin, taps, round_up(Cout, 8)), dtype=BF, device=weight.device) if need_t else None
+    _lib.call('sg_pack_weight', _ptr(m3), Cout, taps, Cin, wk.shape[2], 0 if wt is None else wt.shape[2], _ptr(wk), _ptr(wt),
+              _stream())
     _pack_cache[key] = (weight._version, wk, wt, weight)
     return wk, wt
 
@@ -292,13 +301,18 @@ class ConvFn(torch.autograd.Function):
         spec = ctx.spec
         x5, weight, bias, y = ctx.saved_tensors
         cmap = ctx.cmap
-        if cmap is None:
-            _, wt = packed_weights(weight, spec.kind)
-        else:
-            _, wt = packed_weights_cmap(weight, spec.kind, cmap)
-        Cin, taps_n, Coutp = wt.shape[-3:]          # Cin: channels of the operand (compacted: Cc)
         m3 = master3(weight, spec.kind)
         Cout = m3.shape[0]
+        wk = wt = None
+        if cmap is not None:
+            _, wt = packed_weights_cmap(weight, spec.kind, cmap)
+            Cin, taps_n, Coutp = wt.shape[-3:]      # Cin: channels of the operand (compacted: Cc)
+        else:
+            if DGRAD_WT:
+                _, wt = packed_weights(weight, spec.kind, need_t=True)
+            else:
+                wk, _ = packed_weights(weight, spec.kind)
+            Cin, taps_n, Coutp = m3.shape[2], m3.shape[1], round_up(Cout, 8)
         N = x5.shape[0]
         want_planes = spec.kind == 'T'
         # ---- dz: gradient w.r.t. the pre-activation conv output, as a bf16 operand -------------
@@ -359,7 +373,13 @@ class ConvFn(torch.autograd.Function):
             c0 = c0 // 8 * 8          # keep the output pointer 16-byte aligned for the vector-store epilogue
             partial = (c0, c1) != (0, Cin) or Cx != Cin
             dx = (torch.zeros if partial else torch.empty)(x5.shape, dtype=BF, device=x5.device)
-            wsub, wr = (wt[c0:c1], None) if cmap is None else (wt, (c0, c1))
+            # the weight operand of the adjoint: rows [c0, c1) of a transposed copy, or columns [c0, c1) of the fprop copy
+            if wk is not None:
+                wsub, wsel = wk, dict(mn_cols=(c0, c1))
+            elif cmap is None:
+                wsub, wsel = wt[c0:c1], {}
+            else:
+                wsub, wsel = wt, dict(w_rows=(c0, c1))
             _, P, Hx, Wx, _ = x5.shape
             base = dx.view(-1)[c0:]
             if spec.kind == 's1' and spec.pad == 0 and Cout <= 4 and Cin in (32, 64) and Cx == Cin and not partial \
@@ -368,13 +388,13 @@ class ConvFn(torch.autograd.Function):
                 _lib.call('sg_dgrad_small_cout', _ptr(dz5), dz5.shape[4], _ptr(m3), Cout, spec.k, Cin, N, Ho, Wo, _ptr(dx),
                           _stream())
             elif spec.kind == 's1':
-                ops.conv_tc(dz5, wsub, base, (Hx * Wx * Cx, Wx * Cx, Cx, 1), Hx, Wx, convspec.dgrad_s1(spec.k, spec.pad), w_rows=wr)
+                ops.conv_tc(dz5, wsub, base, (Hx * Wx * Cx, Wx * Cx, Cx, 1), Hx, Wx, convspec.dgrad_s1(spec.k, spec.pad), **wsel)
             elif spec.kind == 's2':
                 for (a, b, ptaps) in convspec.dgrad_s2_phase_taps(spec.k, spec.pad):
                     plane = base[(a * 2 + b) * Hx * Wx * Cx:]
-                    ops.conv_tc(dz5, wsub, plane, (4 * Hx * Wx * Cx, Wx * Cx, Cx, 1), Hx, Wx, ptaps, w_rows=wr)
+                    ops.conv_tc(dz5, wsub, plane, (4 * Hx * Wx * Cx, Wx * Cx, Cx, 1), Hx, Wx, ptaps, **wsel)
             else:
-                ops.conv_tc(dz5, wsub, base, (Hx * Wx * Cx, Wx * Cx, Cx, 1), Hx, Wx, convspec.dgrad_convT(spec.k, 1))
+                ops.conv_tc(dz5, wsub, base, (Hx * Wx * Cx, Wx * Cx, Cx, 1), Hx, Wx, convspec.dgrad_convT(spec.k, 1), **wsel)
         return dx, dw, db, None, None
 
 
@@ -404,9 +424,8 @@ class LinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         xb, weight, y = ctx.saved_tensors
-        _, wt = packed_weights(weight, 's1')
         M, Nout, K = dy.shape[0], weight.shape[0], ctx.K
-        Np = wt.shape[2]
+        Np = round_up(Nout, 8)
         dz = cast_pad(dy, Np, mask_y=y, slope=0.0)
         dz5 = dz.view(1, 1, 1, M, Np)
         dx = dw = db = None
@@ -415,7 +434,10 @@ class LinearFn(torch.autograd.Function):
                     torch.zeros_like(weight), torch.zeros(Nout, device=dy.device), None)
         if ctx.needs_input_grad[0]:
             dx = torch.empty((M, K), dtype=torch.float32, device=dy.device)
-            ops.conv_tc(dz5, wt, dx, (0, 0, K, 1), 1, M, ONE_TAP)
+            if DGRAD_WT:
+                ops.conv_tc(dz5, packed_weights(weight, 's1', need_t=True)[1], dx, (0, 0, K, 1), 1, M, ONE_TAP)
+            else:
+                ops.conv_tc(dz5, packed_weights(weight, 's1')[0], dx, (0, 0, K, 1), 1, M, ONE_TAP, mn_cols=(0, K))
         if ctx.needs_input_grad[1]:
             dw = torch.empty((Nout, 1, K), dtype=torch.float32, device=dy.device)
             ops.wgrad_tc(dz5, xb.view(1, 1, 1, M, xb.shape[1]), dw, 1, M, ONE_WTAP, Nout, K)

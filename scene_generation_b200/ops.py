@@ -196,16 +196,18 @@ _desc_cache = {}
 
 
 def conv_tc(x5, w3, y, y_strides, Hout, Wout, taps, phases=None, oh_mul=1, ow_mul=1, in_h0=0, in_w0=0,
-            bias=None, act=_lib.ACT_NONE, slope=0.0, stats=None, w_rows=None):
+            bias=None, act=_lib.ACT_NONE, slope=0.0, stats=None, w_rows=None, mn_cols=None):
     """x5: bf16 (N,P,H,W,C) contiguous; w3: bf16 (Cout,taps,C) contiguous — or (N,R,taps,C) per-image weights
     (channel-compacted operands), of which rows [w_rows[0], w_rows[1]) of every image are the output channels;
     y: f32/bf16 output storage
     addressed as img*os_img + (h*oh_mul+oh_off)*os_h + (w*ow_mul+ow_off)*os_w + co*os_c with
     y_strides=(os_img, os_h, os_w[, os_c]) in elements.  taps: sequence of (dh, dw, plane, wtap).
     phases: sequence of (tap_begin, ntaps, oh_off, ow_off) or None for a single phase.
+    mn_cols=(c0, c1): "transposed" use of an fprop weight tensor (rows, taps, C) — the contraction runs over its rows
+    and the output channels are its columns [c0, c1) (dgrad with the same bf16 copy of the weights as fprop).
     The filled descriptor is cached per call-site geometry; only the pointers change per call."""
     key = ('c', x5.shape, w3.shape, y.dtype, tuple(y_strides), Hout, Wout, id(taps), id(phases), oh_mul, ow_mul,
-           in_h0, in_w0, act, slope, w_rows)
+           in_h0, in_w0, act, slope, w_rows, mn_cols)
     ent = _desc_cache.get(key)
     if ent is None or ent[1] is not taps or ent[2] is not phases:
         _need_cuda(x5, w3, y)
@@ -217,6 +219,11 @@ def conv_tc(x5, w3, y, y_strides, Hout, Wout, taps, phases=None, oh_mul=1, ow_mu
             _, d.w_img_rows, d.w_taps, d.w_C = w3.shape
             r0, r1 = w_rows or (0, w3.shape[1])
             d.w_Cout, d.w_row0 = r1 - r0, r0
+        elif mn_cols is not None:
+            assert w_rows is None and mn_cols[0] % 8 == 0 and 0 <= mn_cols[0] < mn_cols[1] <= w3.shape[2]
+            d.w_rows, d.w_taps, d.w_C = w3.shape
+            d.w_mn, d.w_col0, d.w_Cout = 1, mn_cols[0], mn_cols[1] - mn_cols[0]
+            d.w_img_rows = d.w_row0 = 0
         else:
             assert w_rows is None
             d.w_Cout, d.w_taps, d.w_C = w3.shape

@@ -202,3 +202,49 @@ def test_output_conv_64_to_3_tanh_forward_and_all_adjoints(H, W):
     check(op.grad[:, 0].permute(0, 3, 1, 2), xr.grad, 2e-2)
     check(wd.grad, wr.grad, 2e-2)
     check(bd.grad, br.grad, 2e-2)
+
+
+# ---- MN-major weight operand: the adjoint reads the fprop weight copy (sg_conv_desc_t.w_mn) -------------
+@pytest.mark.parametrize('M,Kdim,Ndim,c0,c1', [
+    (300, 512, 454, 0, 454),        # Linear dgrad: K = out features, N = in features (not a multiple of 8 columns)
+    (208, 4, 512, 0, 512),          # K tail: 4 weight rows (box_net's last layer)
+    (130, 1152, 512, 0, 512),       # long K
+    (77, 172, 1024, 0, 1024),       # K = 172 (class logits), N = 1024 -> BN 256
+    (260, 192, 192, 0, 192),        # N = 192 -> the 192-wide tile
+    (90, 64, 208, 168, 204),        # restricted columns [168, 204) of a 208-wide tensor (partial dgrad)
+    (64, 8, 8, 0, 3),               # tiny everything
+])
+def test_gemm_mn_major_weights(M, Kdim, Ndim, c0, c1):
+    """y[m, n] = sum_k x[m, k] * w[k, c0 + n] with w stored (K rows, 1 tap, N cols): must equal the K-major kernel
+    fed with the explicitly transposed copy, and the fp32 reference."""
+    x, w = rnd(M, Kdim, seed=1), rnd(Kdim, Ndim, seed=2, scale=0.1)
+    Kp, Np = ops.round_up(Kdim, 8), ops.round_up(Ndim, 8)
+    x5 = torch.zeros(1, 1, 1, M, Kp, dtype=torch.bfloat16)
+    x5[0, 0, 0, :, :Kdim] = bf(x)
+    w3 = torch.zeros(Kdim, 1, Np, dtype=torch.bfloat16)
+    w3[:, 0, :Ndim] = bf(w)
+    n = c1 - c0
+    y = torch.full((M, n), 7.0, device=DEV)
+    ops.conv_tc(x5.to(DEV), w3.to(DEV), y, (0, 0, n, 1), 1, M, [(0, 0, 0, 0)], mn_cols=(c0, c1))
+    ref = r32(x) @ r32(w)[:, c0:c1]
+    check(y, ref)
+    wt3 = torch.zeros(n, 1, Kp, dtype=torch.bfloat16)
+    wt3[:, 0, :Kdim] = bf(w)[:, c0:c1].t()
+    y2 = torch.empty((M, n), device=DEV)
+    ops.conv_tc(x5.to(DEV), wt3.to(DEV), y2, (0, 0, n, 1), 1, M, [(0, 0, 0, 0)])
+    check(y, y2.float().cpu(), 1e-5)
+
+
+@pytest.mark.parametrize('Cin,Cout,k,H', [(64, 128, 3, 16), (192, 192, 3, 8), (24, 1024, 3, 8), (8, 64, 4, 9), (304, 256, 3, 8)])
+def test_conv_dgrad_mn_major_weights(Cin, Cout, k, H):
+    """dgrad of a stride-1 zero-padded conv through the fprop weight copy == F.conv_transpose2d reference."""
+    N, pad = 3, k // 2
+    dy, w = rnd(N, Cout, H, H, seed=4), rnd(Cout, Cin, k, k, seed=5, scale=0.05)
+    Ho = H
+    Hx = Ho + k - 1 - 2 * pad
+    ref = F.conv_transpose2d(r32(dy), r32(w), padding=pad)
+    wk = pack_w(w)                                              # (Cout, k*k, Cin_p): the fprop operand
+    Cx = wk.shape[2]
+    dx = torch.zeros((N, Hx, Hx, Cx), dtype=torch.bfloat16, device=DEV)
+    ops.conv_tc(to_nhwc5(dy), wk, dx, (Hx * Hx * Cx, Hx * Cx, Cx, 1), Hx, Hx, convspec.dgrad_s1(k, pad), mn_cols=(0, Cin))
+    check(dx[..., :Cin].permute(0, 3, 1, 2), ref, 1e-2)         # bf16 output rounding
