@@ -241,6 +241,17 @@ int sg_gap_bwd(const float* gy, int N, int HW, int C, void* gx, sg_stream_t stre
 /* bias gradient: column sums of bf16 [rows][ld] (first C columns) ACCUMULATED into f32 out[C]. */
 int sg_colsum_bf16(const void* x, long long rows, int C, int ld, float* out, sg_stream_t stream);
 
+/* ---- trainer.py:60,80,106,133 (torch.optim.Adam.step) + operand refresh ----------------------------------
+ * Multi-tensor Adam (no weight decay, no amsgrad) over n_tensors parameter tensors, each given by its dense
+ * physical storage (p, g, m, v: f32, same layout, numel[i] elements).  step[i] points at the parameter's f32
+ * step counter ON THE DEVICE, already incremented for this step (bias corrections are evaluated in the kernel,
+ * so the call can be captured in a CUDA graph).  wk[i] != NULL: the bf16 tensor-core operand of that weight,
+ * rows of C[i] elements at pitch Cp[i] (see sg_pack_weight), is rewritten from the updated master in the same
+ * pass; the pad columns [C, Cp) are left untouched. */
+int sg_adam_pack(int n_tensors, void* const* p, void* const* g, void* const* m, void* const* v, void* const* wk,
+                 void* const* step, const long long* numel, const int* C, const int* Cp, double lr, double beta1,
+                 double beta2, double eps, sg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,7 +10,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
 LIB_PATH = os.path.join(_HERE, 'libsg_b200.so')
-SOURCES = ['runtime.cu', 'layout.cu', 'graph.cu', 'crop.cu', 'conv_tc.cu', 'elementwise.cu', 'smallconv.cu', 'compact.cu']
+SOURCES = ['runtime.cu', 'layout.cu', 'graph.cu', 'crop.cu', 'conv_tc.cu', 'elementwise.cu', 'smallconv.cu', 'compact.cu', 'adam.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
 
@@ -123,6 +123,8 @@ _SIGS = {
     'sg_gap_fwd': [_P, c_int, c_int, c_int, _P, _P],
     'sg_gap_bwd': [_P, c_int, c_int, c_int, _P, _P],
     'sg_colsum_bf16': [_P, c_long, c_int, c_int, _P, _P],
+    'sg_adam_pack': [c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                     ctypes.c_double, _P],
     'sg_wgrad_tc': [ctypes.POINTER(WgradDesc), _P],
     'sg_dgrad_small_cout': [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
     'sg_wgrad_small_cout': [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],

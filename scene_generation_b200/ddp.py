@@ -37,7 +37,8 @@ class FlatGradReducer:
 
     def __init__(self, module):
         self.params = [p for p in module.parameters() if p.requires_grad]
-        total = sum(p.numel() for p in self.params)
+        al = lambda n: (n + 3) // 4 * 4          # 16-byte aligned slices: the Adam kernel takes its float4 path
+        total = sum(al(p.numel()) for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         off = 0
@@ -46,7 +47,7 @@ class FlatGradReducer:
             # same physical layout as the parameter (dense, possibly permuted)
             g = torch.as_strided(self.flat, p.shape, p.stride(), off)
             p.grad = g
-            off += n
+            off += al(n)
 
     def zero(self):
         self.flat.zero_()

@@ -69,8 +69,33 @@ def packed_weights(weight, kind, need_t=False):
     wt = torch.empty((Cin, taps, round_up(Cout, 8)), dtype=BF, device=weight.device) if need_t else None
     _lib.call('sg_pack_weight', _ptr(m3), Cout, taps, Cin, wk.shape[2], 0 if wt is None else wt.shape[2], _ptr(wk), _ptr(wt),
               _stream())
-    _pack_cache[key] = (weight._version, wk, wt, weight)
+    _pack_cache[key] = (weight._version, wk, wt, weight, False, Cin)
     return wk, wt
+
+
+def operand_entry(weight):
+    """cache entry (version, wk, wt, weight, maintained, Cin) of a master whose bf16 operand is current, else None"""
+    ent = _pack_cache.get(id(weight))
+    if ent is not None and ent[3] is weight and ent[0] == weight._version:
+        return ent
+    return None
+
+
+def mark_operands_maintained(params):
+    """optim.PackedAdam rewrote the operands of these masters together with the masters themselves: the entries stay
+    valid (the fused update does not move Tensor._version) and survive drop_unmaintained()."""
+    for p in params:
+        ent = _pack_cache.get(id(p))
+        if ent is not None and ent[3] is p:
+            _pack_cache[id(p)] = ent[:4] + (True,) + ent[5:]
+
+
+def drop_unmaintained():
+    """Forget every operand that no optimizer keeps in step with its master (per-image gathered weights, frozen
+    networks, weights updated by a foreign optimizer).  Called around CUDA-graph captures / replays, which change
+    masters behind the version counters."""
+    for k in [k for k, ent in _pack_cache.items() if not (len(ent) > 4 and ent[4] is True)]:
+        del _pack_cache[k]
 
 
 def packed_weights_cmap(weight, kind, cmap):

@@ -21,12 +21,21 @@ from . import functional as Fn
 from .discriminators import AcCropDiscriminator, define_D, define_mask_D
 from .losses import GANLoss, get_gan_losses
 from .model import Model
+from .optim import PackedAdam
 from .utils import LossManager
 
 try:                                           # logging is optional plumbing (tensorboardX is not in the image)
     from tensorboardX import SummaryWriter
 except Exception:                              # pragma: no cover
     SummaryWriter = None
+
+
+def _adam(params, lr, betas):
+    """Adam(lr, betas=(beta1, 0.999)) of trainer.py:60,80,106,133.  Default: the hand-written multi-tensor kernel that
+    also refreshes the bf16 operands (optim.PackedAdam); SG_TORCH_ADAM=1: torch's fused Adam + per-step re-packing."""
+    if os.environ.get('SG_TORCH_ADAM', '0') == '1':
+        return torch.optim.Adam(params, lr=lr, betas=betas, fused=True, capturable=True)
+    return PackedAdam(params, lr=lr, betas=betas)
 
 
 class _BatchMeta:
@@ -138,7 +147,7 @@ class Trainer:
         self.criterionVGG = None
         self.criterionFeat = torch.nn.L1Loss()
         self.criterionGAN = GANLoss(use_lsgan=not args.no_lsgan)
-        self.optimizer = torch.optim.Adam(model.parameters(), lr=args.learning_rate, betas=(args.beta1, 0.999), fused=True, capturable=True)
+        self.optimizer = _adam(model.parameters(), lr=args.learning_rate, betas=(args.beta1, 0.999))
 
     def init_obj_discriminator(self, args, checkpoint):
         self.obj_discriminator, self.optimizer_d_obj = None, None
@@ -152,8 +161,7 @@ class Trainer:
             self.obj_discriminator = AcCropDiscriminator(**kw).to('cuda')
             self.obj_discriminator.align_corners = getattr(args, 'align_corners', False)
             self.obj_discriminator.train()
-            self.optimizer_d_obj = torch.optim.Adam(self.obj_discriminator.parameters(), lr=args.learning_rate,
-                                                    betas=(args.beta1, 0.999), fused=True, capturable=True)
+            self.optimizer_d_obj = _adam(self.obj_discriminator.parameters(), lr=args.learning_rate, betas=(args.beta1, 0.999))
 
     def init_mask_discriminator(self, args, checkpoint):
         self.mask_discriminator, self.optimizer_d_mask = None, None
@@ -166,8 +174,8 @@ class Trainer:
                 checkpoint['d_mask_kwargs'] = kw
             self.mask_discriminator = define_mask_D(**kw).to('cuda')
             self.mask_discriminator.train()
-            self.optimizer_d_mask = torch.optim.Adam(self.mask_discriminator.parameters(), lr=args.mask_learning_rate,
-                                                     betas=(args.beta1, 0.999), fused=True, capturable=True)
+            self.optimizer_d_mask = _adam(self.mask_discriminator.parameters(), lr=args.mask_learning_rate,
+                                          betas=(args.beta1, 0.999))
 
     def init_image_discriminator(self, args, checkpoint):
         if args.d_img_weight == 0:
@@ -181,8 +189,7 @@ class Trainer:
             checkpoint['d_img_kwargs'] = kw
         self.netD = define_D(**kw).to('cuda')
         self.netD.train()
-        self.optimizer_d_img = torch.optim.Adam(list(self.netD.parameters()), lr=args.learning_rate,
-                                                betas=(args.beta1, 0.999), fused=True, capturable=True)
+        self.optimizer_d_img = _adam(list(self.netD.parameters()), lr=args.learning_rate, betas=(args.beta1, 0.999))
 
     # ---- checkpoint (trainer.py:136-203) -------------------------------------------------------
     def restore_checkpoint(self, checkpoint):
@@ -228,8 +235,10 @@ class Trainer:
         if name in self.reducers:
             self.reducers[name].allreduce()
         optimizer.step()
-        # fused Adam does not bump Tensor._version: tell the bf16 operand cache which masters changed
-        Fn.invalidate_packed(p for group in optimizer.param_groups for p in group['params'])
+        if not isinstance(optimizer, PackedAdam):
+            # torch's fused Adam does not bump Tensor._version: tell the bf16 operand cache which masters changed
+            # (PackedAdam rewrites the operands itself)
+            Fn.invalidate_packed(p for group in optimizer.param_groups for p in group['params'])
 
     def _one_hot(self, objs, like):
         oh = torch.zeros((objs.numel(), self.num_obj), dtype=like.dtype, device=like.device)
@@ -399,7 +408,7 @@ class Trainer:
             ent.load(batch, meta, plan)
         ent.graph.replay()
         _lib.add_launch_count(ent.launches)
-        Fn.clear_weight_cache()       # the replay updated the weights behind the version counters of the bf16 operand cache
+        Fn.drop_unmaintained()        # the replay updated masters behind the version counters of the bf16 operand cache
         self.generator_losses, self.d_mask_losses, self.d_obj_losses, self.d_img_losses = ent.losses
         return ent.out
 
@@ -422,7 +431,7 @@ class Trainer:
         from . import _lib, ops
         dev = ent.batch[0].device
         self._materialize_optimizer_state()
-        Fn.clear_weight_cache()       # every weight is re-packed at its first use inside the graph
+        Fn.drop_unmaintained()        # operands no optimizer keeps current are re-packed at their first use inside the graph
         Fn.ARENA.ensure(dev)
         self.model.pool_plan = ent.pool_idx
         mode = os.environ.get('SG_GRAPH_CAPTURE_MODE', 'global')
@@ -437,7 +446,7 @@ class Trainer:
             self.model.pool_plan = None
             Fn.ARENA.end()
             ops.refresh_stream()      # the cached stream handle is the capture stream
-            Fn.clear_weight_cache()
+            Fn.drop_unmaintained()
         ent.launches = _lib.launch_count() - n0
         ent.losses = (self.generator_losses, self.d_mask_losses, self.d_obj_losses, self.d_img_losses)
         ent.graph = g
