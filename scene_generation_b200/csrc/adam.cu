@@ -17,9 +17,12 @@ namespace {
 
 typedef __nv_bfloat16 bf16;
 
-constexpr int ADAM_MAX_TENSORS = 32;
-constexpr int ADAM_MAX_BLOCKS = 320;
-constexpr int ADAM_CHUNK = 32768;      // elements per block
+// One launch covers up to 16 blocks per SM (148 x 16 = 2368 chunks of 16 k elements = 38.8 M parameters): enough
+// resident warps to keep ~100 KB of loads in flight per SM.  The tensor / chunk tables travel as kernel parameters
+// (19 KB; CUDA >= 12.1 allows 32 KB on sm_70+), so a launch needs no host-to-device copy and is graph-capturable.
+constexpr int ADAM_MAX_TENSORS = 96;
+constexpr int ADAM_MAX_BLOCKS = 2368;
+constexpr int ADAM_CHUNK = 16384;      // elements per block
 constexpr int ADAM_THREADS = 256;
 
 struct AdamTensor {
@@ -70,21 +73,38 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_pack_kernel(const __grid_co
   float* v = t.v + base;
   if (t.vec) {
     bf16* wk = t.wk ? t.wk + base : nullptr;
-    for (int i = threadIdx.x * 4; i < n; i += ADAM_THREADS * 4) {
-      float4 P = *reinterpret_cast<const float4*>(p + i);
-      const float4 G = __ldcs(reinterpret_cast<const float4*>(g + i));
-      float4 M = *reinterpret_cast<const float4*>(m + i);
-      float4 V = *reinterpret_cast<const float4*>(v + i);
-      adam_one(P.x, G.x, M.x, V.x, c);
-      adam_one(P.y, G.y, M.y, V.y, c);
-      adam_one(P.z, G.z, M.z, V.z, c);
-      adam_one(P.w, G.w, M.w, V.w, c);
-      *reinterpret_cast<float4*>(p + i) = P;
-      *reinterpret_cast<float4*>(m + i) = M;
-      *reinterpret_cast<float4*>(v + i) = V;
+    // two float4 groups per trip: all eight loads are issued before the first dependent store
+    constexpr int STRIDE = ADAM_THREADS * 4;
+    for (int i = threadIdx.x * 4; i < n; i += 2 * STRIDE) {
+      const bool two = i + STRIDE < n;
+      const int j = two ? i + STRIDE : i;
+      float4 P0 = *reinterpret_cast<const float4*>(p + i), P1 = *reinterpret_cast<const float4*>(p + j);
+      const float4 G0 = __ldcs(reinterpret_cast<const float4*>(g + i)), G1 = __ldcs(reinterpret_cast<const float4*>(g + j));
+      float4 M0 = *reinterpret_cast<const float4*>(m + i), M1 = *reinterpret_cast<const float4*>(m + j);
+      float4 V0 = *reinterpret_cast<const float4*>(v + i), V1 = *reinterpret_cast<const float4*>(v + j);
+      adam_one(P0.x, G0.x, M0.x, V0.x, c);
+      adam_one(P0.y, G0.y, M0.y, V0.y, c);
+      adam_one(P0.z, G0.z, M0.z, V0.z, c);
+      adam_one(P0.w, G0.w, M0.w, V0.w, c);
+      *reinterpret_cast<float4*>(p + i) = P0;
+      *reinterpret_cast<float4*>(m + i) = M0;
+      *reinterpret_cast<float4*>(v + i) = V0;
       if (wk) {
-        __align__(8) __nv_bfloat162 pk[2] = {__floats2bfloat162_rn(P.x, P.y), __floats2bfloat162_rn(P.z, P.w)};
+        __align__(8) __nv_bfloat162 pk[2] = {__floats2bfloat162_rn(P0.x, P0.y), __floats2bfloat162_rn(P0.z, P0.w)};
         *reinterpret_cast<uint2*>(wk + i) = *reinterpret_cast<uint2*>(pk);
+      }
+      if (two) {
+        adam_one(P1.x, G1.x, M1.x, V1.x, c);
+        adam_one(P1.y, G1.y, M1.y, V1.y, c);
+        adam_one(P1.z, G1.z, M1.z, V1.z, c);
+        adam_one(P1.w, G1.w, M1.w, V1.w, c);
+        *reinterpret_cast<float4*>(p + j) = P1;
+        *reinterpret_cast<float4*>(m + j) = M1;
+        *reinterpret_cast<float4*>(v + j) = V1;
+        if (wk) {
+          __align__(8) __nv_bfloat162 pk[2] = {__floats2bfloat162_rn(P1.x, P1.y), __floats2bfloat162_rn(P1.z, P1.w)};
+          *reinterpret_cast<uint2*>(wk + j) = *reinterpret_cast<uint2*>(pk);
+        }
       }
     }
   } else {
@@ -110,7 +130,8 @@ extern "C" int sg_adam_pack(int n_tensors, void* const* p, void* const* g, void*
                             double beta2, double eps, sg_stream_t stream) {
   SG_CHECK_ARG(n_tensors >= 0 && p && g && m && v && wk && step && numel && C && Cp, "sg_adam_pack: null argument array");
   SG_CHECK_ARG(lr >= 0. && beta1 >= 0. && beta1 < 1. && beta2 >= 0. && beta2 < 1. && eps >= 0., "sg_adam_pack: bad hyper-parameters");
-  AdamArgs a;
+  static thread_local AdamArgs a;     // 19 KB: kept off the stack, one per calling thread (the entry points stay
+                                      // re-entrant across threads and streams)
   a.lr = lr; a.b1d = beta1; a.b2d = beta2;
   a.b1 = (float)beta1; a.b2 = (float)beta2; a.omb1 = (float)(1.0 - beta1); a.omb2 = (float)(1.0 - beta2); a.eps = (float)eps;
   int nt = 0, nb = 0;

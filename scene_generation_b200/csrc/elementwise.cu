@@ -692,7 +692,8 @@ extern "C" int sg_norm_act_pad_bwd(const sg_nap_desc_t* d, const void* grad, con
     const int lanes = threads / nC;
     long total_px = (long)d->N * d->H * d->W;
     int pix_per_block = (int)((total_px + 1183) / 1184);           // ~8 CTAs per SM ...
-    if (pix_per_block < lanes * 8) pix_per_block = lanes * 8;      // ... but at least 8 pixels per thread
+    // ... but at least 2 pixels per thread (small maps — 8x8 resblocks — are latency-bound: more, shorter CTAs)
+    if (pix_per_block < lanes * 2) pix_per_block = lanes * 2;
     pix_per_block = ((pix_per_block + lanes - 1) / lanes) * lanes;
     dim3 grid(sg_cdiv((long)d->H * d->W, pix_per_block), d->N);
     nap_bwd_reduce_kernel<<<grid, threads, sizeof(float) * 16 * threads, stream>>>(b, pix_per_block);
