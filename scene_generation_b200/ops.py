@@ -32,6 +32,24 @@ def refresh_stream():
     _stream_cache[0] = None
 
 
+class on_stream:
+    """`with torch.cuda.stream(s)` that also drops the cached stream handle on entry and exit, so the library launches
+    follow torch's current stream into a side stream and back."""
+
+    def __init__(self, stream):
+        self.ctx = torch.cuda.stream(stream)
+
+    def __enter__(self):
+        self.ctx.__enter__()
+        refresh_stream()
+        return self
+
+    def __exit__(self, *exc):
+        r = self.ctx.__exit__(*exc)
+        refresh_stream()
+        return r
+
+
 def _ptr(t):
     return ctypes.c_void_p(0 if t is None else t.data_ptr())
 

@@ -120,6 +120,7 @@ class Trainer:
         self.use_graphs = bool(getattr(args, 'cuda_graphs', True)) and os.environ.get('SG_CUDA_GRAPH', '1') != '0'
         self._graphs = {}             # batch geometry -> 'warm' (seen once, ran eagerly) | _StepGraph
         self._graph_pool = None       # one private memory pool shared by all captured iterations (replayed one at a time)
+        self._side_streams = None     # captured iterations run the mask / object discriminator updates as parallel branches
         self.generator_losses = self.d_mask_losses = self.d_obj_losses = self.d_img_losses = None
         self.reducers = {}
         if ddp.world_size() > 1:
@@ -360,9 +361,29 @@ class Trainer:
         out = self.model(imgs, objs, triples, obj_to_img, boxes_gt=boxes, masks_gt=masks, attributes=attributes)
         imgs_pred, boxes_pred, masks_pred, layout, layout_pred, layout_wrong = out
         self.train_generator(imgs, imgs_pred, masks, masks_pred, layout, objs, boxes, boxes_pred, obj_to_img, use_gt)
-        self.train_mask_discriminator(masks, masks_pred.detach(), objs)
-        self.train_obj_discriminator(imgs, imgs_pred.detach(), objs, boxes, boxes.detach(), obj_to_img)
-        self.train_image_discriminator(imgs, imgs_pred.detach(), layout, layout_wrong)
+        masks_fake, imgs_fake = masks_pred.detach(), imgs_pred.detach()
+        side = self._side_streams if (arena and torch.cuda.is_current_stream_capturing()) else None
+        if side:
+            # The three discriminator updates only share read-only inputs (train.py:207-215): inside a captured
+            # iteration they become parallel branches of the graph — the small mask / object discriminator kernels
+            # fill the SMs the image discriminator's kernels leave idle.  Every tensor that crosses streams stays
+            # referenced until the branches are joined (no allocator reuse while a side stream may still read it).
+            from . import ops
+            main = torch.cuda.current_stream()
+            for s in side:
+                s.wait_stream(main)
+            with ops.on_stream(side[0]):
+                self.train_mask_discriminator(masks, masks_fake, objs)
+            with ops.on_stream(side[1]):
+                self.train_obj_discriminator(imgs, imgs_fake, objs, boxes, boxes.detach(), obj_to_img)
+            self.train_image_discriminator(imgs, imgs_fake, layout, layout_wrong)
+            for s in side:
+                main.wait_stream(s)
+            ops.refresh_stream()
+        else:
+            self.train_mask_discriminator(masks, masks_fake, objs)
+            self.train_obj_discriminator(imgs, imgs_fake, objs, boxes, boxes.detach(), obj_to_img)
+            self.train_image_discriminator(imgs, imgs_fake, layout, layout_wrong)
         Fn.ARENA.end()
         return out
 
@@ -431,6 +452,8 @@ class Trainer:
         from . import _lib, ops
         dev = ent.batch[0].device
         self._materialize_optimizer_state()
+        if self._side_streams is None and os.environ.get('SG_PARALLEL_D', '1') != '0':
+            self._side_streams = (torch.cuda.Stream(), torch.cuda.Stream())
         Fn.drop_unmaintained()        # operands no optimizer keeps current are re-packed at their first use inside the graph
         Fn.ARENA.ensure(dev)
         self.model.pool_plan = ent.pool_idx
