@@ -323,6 +323,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'      # keep NCCL's version banner out of stdout (ONE JSON line)
         dist.init_process_group('nccl', device_id=dev)
     assert world == a.gpus or world == 1, 'launch with torchrun --nproc-per-node %d' % a.gpus
 
@@ -499,8 +501,18 @@ def main():
             'roofline': roofline, 'kernels': kernels,
             'cpu_baseline': cpu,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        # captured iterations hold NCCL kernels of this communicator: drop the graphs before tearing it down, and do
+        # not let a slow teardown keep the launcher waiting (the result line is already out)
+        import gc
+        tr.release_graphs()
+        del tr
+        gc.collect()
+        torch.cuda.synchronize()
+        killer = threading.Timer(30.0, lambda: os._exit(0))
+        killer.daemon = True
+        killer.start()
         dist.destroy_process_group()
 
 

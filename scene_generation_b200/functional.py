@@ -65,11 +65,16 @@ def packed_weights(weight, kind, need_t=False):
         return ent[1], ent[2]
     m3 = master3(weight.detach(), kind)
     Cout, taps, Cin = m3.shape
-    wk = torch.empty((Cout, taps, round_up(Cin, 8)), dtype=BF, device=weight.device)
-    wt = torch.empty((Cin, taps, round_up(Cout, 8)), dtype=BF, device=weight.device) if need_t else None
+    stale = ent is not None and ent[3] is weight and ent[1].shape == (Cout, taps, round_up(Cin, 8))
+    # A stale entry of the same weight is re-packed IN PLACE: captured CUDA graphs (and PackedAdam launches inside
+    # them) hold the operand's address, which must survive a load_state_dict / any in-place edit of the master.
+    wk = ent[1] if stale else torch.empty((Cout, taps, round_up(Cin, 8)), dtype=BF, device=weight.device)
+    wt = None
+    if need_t:
+        wt = ent[2] if (stale and ent[2] is not None) else torch.empty((Cin, taps, round_up(Cout, 8)), dtype=BF, device=weight.device)
     _lib.call('sg_pack_weight', _ptr(m3), Cout, taps, Cin, wk.shape[2], 0 if wt is None else wt.shape[2], _ptr(wk), _ptr(wt),
               _stream())
-    _pack_cache[key] = (weight._version, wk, wt, weight, False, Cin)
+    _pack_cache[key] = (weight._version, wk, wt, weight, bool(stale and ent[4] is True and wt is None), Cin)
     return wk, wt
 
 

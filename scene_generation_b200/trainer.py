@@ -121,6 +121,8 @@ class Trainer:
         self._graphs = {}             # batch geometry -> 'warm' (seen once, ran eagerly) | _StepGraph
         self._graph_pool = None       # one private memory pool shared by all captured iterations (replayed one at a time)
         self._side_streams = None     # captured iterations run the mask / object discriminator updates as parallel branches
+        self._defer_g_update = False
+        self._g_update_pending = False
         self.generator_losses = self.d_mask_losses = self.d_obj_losses = self.d_img_losses = None
         self.reducers = {}
         if ddp.world_size() > 1:
@@ -223,6 +225,10 @@ class Trainer:
 
     # ---- the four sub-steps (trainer.py:205-325) -----------------------------------------------
     def _step(self, name, optimizer, losses):
+        self._backward(name, optimizer, losses)
+        self._update(name, optimizer)
+
+    def _backward(self, name, optimizer, losses):
         from . import ops
         ops.refresh_stream()
         if name in self.reducers:
@@ -233,6 +239,11 @@ class Trainer:
         # drop the autograd graph now: a loss kept for logging would keep this iteration's AccumulateGrad nodes (bound
         # to the stream they were created on) alive into the next iteration — fatal for a CUDA graph capture
         losses.total_loss = losses.total_loss.detach()
+
+    def _update(self, name, optimizer):
+        """gradient all-reduce (data parallel) + Adam"""
+        from . import ops
+        ops.refresh_stream()
         if name in self.reducers:
             self.reducers[name].allreduce()
         optimizer.step()
@@ -280,7 +291,11 @@ class Trainer:
                     gl.add_loss(self.calculate_features_loss(img_pred_fake, pred_real), 'g_gan_features_loss_img',
                                 args.d_img_features_weight)
             gl._terms['total_loss'] = gl.total_loss.detach()
-            self._step('g', self.optimizer, gl)
+            self._backward('g', self.optimizer, gl)
+            if self._defer_g_update:          # captured iterations overlap the generator's all-reduce + Adam with the D steps
+                self._g_update_pending = True
+            else:
+                self._update('g', self.optimizer)
         finally:
             for net in d_nets:
                 for p in net.parameters():
@@ -360,18 +375,30 @@ class Trainer:
         Fn.ARENA.begin_step(imgs.device, force=arena)        # zero-initialised scratch of this iteration (one fill per step)
         out = self.model(imgs, objs, triples, obj_to_img, boxes_gt=boxes, masks_gt=masks, attributes=attributes)
         imgs_pred, boxes_pred, masks_pred, layout, layout_pred, layout_wrong = out
-        self.train_generator(imgs, imgs_pred, masks, masks_pred, layout, objs, boxes, boxes_pred, obj_to_img, use_gt)
-        masks_fake, imgs_fake = masks_pred.detach(), imgs_pred.detach()
         side = self._side_streams if (arena and torch.cuda.is_current_stream_capturing()) else None
+        # single GPU: always; data parallel: opt-in until the overlapped all-reduce has been soaked at 4 / 8 ranks
+        self._defer_g_update = bool(side) and (not self.reducers or os.environ.get('SG_OVERLAP_G_ALLREDUCE', '0') == '1')
+        try:
+            self.train_generator(imgs, imgs_pred, masks, masks_pred, layout, objs, boxes, boxes_pred, obj_to_img, use_gt)
+        finally:
+            self._defer_g_update = False
+        masks_fake, imgs_fake = masks_pred.detach(), imgs_pred.detach()
         if side:
-            # The three discriminator updates only share read-only inputs (train.py:207-215): inside a captured
-            # iteration they become parallel branches of the graph — the small mask / object discriminator kernels
-            # fill the SMs the image discriminator's kernels leave idle.  Every tensor that crosses streams stays
-            # referenced until the branches are joined (no allocator reuse while a side stream may still read it).
+            # The three discriminator updates only share read-only inputs (train.py:207-215), and none of them reads
+            # the generator's weights (they see imgs_pred / masks_pred of THIS iteration's forward): inside a captured
+            # iteration the generator's gradient all-reduce + Adam and the three D steps become parallel branches of
+            # the graph — the all-reduce (NVLink) and the HBM-bound Adam pass hide under the discriminators' convolutions,
+            # and the small mask / object discriminator kernels fill the SMs the image discriminator leaves idle.
+            # Every tensor that crosses streams stays referenced until the branches are joined (no allocator reuse
+            # while a side stream may still read it).  Collectives are issued in the same host order on every rank.
             from . import ops
             main = torch.cuda.current_stream()
             for s in side:
                 s.wait_stream(main)
+            if self._g_update_pending:
+                with ops.on_stream(side[2]):
+                    self._update('g', self.optimizer)
+                self._g_update_pending = False
             with ops.on_stream(side[0]):
                 self.train_mask_discriminator(masks, masks_fake, objs)
             with ops.on_stream(side[1]):
@@ -433,6 +460,13 @@ class Trainer:
         self.generator_losses, self.d_mask_losses, self.d_obj_losses, self.d_img_losses = ent.losses
         return ent.out
 
+    def release_graphs(self):
+        """forget every captured iteration (and the memory pool they share); the next train_step starts over with eager
+        sightings.  Call before destroying a process group whose collectives were captured."""
+        self._graphs.clear()
+        self._graph_pool = None
+        self.generator_losses = self.d_mask_losses = self.d_obj_losses = self.d_img_losses = None
+
     def _materialize_optimizer_state(self):
         """Adam creates a parameter's moments lazily at its first gradient (torch/optim/adam.py, _init_group).  Inside a
         capture that creation would be recorded — and the moments re-zeroed by every replay — so parameters that have
@@ -453,7 +487,7 @@ class Trainer:
         dev = ent.batch[0].device
         self._materialize_optimizer_state()
         if self._side_streams is None and os.environ.get('SG_PARALLEL_D', '1') != '0':
-            self._side_streams = (torch.cuda.Stream(), torch.cuda.Stream())
+            self._side_streams = (torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream())
         Fn.drop_unmaintained()        # operands no optimizer keeps current are re-packed at their first use inside the graph
         Fn.ARENA.ensure(dev)
         self.model.pool_plan = ent.pool_idx

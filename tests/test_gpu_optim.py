@@ -66,11 +66,20 @@ def test_packed_adam_matches_torch_adam_and_keeps_operands_current():
             C = m3.shape[2]
             assert torch.equal(wk[..., :C], m3.to(torch.bfloat16)), (step, k)
             assert (wk[..., C:] == 0).all(), (step, k)
-    # a foreign in-place update moves the version counter: the operand is re-packed
+    # a foreign in-place update moves the version counter: the operand is re-packed — into the SAME buffer (captured
+    # CUDA graphs hold its address)
     with torch.no_grad():
         mine['linear'].mul_(0.5)
     wk, _ = Fn.packed_weights(mine['linear'], 's1')
-    assert wk is not wk0['linear']
+    assert wk is wk0['linear']
+    assert torch.equal(wk[..., :454], Fn.master3(mine['linear'].detach(), 's1').to(torch.bfloat16))
+    # and the optimizer keeps maintaining it afterwards
+    gr = torch.randn(300, 454, device=DEV)
+    for k in mine:
+        mine[k].grad = None
+    mine['linear'].grad = gr
+    opt.step()
+    assert Fn.packed_weights(mine['linear'], 's1')[0] is wk0['linear']
     assert torch.equal(wk[..., :454], Fn.master3(mine['linear'].detach(), 's1').to(torch.bfloat16))
 
 
