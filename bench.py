@@ -452,7 +452,13 @@ def main():
         dom = max(fam.items(), key=lambda kv: kv[1]['ms'])
         achieved = dom[1]['flops'] / (dom[1]['ms'] * 1e-3) / 1e12
         roofline = {'kernel': dom[0], 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                    'frac': achieved / peak_tf, 'traffic': None, 'peak_source': which,
+                    'frac': achieved / peak_tf, 'traffic': None,
+                    # ncu --set full of the family's heaviest shape (profiles/r01_conv_tc_resblock_s.md): DRAM bytes of one
+                    # launch next to its algorithmic bytes (bf16 weights + padded activations; the output stays in L2)
+                    'traffic_sample': {'launch': 'resblock 3x3 conv, GEMM 2048x1024x9216', 'dram_bytes': 25765888,
+                                       'algorithmic_bytes': 25480000, 'tensor_pipe_pct': 36.3,
+                                       'source': 'profiles/r01_conv_tc_resblock_s.md'},
+                    'peak_source': which,
                     'launches_per_step': dom[1]['launches'], 'ms_per_step': dom[1]['ms']}
         kernels = {k: {'launches': v['launches'], 'ms': round(v['ms'], 3),
                        'tflops': round(v['flops'] / (v['ms'] * 1e-3) / 1e12, 1)} for k, v in fam.items()}
