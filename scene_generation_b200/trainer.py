@@ -376,8 +376,8 @@ class Trainer:
         out = self.model(imgs, objs, triples, obj_to_img, boxes_gt=boxes, masks_gt=masks, attributes=attributes)
         imgs_pred, boxes_pred, masks_pred, layout, layout_pred, layout_wrong = out
         side = self._side_streams if (arena and torch.cuda.is_current_stream_capturing()) else None
-        # single GPU: always; data parallel: opt-in until the overlapped all-reduce has been soaked at 4 / 8 ranks
-        self._defer_g_update = bool(side) and (not self.reducers or os.environ.get('SG_OVERLAP_G_ALLREDUCE', '0') == '1')
+        # SG_OVERLAP_G_ALLREDUCE=0: keep the generator's all-reduce + Adam in front of the D steps (A/B switch)
+        self._defer_g_update = bool(side) and os.environ.get('SG_OVERLAP_G_ALLREDUCE', '1') != '0'
         try:
             self.train_generator(imgs, imgs_pred, masks, masks_pred, layout, objs, boxes, boxes_pred, obj_to_img, use_gt)
         finally:
