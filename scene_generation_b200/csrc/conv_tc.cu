@@ -315,6 +315,196 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// EXPERIMENTAL (SG_CONV_2CTA=1, not yet run on hardware — round-2 item): CTA-pair variant.  Two CTAs of a cluster own
+// two neighbouring M tiles and ONE N tile; the leader issues tcgen05.mma.cta_group::2 with M = 256: A = 128 rows from
+// each CTA's shared memory, B = BN/2 output channels from each CTA.  Every SM therefore streams its own A tile but
+// only HALF of the weight tile (24 KB instead of 32 KB per 64-channel k-block at BN = 128), which is what limits the
+// single-CTA kernel on the 1024-channel resblock GEMMs (L2 -> SM operand stream, profiles/r01_conv_tc_resblock_s.md).
+// Barrier protocol (CUTLASS PipelineTmaUmmaAsync, 2x1 atom): both producers wait on their own `empty`, only the leader
+// arms `full` with the bytes of BOTH CTAs, both issue their TMA loads against the leader's `full`; the leader's MMA
+// thread commits to `empty` / `accum_full` of both CTAs (multicast).  The epilogue is the single-CTA one, per CTA.
+template <int BN, bool BMN>
+__global__ void __launch_bounds__(192, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ ConvKParams p) {
+  constexpr int B_HALF = (BN / 2) * 128;        // bytes of this CTA's half of the weight tile per stage
+  constexpr int TM_COLS = BN;                   // 128 or 256
+  const int STAGES = p.stages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_HALF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* accum_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const int mt = blockIdx.x;                    // cluster dim x = 2: the pair is (2i, 2i + 1)
+  const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, ti = mt / (p.tiles_w * p.tiles_h);
+  const int w0 = tw * p.BW, h0 = th * p.BH, img0 = ti * p.BI;
+  const int n0 = blockIdx.y * BN;
+  const sg_phase_t ph = p.phases[blockIdx.z];
+  const int iters = ph.ntaps * p.kblocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum_full, 1);
+    fence_barrier_init();
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1) tmem_alloc2<TM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();                               // peer barriers / TMEM exist before any remote signal
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t par = 0;
+      for (int it = 0; it < iters; ++it, ++s) {
+        if (s == STAGES) { s = 0; par ^= 1; }
+        mbar_wait(&empty[s], par ^ 1);
+        const int tap_i = it / p.kblocks, kb = it - tap_i * p.kblocks;
+        const sg_tap_t tp = p.taps[ph.tap_begin + tap_i];
+        if (crank == 0) mbar_expect_tx(&full[s], 2 * (p.a_bytes + B_HALF));
+        const uint32_t bar = leader_bar_addr(&full[s]);
+        tma_load_5d_2cta(sA + s * A_BYTES, &tmA, bar, kb * 64, w0 + tp.dw + p.in_w0, h0 + tp.dh + p.in_h0, tp.plane, img0);
+        if (BMN) {
+#pragma unroll
+          for (int j = 0; j < BN / 128; ++j)
+            tma_load_3d_2cta(sB + s * B_HALF + j * 8192, &tmB, bar, p.w_col0 + n0 + (int)crank * (BN / 2) + 64 * j, tp.wtap,
+                             kb * 64);
+        } else {
+          tma_load_3d_2cta(sB + s * B_HALF, &tmB, bar, kb * 64, tp.wtap, n0 + (int)crank * (BN / 2));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, BMN ? 1 : 0);
+      int s = 0;
+      uint32_t par = 0;
+      for (int it = 0; it < iters; ++it, ++s) {
+        if (s == STAGES) { s = 0; par ^= 1; }
+        mbar_wait(&full[s], par);
+        tc_fence_after();
+        const uint64_t ad = umma_desc_sw128(smem_u32(sA + s * A_BYTES), 16, 1024);
+        const uint64_t bd = BMN ? umma_desc_sw128(smem_u32(sB + s * B_HALF), 8192, 1024)
+                                : umma_desc_sw128(smem_u32(sB + s * B_HALF), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          mma_bf16_2cta(tmem, ad + 2 * k, bd + (BMN ? 128 : 2) * k, idesc, (it | k) != 0 ? 1u : 0u);
+        mma_commit_2cta(&empty[s], (uint16_t)3);
+      }
+      mma_commit_2cta(accum_full, (uint16_t)3);
+    }
+  } else {
+    // ---------------- epilogue: warps 2..5 own TMEM lane quarters (warp % 4) -------------------
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int ww = r % p.BW, hh = (r / p.BW) % p.BH, ii = r / (p.BW * p.BH);
+    const int img = img0 + ii, h = h0 + hh, w = w0 + ww;
+    const bool valid = (ii < p.BI) && (img < p.n_img) && (h < p.Hout) && (w < p.Wout);
+    const long long off = (long long)img * p.os_img + (long long)(h * p.oh_mul + ph.oh_off) * p.os_h +
+                          (long long)(w * p.ow_mul + ph.ow_off) * p.os_w;
+    const bool seg_full = (p.BI == 1) || ((p.BW * p.BH) % 32 == 0);
+    mbar_wait(accum_full, 0);
+    tc_fence_after();
+    constexpr int CH = (BN >= 32) ? 32 : 16;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += CH) {
+      if (n0 + c0 >= p.Cout) break;
+      uint32_t raw[32];
+      if (CH == 32) tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, raw);
+      else tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c0, raw);
+      tmem_ld_wait();
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < CH) {
+          const int c = n0 + c0 + j;
+          float b = (p.bias != nullptr && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
+          f[j] = __uint_as_float(raw[j]) + b;
+        } else {
+          f[j] = 0.f;
+        }
+      }
+      if (p.stats != nullptr) {
+        if (seg_full) {
+          float s1[32], s2[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float v = valid ? f[j] : 0.f;
+            s1[j] = v;
+            s2[j] = v * v;
+          }
+          float t1 = warp_transpose_reduce(s1, lane);
+          float t2 = warp_transpose_reduce(s2, lane);
+          const int simg = __shfl_sync(0xffffffffu, img, 0);
+          const int c = n0 + c0 + lane;
+          if (lane < CH && c < p.Cout && simg < p.n_img) {
+            atomicAdd(p.stats + ((long long)simg * p.Cout + c) * 2, t1);
+            atomicAdd(p.stats + ((long long)simg * p.Cout + c) * 2 + 1, t2);
+          }
+        } else if (valid) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            const int c = n0 + c0 + j;
+            if (c < p.Cout) {
+              atomicAdd(p.stats + ((long long)img * p.Cout + c) * 2, f[j]);
+              atomicAdd(p.stats + ((long long)img * p.Cout + c) * 2 + 1, f[j] * f[j]);
+            }
+          }
+        }
+      }
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) f[j] = apply_act(f[j], p.act, p.slope);
+        const bool full_chunk = (n0 + c0 + CH <= p.Cout) && p.vec_ok;
+        if (p.y_dtype == 1) {
+          __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + off + (long long)(n0 + c0) * p.os_c;
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < CH; j += 8) {
+              __align__(16) __nv_bfloat162 pk[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) pk[t] = __floats2bfloat162_rn(f[j + 2 * t], f[j + 2 * t + 1]);
+              *reinterpret_cast<uint4*>(yp + j) = *reinterpret_cast<uint4*>(pk);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (n0 + c0 + j < p.Cout) yp[(long long)j * p.os_c] = __float2bfloat16(f[j]);
+          }
+        } else {
+          float* yp = reinterpret_cast<float*>(p.y) + off + (long long)(n0 + c0) * p.os_c;
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < CH; j += 4) *reinterpret_cast<float4*>(yp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (n0 + c0 + j < p.Cout) yp[(long long)j * p.os_c] = f[j];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();                               // the leader's MMAs read this CTA's shared memory until the last commit
+  if (warp == 1) tmem_dealloc2<TM_COLS>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------
 struct WgradKParams {
   int tiles_w, tiles_h, BW, BH, BI;
   int ktiles_total, ktiles_per_split;
@@ -527,6 +717,46 @@ int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKParams& k
   return SG_OK;
 }
 
+// SG_CONV_2CTA=1 selects the CTA-pair variant for long-K, wide-N launches (experimental)
+bool two_cta_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SG_CONV_2CTA");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+template <int BN, bool BMN>
+int launch_conv2(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKParams& kp, dim3 grid, cudaStream_t stream) {
+  constexpr int STAGES = (BN == 256) ? 6 : 8;                        // 32 KB / 24 KB per stage and CTA
+  constexpr int SMEM = STAGES * (A_BYTES + (BN / 2) * 128) + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return sg_fail(SG_ERR_CUDA, "conv_tc2 smem attribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  kp.stages = STAGES;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<BN, BMN>, tmA, tmB, kp);
+  if (e != cudaSuccess) return sg_fail(SG_ERR_CUDA, "sg_conv_tc (CTA-pair launch): %s", cudaGetErrorString(e));
+  SG_CHECK_LAUNCH("sg_conv_tc");
+  return SG_OK;
+}
+
 template <int BN>
 int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKParams& kp, dim3 grid, bool mc, bool bmn,
                 cudaStream_t stream) {
@@ -646,12 +876,19 @@ extern "C" int sg_conv_tc(const sg_conv_desc_t* d, sg_stream_t stream) {
                             : (d->w_img_rows > 0 ? (long long)d->w_img_rows * d->x_N : (long long)d->w_Cout)};
   int m_tiles = kp.tiles_w * kp.tiles_h * img_tiles;
   // weight multicast pays when the K loop is long (L2-bound operand streaming) and there are CTA pairs to form
-  const bool mc = multicast_enabled() && !bmn && d->w_img_rows == 0 && (BN == 128 || BN == 256) && m_tiles >= 2 &&
+  // CTA pairs (experimental): the same conditions as multicast, which they supersede
+  const bool pair = two_cta_enabled() && d->w_img_rows == 0 && (BN == 128 || BN == 256) && m_tiles >= 2 &&
+                    (long)d->ntaps * kp.kblocks >= 16;
+  const bool mc = !pair && multicast_enabled() && !bmn && d->w_img_rows == 0 && (BN == 128 || BN == 256) && m_tiles >= 2 &&
                   (long)d->ntaps * kp.kblocks >= 32;
-  if (mc) m_tiles = (m_tiles + 1) & ~1;           // an odd tail tile gets a fully masked partner
-  int bbox[3] = {64, 1, bmn ? 64 : (mc ? BN / 2 : BN)};
+  if (mc || pair) m_tiles = (m_tiles + 1) & ~1;   // an odd tail tile gets a fully masked partner
+  int bbox[3] = {64, 1, bmn ? 64 : ((mc || pair) ? BN / 2 : BN)};
   if (int e = make_tmap(&tmB, d->w, 3, bdims, bbox)) return e;
   dim3 grid(m_tiles, sg_cdiv(d->w_Cout, BN), d->nphases);
+  if (pair) {
+    if (BN == 256) return bmn ? launch_conv2<256, true>(tmA, tmB, kp, grid, stream) : launch_conv2<256, false>(tmA, tmB, kp, grid, stream);
+    return bmn ? launch_conv2<128, true>(tmA, tmB, kp, grid, stream) : launch_conv2<128, false>(tmA, tmB, kp, grid, stream);
+  }
   switch (BN) {
     case 256: return launch_conv<256>(tmA, tmB, kp, grid, mc, bmn, stream);
     case 192: return launch_conv<192>(tmA, tmB, kp, grid, false, bmn, stream);
