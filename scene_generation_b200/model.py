@@ -32,6 +32,7 @@ class Model(nn.Module):
         self.object_size = 64
         self.fake_pool = None        # built below, once the vocabulary size is known
         self.pool_plan = None        # device index vector of VectorPool.plan() when the host half ran outside (graph replay)
+        self.graph_branch_stream = None   # set by the Trainer (SG_PARALLEL_FWD=1): second branch of captured iterations
         self.layout_dtype = layout_dtype
         self.align_corners = align_corners
 
@@ -72,6 +73,9 @@ class Model(nn.Module):
         from . import ops
         ops.refresh_stream()
         O = objs.size(0)
+        if self.graph_branch_stream is not None and not test_mode and features is None and self.training \
+                and torch.cuda.is_current_stream_capturing():
+            return self._forward_train_two_branches(gt_imgs, objs, triples, obj_to_img, boxes_gt, masks_gt, attributes)
         obj_vecs, pred_vecs = self.scene_graph_to_vectors(objs, triples, attributes)
         N = gt_imgs.size(0) if gt_imgs is not None else None
         plan = None if test_mode else self._compact_plan(objs, N)
@@ -95,6 +99,51 @@ class Model(nn.Module):
         pred_layout = masks_to_layout(scene_layout_vecs, boxes_gt, masks_pred, obj_to_img, H, W, **lay)
         wrong_layout = masks_to_layout(wrong_layout_vecs, boxes_gt, masks_gt, obj_to_img, H, W, **lay)
         imgs_pred = self.layout_to_image(gt_layout)
+        return imgs_pred, boxes_pred, masks_pred, gt_layout, pred_layout, wrong_layout
+
+    def _forward_train_two_branches(self, gt_imgs, objs, triples, obj_to_img, boxes_gt, masks_gt, attributes):
+        """EXPERIMENTAL (SG_PARALLEL_FWD=1, captured iterations only; not yet run on hardware).  In training the generator
+        sees the GROUND-TRUTH boxes / masks and the appearance vectors of the image crops (model.py:119-121,158-170):
+        nothing on that path depends on the graph network.  The chain gconv -> box_net / mask_net (~100 tiny GEMMs and five
+        192-channel convs, forward and — since autograd replays each node on its forward stream — backward) therefore
+        runs as a second branch of the captured graph next to crops -> encoder -> layouts -> generator.  Same arithmetic
+        as forward(); the VectorPool / noise draws happen in the same order."""
+        from . import ops
+        N = gt_imgs.size(0)
+        O = objs.size(0)
+        H, W = self.image_size
+        plan = self._compact_plan(objs, N)
+        main, side = torch.cuda.current_stream(), self.graph_branch_stream
+        side.wait_stream(main)
+        with ops.on_stream(side):
+            obj_vecs, pred_vecs = self.scene_graph_to_vectors(objs, triples, attributes)
+            layout_noise = torch.randn((1, self.mask_noise_dim), dtype=obj_vecs.dtype, device=obj_vecs.device).repeat((O, 1))
+            mask_vecs = torch.cat([obj_vecs, layout_noise], dim=1)
+            boxes_pred = self.box_net(obj_vecs)
+            masks_pred = self.mask_net(mask_vecs, fused_sigmoid=True).squeeze(1)
+        # main branch: appearance vectors of the crops -> layout vectors -> layouts -> generator
+        crops = crop_bbox_batch(gt_imgs, boxes_gt, obj_to_img, self.object_size, align_corners=self.align_corners, operand=True)
+        obj_repr = self.repr_net(self.image_encoder(crops))
+        if plan is None:
+            one_hot_obj = torch.zeros((O, self.num_objs), dtype=obj_repr.dtype, device=obj_repr.device)
+            one_hot_obj = one_hot_obj.scatter_(1, objs.view(-1, 1).long(), 1.0)
+        else:
+            one_hot_obj = torch.zeros((O, self.compact_slots), dtype=obj_repr.dtype, device=obj_repr.device)
+            one_hot_obj = one_hot_obj.scatter_(1, plan[0].view(-1, 1), 1.0)
+        scene_layout_vecs = torch.cat([one_hot_obj, obj_repr], dim=1)
+        wrong_objs_rep = self.fake_pool.query(objs, obj_repr, planned=self.pool_plan)
+        wrong_layout_vecs = torch.cat([one_hot_obj, wrong_objs_rep], dim=1)
+        lay = dict(align_corners=self.align_corners, nhwc_bf16=self.layout_dtype == 'bf16', N=N,
+                   cmap=None if plan is None else plan[1])
+        gt_layout = masks_to_layout(scene_layout_vecs, boxes_gt, masks_gt, obj_to_img, H, W, **lay)
+        if self.layout_dtype == 'bf16':
+            c0 = self.num_objs if plan is None else self.compact_slots
+            gt_layout._sg_grad_channels = (c0, scene_layout_vecs.shape[1])
+        wrong_layout = masks_to_layout(wrong_layout_vecs, boxes_gt, masks_gt, obj_to_img, H, W, **lay)
+        imgs_pred = self.layout_to_image(gt_layout)
+        main.wait_stream(side)
+        ops.refresh_stream()
+        pred_layout = masks_to_layout(scene_layout_vecs, boxes_gt, masks_pred, obj_to_img, H, W, **lay)
         return imgs_pred, boxes_pred, masks_pred, gt_layout, pred_layout, wrong_layout
 
     def scene_graph_to_vectors(self, objs, triples, attributes):

@@ -16,12 +16,16 @@ NCHW_F32, NHWC_BF16 = 0, 1
 
 
 _stream_cache = [None]
+CACHE_STREAM = [True]      # False: ask torch for the current stream at every launch (multi-stream captures, where the
+                           # autograd engine switches streams between backward nodes)
 
 
 def _stream():
     """cudaStream_t of torch's current stream.  torch.cuda.current_stream() costs several microseconds, which
     adds up over ~1100 launches per step: the handle is cached until refresh_stream() is called (Model.forward
     and every Trainer sub-step call it on entry, i.e. after any `with torch.cuda.stream(...)` switch)."""
+    if not CACHE_STREAM[0]:
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     s = _stream_cache[0]
     if s is None:
         s = _stream_cache[0] = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -123,6 +123,7 @@ class Trainer:
         self._side_streams = None     # captured iterations run the mask / object discriminator updates as parallel branches
         self._defer_g_update = False
         self._g_update_pending = False
+        self._fwd_stream = None
         self.generator_losses = self.d_mask_losses = self.d_obj_losses = self.d_img_losses = None
         self.reducers = {}
         if ddp.world_size() > 1:
@@ -491,6 +492,12 @@ class Trainer:
         Fn.drop_unmaintained()        # operands no optimizer keeps current are re-packed at their first use inside the graph
         Fn.ARENA.ensure(dev)
         self.model.pool_plan = ent.pool_idx
+        two_branch_fwd = os.environ.get('SG_PARALLEL_FWD', '0') == '1'       # experimental, see Model._forward_train_two_branches
+        if two_branch_fwd:
+            if self._fwd_stream is None:
+                self._fwd_stream = torch.cuda.Stream()
+            self.model.graph_branch_stream = self._fwd_stream
+            ops.CACHE_STREAM[0] = False       # backward nodes of the side branch run on the side stream
         mode = os.environ.get('SG_GRAPH_CAPTURE_MODE', 'global')
         g = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
@@ -501,6 +508,8 @@ class Trainer:
                 del out
         finally:
             self.model.pool_plan = None
+            self.model.graph_branch_stream = None
+            ops.CACHE_STREAM[0] = True
             Fn.ARENA.end()
             ops.refresh_stream()      # the cached stream handle is the capture stream
             Fn.drop_unmaintained()
