@@ -505,6 +505,247 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------------
+// EXPERIMENTAL (SG_CONV_PERSIST=1, not yet run on hardware — round-2 item): persistent variant of conv_tc_kernel.
+// Why: the model in profiles/ (bench_shapes + launch list) puts the tensor-core convolutions of one iteration at
+// 2.3 ms of pure MMA time and 5.2 ms when the L2 -> SM operand stream is the limit, against 12 ms measured.  The
+// difference is per-CTA fixed cost (barrier init, TMEM allocation, descriptor fetch, pipeline fill, accumulator
+// drain): 4-7 us per CTA slot, paid 20-30 times per SM by the short-K convolutions (K loops of 4-16 iterations).
+// Here ONE CTA per SM walks a strided list of output tiles:
+//   * the TMA producer runs ahead ACROSS tile boundaries (the operand ring never drains between tiles),
+//   * the accumulator is double-buffered in TMEM (2 x BN columns): the epilogue warps drain tile i while the MMA
+//     thread already accumulates tile i + 1,
+//   * setup / teardown happen once per SM.
+// Barriers: full/empty per ring stage as in conv_tc_kernel; acc_full[2] (tcgen05.commit -> epilogue) and acc_empty[2]
+// (one arrive per epilogue warp after its last tcgen05.ld of the tile -> MMA thread).
+template <int BN, bool BMN>
+__global__ void __launch_bounds__(192, 1)
+conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ ConvKParams p, const int m_tiles, const int n_tiles, const int total_tiles) {
+  using Cfg = ConvCfg<BN>;
+  constexpr int TM_STRIDE = Cfg::TM_COLS;                // columns of one accumulator buffer (power of two >= 32)
+  constexpr int TM_ALLOC = 2 * TM_STRIDE;                // 64 .. 512
+  const int STAGES = p.stages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_STRIDE);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;                   // [2]
+  uint64_t* acc_empty = acc_full + 2;                    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 4);                       // the four epilogue warps
+    }
+    fence_barrier_init();
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1) tmem_alloc<TM_ALLOC>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // tile id -> (phase, n tile, m tile), m fastest: CTAs of one wave share a weight tile in L2
+  auto decode = [&](int t, int& mt, int& nt, int& z) {
+    mt = t % m_tiles;
+    const int r = t / m_tiles;
+    nt = r % n_tiles;
+    z = r / n_tiles;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t par = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int mt, nt, z;
+        decode(t, mt, nt, z);
+        const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, ti = mt / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.BW, h0 = th * p.BH, img0 = ti * p.BI;
+        const int n0 = nt * BN;
+        const int wrow0 = n0 + img0 * p.w_img_rows + p.w_row0;
+        const sg_phase_t ph = p.phases[z];
+        const int iters = ph.ntaps * p.kblocks;
+        for (int it = 0; it < iters; ++it, ++s) {
+          if (s == STAGES) { s = 0; par ^= 1; }
+          mbar_wait(&empty[s], par ^ 1);
+          const int tap_i = it / p.kblocks, kb = it - tap_i * p.kblocks;
+          const sg_tap_t tp = p.taps[ph.tap_begin + tap_i];
+          mbar_expect_tx(&full[s], p.a_bytes + Cfg::B_BYTES);
+          tma_load_5d(sA + s * A_BYTES, &tmA, &full[s], kb * 64, w0 + tp.dw + p.in_w0, h0 + tp.dh + p.in_h0, tp.plane, img0);
+          if (BMN) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_3d(sB + s * Cfg::B_STRIDE + j * 8192, &tmB, &full[s], p.w_col0 + n0 + 64 * j, tp.wtap, kb * 64);
+          } else {
+            tma_load_3d(sB + s * Cfg::B_STRIDE, &tmB, &full[s], kb * 64, tp.wtap, wrow0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, BMN ? 1 : 0);
+      int s = 0;
+      uint32_t par = 0;
+      int i = 0;                                         // tiles done by this CTA
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+        int mt, nt, z;
+        decode(t, mt, nt, z);
+        const int iters = p.phases[z].ntaps * p.kblocks;
+        const int buf = i & 1;
+        mbar_wait(&acc_empty[buf], ((uint32_t)(i >> 1) & 1u) ^ 1u);      // the epilogue has drained this buffer
+        tc_fence_after();
+        const uint32_t acc = tmem + (uint32_t)(buf * TM_STRIDE);
+        for (int it = 0; it < iters; ++it, ++s) {
+          if (s == STAGES) { s = 0; par ^= 1; }
+          mbar_wait(&full[s], par);
+          tc_fence_after();
+          const uint64_t ad = umma_desc_sw128(smem_u32(sA + s * A_BYTES), 16, 1024);
+          const uint64_t bd = BMN ? umma_desc_sw128(smem_u32(sB + s * Cfg::B_STRIDE), 8192, 1024)
+                                  : umma_desc_sw128(smem_u32(sB + s * Cfg::B_STRIDE), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_bf16(acc, ad + 2 * k, bd + (BMN ? 128 : 2) * k, idesc, (it | k) != 0 ? 1u : 0u);
+          mma_commit(&empty[s]);
+        }
+        mma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    // ---------------- epilogue: warps 2..5 own TMEM lane quarters (warp % 4) -------------------
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int ww = r % p.BW, hh = (r / p.BW) % p.BH, ii = r / (p.BW * p.BH);
+    const bool seg_full = (p.BI == 1) || ((p.BW * p.BH) % 32 == 0);
+    constexpr int CH = (BN >= 32) ? 32 : 16;
+    int i = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+      int mt, nt, z;
+      decode(t, mt, nt, z);
+      const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, ti = mt / (p.tiles_w * p.tiles_h);
+      const int w0 = tw * p.BW, h0 = th * p.BH, img0 = ti * p.BI;
+      const int n0 = nt * BN;
+      const sg_phase_t ph = p.phases[z];
+      const int img = img0 + ii, h = h0 + hh, w = w0 + ww;
+      const bool valid = (ii < p.BI) && (img < p.n_img) && (h < p.Hout) && (w < p.Wout);
+      const long long off = (long long)img * p.os_img + (long long)(h * p.oh_mul + ph.oh_off) * p.os_h +
+                            (long long)(w * p.ow_mul + ph.ow_off) * p.os_w;
+      const int buf = i & 1;
+      mbar_wait(&acc_full[buf], (uint32_t)(i >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t acc = tmem + (uint32_t)(buf * TM_STRIDE) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += CH) {
+        // warp-uniform: `last` = this is the final chunk with output channels in it (the loop always ends through it;
+        // `live` can only be false at c0 == 0, for a tile that lies entirely beyond Cout)
+        const bool live = n0 + c0 < p.Cout;
+        const bool last = !live || (c0 + CH >= BN) || (n0 + c0 + CH >= p.Cout);
+        uint32_t raw[32];
+        if (live) {
+          if (CH == 32) tmem_ld32(acc + c0, raw);
+          else tmem_ld16(acc + c0, raw);
+          tmem_ld_wait();
+        }
+        if (last) {
+          // this warp has read everything it needs from the accumulator: hand the buffer back to the MMA thread
+          // (exactly once per tile and warp)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        if (!live) break;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (j < CH) {
+            const int c = n0 + c0 + j;
+            float b = (p.bias != nullptr && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
+            f[j] = __uint_as_float(raw[j]) + b;
+          } else {
+            f[j] = 0.f;
+          }
+        }
+        if (p.stats != nullptr) {
+          if (seg_full) {
+            float s1[32], s2[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float v = valid ? f[j] : 0.f;
+              s1[j] = v;
+              s2[j] = v * v;
+            }
+            float t1 = warp_transpose_reduce(s1, lane);
+            float t2 = warp_transpose_reduce(s2, lane);
+            const int simg = __shfl_sync(0xffffffffu, img, 0);
+            const int c = n0 + c0 + lane;
+            if (lane < CH && c < p.Cout && simg < p.n_img) {
+              atomicAdd(p.stats + ((long long)simg * p.Cout + c) * 2, t1);
+              atomicAdd(p.stats + ((long long)simg * p.Cout + c) * 2 + 1, t2);
+            }
+          } else if (valid) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+              const int c = n0 + c0 + j;
+              if (c < p.Cout) {
+                atomicAdd(p.stats + ((long long)img * p.Cout + c) * 2, f[j]);
+                atomicAdd(p.stats + ((long long)img * p.Cout + c) * 2 + 1, f[j] * f[j]);
+              }
+            }
+          }
+        }
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) f[j] = apply_act(f[j], p.act, p.slope);
+          const bool full_chunk = (n0 + c0 + CH <= p.Cout) && p.vec_ok;
+          if (p.y_dtype == 1) {
+            __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + off + (long long)(n0 + c0) * p.os_c;
+            if (full_chunk) {
+#pragma unroll
+              for (int j = 0; j < CH; j += 8) {
+                __align__(16) __nv_bfloat162 pk[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) pk[u] = __floats2bfloat162_rn(f[j + 2 * u], f[j + 2 * u + 1]);
+                *reinterpret_cast<uint4*>(yp + j) = *reinterpret_cast<uint4*>(pk);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < CH; ++j)
+                if (n0 + c0 + j < p.Cout) yp[(long long)j * p.os_c] = __float2bfloat16(f[j]);
+            }
+          } else {
+            float* yp = reinterpret_cast<float*>(p.y) + off + (long long)(n0 + c0) * p.os_c;
+            if (full_chunk) {
+#pragma unroll
+              for (int j = 0; j < CH; j += 4) *reinterpret_cast<float4*>(yp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < CH; ++j)
+                if (n0 + c0 + j < p.Cout) yp[(long long)j * p.os_c] = f[j];
+            }
+          }
+        }
+        if (last) break;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TM_ALLOC>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------
 struct WgradKParams {
   int tiles_w, tiles_h, BW, BH, BI;
   int ktiles_total, ktiles_per_split;
@@ -757,9 +998,54 @@ int launch_conv2(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKParams& kp
   return SG_OK;
 }
 
+// SG_CONV_PERSIST=1 selects the persistent variant for multi-wave launches (experimental)
+bool persist_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SG_CONV_PERSIST");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+template <int BN, bool BMN>
+int launch_conv_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKParams& kp, dim3 grid, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tcp_kernel<BN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ConvCfg<BN>::smem_bytes(ConvCfg<BN>::STAGES_DEEP));
+    if (e != cudaSuccess) return sg_fail(SG_ERR_CUDA, "conv_tcp smem attribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  kp.stages = ConvCfg<BN>::STAGES_DEEP;
+  const int total = (int)(grid.x * grid.y * grid.z);
+  const int ctas = total < sm_count() ? total : sm_count();
+  conv_tcp_kernel<BN, BMN><<<ctas, 192, ConvCfg<BN>::smem_bytes(kp.stages), stream>>>(tmA, tmB, kp, (int)grid.x, (int)grid.y, total);
+  SG_CHECK_LAUNCH("sg_conv_tc");
+  return SG_OK;
+}
+
 template <int BN>
 int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKParams& kp, dim3 grid, bool mc, bool bmn,
                 cudaStream_t stream) {
+  // persistent variant: only where a CTA would otherwise be re-launched on the same SM (more tiles than SMs)
+  if (persist_enabled() && !mc && (long)grid.x * grid.y * grid.z > sm_count()) {
+    if (bmn) {
+      if constexpr (BN >= 64) return launch_conv_persist<BN, true>(tmA, tmB, kp, grid, stream);
+    } else {
+      return launch_conv_persist<BN, false>(tmA, tmB, kp, grid, stream);
+    }
+  }
   if (bmn) {
     if constexpr (BN >= 64) return launch_conv_t<BN, false, true>(tmA, tmB, kp, grid, stream);
   }
