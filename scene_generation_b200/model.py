@@ -33,6 +33,7 @@ class Model(nn.Module):
         self.fake_pool = None        # built below, once the vocabulary size is known
         self.pool_plan = None        # device index vector of VectorPool.plan() when the host half ran outside (graph replay)
         self.graph_branch_stream = None   # set by the Trainer (SG_PARALLEL_FWD=1): second branch of captured iterations
+        self.noise_generator = None       # None: torch's default CUDA generator (model.py:149 uses the global RNG)
         self.layout_dtype = layout_dtype
         self.align_corners = align_corners
 
@@ -117,7 +118,8 @@ class Model(nn.Module):
         side.wait_stream(main)
         with ops.on_stream(side):
             obj_vecs, pred_vecs = self.scene_graph_to_vectors(objs, triples, attributes)
-            layout_noise = torch.randn((1, self.mask_noise_dim), dtype=obj_vecs.dtype, device=obj_vecs.device).repeat((O, 1))
+            layout_noise = torch.randn((1, self.mask_noise_dim), dtype=obj_vecs.dtype, device=obj_vecs.device,
+                                   generator=self.noise_generator).repeat((O, 1))
             mask_vecs = torch.cat([obj_vecs, layout_noise], dim=1)
             boxes_pred = self.box_net(obj_vecs)
             masks_pred = self.mask_net(mask_vecs, fused_sigmoid=True).squeeze(1)
@@ -190,7 +192,8 @@ class Model(nn.Module):
         """model.py:145-172.  With a compact plan the one-hot part of the layout vectors indexes the image's
         class slots instead of the vocabulary."""
         O = objs.size(0)
-        layout_noise = torch.randn((1, self.mask_noise_dim), dtype=obj_vecs.dtype, device=obj_vecs.device).repeat((O, 1))
+        layout_noise = torch.randn((1, self.mask_noise_dim), dtype=obj_vecs.dtype, device=obj_vecs.device,
+                                   generator=self.noise_generator).repeat((O, 1))
         mask_vecs = torch.cat([obj_vecs, layout_noise], dim=1)
         if features is None:
             crops = crop_bbox_batch(imgs, boxes, obj_to_img, self.object_size, align_corners=self.align_corners, operand=True)

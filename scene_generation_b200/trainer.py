@@ -445,6 +445,11 @@ class Trainer:
                               % (type(e).__name__, e))
                 self.use_graphs = False
                 self._graphs.clear()
+                # a capture that ended in an error leaves torch's default CUDA generator in capture mode (its epilogue
+                # never ran): draw the mask noise from a generator of our own from here on
+                gen = torch.Generator(device=ent.batch[0].device)
+                gen.manual_seed(torch.initial_seed() + 1)
+                self.model.noise_generator = gen
                 ops.refresh_stream()
                 Fn.clear_weight_cache()
                 self.model.pool_plan = None if plan is None else ent.pool_idx
