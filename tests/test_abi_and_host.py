@@ -231,3 +231,49 @@ def test_class_slots_overflow_and_expand_layout_cpu():
     assert dense[0, :, 0, 0].tolist() == [0, 2, 0, 0, 1, 0, 3, 3, 3]
     plain = torch.ones(1, 9, 2, 2)
     assert L.expand_layout(plain, 9) is plain
+
+
+def test_vector_pool_plan_has_fixed_length_and_pads_to_scratch_row():
+    """graph replay feeds VectorPool.plan() as a static-shape input: [O read rows | O written rows | O sources], the
+    padding writes target the scratch row (index = capacity) which no read ever addresses; max_rows sizes the store
+    once so that nothing grows inside a capture."""
+    import random
+    from scene_generation_b200.utils import VectorPool
+    pool = VectorPool(2, max_rows=5 * 2)
+    vecs = torch.arange(12, dtype=torch.float32).view(6, 2)
+    objs = [3, 3, 1, 3, 4, 1]
+    random.seed(0)
+    pool.reserve(len(objs), vecs)
+    cap = pool.capacity
+    assert cap >= 10 and pool.store.shape == (cap + 1, 2)
+    idx = pool.plan(objs)
+    assert idx.shape == (3 * len(objs),) and idx.dtype == torch.long
+    src, rows, vals = idx[:6], idx[6:12], idx[12:]
+    assert ((src < cap) | (src > cap)).all()                  # never the scratch row
+    n_written = int((rows != cap).sum())
+    assert n_written == len(set(rows[rows != cap].tolist()))  # real writes address distinct pool rows
+    assert (rows[n_written:] == cap).all() and (vals[n_written:] == 0).all()
+    out = pool.apply(idx, vecs)
+    assert out.shape == vecs.shape
+    # first sighting of a class returns the object's own vector (utils.py:73-75)
+    assert torch.equal(out[0], vecs[0]) and torch.equal(out[2], vecs[2]) and torch.equal(out[4], vecs[4])
+    store_before = pool.store
+    for step in range(20):                                    # fill every class pool: the store must never be reallocated
+        pool.reserve(len(objs), vecs)
+        pool.apply(pool.plan(objs), vecs)
+    assert pool.store is store_before and pool.used <= 10
+
+
+def test_batch_meta_geometry_keys_the_iteration_graphs():
+    """Trainer keys its captured iterations on the shapes of the batch and of the loader's index tensors."""
+    from scene_generation_b200.trainer import _BatchMeta
+    b1 = synthetic.make_batch(3, (32, 32), 20, 2, 2, seed=1)
+    b2 = synthetic.make_batch(3, (32, 32), 20, 2, 2, seed=2)      # same geometry, different content
+    b3 = synthetic.make_batch(3, (32, 32), 20, 4, 4, seed=1)      # more objects
+    assert _BatchMeta.of(b1) is None                              # no loader metadata attached -> eager path
+    metas = [synthetic.HostMeta(b) for b in (b1, b2, b3)]
+    m1, m2, m3 = (_BatchMeta.of(m.attach(b)) for m, b in zip(metas, (b1, b2, b3)))
+    assert m1.geometry() == m2.geometry() != m3.geometry()
+    assert m1.objs_host == b1[1].tolist() and m1.slots_used >= 1
+    assert [tuple(t.shape) for t in m1.tensors()] == [(3, 2), (b1[1].numel() + 1,), (2 * b1[4].shape[0],), (b1[1].numel(),),
+                                                      (3, synthetic.MAX_CLASS_SLOTS)]
