@@ -147,6 +147,12 @@ typedef struct {
 } sg_wgrad_desc_t;
 int sg_wgrad_tc(const sg_wgrad_desc_t* desc, sg_stream_t stream);
 
+/* Hardware probe (groundwork for an smem-resident halo tile, not on any product path): a 3x3 convolution of one
+ * 16x8-pixel tile, 64 -> 64 channels, whose nine taps read ONE halo tile through tap-shifted UMMA descriptors.
+ * x: bf16 [1][1][18][10][64], w: bf16 [64][9][64], y: f32 [128][64]; mode 0 / 1 = descriptor base_offset 0 / derived
+ * from the start address.  tests/halo_probe.py compares both against sg_conv_tc. */
+int sg_probe_shifted_desc(const void* x, const void* w, float* y, int mode, sg_stream_t stream);
+
 /* Input gradient of a stride-1 "valid" convolution with a tiny output-channel count (the generator's last
  * 7x7 conv 64 -> 3, generators.py:87) as a direct CUDA-core convolution:
  *   dx[n,u,v,ci] = sum_{kh,kw,co} dz[n,u-kh,v-kw,co] * w[co,kh,kw,ci],  u < H+k-1, v < W+k-1

@@ -1231,3 +1231,95 @@ extern "C" int sg_wgrad_tc(const sg_wgrad_desc_t* d, sg_stream_t stream) {
     default: return launch_wgrad<64>(tmA, tmB, kp, grid, stream);
   }
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// PROBE (round-2 groundwork, not on any product path): can one shared-memory HALO tile feed all taps of a 3x3
+// convolution through tap-shifted UMMA descriptors?  The halo of a 16x8-pixel tile (18 x 10 pixels x 64 channels,
+// one TMA box, SWIZZLE_128B) is loaded ONCE; tap (dh, dw) then reads the 128 output pixels' operand rows as 16
+// groups of 8 consecutive pixels starting at row (dh * 10 + dw), group stride (SBO) = 10 rows = 1280 B — i.e. a
+// start address that is 128-byte but not 1024-byte aligned and an SBO that is not a multiple of the swizzle period.
+// mode 0: descriptor base_offset = 0; mode 1: base_offset = (start >> 7) & 7 (the field PTX defines for start
+// addresses that are not aligned to the swizzle repeat).  If either mode reproduces the reference convolution, the
+// 7x7 / 3x3 convolutions can stop re-reading their input tile once per tap (49x / 9x less L2 -> SM traffic for A).
+namespace {
+
+__global__ void __launch_bounds__(128) probe_shift_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                          float* y, int mode) {
+  constexpr int HALO_ROWS = 18 * 10, A_HALO = HALO_ROWS * 128, B_TAP = 64 * 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + ((A_HALO + 1023) / 1024) * 1024;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + 9 * B_TAP);
+  uint64_t* done = full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(full, 1);
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<64>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(full, A_HALO + 9 * B_TAP);
+    tma_load_5d(sA, &tmA, full, 0, 0, 0, 0, 0);
+    for (int tap = 0; tap < 9; ++tap) tma_load_3d(sB + tap * B_TAP, &tmB, full, 0, tap, 0);
+    mbar_wait(full, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+    for (int tap = 0; tap < 9; ++tap) {
+      const int dh = tap / 3, dw = tap % 3;
+      const uint32_t start = smem_u32(sA + (dh * 10 + dw) * 128);
+      uint64_t ad = umma_desc_sw128(start, 16, 10 * 128);
+      if (mode == 1) ad |= (uint64_t)((start >> 7) & 7u) << 49;
+      const uint64_t bd = umma_desc_sw128(smem_u32(sB + tap * B_TAP), 16, 1024);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mma_bf16(tmem, ad + 2 * k, bd + 2 * k, idesc, (tap | k) != 0 ? 1u : 0u);
+    }
+    mma_commit(done);
+  }
+  mbar_wait(done, 0);
+  tc_fence_after();
+  const int row = warp * 32 + lane;
+#pragma unroll 1
+  for (int c0 = 0; c0 < 64; c0 += 32) {
+    uint32_t raw[32];
+    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, raw);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) y[row * 64 + c0 + j] = __uint_as_float(raw[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<64>(tmem);
+}
+
+}  // namespace
+
+/* x: bf16 [1][1][18][10][64] (reflection / zero halo already materialised), w: bf16 [64][9][64], y: f32 [128][64]
+ * (pixel = h * 8 + w of the 16 x 8 tile, then output channel). */
+extern "C" int sg_probe_shifted_desc(const void* x, const void* w, float* y, int mode, sg_stream_t stream) {
+  SG_CHECK_ARG(x && w && y && (mode == 0 || mode == 1), "sg_probe_shifted_desc: bad arguments");
+  CUtensorMap tmA, tmB;
+  long long adims[5] = {64, 10, 18, 1, 1};
+  int abox[5] = {64, 10, 18, 1, 1};
+  if (int e = make_tmap(&tmA, x, 5, adims, abox)) return e;
+  long long bdims[3] = {64, 9, 64};
+  int bbox[3] = {64, 1, 64};
+  if (int e = make_tmap(&tmB, w, 3, bdims, bbox)) return e;
+  const int smem = 24 * 1024 + 9 * 8192 + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(probe_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return sg_fail(SG_ERR_CUDA, "probe smem attribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  probe_shift_kernel<<<1, 128, smem, stream>>>(tmA, tmB, y, mode);
+  SG_CHECK_LAUNCH("sg_probe_shifted_desc");
+  return SG_OK;
+}
