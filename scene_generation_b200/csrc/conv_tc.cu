@@ -885,6 +885,174 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 1) tmem_dealloc<Cfg::TM_COLS>(tmem);
 }
 
+// EXPERIMENTAL (SG_WGRAD_PERSIST=1, not yet run on hardware — round-2 item): persistent variant of wgrad_tc_kernel,
+// same scheme as conv_tcp_kernel.  A weight-gradient tile's epilogue moves 128 x BN fp32 (up to 128 KB) out of TMEM
+// with vector stores / reductions; double-buffering the accumulator lets it overlap the next tile's MMAs.
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+wgrad_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ WgradKParams p, const int gx, const int gy, const int total_tiles) {
+  using Cfg = WgradCfg<BN>;
+  constexpr int TM_STRIDE = Cfg::TM_COLS;
+  constexpr int TM_ALLOC = 2 * TM_STRIDE;
+  const int STAGES = p.stages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 4);
+    }
+    fence_barrier_init();
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1) tmem_alloc<TM_ALLOC>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // tile id -> (x = co/ci tile, y = tap, z = k split) of the non-persistent grid; returns the k-tile range
+  auto decode = [&](int t, int& x, int& y, int& z, int& kt_begin, int& iters) {
+    x = t % gx;
+    const int r = t / gx;
+    y = r % gy;
+    z = r / gy;
+    kt_begin = z * p.ktiles_per_split;
+    const int kt_end = min(kt_begin + p.ktiles_per_split, p.ktiles_total);
+    iters = max(kt_end - kt_begin, 0);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t par = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int x, y, z, kt_begin, iters;
+        decode(t, x, y, z, kt_begin, iters);
+        const int ci_tile = x % p.n_ci_tiles, co_tile = x / p.n_ci_tiles;
+        const int co0 = co_tile * 128, ci0 = ci_tile * BN;
+        const sg_wtap_t tp = p.taps[y];
+        for (int it = 0; it < iters; ++it, ++s) {
+          if (s == STAGES) { s = 0; par ^= 1; }
+          mbar_wait(&empty[s], par ^ 1);
+          const int kt = kt_begin + it;
+          const int tw = kt % p.tiles_w, th = (kt / p.tiles_w) % p.tiles_h, ti = kt / (p.tiles_w * p.tiles_h);
+          const int w0 = tw * p.BW, h0 = th * p.BH, img0 = ti * p.BI;
+          uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+          mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+          tma_load_5d(st, &tmA, &full[s], co0, w0 + tp.dwa, h0 + tp.dha, tp.pa, img0);
+          tma_load_5d(st + WG_BOX_BYTES, &tmA, &full[s], co0 + 64, w0 + tp.dwa, h0 + tp.dha, tp.pa, img0);
+#pragma unroll
+          for (int j = 0; j < Cfg::NB; ++j)
+            tma_load_5d(st + (2 + j) * WG_BOX_BYTES, &tmB, &full[s], ci0 + 64 * j, w0 + tp.dwb, h0 + tp.dhb, tp.pb, img0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
+      int s = 0;
+      uint32_t par = 0;
+      int i = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int x, y, z, kt_begin, iters;
+        decode(t, x, y, z, kt_begin, iters);
+        if (iters == 0) continue;                        // every role skips empty tiles the same way
+        const int buf = i & 1;
+        mbar_wait(&acc_empty[buf], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t acc = tmem + (uint32_t)(buf * TM_STRIDE);
+        for (int it = 0; it < iters; ++it, ++s) {
+          if (s == STAGES) { s = 0; par ^= 1; }
+          mbar_wait(&full[s], par);
+          tc_fence_after();
+          uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+          const uint64_t ad = umma_desc_sw128(smem_u32(st), WG_BOX_BYTES, 1024);
+          const uint64_t bd = umma_desc_sw128(smem_u32(st + 2 * WG_BOX_BYTES), WG_BOX_BYTES, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_bf16(acc, ad + 128 * k, bd + 128 * k, idesc, (it | k) != 0 ? 1u : 0u);
+          mma_commit(&empty[s]);
+        }
+        mma_commit(&acc_full[buf]);
+        ++i;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int i = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int x, y, z, kt_begin, iters;
+      decode(t, x, y, z, kt_begin, iters);
+      if (iters == 0) continue;
+      const int ci_tile = x % p.n_ci_tiles, co_tile = x / p.n_ci_tiles;
+      const int co0 = co_tile * 128, ci0 = ci_tile * BN;
+      const sg_wtap_t tp = p.taps[y];
+      const int co = co0 + q * 32 + lane;
+      const int buf = i & 1;
+      mbar_wait(&acc_full[buf], (uint32_t)(i >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t acc = tmem + (uint32_t)(buf * TM_STRIDE) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        const bool live = ci0 + c0 < p.Cin;              // warp-uniform
+        const bool last = !live || (c0 + 32 >= BN) || (ci0 + c0 + 32 >= p.Cin);
+        uint32_t raw[32];
+        if (live) {
+          tmem_ld32(acc + c0, raw);
+          tmem_ld_wait();
+        }
+        if (last) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        if (!live) break;
+        if (co < p.Cout) {
+          float* dst = p.dw + (long long)z * p.dw_split_stride + ((long long)co * p.w_taps + tp.wtap) * p.dw_C + ci0 + c0;
+          const bool vec = (ci0 + c0 + 32 <= p.Cin) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+          if (vec && !p.atomic) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]),
+                                                                __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3]));
+          } else if (vec) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(raw[j])),
+                           "f"(__uint_as_float(raw[j + 1])), "f"(__uint_as_float(raw[j + 2])), "f"(__uint_as_float(raw[j + 3]))
+                           : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (ci0 + c0 + j < p.Cin) {
+                if (p.atomic) atomicAdd(dst + j, __uint_as_float(raw[j]));
+                else dst[j] = __uint_as_float(raw[j]);
+              }
+          }
+        }
+        if (last) break;
+      }
+      ++i;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TM_ALLOC>(tmem);
+}
+
 // Choose the TMA box (BW, BH, BI) of one M tile.  exact=false (conv): any box with BW*BH*BI <= rows —
 // smem rows beyond the box stay stale and their accumulator rows are masked in the epilogue, so
 // odd extents (10x10, 65x65, 134x134) do not round up to powers of two.  exact=true (wgrad): the box
@@ -1008,6 +1176,16 @@ bool persist_enabled() {
   return v == 1;
 }
 
+// SG_WGRAD_PERSIST=1 selects the persistent wgrad variant for multi-wave launches (experimental)
+bool wgrad_persist_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SG_WGRAD_PERSIST");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -1085,6 +1263,21 @@ int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, WgradKParams& k
     attr_set = true;
   }
   const bool one_wave = (long)grid.x * grid.y * grid.z <= 148;
+  if (wgrad_persist_enabled() && !one_wave) {
+    static bool attr2_set = false;
+    if (!attr2_set) {
+      cudaError_t e = cudaFuncSetAttribute(wgrad_tcp_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           WgradCfg<BN>::smem_bytes(WgradCfg<BN>::STAGES_DEEP));
+      if (e != cudaSuccess) return sg_fail(SG_ERR_CUDA, "wgrad_tcp smem attribute: %s", cudaGetErrorString(e));
+      attr2_set = true;
+    }
+    kp.stages = WgradCfg<BN>::STAGES_DEEP;
+    const int total = (int)(grid.x * grid.y * grid.z);
+    const int ctas = total < sm_count() ? total : sm_count();
+    wgrad_tcp_kernel<BN><<<ctas, 192, WgradCfg<BN>::smem_bytes(kp.stages), stream>>>(tmA, tmB, kp, (int)grid.x, (int)grid.y, total);
+    SG_CHECK_LAUNCH("sg_wgrad_tc");
+    return SG_OK;
+  }
   kp.stages = (deep_pipeline() || one_wave) ? WgradCfg<BN>::STAGES_DEEP : WgradCfg<BN>::STAGES_SHALLOW;
   wgrad_tc_kernel<BN><<<grid, 192, WgradCfg<BN>::smem_bytes(kp.stages), stream>>>(tmA, tmB, kp);
   SG_CHECK_LAUNCH("sg_wgrad_tc");

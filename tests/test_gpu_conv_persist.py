@@ -1,5 +1,5 @@
-"""Persistent (one CTA per SM, double-buffered TMEM accumulator) variant of the conv kernel — EXPERIMENTAL and off by
-default (SG_CONV_PERSIST=1).  Written at the end of round 1 without hardware access: the checks only run on request
+"""Persistent (one CTA per SM, double-buffered TMEM accumulator) variants of the conv and wgrad kernels — EXPERIMENTAL and
+off by default (SG_CONV_PERSIST=1, SG_WGRAD_PERSIST=1).  Written at the end of round 1 without hardware access: the checks only run on request
 (SG_TEST_PERSIST=1).  They re-run the conv / module / compact suites and the short-K timing script with the switch on."""
 import os
 import subprocess
@@ -24,7 +24,7 @@ def test_persistent_conv_short_k_shapes():
 
 @pytest.mark.skipif(not ON, reason='experimental kernel variant: set SG_TEST_PERSIST=1 to run')
 def test_conv_and_module_suites_with_persistent_kernel():
-    env = dict(os.environ, SG_CONV_PERSIST='1')
+    env = dict(os.environ, SG_CONV_PERSIST='1', SG_WGRAD_PERSIST='1')
     env.pop('SG_TEST_PERSIST', None)
     r = subprocess.run([sys.executable, '-m', 'pytest', '-q', '-x', '-m', 'gpu', 'tests/test_gpu_conv_tc.py',
                         'tests/test_gpu_modules.py', 'tests/test_gpu_compact.py', 'tests/test_gpu_train_step.py'],
