@@ -7,6 +7,7 @@
 //     out = pad/planes/upsample( act( src * scale + shift ) + residual )
 // and writes the bf16 NHWC operand of the next convolution; its adjoint folds the padding halo,
 // applies act' and the norm backward in a reduce + apply pair.
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/sg_b200.h"
 
@@ -419,6 +420,83 @@ __global__ void nap_bwd_apply_kernel(NapBwdArgs b) {
   store8(b.dsrc + off, o);
 }
 
+// EXPERIMENTAL (SG_NAP_FUSED=1, not yet run on hardware — round-2 item): InstanceNorm backward of SMALL maps in one
+// kernel.  nap_bwd_reduce + nap_bwd_apply read the gradient operand and the source twice, need a memset and — on the
+// 8x8 resblock maps — are latency-bound (20 + 12 us for 4 MB).  Here one CTA owns (image, slab of SC 8-channel chunks):
+// every (pixel, chunk) item is loaded once into registers, the per-channel sums S1 = sum g', S2 = sum g' xhat are
+// reduced inside the CTA (deterministic, no atomics, no workspace) and the gradient is applied from the registers.
+constexpr int NAPF_THREADS = 256;
+constexpr int NAPF_MAX_ITEMS = 4;      // items per thread: H*W*SC <= 1024
+
+__global__ void __launch_bounds__(NAPF_THREADS) nap_bwd_fused_kernel(NapBwdArgs b, int SC) {
+  __shared__ float part[NAPF_THREADS][17];        // per-thread partial (S1,S2) x 8 channels (+1: bank spread)
+  __shared__ float stat[32][16];                  // per chunk of the slab: m1[8], m2[8]
+  const NapArgs& a = b.f;
+  const int nC = a.C / 8;
+  const int HW = a.H * a.W;
+  const int n = blockIdx.y;
+  const int ch0 = blockIdx.x * SC;
+  const int c = threadIdx.x % SC;                 // NAPF_THREADS % SC == 0: a thread's items all have this chunk
+  const int ch = ch0 + c;
+  const int items = HW * SC;
+  float gp[NAPF_MAX_ITEMS][8], xh[NAPF_MAX_ITEMS][8];
+  float s1[8], s2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
+#pragma unroll
+  for (int j = 0; j < NAPF_MAX_ITEMS; ++j) {
+    const int i = threadIdx.x + j * NAPF_THREADS;
+    if (i < items && ch < nC) {
+      const int p = i / SC;
+      gprime(b, n, p / a.W, p % a.W, ch, gp[j], xh[j]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        s1[k] += gp[j][k];
+        s2[k] += gp[j][k] * xh[j][k];
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    part[threadIdx.x][2 * k] = s1[k];
+    part[threadIdx.x][2 * k + 1] = s2[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < SC * 16) {
+    const int cc = threadIdx.x / 16, e = threadIdx.x % 16;
+    float v = 0.f;
+    for (int t = cc; t < NAPF_THREADS; t += SC) v += part[t][e];     // fixed order: deterministic
+    stat[cc][e] = v / b.count;
+  }
+  __syncthreads();
+  if (ch >= nC) return;
+  float sc[8];
+  load8f(a.scale + (long)n * a.C + ch * 8, sc);
+#pragma unroll
+  for (int j = 0; j < NAPF_MAX_ITEMS; ++j) {
+    const int i = threadIdx.x + j * NAPF_THREADS;
+    if (i >= items) continue;
+    const int p = i / SC;
+    const int h = p / a.W, w = p % a.W;
+    if (b.dres) {
+      float fg[8];
+      fold_grad(a, b.g, n, h, w, ch, fg);
+      store8(b.dres + (long)n * a.res_os_img + (long)h * a.res_os_h + (long)w * a.res_os_w + ch * 8, fg);
+    }
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = sc[k] * (gp[j][k] - stat[c][2 * k] - xh[j][k] * stat[c][2 * k + 1]);
+    long off;
+    if (b.out_planes) {
+      const int Hh = (a.H + 1) / 2, Wh = (a.W + 1) / 2;
+      off = ((((long)n * 4 + (h & 1) * 2 + (w & 1)) * Hh + (h >> 1)) * Wh + (w >> 1)) * a.C + ch * 8;
+    } else {
+      off = (((long)n * a.H + h) * a.W + w) * a.C + ch * 8;
+    }
+    store8(b.dsrc + off, o);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // small layout / pooling kernels
 // ---------------------------------------------------------------------------------------------
@@ -639,6 +717,16 @@ extern "C" int sg_norm_finalize(const float* stats, int mode, int n_img, int C, 
   return SG_OK;
 }
 
+// SG_NAP_FUSED=1: single-kernel InstanceNorm backward for small maps (experimental)
+static bool nap_fused_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SG_NAP_FUSED");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 static int nap_check(const sg_nap_desc_t* d) {
   SG_CHECK_ARG(d && d->src, "norm_act_pad: null pointer");
   SG_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0 && d->C > 0 && d->C % 8 == 0, "norm_act_pad: bad sizes (C must be a multiple of 8)");
@@ -684,6 +772,18 @@ extern "C" int sg_norm_act_pad_bwd(const sg_nap_desc_t* d, const void* grad, con
   b.g = (const bf16*)grad; b.save_mean = save_mean; b.save_rstd = save_rstd; b.bn = bn; b.count = count; b.sums = sums;
   b.out_planes = out_planes; b.dsrc = (bf16*)dsrc; b.dres = (bf16*)dres;
   const int nC = d->C / 8;
+  if (save_mean && !bn && nap_fused_enabled() && (long)d->H * d->W <= 256) {
+    // experimental single-kernel path for small InstanceNorm maps: SC chunks per CTA with H*W*SC <= 1024 items
+    int SC = 8;
+    while (SC > 1 && (long)d->H * d->W * SC > (long)NAPF_THREADS * NAPF_MAX_ITEMS) SC >>= 1;
+    if ((long)d->H * d->W * SC <= (long)NAPF_THREADS * NAPF_MAX_ITEMS) {
+      if (out_planes && ((d->H & 1) || (d->W & 1)))
+        cudaMemsetAsync(dsrc, 0, sizeof(bf16) * 4 * (size_t)d->N * ((d->H + 1) / 2) * ((d->W + 1) / 2) * d->C, stream);
+      nap_bwd_fused_kernel<<<dim3(sg_cdiv(nC, SC), d->N), NAPF_THREADS, 0, stream>>>(b, SC);
+      SG_CHECK_LAUNCH("sg_norm_act_pad_bwd(fused)");
+      return SG_OK;
+    }
+  }
   if (save_mean) {
     cudaMemsetAsync(sums, 0, sizeof(float) * 2 * (size_t)d->N * d->C, stream);
     int threads = nC >= 256 ? nC : 256;
