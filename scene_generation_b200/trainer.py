@@ -131,7 +131,9 @@ class Trainer:
                               ('mask', self.mask_discriminator)):
                 if net is not None:
                     ddp.broadcast_parameters(net)
-                    self.reducers[name] = ddp.FlatGradReducer(net)
+                    # SG_DDP_BUCKET_MB (experimental): bucketed all-reduce launched from gradient hooks during backward
+                    mb = float(os.environ.get('SG_DDP_BUCKET_MB', '0') or 0)
+                    self.reducers[name] = ddp.FlatGradReducer(net, bucket_mb=mb if (mb > 0 and name == 'g') else None)
 
     # ---- construction (trainer.py:30-134) ------------------------------------------------------
     def init_generator(self, args, checkpoint):
