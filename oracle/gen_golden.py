@@ -238,10 +238,62 @@ def step_golden():
     print('wrote step_cfg1.pt')
 
 
+TRAJ_TOL = (2e-4, 1e-3, 1e-2)       # oracle vs reference, relative to max(1, |reference|), per iteration; a fourth
+                                    # iteration already differs by 4 % in g_gan_img_loss between the two CPU programs
+
+
+def traj_golden(steps=3, seed=9, noise_seed=21):
+    """Three consecutive reference iterations (use_gt alternating, train.py:190-215) on the configs[0] batch: the
+    loss terms of every iteration.  Pins what carries over between iterations — Adam moments, BatchNorm running
+    statistics, the VectorPool and its python-random stream — which a single-iteration golden cannot see."""
+    cfg = cases.CFG1
+    vocab = synthetic.make_vocab(cfg['num_objs'])
+    sds = R.make_state_dicts(cfg, seed=5)
+    batch = cases.cfg1_batch()
+    imgs, objs, boxes, masks, triples, o2i, t2i, attrs = batch
+    trainer, args = ref_harness.make_trainer(vocab, image_size=cfg['image_size'])
+    ref_harness.load(trainer.model, sds['g'])
+    ref_harness.load(trainer.obj_discriminator, sds['obj'])
+    ref_harness.load(trainer.mask_discriminator, sds['mask'])
+    ref_harness.load(trainer.netD, sds['img'])
+    random.seed(seed)
+    traj = []
+    for i in range(steps):
+        use_gt = i % 2 == 0
+        torch.manual_seed(noise_seed)            # the reference draws its mask noise from the global RNG (model.py:149)
+        a = attrs if use_gt else torch.zeros_like(attrs)
+        out = trainer.model(imgs, objs, triples, o2i, boxes_gt=boxes, masks_gt=masks, attributes=a)
+        imgs_pred, boxes_pred, masks_pred, layout, layout_pred, layout_wrong = out
+        trainer.train_generator(imgs, imgs_pred, masks, masks_pred, layout, objs, boxes, boxes_pred, o2i, use_gt)
+        trainer.train_mask_discriminator(masks, masks_pred.detach(), objs)
+        trainer.train_obj_discriminator(imgs, imgs_pred.detach(), objs, boxes, boxes.detach(), o2i)
+        trainer.train_image_discriminator(imgs, imgs_pred.detach(), layout.detach(), layout_wrong.detach())
+        traj.append({'g': dict(trainer.generator_losses.all_losses), 'mask': dict(trainer.d_mask_losses.all_losses),
+                     'obj': dict(trainer.d_obj_losses.all_losses), 'img': dict(trainer.d_img_losses.all_losses)})
+        print('ref step', i, traj[-1]['g'])
+    ot = R.OracleTrainer(sds, cfg)
+    random.seed(seed)
+    for i in range(steps):
+        ot.step(batch, cases.noise_for(noise_seed), use_gt=(i % 2 == 0))
+        for net, terms in traj[i].items():
+            for name, val in terms.items():
+                mine = ot.losses[net][name]
+                rel = abs(mine - val) / max(1.0, abs(val))
+                print('  step %d %-5s %-26s ref %.6f oracle %.6f rel %.2e' % (i, net, name, val, mine, rel))
+                # fp32 on both sides but different summation orders, and Adam's first steps are sign-like: rounding
+                # differences flip the direction of near-zero gradients, so the two CPU trajectories separate with
+                # every iteration (measured: <= 4e-4 after one update, <= 4e-3 after two)
+                assert rel <= TRAJ_TOL[min(i, len(TRAJ_TOL) - 1)], (i, net, name, mine, val)
+    torch.save({'steps': steps, 'seed': seed, 'noise_seed': noise_seed, 'losses': traj}, os.path.join(OUT, 'traj_cfg1.pt'))
+    print('wrote traj_cfg1.pt (oracle reproduces all %d iterations)' % steps)
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ['ops', 'step']
+    which = sys.argv[1:] or ['ops', 'step', 'traj']
     if 'ops' in which:
         ops_golden()
     if 'step' in which:
         step_golden()
+    if 'traj' in which:
+        traj_golden()

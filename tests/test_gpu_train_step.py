@@ -227,6 +227,16 @@ def test_four_step_trajectory_vs_oracle(graphs):
         # bf16 tensor-core arithmetic vs fp32: 6 % on the first iteration (the golden test's bound); the adversarial terms
         # feed back through both players' updates, so the bound widens by 3 % per further iteration
         assert abs(m - r) <= (0.06 + 0.03 * i) * abs(r) + 5e-3, (i, net, name, m, r)
+    # the same iterations of the UNMODIFIED reference (tests/golden/traj_cfg1.pt, written by oracle/gen_golden.py)
+    gold = torch.load(os.path.join(GOLD, 'traj_cfg1.pt'))
+    assert (gold['seed'], gold['noise_seed']) == (9, 21)
+    mine_by_key = {(i, net, name): m for i, net, name, m, r in rows}
+    for i in range(gold['steps']):
+        for net, terms in gold['losses'][i].items():
+            for name, val in terms.items():
+                if (i, net, name) in mine_by_key:
+                    m = mine_by_key[(i, net, name)]
+                    assert abs(m - val) <= (0.07 + 0.03 * i) * abs(val) + 5e-3, ('reference golden', i, net, name, m, val)
     if graphs:
         assert tr.use_graphs and sum(1 for v in tr._graphs.values() if not isinstance(v, str)) == 2
     # the bbox loss must actually have moved (it barely does when stale operand weights are used)

@@ -100,3 +100,26 @@ def test_full_train_step_vs_reference_golden():
             net, name = k[len('gt_after_'):].split('.', 1)
             d = (ot.sd[net][name].detach().float() - v.float()).abs()
             assert d.max().item() <= 2.2e-4 + 1e-6, k
+
+
+def test_three_iteration_trajectory_vs_reference_golden():
+    """tests/golden/traj_cfg1.pt: loss terms of three consecutive iterations of the UNMODIFIED reference (use_gt
+    alternating).  The oracle must follow it — this pins what carries over between iterations (Adam moments, BatchNorm
+    running statistics, VectorPool contents and its python-random stream).  Tolerances per iteration as measured when
+    the golden was written (two fp32 CPU programs with different summation orders separate under Adam's sign-like
+    first steps): 2e-4, 1e-3, 1e-2 of max(1, |reference|)."""
+    import random
+    g = torch.load(os.path.join(GOLD, 'traj_cfg1.pt'))
+    cfg = cases.CFG1
+    ot = R.OracleTrainer(R.make_state_dicts(cfg, seed=5), cfg)
+    batch = cases.cfg1_batch()
+    random.seed(g['seed'])
+    tol = (2e-4, 1e-3, 1e-2)
+    for i in range(g['steps']):
+        ot.step(batch, cases.noise_for(g['noise_seed']), use_gt=(i % 2 == 0))
+        for net, terms in g['losses'][i].items():
+            for name, val in terms.items():
+                mine = ot.losses[net][name]
+                assert abs(mine - val) <= tol[i] * max(1.0, abs(val)), (i, net, name, mine, val)
+    # the box loss must have moved between the two use_gt iterations (it barely does when stale weights are used)
+    assert g['losses'][2]['g']['bbox_pred'] < 0.95 * g['losses'][0]['g']['bbox_pred']
