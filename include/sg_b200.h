@@ -241,6 +241,10 @@ int sg_slice_channels(const void* src, long long rows, int Cd, int Cs, void* out
 /* discriminators.py:99,184: AvgPool2d(3, stride 2, pad 1, count_include_pad=False), bf16 NHWC. */
 int sg_avgpool3x3s2_fwd(const void* x, int N, int H, int W, int C, void* y, sg_stream_t stream);
 int sg_avgpool3x3s2_bwd(const void* gy, int N, int H, int W, int C, void* gx, sg_stream_t stream);
+/* MaxPool2d(2, 2) of torchvision's VGG19 (losses.py:187-196) on bf16 [N][H][W][C] (floor mode); the adjoint routes the
+ * gradient to the first maximum of each window in scan order, like ATen. */
+int sg_maxpool2x2_fwd(const void* x, int N, int H, int W, int C, void* y, sg_stream_t stream);
+int sg_maxpool2x2_bwd(const void* gy, const void* x, int N, int H, int W, int C, void* gx, sg_stream_t stream);
 /* layers.py:82-85 GlobalAvgPool: bf16 [N][HW][C] -> f32 [N][C], and the adjoint. */
 int sg_gap_fwd(const void* x, int N, int HW, int C, float* y, sg_stream_t stream);
 int sg_gap_bwd(const float* gy, int N, int HW, int C, void* gx, sg_stream_t stream);

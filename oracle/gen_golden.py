@@ -238,6 +238,50 @@ def step_golden():
     print('wrote step_cfg1.pt')
 
 
+def vgg_golden():
+    """losses.py:178-224 (Vgg19 / VGGLoss) with seeded random weights — torchvision's pretrained download is replaced by
+    `weights=None` (no network), everything else is the reference's code."""
+    import torchvision
+    ref_harness.install()
+    orig = torchvision.models.vgg19
+    torchvision.models.vgg19 = lambda pretrained=False, **k: orig(weights=None)
+    try:
+        from scene_generation import losses as RL
+        RL.Vgg19.cuda = lambda self, *a, **k: self
+        crit = RL.VGGLoss()
+    finally:
+        torchvision.models.vgg19 = orig
+    sd = R.make_vgg_state_dict(seed=3)
+    slice_of = {0: 1, 2: 2, 5: 2, 7: 3, 10: 3, 12: 4, 14: 4, 16: 4, 19: 4, 21: 5, 23: 5, 25: 5, 28: 5}
+    ref_sd = {'slice%d.%d.%s' % (slice_of[int(k.split('.')[1])], int(k.split('.')[1]), k.split('.')[2]): v for k, v in sd.items()}
+    crit.vgg.load_state_dict(ref_sd, strict=True)
+    x = cases.rand((2, 3, 64, 64), 41, -1.0, 1.0)
+    y = cases.rand((2, 3, 64, 64), 42, -1.0, 1.0)
+    xr = x.clone().requires_grad_(True)
+    feats = crit.vgg(xr)
+    loss = crit(xr, y)
+    loss.backward()
+    g = {'x': x, 'y': y, 'loss': loss.detach().clone(), 'dx': xr.grad.clone()}
+    for i, f in enumerate(feats):
+        g['feat%d' % i] = f.detach().clone()
+    # oracle replay
+    xo = x.clone().requires_grad_(True)
+    fo = R.vgg19_features(sd, xo)
+    for i, f in enumerate(fo):
+        close(f.detach(), g['feat%d' % i], 1e-5, 'vgg relu%d_1' % (i + 1))
+    lo = R.vgg_loss(sd, xo, y)
+    lo.backward()
+    close(lo.detach(), g['loss'], 1e-5, 'vgg loss')
+    close(xo.grad, g['dx'], 1e-4, 'vgg d loss / d x')
+    # features are large (64 ch x 64 x 64 ...): keep the small ones whole and checksums of the large ones
+    out = {'x': x, 'y': y, 'loss': g['loss'], 'dx': g['dx'], 'feat3': g['feat3'], 'feat4': g['feat4']}
+    for i in range(3):
+        out['feat%d_mean_hw' % i] = g['feat%d' % i].mean(dim=(2, 3))
+        out['feat%d_mean_c' % i] = g['feat%d' % i].mean(dim=1)
+    torch.save(out, os.path.join(OUT, 'vgg.pt'))
+    print('wrote vgg.pt')
+
+
 TRAJ_TOL = (2e-4, 1e-3, 1e-2)       # oracle vs reference, relative to max(1, |reference|), per iteration; a fourth
                                     # iteration already differs by 4 % in g_gan_img_loss between the two CPU programs
 
@@ -290,10 +334,12 @@ def traj_golden(steps=3, seed=9, noise_seed=21):
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ['ops', 'step', 'traj']
+    which = sys.argv[1:] or ['ops', 'step', 'traj', 'vgg']
     if 'ops' in which:
         ops_golden()
     if 'step' in which:
         step_golden()
     if 'traj' in which:
         traj_golden()
+    if 'vgg' in which:
+        vgg_golden()

@@ -664,6 +664,57 @@ class OracleTrainer:
 
 
 # --------------------------------------------------------------------------------------
+# losses.py:178-224  VGG19 feature-matching loss
+# --------------------------------------------------------------------------------------
+# torchvision vgg19().features[0:30]: (layer index of the conv, Cin, Cout); 'M' = MaxPool2d(2, 2).  The reference cuts
+# it into five slices ending at relu1_1, relu2_1, relu3_1, relu4_1, relu5_1 (losses.py:187-196).
+VGG19_LAYERS = ((0, 3, 64), (2, 64, 64), 'M', (5, 64, 128), (7, 128, 128), 'M', (10, 128, 256), (12, 256, 256),
+                (14, 256, 256), (16, 256, 256), 'M', (19, 256, 512), (21, 512, 512), (23, 512, 512), (25, 512, 512), 'M',
+                (28, 512, 512))
+VGG19_TAPS = (0, 5, 10, 19, 28)          # conv indices whose ReLU output is a feature map
+VGG_LOSS_WEIGHTS = (1.0 / 32, 1.0 / 16, 1.0 / 8, 1.0 / 4, 1.0)      # losses.py:216
+
+
+def make_vgg_state_dict(seed=0):
+    """Seeded random VGG19 feature weights under torchvision's keys ('features.<i>.weight/bias'), He-scaled so that
+    activations keep their magnitude through 13 ReLU layers (the pretrained weights cannot be downloaded here; real
+    ones load through the same keys)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for l in VGG19_LAYERS:
+        if l == 'M':
+            continue
+        i, cin, cout = l
+        sd['features.%d.weight' % i] = torch.randn(cout, cin, 3, 3, generator=g) * math.sqrt(2.0 / (cin * 9))
+        sd['features.%d.bias' % i] = (torch.rand(cout, generator=g) - 0.5) * 0.1
+    return sd
+
+
+def vgg19_features(sd, x):
+    """Vgg19.forward (losses.py:202-209): [relu1_1, relu2_1, relu3_1, relu4_1, relu5_1] of x (N,3,H,W)."""
+    feats = []
+    h = x
+    for l in VGG19_LAYERS:
+        if l == 'M':
+            h = F.max_pool2d(h, 2, 2)
+            continue
+        i = l[0]
+        h = F.relu(F.conv2d(h, sd['features.%d.weight' % i], sd['features.%d.bias' % i], padding=1))
+        if i in VGG19_TAPS:
+            feats.append(h)
+    return feats
+
+
+def vgg_loss(sd, x, y):
+    """VGGLoss.forward (losses.py:218-224): sum_i w_i * L1(vgg(x)_i, vgg(y)_i.detach())."""
+    fx, fy = vgg19_features(sd, x), vgg19_features(sd, y)
+    loss = 0
+    for w, a, b in zip(VGG_LOSS_WEIGHTS, fx, fy):
+        loss = loss + w * (a - b.detach()).abs().mean()
+    return loss
+
+
+# --------------------------------------------------------------------------------------
 # deterministic weights (shared by golden generation, tests, smoke and bench)
 # --------------------------------------------------------------------------------------
 

@@ -120,6 +120,8 @@ _SIGS = {
     'sg_slice_channels': [_P, c_long, c_int, c_int, _P, _P],
     'sg_avgpool3x3s2_fwd': [_P, c_int, c_int, c_int, c_int, _P, _P],
     'sg_avgpool3x3s2_bwd': [_P, c_int, c_int, c_int, c_int, _P, _P],
+    'sg_maxpool2x2_fwd': [_P, c_int, c_int, c_int, c_int, _P, _P],
+    'sg_maxpool2x2_bwd': [_P, _P, c_int, c_int, c_int, c_int, _P, _P],
     'sg_gap_fwd': [_P, c_int, c_int, c_int, _P, _P],
     'sg_gap_bwd': [_P, c_int, c_int, c_int, _P, _P],
     'sg_colsum_bf16': [_P, c_long, c_int, c_int, _P, _P],

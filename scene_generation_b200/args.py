@@ -34,6 +34,7 @@ parser.add_argument('--appearance_normalization', default='batch')
 parser.add_argument('--l1_pixel_loss_weight', default=.0, type=float)
 parser.add_argument('--bbox_pred_loss_weight', default=10, type=float)
 parser.add_argument('--vgg_features_weight', default=0.0, type=float)   # reference default 10: needs pretrained VGG19
+parser.add_argument('--vgg_weights', default=None, type=str)             # torchvision vgg19 state_dict file (no download here)
 parser.add_argument('--d_img_weight', default=1.0, type=float)
 parser.add_argument('--d_img_features_weight', default=10.0, type=float)
 parser.add_argument('--d_mask_weight', default=1.0, type=float)

@@ -567,6 +567,69 @@ __global__ void slice_channels_kernel(const bf16* __restrict__ src, long rows, i
   out[idx] = src[r * Cd + c];
 }
 
+// MaxPool2d(2, 2) on bf16 NHWC (torchvision VGG19 features 4/9/18/27, losses.py:187-196) and its adjoint.  The gradient
+// goes to the FIRST maximum of the window in scan order (h, then w), like ATen's max_pool2d_with_indices — after a ReLU
+// all-zero windows are common, so the tie rule matters.  Odd trailing rows / columns are dropped (floor mode).
+__global__ void maxpool2_fwd_kernel(const bf16* __restrict__ x, int N, int H, int W, int C, int Ho, int Wo, bf16* __restrict__ y) {
+  const int nC = C / 8;
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long total = (long)N * Ho * Wo * nC;
+  if (idx >= total) return;
+  int ch = idx % nC;
+  long r = idx / nC;
+  int j = r % Wo; r /= Wo;
+  int i = r % Ho;
+  int n = r / Ho;
+  float m[8];
+  load8(x + (((long)n * H + 2 * i) * W + 2 * j) * C + ch * 8, m);
+#pragma unroll
+  for (int q = 1; q < 4; ++q) {
+    float t[8];
+    load8(x + (((long)n * H + 2 * i + (q >> 1)) * W + 2 * j + (q & 1)) * C + ch * 8, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = (t[k] > m[k] || t[k] != t[k]) ? t[k] : m[k];     // NaN propagates like ATen
+  }
+  store8(y + idx * 8, m);
+}
+
+// one thread per (input pixel, 8-channel chunk): recompute the window's arg-max from x and take gy if it is this pixel
+__global__ void maxpool2_bwd_kernel(const bf16* __restrict__ gy, const bf16* __restrict__ x, int N, int H, int W, int C, int Ho,
+                                    int Wo, bf16* __restrict__ gx) {
+  const int nC = C / 8;
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long total = (long)N * H * W * nC;
+  if (idx >= total) return;
+  int ch = idx % nC;
+  long r = idx / nC;
+  int w = r % W; r /= W;
+  int h = r % H;
+  int n = r / H;
+  float o[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) o[k] = 0.f;
+  const int i = h >> 1, j = w >> 1;
+  if (i < Ho && j < Wo) {
+    const int me = (h & 1) * 2 + (w & 1);
+    float m[8], g[8];
+    int arg[8];
+    load8(x + (((long)n * H + 2 * i) * W + 2 * j) * C + ch * 8, m);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) arg[k] = 0;
+#pragma unroll
+    for (int q = 1; q < 4; ++q) {
+      float t[8];
+      load8(x + (((long)n * H + 2 * i + (q >> 1)) * W + 2 * j + (q & 1)) * C + ch * 8, t);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (t[k] > m[k] || t[k] != t[k]) { m[k] = t[k]; arg[k] = q; }
+    }
+    load8(gy + (((long)n * Ho + i) * Wo + j) * C + ch * 8, g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = (arg[k] == me) ? g[k] : 0.f;
+  }
+  store8(gx + idx * 8, o);
+}
+
 // AvgPool2d(3, stride 2, pad 1, count_include_pad=False) on bf16 NHWC
 __global__ void avgpool_fwd_kernel(const bf16* __restrict__ x, int N, int H, int W, int C, int Ho, int Wo, bf16* __restrict__ y) {
   const int nC = C / 8;
@@ -869,6 +932,22 @@ extern "C" int sg_avgpool3x3s2_bwd(const void* gy, int N, int H, int W, int C, v
   int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   LAUNCH_1D(avgpool_bwd_kernel, (long)N * H * W * (C / 8), stream, (const bf16*)gy, N, H, W, C, Ho, Wo, (bf16*)gx);
   SG_CHECK_LAUNCH("sg_avgpool3x3s2_bwd");
+  return SG_OK;
+}
+
+extern "C" int sg_maxpool2x2_fwd(const void* x, int N, int H, int W, int C, void* y, sg_stream_t stream) {
+  SG_CHECK_ARG(x && y && C % 8 == 0 && H >= 2 && W >= 2 && N > 0, "maxpool2x2_fwd: bad arguments");
+  int Ho = H / 2, Wo = W / 2;
+  LAUNCH_1D(maxpool2_fwd_kernel, (long)N * Ho * Wo * (C / 8), stream, (const bf16*)x, N, H, W, C, Ho, Wo, (bf16*)y);
+  SG_CHECK_LAUNCH("sg_maxpool2x2_fwd");
+  return SG_OK;
+}
+
+extern "C" int sg_maxpool2x2_bwd(const void* gy, const void* x, int N, int H, int W, int C, void* gx, sg_stream_t stream) {
+  SG_CHECK_ARG(gy && x && gx && C % 8 == 0 && H >= 2 && W >= 2 && N > 0, "maxpool2x2_bwd: bad arguments");
+  int Ho = H / 2, Wo = W / 2;
+  LAUNCH_1D(maxpool2_bwd_kernel, (long)N * H * W * (C / 8), stream, (const bf16*)gy, (const bf16*)x, N, H, W, C, Ho, Wo, (bf16*)gx);
+  SG_CHECK_LAUNCH("sg_maxpool2x2_bwd");
   return SG_OK;
 }
 

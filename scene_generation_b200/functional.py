@@ -699,6 +699,28 @@ class AvgPoolFn(torch.autograd.Function):
         return gx
 
 
+class MaxPool2Fn(torch.autograd.Function):
+    """nn.MaxPool2d(2, 2) of torchvision's VGG19 (losses.py:187-196) on bf16 (N,H,W,C); gradient to the first maximum
+    of every window (ATen's rule)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        N, H, W, C = x.shape
+        y = torch.empty((N, H // 2, W // 2, C), dtype=BF, device=x.device)
+        _lib.call('sg_maxpool2x2_fwd', _ptr(x), N, H, W, C, _ptr(y), _stream())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, = ctx.saved_tensors
+        N, H, W, C = x.shape
+        gx = torch.empty_like(x)
+        _lib.call('sg_maxpool2x2_bwd', _ptr(g.contiguous()), _ptr(x), N, H, W, C, _ptr(gx), _stream())
+        return gx
+
+
 class ConcatCondFn(torch.autograd.Function):
     """concat of a broadcast one-hot class vector behind the feature channels (discriminators.py:107-109)."""
 

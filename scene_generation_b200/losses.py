@@ -1,8 +1,13 @@
-"""GAN losses (mirror of scene_generation/losses.py:26-175).  Tiny reductions kept in PyTorch —
-SURVEY.md §2 marks losses.py out of kernel scope (next row §8f-1)."""
+"""GAN losses (mirror of scene_generation/losses.py:26-175) and the VGG19 feature-matching loss (losses.py:178-224).
+The tiny loss reductions are kept in PyTorch — SURVEY.md §2 marks losses.py out of kernel scope (next row §8f-1); the
+VGG19 stack itself (13 frozen 3x3 convolutions, 35.5 GFLOP / image) runs on the tensor-core conv kernel."""
 import torch
 import torch.nn.functional as F
 from torch import nn
+
+from . import _lib
+from . import functional as Fn
+from .functional import ConvSpec
 
 
 def bce_loss(input, target):
@@ -41,3 +46,89 @@ class GANLoss(nn.Module):
         if isinstance(input[0], list):
             return sum(F.mse_loss(i[-1].float(), torch.full_like(i[-1], t, dtype=torch.float32)) for i in input)
         return F.mse_loss(input[-1].float(), torch.full_like(input[-1], t, dtype=torch.float32))
+
+
+# ---------------------------------------------------------------------------------------------
+# VGG19 feature matching (losses.py:178-224) — SURVEY.md §8f-2.  NOT yet validated on hardware (written after the
+# round-1 GPU budget was spent): off unless --vgg_features_weight > 0; check with SG_TEST_VGG=1 pytest tests/test_gpu_vgg.py
+# ---------------------------------------------------------------------------------------------
+_VGG_SLICES = ((0,), (2, 'M', 5), (7, 'M', 10), (12, 14, 16, 'M', 19), (21, 23, 25, 'M', 28))      # losses.py:187-196
+_VGG_CH = {0: (3, 64), 2: (64, 64), 5: (64, 128), 7: (128, 128), 10: (128, 256), 12: (256, 256), 14: (256, 256),
+           16: (256, 256), 19: (256, 512), 21: (512, 512), 23: (512, 512), 25: (512, 512), 28: (512, 512)}
+
+
+class Vgg19(nn.Module):
+    """losses.py:179-209: the five slices of torchvision's vgg19().features ending at relu1_1 .. relu5_1, with the
+    reference's parameter names ('slice<k>.<i>.weight').  Weights are frozen.  The reference downloads the ImageNet
+    weights; here they come from `load_torchvision_state_dict` (a vgg19 state_dict file, keys 'features.<i>.*') or
+    stay at a seeded He initialisation (throughput measurements, tests)."""
+
+    def __init__(self, requires_grad=False, seed=0):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        for k, items in enumerate(_VGG_SLICES):
+            seq = nn.Sequential()
+            for it in items:
+                if it == 'M':
+                    continue
+                cin, cout = _VGG_CH[it]
+                conv = nn.Conv2d(cin, cout, 3, padding=1)
+                conv.weight.data.copy_(torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5)
+                conv.bias.data.copy_((torch.rand(cout, generator=g) - 0.5) * 0.1)
+                seq.add_module(str(it), conv)
+            setattr(self, 'slice%d' % (k + 1), seq)
+        from .layers import channels_last_
+        channels_last_(self)
+        if not requires_grad:
+            for p in self.parameters():
+                p.requires_grad = False
+
+    def load_torchvision_state_dict(self, sd):
+        """sd: state_dict of torchvision.models.vgg19 (or of its .features): 'features.<i>.weight' / '<i>.weight'."""
+        own = {}
+        for k, items in enumerate(_VGG_SLICES):
+            for it in items:
+                if it == 'M':
+                    continue
+                for leaf in ('weight', 'bias'):
+                    src = sd.get('features.%d.%s' % (it, leaf), sd.get('%d.%s' % (it, leaf)))
+                    if src is None:
+                        raise KeyError('vgg19 state_dict lacks features.%d.%s' % (it, leaf))
+                    own['slice%d.%d.%s' % (k + 1, it, leaf)] = src
+        return self.load_state_dict(own, strict=True)
+
+    def forward(self, X):
+        """X: (N,3,H,W) f32 -> [relu1_1, ..., relu5_1] as NCHW views of bf16 channels-last feature maps."""
+        x = Fn.ToNhwcFn.apply(X, 8)
+        feats = []
+        for k, items in enumerate(_VGG_SLICES):
+            seq = getattr(self, 'slice%d' % (k + 1))
+            for it in items:
+                if it == 'M':
+                    x = Fn.MaxPool2Fn.apply(x)
+                    continue
+                conv = getattr(seq, str(it))
+                x = Fn.conv(Fn.plain_fn(x), conv.weight, conv.bias, ConvSpec('s1', 3, 1, act=_lib.ACT_RELU))
+            feats.append(Fn.FeatureViewFn.apply(x))
+        return feats
+
+
+class VGGLoss(nn.Module):
+    """losses.py:212-224."""
+
+    def __init__(self, weights_path=None):
+        super().__init__()
+        self.vgg = Vgg19().cuda()
+        if weights_path:
+            self.vgg.load_torchvision_state_dict(torch.load(weights_path, map_location='cpu'))
+        self.criterion = nn.L1Loss()
+        self.weights = [1.0 / 32, 1.0 / 16, 1.0 / 8, 1.0 / 4, 1.0]
+
+    def forward(self, x, y):
+        x_vgg = self.vgg(x)
+        with torch.no_grad():
+            y_vgg = self.vgg(y)
+        loss = 0
+        for w, a, b in zip(self.weights, x_vgg, y_vgg):
+            loss = loss + w * self.criterion(a.float(), b.detach().float())
+        return loss

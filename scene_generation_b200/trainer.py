@@ -147,10 +147,12 @@ class Trainer:
             checkpoint['model_kwargs'] = model_kwargs
         extra = {k: getattr(args, k) for k in ('layout_dtype', 'align_corners') if hasattr(args, k)}
         self.model = model = Model(**model_kwargs, **extra).to('cuda')
-        if getattr(args, 'vgg_features_weight', 0) > 0:
-            raise NotImplementedError('VGG perceptual loss needs pretrained weights (no network): run with '
-                                      '--vgg_features_weight 0 (SURVEY.md §8f-2)')
         self.criterionVGG = None
+        if getattr(args, 'vgg_features_weight', 0) > 0:
+            # trainer.py:57.  The ImageNet weights cannot be downloaded here: args.vgg_weights names a torchvision
+            # vgg19 state_dict file; without it the stack keeps a seeded initialisation (throughput runs, tests).
+            from .losses import VGGLoss
+            self.criterionVGG = VGGLoss(getattr(args, 'vgg_weights', None))
         self.criterionFeat = torch.nn.L1Loss()
         self.criterionGAN = GANLoss(use_lsgan=not args.no_lsgan)
         self.optimizer = _adam(model.parameters(), lr=args.learning_rate, betas=(args.beta1, 0.999))
@@ -266,6 +268,8 @@ class Trainer:
             if args.l1_pixel_loss_weight > 0:
                 gl.add_loss(F.l1_loss(imgs_pred, imgs), 'L1_pixel_loss', args.l1_pixel_loss_weight)
             gl.add_loss(F.mse_loss(boxes_pred, boxes), 'bbox_pred', args.bbox_pred_loss_weight)
+        if self.criterionVGG is not None:                           # trainer.py:218-221 (with and without use_gt)
+            gl.add_loss(self.criterionVGG(imgs_pred, imgs), 'g_vgg', args.vgg_features_weight)
         # The G step back-propagates THROUGH the discriminators; the gradients it would deposit in their
         # parameters (trainer.py:262) are cleared by every D step's zero_grad before use, so the D weights are
         # frozen for this graph and their wgrad kernels are skipped.

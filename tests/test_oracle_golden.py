@@ -123,3 +123,22 @@ def test_three_iteration_trajectory_vs_reference_golden():
                 assert abs(mine - val) <= tol[i] * max(1.0, abs(val)), (i, net, name, mine, val)
     # the box loss must have moved between the two use_gt iterations (it barely does when stale weights are used)
     assert g['losses'][2]['g']['bbox_pred'] < 0.95 * g['losses'][0]['g']['bbox_pred']
+
+
+def test_vgg_feature_loss_vs_reference_golden():
+    """losses.py:178-224 (Vgg19 slices relu1_1..relu5_1, VGGLoss weights 1/32..1) with seeded random weights: features,
+    loss and d loss / d x of the reference's own classes (tests/golden/vgg.pt)."""
+    g = torch.load(os.path.join(GOLD, 'vgg.pt'))
+    sd = R.make_vgg_state_dict(seed=3)
+    x = g['x'].clone().requires_grad_(True)
+    feats = R.vgg19_features(sd, x)
+    assert [f.shape[1] for f in feats] == [64, 128, 256, 512, 512]
+    assert [f.shape[2] for f in feats] == [64, 32, 16, 8, 4]
+    for i in range(3):
+        assert torch.allclose(feats[i].mean(dim=(2, 3)), g['feat%d_mean_hw' % i], atol=1e-5)
+        assert torch.allclose(feats[i].mean(dim=1), g['feat%d_mean_c' % i], atol=1e-5)
+    assert torch.allclose(feats[3], g['feat3'], atol=1e-5) and torch.allclose(feats[4], g['feat4'], atol=1e-5)
+    loss = R.vgg_loss(sd, x, g['y'])
+    loss.backward()
+    assert abs(float(loss) - float(g['loss'])) <= 1e-6
+    assert torch.allclose(x.grad, g['dx'], atol=1e-7)

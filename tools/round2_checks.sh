@@ -8,7 +8,7 @@ set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 steps=("$@")
-[ ${#steps[@]} -eq 0 ] && steps=(probe 2cta persist napfused parfwd convab bench)
+[ ${#steps[@]} -eq 0 ] && steps=(probe 2cta persist napfused parfwd vgg convab bench)
 run() {   # name, timeout seconds, command...
   local name=$1 t=$2; shift 2
   echo "=== $name ($(date +%T)) ==="
@@ -29,6 +29,7 @@ for s in "${steps[@]}"; do
     persist)  run persist 1000 env SG_TEST_PERSIST=1 python -m pytest tests/test_gpu_conv_persist.py -q -s ;;
     napfused) run napfused 600 env SG_TEST_NAP_FUSED=1 python -m pytest tests/test_gpu_nap_fused.py -q -s ;;
     parfwd)   run parfwd 600 env SG_PARALLEL_FWD=1 python -m pytest tests/test_gpu_graph_step.py tests/test_gpu_train_step.py -q -k "graph or four_step or replayed or captured" ;;
+    vgg)      run vgg 300 env SG_TEST_VGG=1 python -m pytest tests/test_gpu_vgg.py -q ;;
     convab)   run convab 900 python tools/conv_ab.py --configs base SG_CONV_PERSIST=1 SG_CONV_2CTA=1 SG_CONV_PERSIST=1,SG_CONV_2CTA=1 ;;
     bench)
       bench_line base SG_NOOP=1
