@@ -23,6 +23,7 @@ sys.path.insert(0, ROOT)
 
 FLOPS_PER_IMAGE_STEP = 224.1e9     # algorithmic FLOPs of one image through one train step
 NUM_OBJS = 172
+VGG_FLOPS_PER_IMAGE = 35.5e9       # VGG19 feature loss, fwd on two images + dgrad through one
 
 
 def parse():
@@ -41,6 +42,9 @@ def parse():
     ap.add_argument('--cpu-worker', action='store_true', help=argparse.SUPPRESS)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--vgg', action='store_true',
+                    help='include the VGG19 feature-matching loss (weight 10, seeded random VGG weights) in BOTH arms; '
+                         'the CUDA side of it is not validated yet (DESIGN.md §7)')
     ap.add_argument('--host-profile', action='store_true',
                     help='cProfile 5 steps of the host side (launch path) into gpurun_out/host_profile_*.txt and exit')
     ap.add_argument('--profile-step', action='store_true',
@@ -76,7 +80,7 @@ def cpu_worker(a):
     H = a.image_size
     cfg = dict(image_size=(H, H), num_objs=NUM_OBJS, rep_size=32, mask_size=32, n_downsample_global=4,
                gconv_num_layers=5, crop_size=32, ngf=64, n_blocks=9)
-    tr = R.OracleTrainer(R.make_state_dicts(cfg, seed=0), cfg)
+    tr = R.OracleTrainer(R.make_state_dicts(cfg, seed=0), cfg, vgg_sd=R.make_vgg_state_dict(0) if a.vgg else None)
     random.seed(0)
     print(json.dumps({'ready': True, 'cores': cores}), flush=True)
     s = 0
@@ -92,7 +96,7 @@ def cpu_reference_bounded(a, steps, warmup, budget_s):
     """Run the CPU worker for at most budget_s seconds; returns (images/s, s/step, cores, steps measured)."""
     import select
     cmd = [sys.executable, os.path.abspath(__file__), '--cpu-worker', '--cpu-batch', str(a.cpu_batch), '--image-size',
-           str(a.image_size), '--kmin', str(a.kmin), '--kmax', str(a.kmax)]
+           str(a.image_size), '--kmin', str(a.kmin), '--kmax', str(a.kmax)] + (['--vgg'] if a.vgg else [])
     env = dict(os.environ)
     env.pop('RANK', None)
     p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env)
@@ -330,6 +334,8 @@ def main():
 
     H = a.image_size
     targs = sgargs.default_args(image_size=(H, H), num_objs=NUM_OBJS)
+    if a.vgg:
+        targs.vgg_features_weight = 10.0
     torch.manual_seed(1234)           # identical replicas; the reducers broadcast rank 0's weights anyway
     tr = Trainer(targs, synthetic.make_vocab(NUM_OBJS), {})
     # distinct synthetic batches per rank and per step, pre-built in pinned host memory
@@ -493,14 +499,15 @@ def main():
             'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3), 'ms_per_step': ms_total / a.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
             'config': {'workload': 'COCO-Stuff-shaped synthetic scene graphs (%d-%d objects + __image__), %dx%d, full '
-                                   'train step: Model.forward + G step + mask/obj/image D steps + 4x Adam%s; VGG loss off '
-                                   '(no pretrained weights offline)' % (a.kmin, a.kmax, H, H,
-                                                                        ' + NCCL grad all-reduce' if world > 1 else ''),
+                                   'train step: Model.forward + G step + mask/obj/image D steps + 4x Adam%s; VGG loss %s' % (
+                                       a.kmin, a.kmax, H, H, ' + NCCL grad all-reduce' if world > 1 else '',
+                                       'ON (weight 10, seeded random VGG19 weights: none can be downloaded offline)' if a.vgg
+                                       else 'off (no pretrained weights offline)'),
                        'global_batch': a.batch * world, 'parallelism': 'dp%d' % world,
                        'l2': 'working set (732 MB of f32 weights + activations) >> 126 MB L2; %d distinct batches cycled'
                              % n_distinct,
-                       'algorithmic_gflop_per_image': FLOPS_PER_IMAGE_STEP / 1e9},
-            'model_tflops': value * FLOPS_PER_IMAGE_STEP / 1e12,
+                       'algorithmic_gflop_per_image': (FLOPS_PER_IMAGE_STEP + (VGG_FLOPS_PER_IMAGE if a.vgg else 0)) / 1e9},
+            'model_tflops': value * (FLOPS_PER_IMAGE_STEP + (VGG_FLOPS_PER_IMAGE if a.vgg else 0)) / 1e12,
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'host_enqueue_ms_per_step': round(host_enqueue_ms, 2),
             'cuda_graphs': {'enabled': bool(tr.use_graphs),
                             'captured': sum(1 for v in tr._graphs.values() if not isinstance(v, str))},

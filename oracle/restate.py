@@ -546,8 +546,9 @@ def model_forward(sd, cfg, batch, noise, pool=None, update=False, test_mode=Fals
 DEFAULT_WEIGHTS = dict(bbox=10.0, ac=0.1, d_obj=0.1, d_mask=1.0, d_mask_feat=10.0, d_img=1.0, d_img_feat=10.0)
 
 
-def generator_losses(sd_g, sd_obj, sd_mask, sd_img, cfg, batch, fwd, use_gt, update_obj=None, weights=None):
-    """Trainer.train_generator loss assembly (trainer.py:205-259), no VGG, no L1."""
+def generator_losses(sd_g, sd_obj, sd_mask, sd_img, cfg, batch, fwd, use_gt, update_obj=None, weights=None, vgg_sd=None):
+    """Trainer.train_generator loss assembly (trainer.py:205-259), no L1; the VGG term (trainer.py:218-221) when
+    vgg_sd (VGG19 feature weights, make_vgg_state_dict keys) is given, weight w['vgg'] (reference default 10)."""
     w = dict(DEFAULT_WEIGHTS, **(weights or {}))
     imgs, objs, boxes, masks, _tr, obj_to_img, _t2i, _attr = batch
     imgs_pred, boxes_pred, masks_pred, layout = fwd[0], fwd[1], fwd[2], fwd[3]
@@ -555,6 +556,8 @@ def generator_losses(sd_g, sd_obj, sd_mask, sd_img, cfg, batch, fwd, use_gt, upd
     losses = {}
     if use_gt:
         losses['bbox_pred'] = ((boxes_pred - boxes) ** 2).mean() * w['bbox']                       # :215
+    if vgg_sd is not None:
+        losses['g_vgg'] = vgg_loss(vgg_sd, imgs_pred, imgs) * w.get('vgg', 10.0)                   # :218-221
     real, ac, _ = ac_crop_discriminator(sd_obj, imgs_pred, objs, boxes, obj_to_img,
                                         cfg.get('crop_size', 32), update=update_obj, align_corners=ac_flag)
     losses['ac_loss'] = ac * w['ac']                                                               # :224
@@ -568,7 +571,7 @@ def generator_losses(sd_g, sd_obj, sd_mask, sd_img, cfg, batch, fwd, use_gt, upd
     pred_fake = multiscale_discriminator(sd_img, torch.cat([layout.detach(), imgs_pred], dim=1))   # :250
     losses['g_gan_img_loss'] = lsgan_loss(pred_fake, True) * w['d_img']
     losses['g_gan_features_loss_img'] = features_loss(pred_fake, pred_real) * w['d_img_feat']     # :255
-    order = (['bbox_pred'] if use_gt else []) + ['ac_loss', 'g_gan_obj_loss', 'g_gan_mask_obj_loss',
+    order = (['bbox_pred'] if use_gt else []) + (['g_vgg'] if vgg_sd is not None else []) + ['ac_loss', 'g_gan_obj_loss', 'g_gan_mask_obj_loss',
                                                  'g_mask_features_loss', 'g_gan_img_loss',
                                                  'g_gan_features_loss_img']
     total = None
@@ -617,8 +620,9 @@ class OracleTrainer:
     D steps with Adam(lr, betas=(0.5, 0.999)) each (trainer.py:60,80,106,133).  State is four
     flat dicts of leaf tensors keyed like the reference state_dicts."""
 
-    def __init__(self, sds, cfg, lr=1e-4, mask_lr=1e-5, beta1=0.5, pool_size=100):
+    def __init__(self, sds, cfg, lr=1e-4, mask_lr=1e-5, beta1=0.5, pool_size=100, vgg_sd=None):
         self.cfg = cfg
+        self.vgg_sd = vgg_sd          # frozen VGG19 feature weights: adds the g_vgg term (vgg_features_weight 10)
         self.sd = {k: {n: (t.clone().requires_grad_(t.is_floating_point())) for n, t in sd.items()}
                    for k, sd in sds.items()}
         self.opt = {}
@@ -639,7 +643,7 @@ class OracleTrainer:
             batch = (imgs, objs, boxes, masks, triples, obj_to_img, t2i, attributes)
         fwd = model_forward(self.sd['g'], cfg, batch, noise, pool=self.pool, update=True)
         gl = generator_losses(self.sd['g'], self.sd['obj'], self.sd['mask'], self.sd['img'], cfg, batch, fwd,
-                              use_gt, update_obj=True)
+                              use_gt, update_obj=True, vgg_sd=self.vgg_sd)
         for k in ('g', 'obj', 'mask', 'img'):
             self.opt[k].zero_grad()
         gl['total_loss'].backward()
