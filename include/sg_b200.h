@@ -107,8 +107,11 @@ typedef struct {
   const float* bias;      /* (Cout) or NULL */
   int act;
   float slope;
-  float* stats;           /* (x_N, Cout, 2) f32 sum / sum-of-squares of the pre-activation output, or NULL
-                             (caller zeroes it); feeds InstanceNorm / BatchNorm */
+  float* stats;           /* NULL, or f32 (x_N, stats_slots, Cout, 2): partial sum / sum-of-squares of the
+                             pre-activation output per (image, slot, channel) for InstanceNorm / BatchNorm.  Every
+                             entry is written exactly once, by a fixed-order reduction (no atomics, no zeroing needed):
+                             bit-reproducible.  sg_norm_finalize adds the slots in slot order. */
+  int stats_slots;        /* slots per (image, channel) this launch writes: sg_conv_stats_slots() */
   int w_img_rows;         /* 0: one weight tensor for all images.  > 0: per-image weights, w is
                              [x_N * w_img_rows][w_taps][w_C] and image i uses rows [i * w_img_rows, + w_Cout)
                              (channel-compacted layouts, see sg_pack_weight_cmap); needs Hout*Wout >= 128 */
@@ -121,11 +124,15 @@ typedef struct {
   int w_rows, w_col0;     /* w_mn only; w_col0 % 8 == 0, w_col0 + w_Cout <= w_C */
 } sg_conv_desc_t;
 int sg_conv_tc(const sg_conv_desc_t* desc, sg_stream_t stream);
+/* number of partial-sum slots per (image, channel) sg_conv_tc writes to desc->stats for this geometry
+ * (= phases x M tiles per image); host-only, needs no pointers in desc. */
+int sg_conv_stats_slots(const sg_conv_desc_t* desc, int* slots);
 
 /* Weight gradient (cuDNN wgrad in the reference):
  *   dw[co, wtap, ci] += sum_{img,h,w} dy[img, pa, h+dha, w+dwa, co] * x[img, pb, h+dhb, w+dwb, ci]
  * for every entry of the tap table (a = dy side, b = x side).  dw is f32 [Cout][w_taps][dw_C] and is
- * OVERWRITTEN (the call zeroes it itself when it splits the reduction and accumulates atomically).
+ * OVERWRITTEN.  When the reduction over pixels is split across CTAs, the splits add their partial sums
+ * one after the other in split order (turn counters in `locks`), so the result is bit-reproducible.
  * At least one side must have zero tap offsets and extents equal to (Hred, Wred), so that pixels
  * outside the reduction extent read as zero through the TMA fill. */
 typedef struct {
@@ -144,6 +151,9 @@ typedef struct {
   int ksplit;             /* 0 = auto */
   int per_image;          /* 1: dw is f32 [N][Cout][w_taps][dw_C], one slab per image (no reduction over
                              images; the per-image weight gradients of a channel-compacted operand) */
+  int* locks;             /* int32 turn counters, one per (Cout tile, Cin tile, tap) <= n_locks; ZERO on entry and
+                             left zero on return (stream-ordered reuse is fine; never share between streams) */
+  int n_locks;
 } sg_wgrad_desc_t;
 int sg_wgrad_tc(const sg_wgrad_desc_t* desc, sg_stream_t stream);
 
@@ -163,9 +173,11 @@ int sg_dgrad_small_cout(const void* dz, int dzC, const float* w, int Cout, int k
 
 /* Weight gradient of the same layer (tiny Cout): dw[co,kh*k+kw,ci] = sum dz[n,h,w,co] * xop[n,h+kh,w+kw,ci]
  * with the pre-padded bf16 operand xop [N][H+k-1][W+k-1][64]; dw f32 [Cout][k*k][64] is overwritten.
- * Cout <= 3, Cin == 64, k in {3, 7}. */
+ * Cout <= 3, Cin == 64, k in {3, 7}.  ws: f32 scratch of SG_WGRAD_SMALL_BLOCKS * Cout*k*k*64 floats (per-CTA partial
+ * sums, added in CTA order). */
+#define SG_WGRAD_SMALL_BLOCKS 296
 int sg_wgrad_small_cout(const void* dz, int dzC, const void* xop, int Cout, int k, int Cin, int N, int H, int W,
-                        float* dw, sg_stream_t stream);
+                        float* dw, float* ws, long long ws_floats, sg_stream_t stream);
 
 /* ---- operand preparation ------------------------------------------------------------------ */
 /* f32 (rows, cols) with row pitch ld_src -> bf16 (rows, ld_dst); columns >= cols are zero.  With
@@ -189,17 +201,19 @@ int sg_pack_weight(const float* w, int Cout, int taps, int Cin, int Cin_p, int C
  * (zero where cmap is -1 or >= Cin); either output may be NULL. */
 int sg_pack_weight_cmap(const float* w, int Cout, int taps, int Cin, const int* cmap, int N, int Cc, int Cout_p,
                         void* wk, void* wt, sg_stream_t stream);
-/* adjoint: per-image weight gradients dwc f32 [N][Cout][taps][Cc] (sg_wgrad_desc_t.per_image) summed into the
- * dense dw f32 [Cout][taps][Cin], which is overwritten. */
+/* adjoint: per-image weight gradients dwc f32 [N][Cout][taps][Cc] (sg_wgrad_desc_t.per_image) summed, in image
+ * order, into the dense dw f32 [Cout][taps][Cin], which is overwritten.  A dense channel may occur at most once in
+ * an image's row of cmap; Cc <= 127. */
 int sg_wgrad_cmap_scatter(const float* dwc, const int* cmap, int N, int Cout, int taps, int Cc, int Cin, float* dw,
                           sg_stream_t stream);
 
 /* ---- layers.py:292-301 InstanceNorm2d / BatchNorm2d, ReLU / LeakyReLU, ReflectionPad2d,
  *      Interpolate(nearest x2), fused into one operand-writer pass (and its adjoint) ----------- */
-/* conv-epilogue sums (n_img, C, 2) -> scale/shift/mean/rstd (n_img*C each).  mode 0: InstanceNorm2d
- * (affine=False), mode 1: BatchNorm2d train mode (statistics over all n_img*count elements, running
- * stats updated in place with the unbiased variance when running_mean != NULL). */
-int sg_norm_finalize(const float* stats, int mode, int n_img, int C, float count, float eps, const float* gamma,
+/* conv-epilogue partial sums (n_img, n_slots, C, 2) (sg_conv_desc_t.stats) -> scale/shift/mean/rstd (n_img*C each);
+ * the slots are added in slot order.  mode 0: InstanceNorm2d (affine=False), mode 1: BatchNorm2d train mode
+ * (statistics over all n_img*count elements, running stats updated in place with the unbiased variance when
+ * running_mean != NULL). */
+int sg_norm_finalize(const float* stats, int n_slots, int mode, int n_img, int C, float count, float eps, const float* gamma,
                      const float* beta, float* running_mean, float* running_var, float momentum, float* scale,
                      float* shift, float* save_mean, float* save_rstd, sg_stream_t stream);
 typedef struct {
@@ -219,13 +233,17 @@ typedef struct {
 int sg_norm_act_pad_fwd(const sg_nap_desc_t* d, void* out, sg_stream_t stream);
 /* adjoint: grad has the layout of the forward output.  With save_mean != NULL the norm backward
  * dsrc = scale * (g' - mean(g') - xhat * mean(g' xhat)) is applied (bn=1: statistics over all images);
- * sums is f32 scratch of N*C*2 floats (per-image S1 = sum g', S2 = sum g' xhat) plus, for bn=1, C*2 more
- * floats behind them that return the batch totals (= d beta, d gamma for BatchNorm).  dsrc is plain bf16 NHWC or (out_planes=1) parity planes.
+ * sums is f32 scratch of N*parts*C*2 floats, parts = sg_norm_act_pad_bwd_parts(N,H,W,C) <= SG_NAP_MAX_PARTS
+ * (partial S1 = sum g', S2 = sum g' xhat per image and reduction CTA, added in a fixed order: no atomics, no zeroing)
+ * plus, for bn=1, C*2 more floats behind them that return the batch totals (= d beta, d gamma for BatchNorm).
+ * dsrc is plain bf16 NHWC or (out_planes=1) parity planes.
  * dres (optional, bf16, addressed with the residual's res_os_* strides) receives the folded
  * gradient of the residual input. */
+#define SG_NAP_MAX_PARTS 8
 int sg_norm_act_pad_bwd(const sg_nap_desc_t* d, const void* grad, const float* save_mean, const float* save_rstd,
                         int bn, float count, float* sums, int out_planes, void* dsrc, void* dres,
                         sg_stream_t stream);
+int sg_norm_act_pad_bwd_parts(int N, int H, int W, int C);   /* host-only; 0 on bad arguments */
 /* f32 NCHW grad * act'(y) (tanh / sigmoid heads, generators.py:87, model.py:107) -> bf16 NHWC (Cp). */
 int sg_act_bwd_nchw(const float* dy, const float* y, int N, int C, int H, int W, int act, int Cp, void* out,
                     sg_stream_t stream);
@@ -248,8 +266,12 @@ int sg_maxpool2x2_bwd(const void* gy, const void* x, int N, int H, int W, int C,
 /* layers.py:82-85 GlobalAvgPool: bf16 [N][HW][C] -> f32 [N][C], and the adjoint. */
 int sg_gap_fwd(const void* x, int N, int HW, int C, float* y, sg_stream_t stream);
 int sg_gap_bwd(const float* gy, int N, int HW, int C, void* gx, sg_stream_t stream);
-/* bias gradient: column sums of bf16 [rows][ld] (first C columns) ACCUMULATED into f32 out[C]. */
-int sg_colsum_bf16(const void* x, long long rows, int C, int ld, float* out, sg_stream_t stream);
+/* bias gradient: column sums of bf16 [rows][ld] (first C columns) written to f32 out[C].  Fixed-order reduction:
+ * ws = f32 scratch of SG_COLSUM_MAX_BLOCKS * C floats (one partial row per CTA), ticket = one uint32 that is ZERO on
+ * entry and left zero on return (stream-ordered reuse is fine; never share between streams). */
+#define SG_COLSUM_MAX_BLOCKS 296
+int sg_colsum_bf16(const void* x, long long rows, int C, int ld, float* out, float* ws, long long ws_floats,
+                   unsigned* ticket, sg_stream_t stream);
 
 /* ---- trainer.py:60,80,106,133 (torch.optim.Adam.step) + operand refresh ----------------------------------
  * Multi-tensor Adam (no weight decay, no amsgrad) over n_tensors parameter tensors, each given by its dense

@@ -38,7 +38,7 @@ class ConvDesc(ctypes.Structure):
         ('in_h0', c_int), ('in_w0', c_int),
         ('nphases', c_int), ('phases', Phase * 4),
         ('ntaps', c_int), ('taps', Tap * SG_MAX_TAPS),
-        ('bias', c_void_p), ('act', c_int), ('slope', c_float), ('stats', c_void_p),
+        ('bias', c_void_p), ('act', c_int), ('slope', c_float), ('stats', c_void_p), ('stats_slots', c_int),
         ('w_img_rows', c_int), ('w_row0', c_int),
         ('w_mn', c_int), ('w_rows', c_int), ('w_col0', c_int),
     ]
@@ -66,7 +66,7 @@ class WgradDesc(ctypes.Structure):
         ('Hred', c_int), ('Wred', c_int),
         ('dw', c_void_p), ('Cout', c_int), ('Cin', c_int), ('w_taps', c_int), ('dw_C', c_int),
         ('ntaps', c_int), ('taps', WTap * SG_MAX_TAPS),
-        ('ksplit', c_int), ('per_image', c_int),
+        ('ksplit', c_int), ('per_image', c_int), ('locks', c_void_p), ('n_locks', c_int),
     ]
 
 
@@ -106,11 +106,12 @@ _SIGS = {
     'sg_crop_bbox_fwd': [_P, _P, _P] + [c_int] * 10 + [_P, _P],
     'sg_crop_bbox_bwd': [_P, _P] + [c_int] * 10 + [_P, _P, _P],
     'sg_conv_tc': [ctypes.POINTER(ConvDesc), _P],
+    'sg_conv_stats_slots': [ctypes.POINTER(ConvDesc), ctypes.POINTER(c_int)],
     'sg_cast_pad_bf16': [_P, c_long, c_int, c_long, c_int, _P, c_float, _P, _P],
     'sg_pack_weight': [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P],
     'sg_pack_weight_cmap': [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P, _P, _P],
     'sg_wgrad_cmap_scatter': [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P],
-    'sg_norm_finalize': [_P, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, c_float, _P, _P, _P, _P, _P],
+    'sg_norm_finalize': [_P, c_int, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, c_float, _P, _P, _P, _P, _P],
     'sg_norm_act_pad_fwd': [ctypes.POINTER(NapDesc), _P, _P],
     'sg_norm_act_pad_bwd': [ctypes.POINTER(NapDesc), _P, _P, _P, c_int, c_float, _P, c_int, _P, _P, _P],
     'sg_act_bwd_nchw': [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
@@ -124,13 +125,14 @@ _SIGS = {
     'sg_maxpool2x2_bwd': [_P, _P, c_int, c_int, c_int, c_int, _P, _P],
     'sg_gap_fwd': [_P, c_int, c_int, c_int, _P, _P],
     'sg_gap_bwd': [_P, c_int, c_int, c_int, _P, _P],
-    'sg_colsum_bf16': [_P, c_long, c_int, c_int, _P, _P],
+    'sg_colsum_bf16': [_P, c_long, c_int, c_int, _P, _P, c_long, _P, _P],
+    'sg_norm_act_pad_bwd_parts': [c_int, c_int, c_int, c_int],
     'sg_adam_pack': [c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                      ctypes.c_double, _P],
     'sg_wgrad_tc': [ctypes.POINTER(WgradDesc), _P],
     'sg_probe_shifted_desc': [_P, _P, _P, c_int, _P],
     'sg_dgrad_small_cout': [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
-    'sg_wgrad_small_cout': [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
+    'sg_wgrad_small_cout': [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_long, _P],
 }
 _RESTYPES = {'sg_last_error': ctypes.c_char_p, 'sg_version': ctypes.c_char_p, 'sg_arch': c_int,
              'sg_launch_count': ctypes.c_ulonglong, 'sg_reset_launch_count': None, 'sg_add_launch_count': None}

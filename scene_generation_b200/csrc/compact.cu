@@ -45,32 +45,32 @@ __global__ void pack_cmap_t_kernel(const float* __restrict__ w, int Cout, int ta
   wt[idx] = __float2bfloat16(v);
 }
 
-// dw[co][tap][c] = sum over (n, j) with cmap[n][j] == c of dwc[n][co][tap][j].  One thread per (co, tap, j)
-// walks the images; runs of equal targets (the appearance / image channels map to the same dense channel
-// in every image) are summed in a register and flushed with one atomic.
+// dw[co][tap][c] = sum over (n, j) with cmap[n][j] == c of dwc[n][co][tap][j] — as a GATHER in image order (no
+// atomics, no zero-fill): the CTA first inverts the channel map into shared memory (inv[n][c] = j or -1; a dense
+// channel occurs at most once per image), then one thread per (co*taps + tap, c) adds its images in ascending n.
 __global__ void scatter_cmap_kernel(const float* __restrict__ dwc, const int* __restrict__ cmap, int N, int Cout, int taps,
-                                    int Cc, int Cin, float* __restrict__ dw) {
-  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long total = (long)Cout * taps * Cc;
-  if (idx >= total) return;
-  const int j = (int)(idx % Cc);
-  const long ct = idx / Cc;            // co * taps + tap
-  const long slab = (long)Cout * taps * Cc;
-  int cur = -1;
-  float acc = 0.f;
-  for (int n = 0; n < N; ++n) {
-    int c = cmap[n * Cc + j];
-    if (c < 0 || c >= Cin) continue;
-    float v = dwc[(long)n * slab + idx];
-    if (c != cur) {
-      if (cur >= 0) atomicAdd(dw + ct * Cin + cur, acc);
-      cur = c;
-      acc = v;
-    } else {
-      acc += v;
-    }
+                                    int Cc, int Cin, int rows_per_block, float* __restrict__ dw) {
+  extern __shared__ signed char inv[];       // [N][Cin]
+  for (int i = threadIdx.x; i < N * Cin; i += blockDim.x) inv[i] = -1;
+  __syncthreads();
+  for (int i = threadIdx.x; i < N * Cc; i += blockDim.x) {
+    const int c = cmap[i];
+    if (c >= 0 && c < Cin) inv[(i / Cc) * Cin + c] = (signed char)(i % Cc);
   }
-  if (cur >= 0) atomicAdd(dw + ct * Cin + cur, acc);
+  __syncthreads();
+  const long slab = (long)Cout * taps * Cc;
+  const long ct0 = (long)blockIdx.x * rows_per_block;
+  for (long i = threadIdx.x; i < (long)rows_per_block * Cin; i += blockDim.x) {
+    const long ct = ct0 + i / Cin;
+    const int c = (int)(i % Cin);
+    if (ct >= (long)Cout * taps) break;
+    float acc = 0.f;
+    for (int n = 0; n < N; ++n) {
+      const int j = inv[n * Cin + c];
+      if (j >= 0) acc += dwc[(long)n * slab + ct * Cc + j];
+    }
+    dw[ct * Cin + c] = acc;
+  }
 }
 
 }  // namespace
@@ -97,9 +97,17 @@ extern "C" int sg_wgrad_cmap_scatter(const float* dwc, const int* cmap, int N, i
                                      sg_stream_t stream) {
   SG_CHECK_ARG(dwc && cmap && dw, "wgrad_cmap_scatter: null pointer");
   SG_CHECK_ARG(Cout > 0 && taps > 0 && Cin > 0 && N > 0 && Cc > 0, "wgrad_cmap_scatter: bad sizes");
-  cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * taps * Cin, stream);
-  long total = (long)Cout * taps * Cc;
-  scatter_cmap_kernel<<<(unsigned)sg_cdiv(total, 256), 256, 0, stream>>>(dwc, cmap, N, Cout, taps, Cc, Cin, dw);
+  SG_CHECK_ARG(Cc <= 127 && (size_t)N * Cin <= 160 * 1024, "wgrad_cmap_scatter: channel map too large (N * Cin = %ld, Cc = %d)",
+               (long)N * Cin, Cc);
+  const long rows = (long)Cout * taps;
+  const int rpb = (int)((rows + 591) / 592) > 0 ? (int)((rows + 591) / 592) : 1;      // ~4 CTAs per SM
+  const size_t smem = (size_t)N * Cin;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaFuncSetAttribute(scatter_cmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    smem_set = smem;
+  }
+  scatter_cmap_kernel<<<(unsigned)sg_cdiv(rows, rpb), 256, smem, stream>>>(dwc, cmap, N, Cout, taps, Cc, Cin, rpb, dw);
   SG_CHECK_LAUNCH("sg_wgrad_cmap_scatter");
   return SG_OK;
 }

@@ -11,7 +11,8 @@
 //     Warp roles: w0 TMA producer, w1 TMEM alloc + single-thread tcgen05.mma issuer, w2-5 epilogue
 //     (tcgen05.ld -> bias -> InstanceNorm/BatchNorm partial sums -> activation -> vector stores).
 //   wgrad_tc_kernel : D[128 couts, BN cins] = sum over 64-pixel boxes dy[pix, co]^T x[pix(+tap), ci]
-//     both operands MN-major (pixel = K is the strided smem dimension), split-K with fp32 atomics.
+//     both operands MN-major (pixel = K is the strided smem dimension), split-K reduced in split order.
+// Every reduction in this file has a fixed order (no floating-point atomics): results are bit-reproducible.
 #include <stdlib.h>
 #include "common.cuh"
 #include "ptx.cuh"
@@ -103,6 +104,8 @@ struct ConvKParams {
   int act;
   float slope;
   float* stats;
+  int stat_slots;       // partial-sum slots per (image, channel): nphases * slots_per_phase
+  int slots_per_phase;  // M tiles per image (BI == 1) or 1 (whole images inside a tile)
   int vec_ok;
   sg_phase_t phases[4];
   sg_tap_t taps[SG_MAX_TAPS];
@@ -123,13 +126,140 @@ struct ConvCfg {
   static constexpr int smem_bytes(int stages) { return stages * (A_BYTES + B_STRIDE) + 1024 /*align slack*/ + 256 /*barriers*/; }
 };
 
-// MC = true: launched as clusters of 2 CTAs along M that work on the same weight tile; each CTA fetches
-// half of B and multicasts it to both, which removes a third of the L2 -> SM operand traffic of a
-// 128 x BN tile (the limiter of the 1024-channel resblock GEMMs with single-CTA tiles).
+// The 128 epilogue threads (warps 2..5) synchronise among themselves on named barrier 1.
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+constexpr int EPI_SCRATCH_FLOATS = 128 * 33;   // shared-memory scratch of the epilogue (aliases the drained operand ring)
+
+// Epilogue of one 128 x BN accumulator tile: tcgen05.ld -> bias -> InstanceNorm/BatchNorm partial sums -> activation
+// -> vector stores.  Executed by the four epilogue warps (q = TMEM lane quarter).
+//
+// Statistics are DETERMINISTIC: no atomics.  Every (image, channel) of the output gets `stat_slots` partial
+// (sum, sum of squares) pairs — one per (phase, M tile of that image) — each written by exactly one thread after a
+// fixed-order reduction (warp shuffle tree over 32 rows, then the warps of the image in order);
+// sg_norm_finalize adds the slots in slot order.  Layout: stats[img][slot][Cout][2].
+template <int BN>
+__device__ __forceinline__ void conv_epilogue(const ConvKParams& p, const sg_phase_t& ph, const uint32_t tmem, const int q,
+                                              const int lane, const int w0, const int h0, const int img0, const int n0,
+                                              const int slot, float* scratch) {
+  const int r = q * 32 + lane;
+  const int ww = r % p.BW, hh = (r / p.BW) % p.BH, ii = r / (p.BW * p.BH);
+  const int img = img0 + ii, h = h0 + hh, w = w0 + ww;
+  const bool valid = (ii < p.BI) && (img < p.n_img) && (h < p.Hout) && (w < p.Wout);
+  const long long off = (long long)img * p.os_img + (long long)(h * p.oh_mul + ph.oh_off) * p.os_h +
+                        (long long)(w * p.ow_mul + ph.ow_off) * p.os_w;
+  // seg_full: the 32 rows of a warp belong to one image.  Otherwise several (tiny) images share a warp: BI > 1, which
+  // choose_tile only picks when a whole image fits the tile, i.e. BW == Wout and BH == Hout.
+  const bool seg_full = (p.BI == 1) || ((p.BW * p.BH) % 32 == 0);
+  constexpr int CH = (BN >= 32) ? 32 : 16;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += CH) {
+    if (n0 + c0 >= p.Cout) break;                       // CTA-uniform
+    uint32_t raw[32];
+    if (CH == 32) tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, raw);
+    else tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c0, raw);
+    tmem_ld_wait();
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < CH) {
+        const int c = n0 + c0 + j;
+        float b = (p.bias != nullptr && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
+        f[j] = __uint_as_float(raw[j]) + b;
+      } else {
+        f[j] = 0.f;
+      }
+    }
+    if (p.stats != nullptr) {
+      if (seg_full) {
+        float s1[32], s2[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float v = valid ? f[j] : 0.f;
+          s1[j] = v;
+          s2[j] = v * v;
+        }
+        float t1 = warp_transpose_reduce(s1, lane);
+        float t2 = warp_transpose_reduce(s2, lane);
+        if (lane < CH) reinterpret_cast<float2*>(scratch)[q * BN + c0 + lane] = make_float2(t1, t2);
+      } else {
+        epi_bar();                                       // the previous chunk's readers are done with the scratch
+#pragma unroll
+        for (int j = 0; j < CH; ++j) scratch[r * 33 + j] = f[j];
+        epi_bar();
+        const int px = p.BW * p.BH;
+        for (int idx = r; idx < p.BI * CH; idx += 128) {
+          const int si = idx / CH, j = idx - si * CH;
+          const int c = n0 + c0 + j, simg = img0 + si;
+          if (c < p.Cout && simg < p.n_img) {
+            float a = 0.f, b = 0.f;
+            for (int rr = si * px; rr < (si + 1) * px; ++rr) {      // rows of this image, in order
+              const float v = scratch[rr * 33 + j];
+              a += v;
+              b = fmaf(v, v, b);
+            }
+            *reinterpret_cast<float2*>(p.stats + (((long long)simg * p.stat_slots + slot) * p.Cout + c) * 2) = make_float2(a, b);
+          }
+        }
+      }
+    }
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < CH; ++j) f[j] = apply_act(f[j], p.act, p.slope);
+      const bool full_chunk = (n0 + c0 + CH <= p.Cout) && p.vec_ok;
+      if (p.y_dtype == 1) {
+        __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + off + (long long)(n0 + c0) * p.os_c;
+        if (full_chunk) {
+#pragma unroll
+          for (int j = 0; j < CH; j += 8) {
+            __align__(16) __nv_bfloat162 pk[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) pk[t] = __floats2bfloat162_rn(f[j + 2 * t], f[j + 2 * t + 1]);
+            *reinterpret_cast<uint4*>(yp + j) = *reinterpret_cast<uint4*>(pk);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < CH; ++j)
+            if (n0 + c0 + j < p.Cout) yp[(long long)j * p.os_c] = __float2bfloat16(f[j]);
+        }
+      } else {
+        float* yp = reinterpret_cast<float*>(p.y) + off + (long long)(n0 + c0) * p.os_c;
+        if (full_chunk) {
+#pragma unroll
+          for (int j = 0; j < CH; j += 4) *reinterpret_cast<float4*>(yp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < CH; ++j)
+            if (n0 + c0 + j < p.Cout) yp[(long long)j * p.os_c] = f[j];
+        }
+      }
+    }
+  }
+  if (p.stats != nullptr && seg_full) {
+    // combine the warps of each image of the tile in warp order: gq warps per image, 4 / gq images per tile
+    epi_bar();
+    const int gq = (p.BI == 1) ? 4 : (p.BW * p.BH) / 32;
+    const int groups = 4 / gq;
+    for (int idx = r; idx < groups * BN; idx += 128) {
+      const int g = idx / BN, cc = idx - g * BN;
+      const int c = n0 + cc, simg = img0 + g;
+      if (c < p.Cout && simg < p.n_img && g < p.BI) {
+        float a = 0.f, b = 0.f;
+        for (int qq = g * gq; qq < (g + 1) * gq; ++qq) {
+          const float2 v = reinterpret_cast<const float2*>(scratch)[qq * BN + cc];
+          a += v.x;
+          b += v.y;
+        }
+        *reinterpret_cast<float2*>(p.stats + (((long long)simg * p.stat_slots + slot) * p.Cout + c) * 2) = make_float2(a, b);
+      }
+    }
+  }
+}
+
 // BMN = true: the weight operand is read "transposed" from the fprop tensor [K rows][taps][N cols] (dgrad of a
 // convolution uses the SAME bf16 copy of the weights as its fprop): 64 x 64 TMA boxes with the output channel as
 // the contiguous dimension, i.e. an MN-major B operand (the layout wgrad_tc_kernel uses for both operands).
-template <int BN, bool MC, bool BMN>
+template <int BN, bool BMN>
 __global__ void __launch_bounds__(192, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ ConvKParams p) {
@@ -156,7 +286,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], MC ? 2 : 1);      // MC: the slot is free when BOTH CTAs' MMAs have consumed it
+      mbar_init(&empty[s], 1);
     }
     mbar_init(accum_full, 1);
     fence_barrier_init();
@@ -166,10 +296,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) tmem_alloc<Cfg::TM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
-  if (MC) cluster_sync();                    // peer barriers must be initialised before any remote arrive / TMA
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t crank = MC ? cluster_ctarank() : 0;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -186,11 +314,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < BN / 64; ++j)
             tma_load_3d(sB + s * Cfg::B_STRIDE + j * 8192, &tmB, &full[s], p.w_col0 + n0 + 64 * j, tp.wtap, kb * 64);
-        } else if (MC)
-          tma_load_3d_mc(sB + s * Cfg::B_STRIDE + crank * (Cfg::B_BYTES / 2), &tmB, &full[s], kb * 64, tp.wtap,
-                         wrow0 + (int)crank * (BN / 2), (uint16_t)3);
-        else
+        } else {
           tma_load_3d(sB + s * Cfg::B_STRIDE, &tmB, &full[s], kb * 64, tp.wtap, wrow0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -211,548 +337,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           mma_bf16(tmem, ad + 2 * k, bd + (BMN ? 128 : 2) * k, idesc, (it | k) != 0 ? 1u : 0u);
-        if (MC) mma_commit_mc(&empty[s], (uint16_t)3);
-        else mma_commit(&empty[s]);   // frees the smem slot once these MMAs have read it
+        mma_commit(&empty[s]);   // frees the smem slot once these MMAs have read it
       }
       mma_commit(accum_full);
     }
   } else {
     // ---------------- epilogue: warps 2..5 own TMEM lane quarters (warp % 4) -------------------
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const int ww = r % p.BW, hh = (r / p.BW) % p.BH, ii = r / (p.BW * p.BH);
-    const int img = img0 + ii, h = h0 + hh, w = w0 + ww;
-    const bool valid = (ii < p.BI) && (img < p.n_img) && (h < p.Hout) && (w < p.Wout);
-    const long long off = (long long)img * p.os_img + (long long)(h * p.oh_mul + ph.oh_off) * p.os_h +
-                          (long long)(w * p.ow_mul + ph.ow_off) * p.os_w;
-    const bool seg_full = (p.BI == 1) || ((p.BW * p.BH) % 32 == 0);
     mbar_wait(accum_full, 0);
     tc_fence_after();
-    constexpr int CH = (BN >= 32) ? 32 : 16;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += CH) {
-      if (n0 + c0 >= p.Cout) break;
-      uint32_t raw[32];
-      if (CH == 32) tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, raw);
-      else tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c0, raw);
-      tmem_ld_wait();
-      float f[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (j < CH) {
-          const int c = n0 + c0 + j;
-          float b = (p.bias != nullptr && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
-          f[j] = __uint_as_float(raw[j]) + b;
-        } else {
-          f[j] = 0.f;
-        }
-      }
-      if (p.stats != nullptr) {
-        if (seg_full) {
-          float s1[32], s2[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float v = valid ? f[j] : 0.f;
-            s1[j] = v;
-            s2[j] = v * v;
-          }
-          float t1 = warp_transpose_reduce(s1, lane);
-          float t2 = warp_transpose_reduce(s2, lane);
-          const int simg = __shfl_sync(0xffffffffu, img, 0);
-          const int c = n0 + c0 + lane;
-          if (lane < CH && c < p.Cout && simg < p.n_img) {
-            atomicAdd(p.stats + ((long long)simg * p.Cout + c) * 2, t1);
-            atomicAdd(p.stats + ((long long)simg * p.Cout + c) * 2 + 1, t2);
-          }
-        } else if (valid) {
-#pragma unroll
-          for (int j = 0; j < CH; ++j) {
-            const int c = n0 + c0 + j;
-            if (c < p.Cout) {
-              atomicAdd(p.stats + ((long long)img * p.Cout + c) * 2, f[j]);
-              atomicAdd(p.stats + ((long long)img * p.Cout + c) * 2 + 1, f[j] * f[j]);
-            }
-          }
-        }
-      }
-      if (valid) {
-#pragma unroll
-        for (int j = 0; j < CH; ++j) f[j] = apply_act(f[j], p.act, p.slope);
-        const bool full_chunk = (n0 + c0 + CH <= p.Cout) && p.vec_ok;
-        if (p.y_dtype == 1) {
-          __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + off + (long long)(n0 + c0) * p.os_c;
-          if (full_chunk) {
-#pragma unroll
-            for (int j = 0; j < CH; j += 8) {
-              __align__(16) __nv_bfloat162 pk[4];
-#pragma unroll
-              for (int t = 0; t < 4; ++t) pk[t] = __floats2bfloat162_rn(f[j + 2 * t], f[j + 2 * t + 1]);
-              *reinterpret_cast<uint4*>(yp + j) = *reinterpret_cast<uint4*>(pk);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < CH; ++j)
-              if (n0 + c0 + j < p.Cout) yp[(long long)j * p.os_c] = __float2bfloat16(f[j]);
-          }
-        } else {
-          float* yp = reinterpret_cast<float*>(p.y) + off + (long long)(n0 + c0) * p.os_c;
-          if (full_chunk) {
-#pragma unroll
-            for (int j = 0; j < CH; j += 4) *reinterpret_cast<float4*>(yp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < CH; ++j)
-              if (n0 + c0 + j < p.Cout) yp[(long long)j * p.os_c] = f[j];
-          }
-        }
-      }
-    }
+    // every TMA load has landed and every MMA has read its operands: the operand ring is free and serves as scratch
+    const int slot = blockIdx.z * p.slots_per_phase + (p.BI == 1 ? th * p.tiles_w + tw : 0);
+    conv_epilogue<BN>(p, ph, tmem, warp & 3, lane, w0, h0, img0, n0, slot, reinterpret_cast<float*>(sA));
   }
   tc_fence_before();
   __syncthreads();
-  if (MC) cluster_sync();                    // the peer may still multicast into / arrive on this CTA's smem
   if (warp == 1) tmem_dealloc<Cfg::TM_COLS>(tmem);
-}
-
-// ------------------------------------------------------------------------------------------------
-// EXPERIMENTAL (SG_CONV_2CTA=1, not yet run on hardware — round-2 item): CTA-pair variant.  Two CTAs of a cluster own
-// two neighbouring M tiles and ONE N tile; the leader issues tcgen05.mma.cta_group::2 with M = 256: A = 128 rows from
-// each CTA's shared memory, B = BN/2 output channels from each CTA.  Every SM therefore streams its own A tile but
-// only HALF of the weight tile (24 KB instead of 32 KB per 64-channel k-block at BN = 128), which is what limits the
-// single-CTA kernel on the 1024-channel resblock GEMMs (L2 -> SM operand stream, profiles/r01_conv_tc_resblock_s.md).
-// Barrier protocol (CUTLASS PipelineTmaUmmaAsync, 2x1 atom): both producers wait on their own `empty`, only the leader
-// arms `full` with the bytes of BOTH CTAs, both issue their TMA loads against the leader's `full`; the leader's MMA
-// thread commits to `empty` / `accum_full` of both CTAs (multicast).  The epilogue is the single-CTA one, per CTA.
-template <int BN, bool BMN>
-__global__ void __launch_bounds__(192, 1)
-conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ ConvKParams p) {
-  constexpr int B_HALF = (BN / 2) * 128;        // bytes of this CTA's half of the weight tile per stage
-  constexpr int TM_COLS = BN;                   // 128 or 256
-  const int STAGES = p.stages;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_HALF);
-  uint64_t* empty = full + STAGES;
-  uint64_t* accum_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t crank = cluster_ctarank();
-  const int mt = blockIdx.x;                    // cluster dim x = 2: the pair is (2i, 2i + 1)
-  const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, ti = mt / (p.tiles_w * p.tiles_h);
-  const int w0 = tw * p.BW, h0 = th * p.BH, img0 = ti * p.BI;
-  const int n0 = blockIdx.y * BN;
-  const sg_phase_t ph = p.phases[blockIdx.z];
-  const int iters = ph.ntaps * p.kblocks;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
-    }
-    mbar_init(accum_full, 1);
-    fence_barrier_init();
-    prefetch_tmap(&tmA);
-    prefetch_tmap(&tmB);
-  }
-  if (warp == 1) tmem_alloc2<TM_COLS>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync();                               // peer barriers / TMEM exist before any remote signal
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t par = 0;
-      for (int it = 0; it < iters; ++it, ++s) {
-        if (s == STAGES) { s = 0; par ^= 1; }
-        mbar_wait(&empty[s], par ^ 1);
-        const int tap_i = it / p.kblocks, kb = it - tap_i * p.kblocks;
-        const sg_tap_t tp = p.taps[ph.tap_begin + tap_i];
-        if (crank == 0) mbar_expect_tx(&full[s], 2 * (p.a_bytes + B_HALF));
-        const uint32_t bar = leader_bar_addr(&full[s]);
-        tma_load_5d_2cta(sA + s * A_BYTES, &tmA, bar, kb * 64, w0 + tp.dw + p.in_w0, h0 + tp.dh + p.in_h0, tp.plane, img0);
-        if (BMN) {
-#pragma unroll
-          for (int j = 0; j < BN / 128; ++j)
-            tma_load_3d_2cta(sB + s * B_HALF + j * 8192, &tmB, bar, p.w_col0 + n0 + (int)crank * (BN / 2) + 64 * j, tp.wtap,
-                             kb * 64);
-        } else {
-          tma_load_3d_2cta(sB + s * B_HALF, &tmB, bar, kb * 64, tp.wtap, n0 + (int)crank * (BN / 2));
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0 && crank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, BMN ? 1 : 0);
-      int s = 0;
-      uint32_t par = 0;
-      for (int it = 0; it < iters; ++it, ++s) {
-        if (s == STAGES) { s = 0; par ^= 1; }
-        mbar_wait(&full[s], par);
-        tc_fence_after();
-        const uint64_t ad = umma_desc_sw128(smem_u32(sA + s * A_BYTES), 16, 1024);
-        const uint64_t bd = BMN ? umma_desc_sw128(smem_u32(sB + s * B_HALF), 8192, 1024)
-                                : umma_desc_sw128(smem_u32(sB + s * B_HALF), 16, 1024);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          mma_bf16_2cta(tmem, ad + 2 * k, bd + (BMN ? 128 : 2) * k, idesc, (it | k) != 0 ? 1u : 0u);
-        mma_commit_2cta(&empty[s], (uint16_t)3);
-      }
-      mma_commit_2cta(accum_full, (uint16_t)3);
-    }
-  } else {
-    // ---------------- epilogue: warps 2..5 own TMEM lane quarters (warp % 4) -------------------
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const int ww = r % p.BW, hh = (r / p.BW) % p.BH, ii = r / (p.BW * p.BH);
-    const int img = img0 + ii, h = h0 + hh, w = w0 + ww;
-    const bool valid = (ii < p.BI) && (img < p.n_img) && (h < p.Hout) && (w < p.Wout);
-    const long long off = (long long)img * p.os_img + (long long)(h * p.oh_mul + ph.oh_off) * p.os_h +
-                          (long long)(w * p.ow_mul + ph.ow_off) * p.os_w;
-    const bool seg_full = (p.BI == 1) || ((p.BW * p.BH) % 32 == 0);
-    mbar_wait(accum_full, 0);
-    tc_fence_after();
-    constexpr int CH = (BN >= 32) ? 32 : 16;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += CH) {
-      if (n0 + c0 >= p.Cout) break;
-      uint32_t raw[32];
-      if (CH == 32) tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, raw);
-      else tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c0, raw);
-      tmem_ld_wait();
-      float f[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (j < CH) {
-          const int c = n0 + c0 + j;
-          float b = (p.bias != nullptr && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
-          f[j] = __uint_as_float(raw[j]) + b;
-        } else {
-          f[j] = 0.f;
-        }
-      }
-      if (p.stats != nullptr) {
-        if (seg_full) {
-          float s1[32], s2[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float v = valid ? f[j] : 0.f;
-            s1[j] = v;
-            s2[j] = v * v;
-          }
-          float t1 = warp_transpose_reduce(s1, lane);
-          float t2 = warp_transpose_reduce(s2, lane);
-          const int simg = __shfl_sync(0xffffffffu, img, 0);
-          const int c = n0 + c0 + lane;
-          if (lane < CH && c < p.Cout && simg < p.n_img) {
-            atomicAdd(p.stats + ((long long)simg * p.Cout + c) * 2, t1);
-            atomicAdd(p.stats + ((long long)simg * p.Cout + c) * 2 + 1, t2);
-          }
-        } else if (valid) {
-#pragma unroll
-          for (int j = 0; j < CH; ++j) {
-            const int c = n0 + c0 + j;
-            if (c < p.Cout) {
-              atomicAdd(p.stats + ((long long)img * p.Cout + c) * 2, f[j]);
-              atomicAdd(p.stats + ((long long)img * p.Cout + c) * 2 + 1, f[j] * f[j]);
-            }
-          }
-        }
-      }
-      if (valid) {
-#pragma unroll
-        for (int j = 0; j < CH; ++j) f[j] = apply_act(f[j], p.act, p.slope);
-        const bool full_chunk = (n0 + c0 + CH <= p.Cout) && p.vec_ok;
-        if (p.y_dtype == 1) {
-          __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + off + (long long)(n0 + c0) * p.os_c;
-          if (full_chunk) {
-#pragma unroll
-            for (int j = 0; j < CH; j += 8) {
-              __align__(16) __nv_bfloat162 pk[4];
-#pragma unroll
-              for (int t = 0; t < 4; ++t) pk[t] = __floats2bfloat162_rn(f[j + 2 * t], f[j + 2 * t + 1]);
-              *reinterpret_cast<uint4*>(yp + j) = *reinterpret_cast<uint4*>(pk);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < CH; ++j)
-              if (n0 + c0 + j < p.Cout) yp[(long long)j * p.os_c] = __float2bfloat16(f[j]);
-          }
-        } else {
-          float* yp = reinterpret_cast<float*>(p.y) + off + (long long)(n0 + c0) * p.os_c;
-          if (full_chunk) {
-#pragma unroll
-            for (int j = 0; j < CH; j += 4) *reinterpret_cast<float4*>(yp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < CH; ++j)
-              if (n0 + c0 + j < p.Cout) yp[(long long)j * p.os_c] = f[j];
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync();                               // the leader's MMAs read this CTA's shared memory until the last commit
-  if (warp == 1) tmem_dealloc2<TM_COLS>(tmem);
-}
-
-// ------------------------------------------------------------------------------------------------
-// EXPERIMENTAL (SG_CONV_PERSIST=1, not yet run on hardware — round-2 item): persistent variant of conv_tc_kernel.
-// Why: the model in profiles/ (bench_shapes + launch list) puts the tensor-core convolutions of one iteration at
-// 2.3 ms of pure MMA time and 5.2 ms when the L2 -> SM operand stream is the limit, against 12 ms measured.  The
-// difference is per-CTA fixed cost (barrier init, TMEM allocation, descriptor fetch, pipeline fill, accumulator
-// drain): 4-7 us per CTA slot, paid 20-30 times per SM by the short-K convolutions (K loops of 4-16 iterations).
-// Here ONE CTA per SM walks a strided list of output tiles:
-//   * the TMA producer runs ahead ACROSS tile boundaries (the operand ring never drains between tiles),
-//   * the accumulator is double-buffered in TMEM (2 x BN columns): the epilogue warps drain tile i while the MMA
-//     thread already accumulates tile i + 1,
-//   * setup / teardown happen once per SM.
-// Barriers: full/empty per ring stage as in conv_tc_kernel; acc_full[2] (tcgen05.commit -> epilogue) and acc_empty[2]
-// (one arrive per epilogue warp after its last tcgen05.ld of the tile -> MMA thread).
-template <int BN, bool BMN>
-__global__ void __launch_bounds__(192, 1)
-conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ ConvKParams p, const int m_tiles, const int n_tiles, const int total_tiles) {
-  using Cfg = ConvCfg<BN>;
-  constexpr int TM_STRIDE = Cfg::TM_COLS;                // columns of one accumulator buffer (power of two >= 32)
-  constexpr int TM_ALLOC = 2 * TM_STRIDE;                // 64 .. 512
-  const int STAGES = p.stages;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_STRIDE);
-  uint64_t* empty = full + STAGES;
-  uint64_t* acc_full = empty + STAGES;                   // [2]
-  uint64_t* acc_empty = acc_full + 2;                    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], 4);                       // the four epilogue warps
-    }
-    fence_barrier_init();
-    prefetch_tmap(&tmA);
-    prefetch_tmap(&tmB);
-  }
-  if (warp == 1) tmem_alloc<TM_ALLOC>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  // tile id -> (phase, n tile, m tile), m fastest: CTAs of one wave share a weight tile in L2
-  auto decode = [&](int t, int& mt, int& nt, int& z) {
-    mt = t % m_tiles;
-    const int r = t / m_tiles;
-    nt = r % n_tiles;
-    z = r / n_tiles;
-  };
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t par = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        int mt, nt, z;
-        decode(t, mt, nt, z);
-        const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, ti = mt / (p.tiles_w * p.tiles_h);
-        const int w0 = tw * p.BW, h0 = th * p.BH, img0 = ti * p.BI;
-        const int n0 = nt * BN;
-        const int wrow0 = n0 + img0 * p.w_img_rows + p.w_row0;
-        const sg_phase_t ph = p.phases[z];
-        const int iters = ph.ntaps * p.kblocks;
-        for (int it = 0; it < iters; ++it, ++s) {
-          if (s == STAGES) { s = 0; par ^= 1; }
-          mbar_wait(&empty[s], par ^ 1);
-          const int tap_i = it / p.kblocks, kb = it - tap_i * p.kblocks;
-          const sg_tap_t tp = p.taps[ph.tap_begin + tap_i];
-          mbar_expect_tx(&full[s], p.a_bytes + Cfg::B_BYTES);
-          tma_load_5d(sA + s * A_BYTES, &tmA, &full[s], kb * 64, w0 + tp.dw + p.in_w0, h0 + tp.dh + p.in_h0, tp.plane, img0);
-          if (BMN) {
-#pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_3d(sB + s * Cfg::B_STRIDE + j * 8192, &tmB, &full[s], p.w_col0 + n0 + 64 * j, tp.wtap, kb * 64);
-          } else {
-            tma_load_3d(sB + s * Cfg::B_STRIDE, &tmB, &full[s], kb * 64, tp.wtap, wrow0);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, BMN ? 1 : 0);
-      int s = 0;
-      uint32_t par = 0;
-      int i = 0;                                         // tiles done by this CTA
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
-        int mt, nt, z;
-        decode(t, mt, nt, z);
-        const int iters = p.phases[z].ntaps * p.kblocks;
-        const int buf = i & 1;
-        mbar_wait(&acc_empty[buf], ((uint32_t)(i >> 1) & 1u) ^ 1u);      // the epilogue has drained this buffer
-        tc_fence_after();
-        const uint32_t acc = tmem + (uint32_t)(buf * TM_STRIDE);
-        for (int it = 0; it < iters; ++it, ++s) {
-          if (s == STAGES) { s = 0; par ^= 1; }
-          mbar_wait(&full[s], par);
-          tc_fence_after();
-          const uint64_t ad = umma_desc_sw128(smem_u32(sA + s * A_BYTES), 16, 1024);
-          const uint64_t bd = BMN ? umma_desc_sw128(smem_u32(sB + s * Cfg::B_STRIDE), 8192, 1024)
-                                  : umma_desc_sw128(smem_u32(sB + s * Cfg::B_STRIDE), 16, 1024);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            mma_bf16(acc, ad + 2 * k, bd + (BMN ? 128 : 2) * k, idesc, (it | k) != 0 ? 1u : 0u);
-          mma_commit(&empty[s]);
-        }
-        mma_commit(&acc_full[buf]);
-      }
-    }
-  } else {
-    // ---------------- epilogue: warps 2..5 own TMEM lane quarters (warp % 4) -------------------
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const int ww = r % p.BW, hh = (r / p.BW) % p.BH, ii = r / (p.BW * p.BH);
-    const bool seg_full = (p.BI == 1) || ((p.BW * p.BH) % 32 == 0);
-    constexpr int CH = (BN >= 32) ? 32 : 16;
-    int i = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
-      int mt, nt, z;
-      decode(t, mt, nt, z);
-      const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, ti = mt / (p.tiles_w * p.tiles_h);
-      const int w0 = tw * p.BW, h0 = th * p.BH, img0 = ti * p.BI;
-      const int n0 = nt * BN;
-      const sg_phase_t ph = p.phases[z];
-      const int img = img0 + ii, h = h0 + hh, w = w0 + ww;
-      const bool valid = (ii < p.BI) && (img < p.n_img) && (h < p.Hout) && (w < p.Wout);
-      const long long off = (long long)img * p.os_img + (long long)(h * p.oh_mul + ph.oh_off) * p.os_h +
-                            (long long)(w * p.ow_mul + ph.ow_off) * p.os_w;
-      const int buf = i & 1;
-      mbar_wait(&acc_full[buf], (uint32_t)(i >> 1) & 1u);
-      tc_fence_after();
-      const uint32_t acc = tmem + (uint32_t)(buf * TM_STRIDE) + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += CH) {
-        // warp-uniform: `last` = this is the final chunk with output channels in it (the loop always ends through it;
-        // `live` can only be false at c0 == 0, for a tile that lies entirely beyond Cout)
-        const bool live = n0 + c0 < p.Cout;
-        const bool last = !live || (c0 + CH >= BN) || (n0 + c0 + CH >= p.Cout);
-        uint32_t raw[32];
-        if (live) {
-          if (CH == 32) tmem_ld32(acc + c0, raw);
-          else tmem_ld16(acc + c0, raw);
-          tmem_ld_wait();
-        }
-        if (last) {
-          // this warp has read everything it needs from the accumulator: hand the buffer back to the MMA thread
-          // (exactly once per tile and warp)
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[buf]);
-        }
-        if (!live) break;
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (j < CH) {
-            const int c = n0 + c0 + j;
-            float b = (p.bias != nullptr && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
-            f[j] = __uint_as_float(raw[j]) + b;
-          } else {
-            f[j] = 0.f;
-          }
-        }
-        if (p.stats != nullptr) {
-          if (seg_full) {
-            float s1[32], s2[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float v = valid ? f[j] : 0.f;
-              s1[j] = v;
-              s2[j] = v * v;
-            }
-            float t1 = warp_transpose_reduce(s1, lane);
-            float t2 = warp_transpose_reduce(s2, lane);
-            const int simg = __shfl_sync(0xffffffffu, img, 0);
-            const int c = n0 + c0 + lane;
-            if (lane < CH && c < p.Cout && simg < p.n_img) {
-              atomicAdd(p.stats + ((long long)simg * p.Cout + c) * 2, t1);
-              atomicAdd(p.stats + ((long long)simg * p.Cout + c) * 2 + 1, t2);
-            }
-          } else if (valid) {
-#pragma unroll
-            for (int j = 0; j < CH; ++j) {
-              const int c = n0 + c0 + j;
-              if (c < p.Cout) {
-                atomicAdd(p.stats + ((long long)img * p.Cout + c) * 2, f[j]);
-                atomicAdd(p.stats + ((long long)img * p.Cout + c) * 2 + 1, f[j] * f[j]);
-              }
-            }
-          }
-        }
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < CH; ++j) f[j] = apply_act(f[j], p.act, p.slope);
-          const bool full_chunk = (n0 + c0 + CH <= p.Cout) && p.vec_ok;
-          if (p.y_dtype == 1) {
-            __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + off + (long long)(n0 + c0) * p.os_c;
-            if (full_chunk) {
-#pragma unroll
-              for (int j = 0; j < CH; j += 8) {
-                __align__(16) __nv_bfloat162 pk[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) pk[u] = __floats2bfloat162_rn(f[j + 2 * u], f[j + 2 * u + 1]);
-                *reinterpret_cast<uint4*>(yp + j) = *reinterpret_cast<uint4*>(pk);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < CH; ++j)
-                if (n0 + c0 + j < p.Cout) yp[(long long)j * p.os_c] = __float2bfloat16(f[j]);
-            }
-          } else {
-            float* yp = reinterpret_cast<float*>(p.y) + off + (long long)(n0 + c0) * p.os_c;
-            if (full_chunk) {
-#pragma unroll
-              for (int j = 0; j < CH; j += 4) *reinterpret_cast<float4*>(yp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < CH; ++j)
-                if (n0 + c0 + j < p.Cout) yp[(long long)j * p.os_c] = f[j];
-            }
-          }
-        }
-        if (last) break;
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<TM_ALLOC>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------------
 struct WgradKParams {
   int tiles_w, tiles_h, BW, BH, BI;
   int ktiles_total, ktiles_per_split;
-  int atomic;       // 0: this CTA owns its dw tile (ksplit == 1) -> plain stores
+  int serial;       // 1: the k-splits of a dw tile add their partial sums one after the other, in split order
   int Cout, Cin, w_taps, dw_C, n_ci_tiles, stages;
   long long dw_split_stride;   // per_image: floats between the dw slabs of consecutive k-splits (= images)
   float* dw;
+  int* locks;       // serial: one turn counter per dw tile (zero on entry, zero again on exit)
   sg_wtap_t taps[SG_MAX_TAPS];
 };
 
@@ -768,6 +378,19 @@ struct WgradCfg {
   static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 + 256; }
 };
 
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Split-K is DETERMINISTIC: the k-splits (blockIdx.z) of one dw tile take turns in split order (a turn counter per
+// tile, acquire/release at gpu scope): split 0 stores its partial sums, split z > 0 waits for split z - 1 and adds its
+// own with plain loads and stores; the last split resets the counter.  Thread blocks are dispatched in increasing
+// linear block index (z slowest), so the split a CTA waits for is always resident or finished.
 template <int BN>
 __global__ void __launch_bounds__(192, 2)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -844,213 +467,64 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       mma_commit(accum_full);
     }
-  } else if (iters > 0) {
+  } else {
     const int q = warp & 3;
     const int co = co0 + q * 32 + lane;
-    mbar_wait(accum_full, 0);
-    tc_fence_after();
+    int* lock = p.serial ? p.locks + (blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+    const bool add = p.serial && blockIdx.z > 0;
+    if (iters > 0) {
+      mbar_wait(accum_full, 0);
+      tc_fence_after();
+    }
+    if (p.serial) {
+      if (q == 0 && lane == 0) {
+        while (ld_acquire_gpu(lock) != (int)blockIdx.z) __nanosleep(64);
+      }
+      epi_bar();
+    }
+    if (iters > 0) {
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (ci0 + c0 >= p.Cin) break;
-      uint32_t raw[32];
-      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, raw);
-      tmem_ld_wait();
-      if (co < p.Cout) {
-        float* dst = p.dw + (long long)blockIdx.z * p.dw_split_stride + ((long long)co * p.w_taps + tp.wtap) * p.dw_C + ci0 + c0;
-        const bool vec = (ci0 + c0 + 32 <= p.Cin) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-        if (vec && !p.atomic) {
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (ci0 + c0 >= p.Cin) break;
+        uint32_t raw[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, raw);
+        tmem_ld_wait();
+        if (co < p.Cout) {
+          float* dst = p.dw + (long long)(p.serial ? 0 : blockIdx.z) * p.dw_split_stride +
+                       ((long long)co * p.w_taps + tp.wtap) * p.dw_C + ci0 + c0;
+          const bool vec = (ci0 + c0 + 32 <= p.Cin) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+          if (vec) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]),
-                                                              __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3]));
-        } else if (vec) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(raw[j])),
-                         "f"(__uint_as_float(raw[j + 1])), "f"(__uint_as_float(raw[j + 2])), "f"(__uint_as_float(raw[j + 3]))
-                         : "memory");
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (ci0 + c0 + j < p.Cin) {
-              if (p.atomic) atomicAdd(dst + j, __uint_as_float(raw[j]));
-              else dst[j] = __uint_as_float(raw[j]);
+            for (int j = 0; j < 32; j += 4) {
+              float4 v = make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]), __uint_as_float(raw[j + 2]),
+                                     __uint_as_float(raw[j + 3]));
+              if (add) {
+                const float4 o = __ldcg(reinterpret_cast<const float4*>(dst + j));
+                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+              }
+              __stcg(reinterpret_cast<float4*>(dst + j), v);
             }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (ci0 + c0 + j < p.Cin) {
+                float v = __uint_as_float(raw[j]);
+                if (add) v += __ldcg(dst + j);
+                __stcg(dst + j, v);
+              }
+          }
         }
       }
+    }
+    if (p.serial) {
+      __threadfence();
+      epi_bar();
+      if (q == 0 && lane == 0) st_release_gpu(lock, blockIdx.z + 1 == gridDim.z ? 0 : (int)blockIdx.z + 1);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<Cfg::TM_COLS>(tmem);
-}
-
-// EXPERIMENTAL (SG_WGRAD_PERSIST=1, not yet run on hardware — round-2 item): persistent variant of wgrad_tc_kernel,
-// same scheme as conv_tcp_kernel.  A weight-gradient tile's epilogue moves 128 x BN fp32 (up to 128 KB) out of TMEM
-// with vector stores / reductions; double-buffering the accumulator lets it overlap the next tile's MMAs.
-template <int BN>
-__global__ void __launch_bounds__(192, 1)
-wgrad_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ WgradKParams p, const int gx, const int gy, const int total_tiles) {
-  using Cfg = WgradCfg<BN>;
-  constexpr int TM_STRIDE = Cfg::TM_COLS;
-  constexpr int TM_ALLOC = 2 * TM_STRIDE;
-  const int STAGES = p.stages;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty = full + STAGES;
-  uint64_t* acc_full = empty + STAGES;
-  uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], 4);
-    }
-    fence_barrier_init();
-    prefetch_tmap(&tmA);
-    prefetch_tmap(&tmB);
-  }
-  if (warp == 1) tmem_alloc<TM_ALLOC>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  // tile id -> (x = co/ci tile, y = tap, z = k split) of the non-persistent grid; returns the k-tile range
-  auto decode = [&](int t, int& x, int& y, int& z, int& kt_begin, int& iters) {
-    x = t % gx;
-    const int r = t / gx;
-    y = r % gy;
-    z = r / gy;
-    kt_begin = z * p.ktiles_per_split;
-    const int kt_end = min(kt_begin + p.ktiles_per_split, p.ktiles_total);
-    iters = max(kt_end - kt_begin, 0);
-  };
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t par = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        int x, y, z, kt_begin, iters;
-        decode(t, x, y, z, kt_begin, iters);
-        const int ci_tile = x % p.n_ci_tiles, co_tile = x / p.n_ci_tiles;
-        const int co0 = co_tile * 128, ci0 = ci_tile * BN;
-        const sg_wtap_t tp = p.taps[y];
-        for (int it = 0; it < iters; ++it, ++s) {
-          if (s == STAGES) { s = 0; par ^= 1; }
-          mbar_wait(&empty[s], par ^ 1);
-          const int kt = kt_begin + it;
-          const int tw = kt % p.tiles_w, th = (kt / p.tiles_w) % p.tiles_h, ti = kt / (p.tiles_w * p.tiles_h);
-          const int w0 = tw * p.BW, h0 = th * p.BH, img0 = ti * p.BI;
-          uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-          mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
-          tma_load_5d(st, &tmA, &full[s], co0, w0 + tp.dwa, h0 + tp.dha, tp.pa, img0);
-          tma_load_5d(st + WG_BOX_BYTES, &tmA, &full[s], co0 + 64, w0 + tp.dwa, h0 + tp.dha, tp.pa, img0);
-#pragma unroll
-          for (int j = 0; j < Cfg::NB; ++j)
-            tma_load_5d(st + (2 + j) * WG_BOX_BYTES, &tmB, &full[s], ci0 + 64 * j, w0 + tp.dwb, h0 + tp.dhb, tp.pb, img0);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
-      int s = 0;
-      uint32_t par = 0;
-      int i = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        int x, y, z, kt_begin, iters;
-        decode(t, x, y, z, kt_begin, iters);
-        if (iters == 0) continue;                        // every role skips empty tiles the same way
-        const int buf = i & 1;
-        mbar_wait(&acc_empty[buf], ((uint32_t)(i >> 1) & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t acc = tmem + (uint32_t)(buf * TM_STRIDE);
-        for (int it = 0; it < iters; ++it, ++s) {
-          if (s == STAGES) { s = 0; par ^= 1; }
-          mbar_wait(&full[s], par);
-          tc_fence_after();
-          uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-          const uint64_t ad = umma_desc_sw128(smem_u32(st), WG_BOX_BYTES, 1024);
-          const uint64_t bd = umma_desc_sw128(smem_u32(st + 2 * WG_BOX_BYTES), WG_BOX_BYTES, 1024);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) mma_bf16(acc, ad + 128 * k, bd + 128 * k, idesc, (it | k) != 0 ? 1u : 0u);
-          mma_commit(&empty[s]);
-        }
-        mma_commit(&acc_full[buf]);
-        ++i;
-      }
-    }
-  } else {
-    const int q = warp & 3;
-    int i = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      int x, y, z, kt_begin, iters;
-      decode(t, x, y, z, kt_begin, iters);
-      if (iters == 0) continue;
-      const int ci_tile = x % p.n_ci_tiles, co_tile = x / p.n_ci_tiles;
-      const int co0 = co_tile * 128, ci0 = ci_tile * BN;
-      const sg_wtap_t tp = p.taps[y];
-      const int co = co0 + q * 32 + lane;
-      const int buf = i & 1;
-      mbar_wait(&acc_full[buf], (uint32_t)(i >> 1) & 1u);
-      tc_fence_after();
-      const uint32_t acc = tmem + (uint32_t)(buf * TM_STRIDE) + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        const bool live = ci0 + c0 < p.Cin;              // warp-uniform
-        const bool last = !live || (c0 + 32 >= BN) || (ci0 + c0 + 32 >= p.Cin);
-        uint32_t raw[32];
-        if (live) {
-          tmem_ld32(acc + c0, raw);
-          tmem_ld_wait();
-        }
-        if (last) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[buf]);
-        }
-        if (!live) break;
-        if (co < p.Cout) {
-          float* dst = p.dw + (long long)z * p.dw_split_stride + ((long long)co * p.w_taps + tp.wtap) * p.dw_C + ci0 + c0;
-          const bool vec = (ci0 + c0 + 32 <= p.Cin) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-          if (vec && !p.atomic) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]),
-                                                                __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3]));
-          } else if (vec) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(raw[j])),
-                           "f"(__uint_as_float(raw[j + 1])), "f"(__uint_as_float(raw[j + 2])), "f"(__uint_as_float(raw[j + 3]))
-                           : "memory");
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (ci0 + c0 + j < p.Cin) {
-                if (p.atomic) atomicAdd(dst + j, __uint_as_float(raw[j]));
-                else dst[j] = __uint_as_float(raw[j]);
-              }
-          }
-        }
-        if (last) break;
-      }
-      ++i;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<TM_ALLOC>(tmem);
 }
 
 // Choose the TMA box (BW, BH, BI) of one M tile.  exact=false (conv): any box with BW*BH*BI <= rows —
@@ -1090,147 +564,30 @@ bool deep_pipeline() {
   return v == 1;
 }
 
-template <int BN, bool MC, bool BMN>
+template <int BN, bool BMN>
 int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKParams& kp, dim3 grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, MC, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          ConvCfg<BN>::smem_bytes(ConvCfg<BN>::STAGES_DEEP));
     if (e != cudaSuccess) return sg_fail(SG_ERR_CUDA, "conv_tc smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   // a grid that does not even fill the SMs once gains nothing from co-residency: give each CTA the deep ring
   const bool one_wave = (long)grid.x * grid.y * grid.z <= 148;
-  kp.stages = (deep_pipeline() || MC || one_wave) ? ConvCfg<BN>::STAGES_DEEP : ConvCfg<BN>::STAGES_SHALLOW;
-  const int smem_bytes = ConvCfg<BN>::smem_bytes(kp.stages);
-  if (MC) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(192);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, MC, BMN>, tmA, tmB, kp);
-    if (e != cudaSuccess) return sg_fail(SG_ERR_CUDA, "sg_conv_tc (cluster launch): %s", cudaGetErrorString(e));
-  } else {
-    conv_tc_kernel<BN, MC, BMN><<<grid, 192, smem_bytes, stream>>>(tmA, tmB, kp);
-  }
-  SG_CHECK_LAUNCH("sg_conv_tc");
-  return SG_OK;
-}
-
-// SG_CONV_2CTA=1 selects the CTA-pair variant for long-K, wide-N launches (experimental)
-bool two_cta_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SG_CONV_2CTA");
-    v = (e != nullptr && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
-
-template <int BN, bool BMN>
-int launch_conv2(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKParams& kp, dim3 grid, cudaStream_t stream) {
-  constexpr int STAGES = (BN == 256) ? 6 : 8;                        // 32 KB / 24 KB per stage and CTA
-  constexpr int SMEM = STAGES * (A_BYTES + (BN / 2) * 128) + 1024 + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    if (e != cudaSuccess) return sg_fail(SG_ERR_CUDA, "conv_tc2 smem attribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
-  kp.stages = STAGES;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = grid;
-  cfg.blockDim = dim3(192);
-  cfg.dynamicSmemBytes = SMEM;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<BN, BMN>, tmA, tmB, kp);
-  if (e != cudaSuccess) return sg_fail(SG_ERR_CUDA, "sg_conv_tc (CTA-pair launch): %s", cudaGetErrorString(e));
-  SG_CHECK_LAUNCH("sg_conv_tc");
-  return SG_OK;
-}
-
-// SG_CONV_PERSIST=1 selects the persistent variant for multi-wave launches (experimental)
-bool persist_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SG_CONV_PERSIST");
-    v = (e != nullptr && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
-
-// SG_WGRAD_PERSIST=1 selects the persistent wgrad variant for multi-wave launches (experimental)
-bool wgrad_persist_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SG_WGRAD_PERSIST");
-    v = (e != nullptr && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
-
-int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
-  }
-  return n;
-}
-
-template <int BN, bool BMN>
-int launch_conv_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKParams& kp, dim3 grid, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tcp_kernel<BN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         ConvCfg<BN>::smem_bytes(ConvCfg<BN>::STAGES_DEEP));
-    if (e != cudaSuccess) return sg_fail(SG_ERR_CUDA, "conv_tcp smem attribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
-  kp.stages = ConvCfg<BN>::STAGES_DEEP;
-  const int total = (int)(grid.x * grid.y * grid.z);
-  const int ctas = total < sm_count() ? total : sm_count();
-  conv_tcp_kernel<BN, BMN><<<ctas, 192, ConvCfg<BN>::smem_bytes(kp.stages), stream>>>(tmA, tmB, kp, (int)grid.x, (int)grid.y, total);
+  kp.stages = (deep_pipeline() || one_wave) ? ConvCfg<BN>::STAGES_DEEP : ConvCfg<BN>::STAGES_SHALLOW;
+  static_assert(ConvCfg<BN>::STAGES_SHALLOW * A_BYTES >= EPI_SCRATCH_FLOATS * 4, "epilogue scratch must fit the A ring");
+  conv_tc_kernel<BN, BMN><<<grid, 192, ConvCfg<BN>::smem_bytes(kp.stages), stream>>>(tmA, tmB, kp);
   SG_CHECK_LAUNCH("sg_conv_tc");
   return SG_OK;
 }
 
 template <int BN>
-int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKParams& kp, dim3 grid, bool mc, bool bmn,
-                cudaStream_t stream) {
-  // persistent variant: only where a CTA would otherwise be re-launched on the same SM (more tiles than SMs)
-  if (persist_enabled() && !mc && (long)grid.x * grid.y * grid.z > sm_count()) {
-    if (bmn) {
-      if constexpr (BN >= 64) return launch_conv_persist<BN, true>(tmA, tmB, kp, grid, stream);
-    } else {
-      return launch_conv_persist<BN, false>(tmA, tmB, kp, grid, stream);
-    }
-  }
+int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKParams& kp, dim3 grid, bool bmn, cudaStream_t stream) {
   if (bmn) {
-    if constexpr (BN >= 64) return launch_conv_t<BN, false, true>(tmA, tmB, kp, grid, stream);
+    if constexpr (BN >= 64) return launch_conv_t<BN, true>(tmA, tmB, kp, grid, stream);
   }
-  if (mc) {
-    if constexpr (BN == 128 || BN == 256) return launch_conv_t<BN, true, false>(tmA, tmB, kp, grid, stream);
-  }
-  return launch_conv_t<BN, false, false>(tmA, tmB, kp, grid, stream);
+  return launch_conv_t<BN, false>(tmA, tmB, kp, grid, stream);
 }
 
 // SG_CONV_NO192=1 keeps the N tiles at powers of two (A/B switch for the 192-wide tile)
@@ -1238,16 +595,6 @@ bool no192() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("SG_CONV_NO192");
-    v = (e != nullptr && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
-
-// SG_CONV_MULTICAST=1 enables the 2-CTA-cluster weight-multicast variant for long-K, wide-N launches
-bool multicast_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SG_CONV_MULTICAST");
     v = (e != nullptr && e[0] == '1') ? 1 : 0;
   }
   return v == 1;
@@ -1263,49 +610,50 @@ int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, WgradKParams& k
     attr_set = true;
   }
   const bool one_wave = (long)grid.x * grid.y * grid.z <= 148;
-  if (wgrad_persist_enabled() && !one_wave) {
-    static bool attr2_set = false;
-    if (!attr2_set) {
-      cudaError_t e = cudaFuncSetAttribute(wgrad_tcp_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           WgradCfg<BN>::smem_bytes(WgradCfg<BN>::STAGES_DEEP));
-      if (e != cudaSuccess) return sg_fail(SG_ERR_CUDA, "wgrad_tcp smem attribute: %s", cudaGetErrorString(e));
-      attr2_set = true;
-    }
-    kp.stages = WgradCfg<BN>::STAGES_DEEP;
-    const int total = (int)(grid.x * grid.y * grid.z);
-    const int ctas = total < sm_count() ? total : sm_count();
-    wgrad_tcp_kernel<BN><<<ctas, 192, WgradCfg<BN>::smem_bytes(kp.stages), stream>>>(tmA, tmB, kp, (int)grid.x, (int)grid.y, total);
-    SG_CHECK_LAUNCH("sg_wgrad_tc");
-    return SG_OK;
-  }
   kp.stages = (deep_pipeline() || one_wave) ? WgradCfg<BN>::STAGES_DEEP : WgradCfg<BN>::STAGES_SHALLOW;
   wgrad_tc_kernel<BN><<<grid, 192, WgradCfg<BN>::smem_bytes(kp.stages), stream>>>(tmA, tmB, kp);
   SG_CHECK_LAUNCH("sg_wgrad_tc");
   return SG_OK;
 }
 
-}  // namespace
-
-extern "C" int sg_conv_tc(const sg_conv_desc_t* d, sg_stream_t stream) {
+// tile geometry of a convolution launch (shared by sg_conv_tc and sg_conv_stats_slots)
+int conv_geometry(const sg_conv_desc_t* d, ConvKParams& kp) {
   SG_CHECK_ARG(d != nullptr, "sg_conv_tc: null descriptor");
-  SG_CHECK_ARG(d->x && d->w && d->y, "sg_conv_tc: null tensor pointer");
-  SG_CHECK_ARG(d->x_C % 8 == 0 && d->w_C % 8 == 0, "sg_conv_tc: channel counts must be multiples of 8 (x_C=%d w_C=%d)", d->x_C, d->w_C);
-  SG_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= SG_MAX_TAPS, "sg_conv_tc: ntaps %d out of range", d->ntaps);
   SG_CHECK_ARG(d->nphases >= 1 && d->nphases <= 4, "sg_conv_tc: nphases %d out of range", d->nphases);
   SG_CHECK_ARG(d->Hout > 0 && d->Wout > 0 && d->x_N > 0 && d->w_Cout > 0, "sg_conv_tc: empty problem");
-  SG_CHECK_ARG(d->y_dtype == 0 || d->y_dtype == 1, "sg_conv_tc: y_dtype must be 0 (f32) or 1 (bf16)");
-  SG_CHECK_ARG(d->y_os_c >= 1, "sg_conv_tc: y_os_c (channel stride) must be >= 1");
-  for (int i = 0; i < d->nphases; ++i)
-    SG_CHECK_ARG(d->phases[i].ntaps >= 1 && d->phases[i].tap_begin >= 0 && d->phases[i].tap_begin + d->phases[i].ntaps <= d->ntaps,
-                 "sg_conv_tc: phase %d tap range invalid", i);
-  ConvKParams kp;
   memset(&kp, 0, sizeof(kp));
   choose_tile(128, false, d->Hout, d->Wout, d->x_N, &kp.BW, &kp.BH, &kp.BI);
   kp.a_bytes = 128 * kp.BW * kp.BH * kp.BI;
   kp.Hout = d->Hout; kp.Wout = d->Wout;
   kp.tiles_w = sg_cdiv(d->Wout, kp.BW); kp.tiles_h = sg_cdiv(d->Hout, kp.BH);
-  const int img_tiles = sg_cdiv(d->x_N, kp.BI);
   kp.n_img = d->x_N;
+  kp.slots_per_phase = kp.BI == 1 ? kp.tiles_w * kp.tiles_h : 1;
+  kp.stat_slots = d->nphases * kp.slots_per_phase;
+  return SG_OK;
+}
+
+}  // namespace
+
+extern "C" int sg_conv_stats_slots(const sg_conv_desc_t* d, int* slots) {
+  ConvKParams kp;
+  SG_CHECK_ARG(slots != nullptr, "sg_conv_stats_slots: null output");
+  if (int e = conv_geometry(d, kp)) return e;
+  *slots = kp.stat_slots;
+  return SG_OK;
+}
+
+extern "C" int sg_conv_tc(const sg_conv_desc_t* d, sg_stream_t stream) {
+  ConvKParams kp;
+  if (int e = conv_geometry(d, kp)) return e;
+  SG_CHECK_ARG(d->x && d->w && d->y, "sg_conv_tc: null tensor pointer");
+  SG_CHECK_ARG(d->x_C % 8 == 0 && d->w_C % 8 == 0, "sg_conv_tc: channel counts must be multiples of 8 (x_C=%d w_C=%d)", d->x_C, d->w_C);
+  SG_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= SG_MAX_TAPS, "sg_conv_tc: ntaps %d out of range", d->ntaps);
+  SG_CHECK_ARG(d->y_dtype == 0 || d->y_dtype == 1, "sg_conv_tc: y_dtype must be 0 (f32) or 1 (bf16)");
+  SG_CHECK_ARG(d->y_os_c >= 1, "sg_conv_tc: y_os_c (channel stride) must be >= 1");
+  for (int i = 0; i < d->nphases; ++i)
+    SG_CHECK_ARG(d->phases[i].ntaps >= 1 && d->phases[i].tap_begin >= 0 && d->phases[i].tap_begin + d->phases[i].ntaps <= d->ntaps,
+                 "sg_conv_tc: phase %d tap range invalid", i);
+  const int img_tiles = sg_cdiv(d->x_N, kp.BI);
   const bool bmn = d->w_mn != 0;
   SG_CHECK_ARG(!bmn || (d->w_img_rows == 0 && d->w_rows > 0 && d->w_col0 >= 0 && d->w_col0 % 8 == 0 &&
                         d->w_col0 + d->w_Cout <= d->w_C),
@@ -1324,6 +672,9 @@ extern "C" int sg_conv_tc(const sg_conv_desc_t* d, sg_stream_t stream) {
   kp.os_img = d->y_os_img; kp.os_h = d->y_os_h; kp.os_w = d->y_os_w; kp.os_c = d->y_os_c;
   kp.oh_mul = d->oh_mul; kp.ow_mul = d->ow_mul;
   kp.y = d->y; kp.y_dtype = d->y_dtype; kp.bias = d->bias; kp.act = d->act; kp.slope = d->slope; kp.stats = d->stats;
+  SG_CHECK_ARG(d->stats == nullptr || d->stats_slots == kp.stat_slots,
+               "sg_conv_tc: stats_slots = %d, this launch writes %d partial-sum slots per (image, channel) "
+               "(ask sg_conv_stats_slots)", d->stats_slots, kp.stat_slots);
   const int va = d->y_dtype == 1 ? 8 : 4;
   kp.vec_ok = (d->y_os_c == 1) && (d->y_os_img % va == 0) && (d->y_os_h % va == 0) && (d->y_os_w % va == 0) &&
               (((uintptr_t)d->y) % 16 == 0);
@@ -1353,27 +704,16 @@ extern "C" int sg_conv_tc(const sg_conv_desc_t* d, sg_stream_t stream) {
   long long bdims[3] = {d->w_C, d->w_taps,
                         bmn ? (long long)d->w_rows
                             : (d->w_img_rows > 0 ? (long long)d->w_img_rows * d->x_N : (long long)d->w_Cout)};
-  int m_tiles = kp.tiles_w * kp.tiles_h * img_tiles;
-  // weight multicast pays when the K loop is long (L2-bound operand streaming) and there are CTA pairs to form
-  // CTA pairs (experimental): the same conditions as multicast, which they supersede
-  const bool pair = two_cta_enabled() && d->w_img_rows == 0 && (BN == 128 || BN == 256) && m_tiles >= 2 &&
-                    (long)d->ntaps * kp.kblocks >= 16;
-  const bool mc = !pair && multicast_enabled() && !bmn && d->w_img_rows == 0 && (BN == 128 || BN == 256) && m_tiles >= 2 &&
-                  (long)d->ntaps * kp.kblocks >= 32;
-  if (mc || pair) m_tiles = (m_tiles + 1) & ~1;   // an odd tail tile gets a fully masked partner
-  int bbox[3] = {64, 1, bmn ? 64 : ((mc || pair) ? BN / 2 : BN)};
+  const int m_tiles = kp.tiles_w * kp.tiles_h * img_tiles;
+  int bbox[3] = {64, 1, bmn ? 64 : BN};
   if (int e = make_tmap(&tmB, d->w, 3, bdims, bbox)) return e;
   dim3 grid(m_tiles, sg_cdiv(d->w_Cout, BN), d->nphases);
-  if (pair) {
-    if (BN == 256) return bmn ? launch_conv2<256, true>(tmA, tmB, kp, grid, stream) : launch_conv2<256, false>(tmA, tmB, kp, grid, stream);
-    return bmn ? launch_conv2<128, true>(tmA, tmB, kp, grid, stream) : launch_conv2<128, false>(tmA, tmB, kp, grid, stream);
-  }
   switch (BN) {
-    case 256: return launch_conv<256>(tmA, tmB, kp, grid, mc, bmn, stream);
-    case 192: return launch_conv<192>(tmA, tmB, kp, grid, false, bmn, stream);
-    case 128: return launch_conv<128>(tmA, tmB, kp, grid, mc, bmn, stream);
-    case 64: return launch_conv<64>(tmA, tmB, kp, grid, false, bmn, stream);
-    default: return launch_conv<16>(tmA, tmB, kp, grid, false, false, stream);
+    case 256: return launch_conv<256>(tmA, tmB, kp, grid, bmn, stream);
+    case 192: return launch_conv<192>(tmA, tmB, kp, grid, bmn, stream);
+    case 128: return launch_conv<128>(tmA, tmB, kp, grid, bmn, stream);
+    case 64: return launch_conv<64>(tmA, tmB, kp, grid, bmn, stream);
+    default: return launch_conv<16>(tmA, tmB, kp, grid, false, stream);
   }
 }
 
@@ -1393,14 +733,15 @@ extern "C" int sg_wgrad_tc(const sg_wgrad_desc_t* d, sg_stream_t stream) {
   kp.n_ci_tiles = sg_cdiv(d->Cin, BN);
   const int co_tiles = sg_cdiv(d->Cout, 128);
   int ksplit = d->ksplit;
+  const long base_ctas = (long)co_tiles * kp.n_ci_tiles * d->ntaps;
   if (d->per_image) {
     // one k-split per image: dw is [N][Cout][w_taps][dw_C], every slab is owned by the CTAs of one image
     SG_CHECK_ARG(kp.BI == 1, "sg_wgrad_tc: per_image needs reduction tiles within one image (Hred*Wred >= 64)");
     ksplit = d->N;
     kp.dw_split_stride = (long long)d->Cout * d->w_taps * d->dw_C;
   } else if (ksplit <= 0) {
-    long base_ctas = (long)co_tiles * kp.n_ci_tiles * d->ntaps;
-    ksplit = (int)((2 * 148 + base_ctas - 1) / base_ctas);
+    // fill the 2 x 148 co-resident CTA slots once; a grid that (almost) does so unsplit stays unsplit
+    ksplit = (int)((2 * 148 + base_ctas / 2) / base_ctas);
     if (ksplit > kp.ktiles_total) ksplit = kp.ktiles_total;
     if (ksplit < 1) ksplit = 1;
     // keep at least 8 k-tiles per split so the pipeline prologue amortises
@@ -1408,8 +749,14 @@ extern "C" int sg_wgrad_tc(const sg_wgrad_desc_t* d, sg_stream_t stream) {
   }
   kp.ktiles_per_split = sg_cdiv(kp.ktiles_total, ksplit);
   ksplit = sg_cdiv(kp.ktiles_total, kp.ktiles_per_split);
-  kp.atomic = ksplit > 1 && !d->per_image;
-  if (kp.atomic) cudaMemsetAsync(d->dw, 0, sizeof(float) * (size_t)d->Cout * d->w_taps * d->dw_C, stream);
+  kp.serial = ksplit > 1 && !d->per_image;
+  if (kp.serial) {
+    SG_CHECK_ARG(d->locks != nullptr && d->n_locks >= base_ctas,
+                 "sg_wgrad_tc: split reduction needs %ld zero-initialised int32 turn counters (locks / n_locks = %d)",
+                 base_ctas, d->n_locks);
+    SG_CHECK_ARG(base_ctas * ksplit < (1L << 31), "sg_wgrad_tc: grid too large");
+    kp.locks = d->locks;
+  }
   CUtensorMap tmA, tmB;
   long long adims[5] = {d->dy_C, d->dy_W, d->dy_H, d->dy_P, d->N};
   long long bdims[5] = {d->x_C, d->x_W, d->x_H, d->x_P, d->N};

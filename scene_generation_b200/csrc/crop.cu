@@ -3,7 +3,7 @@
 //   X_j = lin10(j) * (2*x0-1) + lin01(j) * (2*x1-1)   (tensor_linspace, bilinear.py:263-274)
 // The reference replicates every image once per box (bilinear.py:80) and fixes the order up with
 // an inverse permutation (bilinear.py:94-98); here each output element gathers its 4 taps directly,
-// so crops come out in box order by construction.
+// so crops come out in box order by construction.  The adjoint is a gather too: no atomics anywhere.
 #include "common.cuh"
 #include "../../include/sg_b200.h"
 
@@ -51,26 +51,59 @@ __global__ void crop_fwd_kernel(CropArgs a, void* out) {
   }
 }
 
+// Adjoint as a GATHER (no atomics, fixed summation order): thread = one pixel (y, x) of image n; the boxes of that
+// image are visited in box order, their crop rows i and columns j in ascending order, and crop pixel (i, j) adds
+// wy * wx * g to the thread's accumulators when one of its four bilinear taps is (y, x).  The axis taps of a box
+// (HH + WW entries, the forward's own sg_axis values) are tabulated in shared memory once per CTA and box.
+constexpr int CROP_BWD_THREADS = 256;
+constexpr int CROP_MAX_C = 4;
+
 template <bool NHWC_BF16>
-__global__ void crop_bwd_kernel(CropArgs a, const void* grad, float* dfeats) {
-  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  long total = (long)a.B * a.HH * a.WW;
-  if (idx >= total) return;
-  int j = idx % a.WW, i = (idx / a.WW) % a.HH, b = idx / ((long)a.WW * a.HH);
-  SgBilin ax, ay;
-  crop_axes(a, b, i, j, ax, ay);
-  long n = a.map[b];
-  float wnw = ax.w0 * ay.w0, wne = ax.w1 * ay.w0, wsw = ax.w0 * ay.w1, wse = ax.w1 * ay.w1;
-  for (int c = 0; c < a.C; ++c) {
-    float g = NHWC_BF16 ? __bfloat162float(((const __nv_bfloat16*)grad)[idx * a.Cp + c])
-                        : ((const float*)grad)[(((long)b * a.C + c) * a.HH + i) * a.WW + j];
-    if (g == 0.f) continue;
-    float* f = dfeats + ((long)n * a.C + c) * a.H * a.W;
-    if (ay.ok0 && ax.ok0) atomicAdd(f + ay.i0 * a.W + ax.i0, wnw * g);
-    if (ay.ok0 && ax.ok1) atomicAdd(f + ay.i0 * a.W + ax.i0 + 1, wne * g);
-    if (ay.ok1 && ax.ok0) atomicAdd(f + (ay.i0 + 1) * a.W + ax.i0, wsw * g);
-    if (ay.ok1 && ax.ok1) atomicAdd(f + (ay.i0 + 1) * a.W + ax.i0 + 1, wse * g);
+__global__ void __launch_bounds__(CROP_BWD_THREADS) crop_bwd_kernel(CropArgs a, const void* grad, float* dfeats) {
+  extern __shared__ unsigned char crop_smem[];
+  SgBilin* sAx = reinterpret_cast<SgBilin*>(crop_smem);      // [WW]
+  SgBilin* sAy = sAx + a.WW;                                  // [HH]
+  const int n = blockIdx.y;
+  const int p = blockIdx.x * CROP_BWD_THREADS + threadIdx.x;
+  const bool live = p < a.H * a.W;
+  const int y = live ? p / a.W : -4, x = live ? p % a.W : -4;
+  float acc[CROP_MAX_C];
+#pragma unroll
+  for (int c = 0; c < CROP_MAX_C; ++c) acc[c] = 0.f;
+  for (int b = 0; b < a.B; ++b) {
+    if (a.map[b] != n) continue;                              // block-uniform
+    __syncthreads();
+    for (int t = threadIdx.x; t < a.WW + a.HH; t += CROP_BWD_THREADS) {
+      SgBilin ax, ay;
+      crop_axes(a, b, t < a.WW ? 0 : t - a.WW, t < a.WW ? t : 0, ax, ay);
+      if (t < a.WW) sAx[t] = ax; else sAy[t - a.WW] = ay;
+    }
+    __syncthreads();
+    for (int i = 0; i < a.HH; ++i) {
+      const SgBilin ay = sAy[i];
+      float wy = 0.f;
+      if (ay.ok0 && ay.i0 == y) wy = ay.w0;
+      else if (ay.ok1 && ay.i0 + 1 == y) wy = ay.w1;
+      else continue;
+      for (int j = 0; j < a.WW; ++j) {
+        const SgBilin ax = sAx[j];
+        float wx;
+        if (ax.ok0 && ax.i0 == x) wx = ax.w0;
+        else if (ax.ok1 && ax.i0 + 1 == x) wx = ax.w1;
+        else continue;
+        const float wgt = wx * wy;
+        if (NHWC_BF16) {
+          const __nv_bfloat16* g = (const __nv_bfloat16*)grad + (((long)b * a.HH + i) * a.WW + j) * a.Cp;
+          for (int c = 0; c < a.C; ++c) acc[c] = fmaf(wgt, __bfloat162float(g[c]), acc[c]);
+        } else {
+          const float* g = (const float*)grad + (long)b * a.C * a.HH * a.WW + (long)i * a.WW + j;
+          for (int c = 0; c < a.C; ++c) acc[c] = fmaf(wgt, g[(long)c * a.HH * a.WW], acc[c]);
+        }
+      }
+    }
   }
+  if (live)
+    for (int c = 0; c < a.C; ++c) dfeats[((long)n * a.C + c) * a.H * a.W + p] = acc[c];
 }
 
 int check(const CropArgs& a, int fmt) {
@@ -101,11 +134,12 @@ extern "C" int sg_crop_bbox_bwd(const float* boxes, const long long* box_to_feat
   CropArgs a{nullptr, boxes, box_to_feats, N, C, H, W, B, HH, WW, align_corners, Cp};
   if (int e = check(a, grad_format)) return e;
   SG_CHECK_ARG(dfeats != nullptr, "crop_bbox_bwd: dfeats is null");
-  cudaMemsetAsync(dfeats, 0, sizeof(float) * (size_t)N * C * H * W, stream);
-  if (B == 0) return SG_OK;
-  long total = (long)B * HH * WW;
-  if (grad_format == 1) crop_bwd_kernel<true><<<sg_cdiv(total, 256), 256, 0, stream>>>(a, grad_out, dfeats);
-  else crop_bwd_kernel<false><<<sg_cdiv(total, 256), 256, 0, stream>>>(a, grad_out, dfeats);
+  SG_CHECK_ARG(C <= CROP_MAX_C, "crop_bbox_bwd: at most %d feature channels (images)", CROP_MAX_C);
+  // every pixel of every image is written by exactly one thread (zeros where no crop touches it): B == 0 included
+  dim3 grid(sg_cdiv((long)H * W, CROP_BWD_THREADS), N);
+  const size_t smem = sizeof(SgBilin) * (size_t)(HH + WW);
+  if (grad_format == 1) crop_bwd_kernel<true><<<grid, CROP_BWD_THREADS, smem, stream>>>(a, grad_out, dfeats);
+  else crop_bwd_kernel<false><<<grid, CROP_BWD_THREADS, smem, stream>>>(a, grad_out, dfeats);
   SG_CHECK_LAUNCH("sg_crop_bbox_bwd");
   return SG_OK;
 }

@@ -104,27 +104,34 @@ __global__ void pack_weight_t_kernel(const float* __restrict__ w, int Cout, int 
 // ---------------------------------------------------------------------------------------------
 // norm finalize: conv-epilogue sums -> per-(image,channel) scale/shift (+ saved mean/rstd)
 // ---------------------------------------------------------------------------------------------
-__global__ void norm_finalize_kernel(const float* __restrict__ stats, int mode, int n_img, int C, float count, float eps,
-                                     const float* __restrict__ gamma, const float* __restrict__ beta,
-                                     float* running_mean, float* running_var, float momentum,
+__global__ void norm_finalize_kernel(const float* __restrict__ stats, int n_slots, int n_img, int C, float count, float eps,
                                      float* __restrict__ scale, float* __restrict__ shift,
                                      float* __restrict__ save_mean, float* __restrict__ save_rstd) {
+  // InstanceNorm2d(affine=False): the conv epilogue left n_slots partial (sum, sum of squares) pairs per
+  // (image, channel); they are added in slot order (fixed order: bit-reproducible)
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (mode == 0) {   // InstanceNorm2d(affine=False)
-    if (idx >= n_img * C) return;
-    float mean = stats[2 * idx] / count;
-    float var = fmaxf(stats[2 * idx + 1] / count - mean * mean, 0.f);
-    float rstd = rsqrtf(var + eps);
-    scale[idx] = rstd;
-    shift[idx] = -mean * rstd;
-    save_mean[idx] = mean;
-    save_rstd[idx] = rstd;
+  if (idx >= n_img * C) return;
+  const int n = idx / C, c = idx - n * C;
+  const float2* ps = reinterpret_cast<const float2*>(stats) + (long)n * n_slots * C + c;
+  float s = 0.f, ss = 0.f;
+  for (int k = 0; k < n_slots; ++k) {
+    const float2 v = ps[(long)k * C];
+    s += v.x;
+    ss += v.y;
   }
+  float mean = s / count;
+  float var = fmaxf(ss / count - mean * mean, 0.f);
+  float rstd = rsqrtf(var + eps);
+  scale[idx] = rstd;
+  shift[idx] = -mean * rstd;
+  save_mean[idx] = mean;
+  save_rstd[idx] = rstd;
 }
 
-// BatchNorm2d (train): statistics over all images.  One block per channel: the per-image partial sums are
-// reduced across the block, then the (identical) per-image scale / shift rows are written in parallel.
-__global__ void bn_finalize_kernel(const float* __restrict__ stats, int n_img, int C, float count, float eps,
+// BatchNorm2d (train): statistics over all images.  One block per channel: the per-(image, slot) partial sums are
+// reduced across the block in a fixed order (thread-strided serial sums, shuffle tree, warps in order), then the
+// (identical) per-image scale / shift rows are written in parallel.
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, int n_slots, int n_img, int C, float count, float eps,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* running_mean, float* running_var, float momentum,
                                    float* __restrict__ scale, float* __restrict__ shift,
@@ -133,9 +140,10 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, int n_img, i
   __shared__ float res[4];
   const int c = blockIdx.x;
   float s = 0.f, ss = 0.f;
-  for (int n = threadIdx.x; n < n_img; n += blockDim.x) {
-    s += stats[2 * ((long)n * C + c)];
-    ss += stats[2 * ((long)n * C + c) + 1];
+  for (int r = threadIdx.x; r < n_img * n_slots; r += blockDim.x) {
+    const float2 v = reinterpret_cast<const float2*>(stats)[(long)r * C + c];
+    s += v.x;
+    ss += v.y;
   }
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) {
@@ -247,7 +255,9 @@ struct NapBwdArgs {
   const float* save_rstd;
   int bn;                 // 1: statistics shared over images (BatchNorm)
   float count;            // elements per statistic
-  float* sums;            // (N*C*2) [IN]  or (C*2) [BN] : S1 = sum g', S2 = sum g' * xhat
+  float* sums;            // [N][parts][C*2] partial S1 = sum g', S2 = sum g' * xhat per CTA of the reduce kernel
+                          // (+ [C*2] batch totals behind them for BatchNorm)
+  int parts;              // partial slots per image
   int out_planes;         // dsrc written as parity planes (for transposed-conv producers)
   bf16* dsrc;             // [N][H][W][C] plain, or planes [N][4][ceil(H/2)][ceil(W/2)][C]
   bf16* dres;             // optional: folded grad (no act') in plain source layout
@@ -351,23 +361,23 @@ __global__ void nap_bwd_reduce_kernel(NapBwdArgs b, int pix_per_block) {
     mine[2 * k + 1] = s2[k];
   }
   __syncthreads();
-  // one atomic per (block, channel, sum); always into the image's own slots (BatchNorm totals are formed by
-  // bn_total_kernel afterwards) so that same-address contention stays at blocks-per-image
-  float* dst = b.sums + (long)n * a.C * 2;
+  // one partial per (image, CTA, channel, sum), lanes added in lane order: no atomics, fixed order.  The apply
+  // kernel (InstanceNorm) / bn_total_kernel (BatchNorm) add the parts of an image in part order.
+  float* dst = b.sums + ((long)n * b.parts + blockIdx.x) * a.C * 2;
   for (int t = threadIdx.x; t < nC * 16; t += blockDim.x) {
     float v = 0.f;
     for (int l = 0; l < lanes; ++l) v += red[l * nC * 16 + t];
-    atomicAdd(dst + t, v);
+    dst[t] = v;
   }
 }
 
-// BatchNorm: totals[c*2+j] = sum over images of the per-image partials; stored behind them at sums[N*C*2 ...]
-__global__ void bn_total_kernel(float* sums, int N, int C) {
+// BatchNorm: totals[c*2+j] = sum over images and parts (in that order) of the partials; stored behind them
+__global__ void bn_total_kernel(float* sums, int rows, int C) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= C * 2) return;
   float v = 0.f;
-  for (int n = 0; n < N; ++n) v += sums[(long)n * C * 2 + t];
-  sums[(long)N * C * 2 + t] = v;
+  for (int r = 0; r < rows; ++r) v += sums[(long)r * C * 2 + t];
+  sums[(long)rows * C * 2 + t] = v;
 }
 
 // grid.x = source row (n, h), grid.y * blockDim.x covers its (w, channel-chunk) items
@@ -391,9 +401,22 @@ __global__ void nap_bwd_apply_kernel(NapBwdArgs b) {
   if (b.save_mean) {
     float sc[8], s01[8], s23[8];
     load8f(a.scale + pc, sc);                                          // scale = rstd (* gamma)
-    const float* sm = b.sums + ((long)(b.bn ? a.N : n) * a.C + ch * 8) * 2;   // (S1,S2) pairs of 8 channels
-    load8f(sm, s01);
-    load8f(sm + 8, s23);
+    if (b.bn) {                                                          // batch totals behind the partials
+      const float* sm = b.sums + ((long)a.N * b.parts * a.C + ch * 8) * 2;   // (S1,S2) pairs of 8 channels
+      load8f(sm, s01);
+      load8f(sm + 8, s23);
+    } else {                                                             // this image's parts, in part order
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s01[k] = s23[k] = 0.f;
+      for (int part = 0; part < b.parts; ++part) {
+        const float* sm = b.sums + (((long)n * b.parts + part) * a.C + ch * 8) * 2;
+        float t0[8], t1[8];
+        load8f(sm, t0);
+        load8f(sm + 8, t1);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s01[k] += t0[k]; s23[k] += t1[k]; }
+      }
+    }
     const float inv = 1.f / b.count;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -420,8 +443,7 @@ __global__ void nap_bwd_apply_kernel(NapBwdArgs b) {
   store8(b.dsrc + off, o);
 }
 
-// EXPERIMENTAL (SG_NAP_FUSED=1, not yet run on hardware — round-2 item): InstanceNorm backward of SMALL maps in one
-// kernel.  nap_bwd_reduce + nap_bwd_apply read the gradient operand and the source twice, need a memset and — on the
+// InstanceNorm backward of SMALL maps (H*W <= 256) in one kernel (SG_NAP_FUSED=0 falls back to reduce + apply).  nap_bwd_reduce + nap_bwd_apply read the gradient operand and the source twice, need a memset and — on the
 // 8x8 resblock maps — are latency-bound (20 + 12 us for 4 MB).  Here one CTA owns (image, slab of SC 8-channel chunks):
 // every (pixel, chunk) item is loaded once into registers, the per-channel sums S1 = sum g', S2 = sum g' xhat are
 // reduced inside the CTA (deterministic, no atomics, no workspace) and the gradient is applied from the registers.
@@ -705,10 +727,14 @@ __global__ void gap_bwd_kernel(const float* __restrict__ gy, int N, int HW, int 
   gx[idx] = __float2bfloat16(gy[(long)n * C + c] / (float)HW);
 }
 
-// column sums of a bf16 [rows][ld] matrix (ld % 8 == 0) into f32 [C] (bias gradient), accumulated atomically.
-// thread = (8-channel chunk, row lane); 16-byte loads; per-block partials reduced through shared memory.
-__global__ void colsum_kernel(const bf16* __restrict__ x, long rows, int C, int ld, int rows_per_block, float* __restrict__ out) {
+// column sums of a bf16 [rows][ld] matrix (ld % 8 == 0) into f32 [C] (bias gradient).  Deterministic: every CTA
+// leaves one partial row in `ws` (lanes added in lane order); the CTA that finishes last (integer ticket) adds the
+// partial rows in CTA order — the order of the additions never depends on which CTA that is — and resets the ticket.
+// thread = (8-channel chunk, row lane); 16-byte loads.
+__global__ void colsum_kernel(const bf16* __restrict__ x, long rows, int C, int ld, int rows_per_block, float* ws,
+                              unsigned* ticket, float* __restrict__ out) {
   extern __shared__ float red[];     // [lanes][nC*8]
+  __shared__ int is_last;
   const int nC = ld / 8;
   const int lanes = blockDim.x / nC;
   const int ch = threadIdx.x % nC, lane = threadIdx.x / nC;
@@ -728,11 +754,42 @@ __global__ void colsum_kernel(const bf16* __restrict__ x, long rows, int C, int 
     for (int k = 0; k < 8; ++k) red[lane * nC * 8 + ch * 8 + k] = acc[k];
   }
   __syncthreads();
+  if (gridDim.x == 1) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float s = 0.f;
+      for (int l = 0; l < lanes; ++l) s += red[l * nC * 8 + c];
+      out[c] = s;
+    }
+    return;
+  }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = 0.f;
     for (int l = 0; l < lanes; ++l) s += red[l * nC * 8 + c];
-    atomicAdd(out + c, s);
+    __stcg(ws + (long)blockIdx.x * C + c, s);
   }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // last CTA: thread (group g, channel c) adds the partial rows g, g + G, ... in order, then the groups in order
+  const int G = max(1, (int)blockDim.x / C);
+  for (int c0 = 0; c0 < C; c0 += blockDim.x) {
+    const int c = c0 + threadIdx.x % (G > 1 ? C : blockDim.x), g = G > 1 ? threadIdx.x / C : 0;
+    float s = 0.f;
+    if (c < C && g < G)
+      for (int b = g; b < (int)gridDim.x; b += G) s += __ldcg(ws + (long)b * C + c);
+    __syncthreads();
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (g == 0 && c < C) {
+      float t = 0.f;
+      for (int gg = 0; gg < G; ++gg) t += red[G > 1 ? gg * C + c : threadIdx.x];
+      out[c] = t;
+    }
+  }
+  if (threadIdx.x == 0) *ticket = 0;
 }
 
 }  // namespace
@@ -763,31 +820,58 @@ extern "C" int sg_pack_weight(const float* w, int Cout, int taps, int Cin, int C
   return SG_OK;
 }
 
-extern "C" int sg_norm_finalize(const float* stats, int mode, int n_img, int C, float count, float eps, const float* gamma,
+extern "C" int sg_norm_finalize(const float* stats, int n_slots, int mode, int n_img, int C, float count, float eps, const float* gamma,
                                 const float* beta, float* running_mean, float* running_var, float momentum, float* scale,
                                 float* shift, float* save_mean, float* save_rstd, sg_stream_t stream) {
   SG_CHECK_ARG(stats && scale && shift && save_mean && save_rstd, "norm_finalize: null pointer");
-  SG_CHECK_ARG((mode == 0 || mode == 1) && n_img > 0 && C > 0 && count > 0, "norm_finalize: bad arguments");
+  SG_CHECK_ARG((mode == 0 || mode == 1) && n_img > 0 && C > 0 && count > 0 && n_slots > 0, "norm_finalize: bad arguments");
   if (mode == 0) {
-    LAUNCH_1D(norm_finalize_kernel, n_img * C, stream, stats, mode, n_img, C, count, eps, gamma, beta, running_mean, running_var,
-              momentum, scale, shift, save_mean, save_rstd);
+    LAUNCH_1D(norm_finalize_kernel, n_img * C, stream, stats, n_slots, n_img, C, count, eps, scale, shift, save_mean, save_rstd);
   } else {
-    const int threads = n_img >= 128 ? 128 : (n_img > 32 ? 64 : 32);
-    bn_finalize_kernel<<<C, threads, 0, stream>>>(stats, n_img, C, count, eps, gamma, beta, running_mean, running_var, momentum,
-                                                  scale, shift, save_mean, save_rstd);
+    const long rows = (long)n_img * n_slots;
+    const int threads = rows >= 128 ? 128 : (rows > 32 ? 64 : 32);
+    bn_finalize_kernel<<<C, threads, 0, stream>>>(stats, n_slots, n_img, C, count, eps, gamma, beta, running_mean, running_var,
+                                                  momentum, scale, shift, save_mean, save_rstd);
   }
   SG_CHECK_LAUNCH("sg_norm_finalize");
   return SG_OK;
 }
 
-// SG_NAP_FUSED=1: single-kernel InstanceNorm backward for small maps (experimental)
+// SG_NAP_FUSED=0 disables the single-kernel InstanceNorm backward of small maps (A/B switch)
 static bool nap_fused_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("SG_NAP_FUSED");
-    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
+}
+
+// launch shape of the norm-backward reduction: threads per CTA, pixels per CTA, CTAs (= partial slots) per image
+static void nap_reduce_shape(int N, int H, int W, int C, int* threads_out, int* pix_per_block_out, int* parts_out) {
+  const int nC = C / 8;
+  int threads = nC >= 256 ? nC : 256;
+  threads = (threads / nC) * nC;
+  const int lanes = threads / nC;
+  const long HW = (long)H * W;
+  // ~8 CTAs per SM over all images, at most SG_NAP_MAX_PARTS per image (the apply kernel adds an image's parts
+  // itself), at least 2 pixels per thread
+  long parts = (1184 + N - 1) / N;
+  if (parts > SG_NAP_MAX_PARTS) parts = SG_NAP_MAX_PARTS;
+  if (parts < 1) parts = 1;
+  long ppb = (HW + parts - 1) / parts;
+  if (ppb < lanes * 2) ppb = lanes * 2;
+  ppb = ((ppb + lanes - 1) / lanes) * lanes;
+  *threads_out = threads;
+  *pix_per_block_out = (int)ppb;
+  *parts_out = (int)((HW + ppb - 1) / ppb);
+}
+
+extern "C" int sg_norm_act_pad_bwd_parts(int N, int H, int W, int C) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 != 0) return 0;
+  int threads, ppb, parts;
+  nap_reduce_shape(N, H, W, C, &threads, &ppb, &parts);
+  return parts;
 }
 
 static int nap_check(const sg_nap_desc_t* d) {
@@ -833,6 +917,7 @@ extern "C" int sg_norm_act_pad_bwd(const sg_nap_desc_t* d, const void* grad, con
   NapBwdArgs b;
   b.f = nap_args(d);
   b.g = (const bf16*)grad; b.save_mean = save_mean; b.save_rstd = save_rstd; b.bn = bn; b.count = count; b.sums = sums;
+  b.parts = 1;
   b.out_planes = out_planes; b.dsrc = (bf16*)dsrc; b.dres = (bf16*)dres;
   const int nC = d->C / 8;
   if (save_mean && !bn && nap_fused_enabled() && (long)d->H * d->W <= 256) {
@@ -848,21 +933,15 @@ extern "C" int sg_norm_act_pad_bwd(const sg_nap_desc_t* d, const void* grad, con
     }
   }
   if (save_mean) {
-    cudaMemsetAsync(sums, 0, sizeof(float) * 2 * (size_t)d->N * d->C, stream);
-    int threads = nC >= 256 ? nC : 256;
-    threads = (threads / nC) * nC;
+    int threads, pix_per_block, parts;
+    nap_reduce_shape(d->N, d->H, d->W, d->C, &threads, &pix_per_block, &parts);
     SG_CHECK_ARG(threads <= 1024, "norm_act_pad_bwd: too many channels");
-    const int lanes = threads / nC;
-    long total_px = (long)d->N * d->H * d->W;
-    int pix_per_block = (int)((total_px + 1183) / 1184);           // ~8 CTAs per SM ...
-    // ... but at least 2 pixels per thread (small maps — 8x8 resblocks — are latency-bound: more, shorter CTAs)
-    if (pix_per_block < lanes * 2) pix_per_block = lanes * 2;
-    pix_per_block = ((pix_per_block + lanes - 1) / lanes) * lanes;
-    dim3 grid(sg_cdiv((long)d->H * d->W, pix_per_block), d->N);
+    b.parts = parts;
+    dim3 grid(parts, d->N);
     nap_bwd_reduce_kernel<<<grid, threads, sizeof(float) * 16 * threads, stream>>>(b, pix_per_block);
     SG_CHECK_LAUNCH("sg_norm_act_pad_bwd(reduce)");
     if (bn) {
-      bn_total_kernel<<<sg_cdiv(2 * d->C, 256), 256, 0, stream>>>(sums, d->N, d->C);
+      bn_total_kernel<<<sg_cdiv(2 * d->C, 256), 256, 0, stream>>>(sums, d->N * parts, d->C);
       SG_CHECK_LAUNCH("sg_norm_act_pad_bwd(bn totals)");
     }
   }
@@ -965,17 +1044,21 @@ extern "C" int sg_gap_bwd(const float* gy, int N, int HW, int C, void* gx, sg_st
   return SG_OK;
 }
 
-extern "C" int sg_colsum_bf16(const void* x, long long rows, int C, int ld, float* out, sg_stream_t stream) {
+extern "C" int sg_colsum_bf16(const void* x, long long rows, int C, int ld, float* out, float* ws, long long ws_floats,
+                              unsigned* ticket, sg_stream_t stream) {
   SG_CHECK_ARG(x && out && rows > 0 && C > 0 && ld >= C, "colsum: bad arguments");
   SG_CHECK_ARG(ld % 8 == 0 && ld <= 8192, "colsum: ld must be a multiple of 8 (<= 8192)");
   const int nC = ld / 8;
   int threads = nC >= 256 ? nC : (256 / nC) * nC;
   SG_CHECK_ARG(threads <= 1024, "colsum: too many channels");
   const int lanes = threads / nC;
-  int rpb = (int)((rows + 1183) / 1184);
-  if (rpb < lanes * 4) rpb = lanes * 4;
-  size_t smem = sizeof(float) * (size_t)lanes * nC * 8;
-  colsum_kernel<<<sg_cdiv(rows, rpb), threads, smem, stream>>>((const bf16*)x, rows, C, ld, rpb, out);
+  int rpb = (int)((rows + SG_COLSUM_MAX_BLOCKS - 1) / SG_COLSUM_MAX_BLOCKS);
+  if (rpb < lanes * 16) rpb = lanes * 16;                  // few, longer CTAs on small inputs: the last CTA adds one row per CTA
+  const int blocks = sg_cdiv(rows, rpb);
+  SG_CHECK_ARG(blocks == 1 || (ws != nullptr && ticket != nullptr && ws_floats >= (long long)blocks * C),
+               "colsum: needs %lld floats of workspace and a zero-initialised ticket", (long long)blocks * C);
+  size_t smem = sizeof(float) * (size_t)(lanes * nC * 8 > threads ? lanes * nC * 8 : threads);
+  colsum_kernel<<<blocks, threads, smem, stream>>>((const bf16*)x, rows, C, ld, rpb, ws, ticket, out);
   SG_CHECK_LAUNCH("sg_colsum_bf16");
   return SG_OK;
 }

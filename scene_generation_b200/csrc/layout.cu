@@ -345,98 +345,155 @@ __global__ void __launch_bounds__(THREADS) layout_fwd_tile_kernel(LayoutArgs a, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward (train branch): dvecs[o,c] = sum_p S_o(p) g[n,c,p];  dmask via the 4 bilinear corners.
+// backward (train branch): dvecs[o,c] = sum_p S_o(p) g[n,c,p];  dmasks through the bilinear taps.
+// No atomics: every output element is produced by one thread after reductions in a fixed order.
 // ------------------------------------------------------------------------------------------------
+// pixel rectangle outside of which S_o is exactly zero (the dilated box of box_touches_rect); the whole image for
+// boxes the estimate cannot handle (non-finite corners), nothing for zero extents (grid_sample yields 0 everywhere)
+__device__ __forceinline__ void object_rect(const LayoutArgs& a, const float* bx, int& h_lo, int& h_hi, int& w_lo, int& w_hi) {
+  h_lo = 0; h_hi = a.H - 1; w_lo = 0; w_hi = a.W - 1;
+  float x0 = bx[0], y0 = bx[1], x1 = bx[2], y1 = bx[3];
+  float ww = x1 - x0, hh = y1 - y0;
+  if (!(isfinite(ww) && isfinite(hh) && isfinite(x0) && isfinite(y0))) return;
+  if (ww == 0.f || hh == 0.f) { h_hi = -1; w_hi = -1; return; }
+  float mx = fabsf(ww) / (float)max(a.M - 1, 1), my = fabsf(hh) / (float)max(a.M - 1, 1);
+  float xa = fminf(x0, x1) - mx, xb = fmaxf(x0, x1) + mx, ya = fminf(y0, y1) - my, yb = fmaxf(y0, y1) + my;
+  float sx = (float)max(a.W - 1, 1), sy = (float)max(a.H - 1, 1);
+  float wl = floorf(xa * sx - 1.f), wh = ceilf(xb * sx + 1.f), hl = floorf(ya * sy - 1.f), hu = ceilf(yb * sy + 1.f);
+  w_lo = (int)fminf(fmaxf(wl, 0.f), (float)a.W);
+  w_hi = (int)fmaxf(fminf(wh, (float)(a.W - 1)), -1.f);
+  h_lo = (int)fminf(fmaxf(hl, 0.f), (float)a.H);
+  h_hi = (int)fmaxf(fminf(hu, (float)(a.H - 1)), -1.f);
+}
+
+constexpr int BWD_CW = 16;    // channels per CTA of the dvecs kernel (32 B of an NHWC bf16 pixel)
+
+// dvecs.  grid = (channel slabs of BWD_CW, images).  The CTA walks the objects of its image in order; for each, its
+// 256 threads stride over the pixels of the object's rectangle (rows, then columns), each keeping BWD_CW partial sums;
+// these are combined by a shuffle tree inside each warp and then over the 8 warps in warp order.
 template <bool NHWC_BF16>
-__global__ void __launch_bounds__(THREADS) layout_bwd_kernel(LayoutArgs a, const void* grad, float* dvecs, float* dmasks) {
-  extern __shared__ float smem[];
-  float* sS = smem;                         // [MAXO][TP]
-  float* sG = smem + MAXO * TP;             // [TP][Cp+1]
-  float* sV = sG + TP * (a.Cp + 1);         // [MAXO][Cp] only when dmasks
-  __shared__ int sActive[MAXO];
+__global__ void __launch_bounds__(THREADS) layout_bwd_vecs_kernel(LayoutArgs a, const void* grad, float* dvecs) {
+  __shared__ float red[THREADS / 32][BWD_CW];
   const int n = blockIdx.y;
-  const int p0 = blockIdx.x * TP;
+  const int c0 = blockIdx.x * BWD_CW;
   const int HW = a.H * a.W;
   const int o_begin = a.ranges[2 * n], o_end = a.ranges[2 * n + 1];
-  const int ldg = a.Cp + 1;
-  // stage the gradient tile as fp32
-  if (NHWC_BF16) {
-    const __nv_bfloat16* g16 = (const __nv_bfloat16*)grad;
-    const int chunks = a.Cp / 8;
-    for (int idx = threadIdx.x; idx < TP * chunks; idx += THREADS) {
-      int px = idx / chunks, ch = idx % chunks;
-      int p = p0 + px;
-      uint4 raw = make_uint4(0, 0, 0, 0);
-      if (p < HW) raw = *reinterpret_cast<const uint4*>(g16 + ((long)n * HW + p) * a.Cp + ch * 8);
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int o = o_begin; o < o_end; ++o) {
+    const float* bx = a.boxes + 4 * o;
+    int h_lo, h_hi, w_lo, w_hi;
+    object_rect(a, bx, h_lo, h_hi, w_lo, w_hi);
+    const int rw = w_hi - w_lo + 1, rh = h_hi - h_lo + 1;
+    float acc[BWD_CW];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float2 f = __bfloat1622float2(h2[j]);
-        sG[px * ldg + ch * 8 + 2 * j] = f.x;
-        sG[px * ldg + ch * 8 + 2 * j + 1] = f.y;
+    for (int k = 0; k < BWD_CW; ++k) acc[k] = 0.f;
+    if (rw > 0 && rh > 0) {
+      for (int i = threadIdx.x; i < rw * rh; i += THREADS) {
+        const int h = h_lo + i / rw, w = w_lo + i % rw;
+        const float sv = sample_mask(a, o, h, w, bx);
+        if (sv == 0.f) continue;
+        if (NHWC_BF16) {
+          const __nv_bfloat16* g = (const __nv_bfloat16*)grad + ((long)n * HW + (long)h * a.W + w) * a.Cp + c0;
+          const uint4 r0 = *reinterpret_cast<const uint4*>(g);
+          const uint4 r1 = (c0 + 8 < a.Cp) ? *reinterpret_cast<const uint4*>(g + 8) : make_uint4(0, 0, 0, 0);
+          const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
+          const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f0 = __bfloat1622float2(h0[j]), f1 = __bfloat1622float2(h1[j]);
+            acc[2 * j] = __fmaf_rn(sv, f0.x, acc[2 * j]);
+            acc[2 * j + 1] = __fmaf_rn(sv, f0.y, acc[2 * j + 1]);
+            acc[8 + 2 * j] = __fmaf_rn(sv, f1.x, acc[8 + 2 * j]);
+            acc[8 + 2 * j + 1] = __fmaf_rn(sv, f1.y, acc[8 + 2 * j + 1]);
+          }
+        } else {
+          const float* g = (const float*)grad + (long)n * a.D * HW + (long)h * a.W + w;
+#pragma unroll
+          for (int k = 0; k < BWD_CW; ++k)
+            if (c0 + k < a.D) acc[k] = __fmaf_rn(sv, g[(long)(c0 + k) * HW], acc[k]);
+        }
       }
     }
-  } else {
-    const float* g32 = (const float*)grad;
-    for (int idx = threadIdx.x; idx < a.D * TP; idx += THREADS) {
-      int c = idx / TP, px = idx % TP;
-      int p = p0 + px;
-      sG[px * ldg + c] = (p < HW) ? g32[((long)n * a.D + c) * HW + p] : 0.f;
+#pragma unroll
+    for (int k = 0; k < BWD_CW; ++k) {
+      float v = acc[k];
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      acc[k] = v;
+    }
+    __syncthreads();                                     // the previous object's readers are done
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < BWD_CW; ++k) red[warp][k] = acc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < BWD_CW && c0 + threadIdx.x < a.D) {
+      float v = 0.f;
+      for (int wq = 0; wq < THREADS / 32; ++wq) v += red[wq][threadIdx.x];
+      dvecs[(long)o * a.D + c0 + threadIdx.x] = v;
     }
   }
-  for (int ob = o_begin; ob < o_end; ob += MAXO) {
-    const int nobj = min(MAXO, o_end - ob);
-    __syncthreads();
-    if (threadIdx.x < MAXO) sActive[threadIdx.x] = 0;
-    if (dmasks) {
-      for (int i = threadIdx.x; i < nobj * a.Cp; i += THREADS) {
-        int o = i / a.Cp, c = i % a.Cp;
-        sV[o * a.Cp + c] = (c < a.D) ? a.vecs[(long)(ob + o) * a.D + c] : 0.f;
-      }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < nobj * TP; i += THREADS) {
-      int o = i / TP, px = i % TP;
-      int p = p0 + px;
-      float s = 0.f;
-      if (p < HW) s = sample_mask(a, ob + o, p / a.W, p % a.W, a.boxes + 4 * (ob + o));
-      sS[o * TP + px] = s;
-      if (s != 0.f) sActive[o] = 1;
-    }
-    __syncthreads();
-    // dvecs: thread per (o, c); serial over the tile's pixels
-    for (int i = threadIdx.x; i < nobj * a.D; i += THREADS) {
-      int o = i / a.D, c = i % a.D;
-      if (!sActive[o]) continue;
-      float r = 0.f;
-      for (int px = 0; px < TP; ++px) r = __fmaf_rn(sS[o * TP + px], sG[px * ldg + c], r);
-      atomicAdd(dvecs + (long)(ob + o) * a.D + c, r);
-    }
-    if (dmasks) {
-      // dS[o,px] = sum_c vecs[o,c] g[px,c]; then scatter through the bilinear corners
-      for (int i = threadIdx.x; i < nobj * TP; i += THREADS) {
-        int o = i / TP, px = i % TP;
-        int p = p0 + px;
-        if (p >= HW) continue;
+}
+
+// dmasks[o] = Ay^T * dS * Ax with dS[h,w] = sum_c vecs[o,c] g[n,c,h,w] and Ay / Ax the (at most two taps per pixel)
+// bilinear row / column operators.  One CTA per object; pixel rows are visited in order: the 256 threads form
+// dS[h, .] in shared memory, then thread mx < M owns column mx of the result: it adds the row's pixels whose x taps
+// hit mx in ascending w and deposits the sum through the row's (at most two) y taps.
+template <bool NHWC_BF16>
+__global__ void __launch_bounds__(THREADS) layout_bwd_masks_kernel(LayoutArgs a, const void* grad, float* dmasks) {
+  extern __shared__ float smem[];
+  float* sV = smem;                          // [D]
+  float* sDs = sV + a.D;                     // [W]
+  float* sDm = sDs + a.W;                    // [M][M]
+  SgBilin* sAx = reinterpret_cast<SgBilin*>(sDm + a.M * a.M);   // [W]
+  __shared__ int sImg;
+  const int o = blockIdx.x;
+  if (threadIdx.x == 0) {
+    int img = -1;
+    for (int n = 0; n < a.N; ++n)
+      if (o >= a.ranges[2 * n] && o < a.ranges[2 * n + 1]) { img = n; break; }
+    sImg = img;
+  }
+  for (int c = threadIdx.x; c < a.D; c += THREADS) sV[c] = a.vecs[(long)o * a.D + c];
+  for (int i = threadIdx.x; i < a.M * a.M; i += THREADS) sDm[i] = 0.f;
+  const float* bx = a.boxes + 4 * o;
+  for (int w = threadIdx.x; w < a.W; w += THREADS) sAx[w] = grid_axis(a, w, a.W, bx[0], bx[2]);
+  __syncthreads();
+  const int n = sImg;
+  const int HW = a.H * a.W;
+  int h_lo, h_hi, w_lo, w_hi;
+  object_rect(a, bx, h_lo, h_hi, w_lo, w_hi);
+  if (n >= 0 && w_hi >= w_lo) {
+    for (int h = h_lo; h <= h_hi; ++h) {
+      const SgBilin ay = grid_axis(a, h, a.H, bx[1], bx[3]);
+      if (!ay.ok0 && !ay.ok1) continue;                 // block-uniform
+      for (int w = w_lo + threadIdx.x; w <= w_hi; w += THREADS) {
         float ds = 0.f;
-        for (int c = 0; c < a.D; ++c) ds = __fmaf_rn(sV[o * a.Cp + c], sG[px * ldg + c], ds);
-        if (ds == 0.f) continue;
-        const float* bx = a.boxes + 4 * (ob + o);
-        int h = p / a.W, w = p % a.W;
-        float x0 = bx[0], y0 = bx[1];
-        float ww = __fsub_rn(bx[2], x0), hh = __fsub_rn(bx[3], y0);
-        float gx = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(sg_linspace01(w, a.W), x0), ww), 2.f), 1.f);
-        float gy = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(sg_linspace01(h, a.H), y0), hh), 2.f), 1.f);
-        SgBilin ax = sg_axis(gx, a.M, a.align_corners);
-        SgBilin ay = sg_axis(gy, a.M, a.align_corners);
-        float* dm = dmasks + (long)(ob + o) * a.M * a.M;
-        if (ay.ok0 && ax.ok0) atomicAdd(dm + ay.i0 * a.M + ax.i0, ax.w0 * ay.w0 * ds);
-        if (ay.ok0 && ax.ok1) atomicAdd(dm + ay.i0 * a.M + ax.i0 + 1, ax.w1 * ay.w0 * ds);
-        if (ay.ok1 && ax.ok0) atomicAdd(dm + (ay.i0 + 1) * a.M + ax.i0, ax.w0 * ay.w1 * ds);
-        if (ay.ok1 && ax.ok1) atomicAdd(dm + (ay.i0 + 1) * a.M + ax.i0 + 1, ax.w1 * ay.w1 * ds);
+        if (NHWC_BF16) {
+          const __nv_bfloat16* g = (const __nv_bfloat16*)grad + ((long)n * HW + (long)h * a.W + w) * a.Cp;
+          for (int c = 0; c < a.D; ++c) ds = __fmaf_rn(sV[c], __bfloat162float(g[c]), ds);
+        } else {
+          const float* g = (const float*)grad + (long)n * a.D * HW + (long)h * a.W + w;
+          for (int c = 0; c < a.D; ++c) ds = __fmaf_rn(sV[c], g[(long)c * HW], ds);
+        }
+        sDs[w] = ds;
       }
+      __syncthreads();
+      if ((int)threadIdx.x < a.M) {
+        const int mx = threadIdx.x;
+        float t = 0.f;
+        for (int w = w_lo; w <= w_hi; ++w) {
+          const SgBilin ax = sAx[w];
+          if (ax.ok0 && ax.i0 == mx) t = __fmaf_rn(ax.w0, sDs[w], t);
+          else if (ax.ok1 && ax.i0 + 1 == mx) t = __fmaf_rn(ax.w1, sDs[w], t);
+        }
+        if (ay.ok0) sDm[ay.i0 * a.M + mx] = __fmaf_rn(ay.w0, t, sDm[ay.i0 * a.M + mx]);
+        if (ay.ok1) sDm[(ay.i0 + 1) * a.M + mx] = __fmaf_rn(ay.w1, t, sDm[(ay.i0 + 1) * a.M + mx]);
+      }
+      __syncthreads();
     }
   }
+  for (int i = threadIdx.x; i < a.M * a.M; i += THREADS) dmasks[(long)o * a.M * a.M + i] = sDm[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -568,19 +625,27 @@ extern "C" int sg_masks_to_layout_bwd(const float* vecs, const float* boxes, con
   LayoutArgs a{vecs, boxes, masks, img_ranges, mask_dtype, O, D, M, N, H, W, Cp, align_corners};
   if (int e = check_args(a, grad_format)) return e;
   SG_CHECK_ARG(dvecs != nullptr, "masks_to_layout_bwd: dvecs is null");
+  SG_CHECK_ARG(!dmasks || M <= THREADS, "masks_to_layout_bwd: mask size must be <= %d for the mask gradient", THREADS);
+  if (O == 0) return SG_OK;
+  // objects outside every image range (none in a well-formed batch) get zero gradients
   cudaMemsetAsync(dvecs, 0, sizeof(float) * (size_t)O * D, stream);
-  if (dmasks) cudaMemsetAsync(dmasks, 0, sizeof(float) * (size_t)O * M * M, stream);
-  if (N == 0 || O == 0) return SG_OK;
-  dim3 grid(sg_cdiv((long)H * W, TP), N);
-  size_t smem = sizeof(float) * (MAXO * TP + TP * (Cp + 1) + (dmasks ? MAXO * Cp : 0));
-  if (grad_format == 1) {
-    cudaFuncSetAttribute(layout_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    layout_bwd_kernel<true><<<grid, THREADS, smem, stream>>>(a, grad_out, dvecs, dmasks);
-  } else {
-    cudaFuncSetAttribute(layout_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    layout_bwd_kernel<false><<<grid, THREADS, smem, stream>>>(a, grad_out, dvecs, dmasks);
+  if (N > 0) {
+    dim3 grid(sg_cdiv(grad_format == 1 ? Cp : D, BWD_CW), N);
+    if (grad_format == 1) layout_bwd_vecs_kernel<true><<<grid, THREADS, 0, stream>>>(a, grad_out, dvecs);
+    else layout_bwd_vecs_kernel<false><<<grid, THREADS, 0, stream>>>(a, grad_out, dvecs);
+    SG_CHECK_LAUNCH("sg_masks_to_layout_bwd");
   }
-  SG_CHECK_LAUNCH("sg_masks_to_layout_bwd");
+  if (dmasks) {
+    size_t smem = sizeof(float) * ((size_t)D + W + (size_t)M * M) + sizeof(SgBilin) * (size_t)W + 16;
+    if (grad_format == 1) {
+      cudaFuncSetAttribute(layout_bwd_masks_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      layout_bwd_masks_kernel<true><<<O, THREADS, smem, stream>>>(a, grad_out, dmasks);
+    } else {
+      cudaFuncSetAttribute(layout_bwd_masks_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      layout_bwd_masks_kernel<false><<<O, THREADS, smem, stream>>>(a, grad_out, dmasks);
+    }
+    SG_CHECK_LAUNCH("sg_masks_to_layout_bwd(masks)");
+  }
   return SG_OK;
 }
 

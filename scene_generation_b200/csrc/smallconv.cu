@@ -74,7 +74,7 @@ constexpr int WT_H = 8, WT_W = 32;
 template <int K>
 __global__ void __launch_bounds__(256)
 wgrad_small_cout_kernel(const __nv_bfloat16* __restrict__ dz, int dzC, const __nv_bfloat16* __restrict__ xop, int Cout, int N,
-                        int H, int W, float* __restrict__ dw) {
+                        int H, int W, float* __restrict__ ws) {
   constexpr int CIN = 64, TAPS = K * K, PH = WT_H + K - 1, PW = WT_W + K - 1, TPG = (TAPS + 3) / 4;
   extern __shared__ __nv_bfloat16 sm16[];
   __nv_bfloat16* sX = sm16;                                                  // [PH][PW][CIN]
@@ -128,30 +128,44 @@ wgrad_small_cout_kernel(const __nv_bfloat16* __restrict__ dz, int dzC, const __n
   for (int t = 0; t < TPG; ++t) {
     const int tap = tq + 4 * t;
     if (tap < TAPS)
-      for (int co = 0; co < Cout && co < MAXCO - 1; ++co) atomicAdd(dw + ((long)co * TAPS + tap) * CIN + ci, acc[t][co]);
+      for (int co = 0; co < Cout && co < MAXCO - 1; ++co)
+        ws[((long)blockIdx.x * Cout + co) * TAPS * CIN + (long)tap * CIN + ci] = acc[t][co];   // this CTA's partial sums
   }
+}
+
+// dw[e] = sum over the CTAs of wgrad_small_cout_kernel of their partial sums, in CTA order (fixed order, no atomics)
+__global__ void wgrad_small_reduce_kernel(const float* __restrict__ ws, int n_blocks, int elems, float* __restrict__ dw) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= elems) return;
+  float v = 0.f;
+  for (int b = 0; b < n_blocks; ++b) v += ws[(long)b * elems + e];
+  dw[e] = v;
 }
 
 }  // namespace
 
 extern "C" int sg_wgrad_small_cout(const void* dz, int dzC, const void* xop, int Cout, int k, int Cin, int N, int H, int W,
-                                   float* dw, sg_stream_t stream) {
+                                   float* dw, float* ws, long long ws_floats, sg_stream_t stream) {
   SG_CHECK_ARG(dz && xop && dw, "wgrad_small_cout: null pointer");
   SG_CHECK_ARG(Cout >= 1 && Cout <= 3 && dzC >= Cout && Cin == 64 && (k == 7 || k == 3), "wgrad_small_cout: needs Cout <= 3, Cin == 64, k in {3, 7}");
   SG_CHECK_ARG(N > 0 && H > 0 && W > 0, "wgrad_small_cout: empty problem");
-  cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * k * k * Cin, stream);
   const int tiles = N * sg_cdiv(H, WT_H) * sg_cdiv(W, WT_W);
-  const int grid = tiles < 296 ? tiles : 296;
+  const int grid = tiles < SG_WGRAD_SMALL_BLOCKS ? tiles : SG_WGRAD_SMALL_BLOCKS;
+  const int elems = Cout * k * k * Cin;
+  SG_CHECK_ARG(ws != nullptr && ws_floats >= (long long)grid * elems, "wgrad_small_cout: workspace of %lld floats needed",
+               (long long)grid * elems);
   const int PH = WT_H + k - 1, PW = WT_W + k - 1;
   size_t smem = sizeof(__nv_bfloat16) * (size_t)PH * PW * 64 + sizeof(float) * WT_H * WT_W * 3;
   if (k == 7) {
     cudaFuncSetAttribute(wgrad_small_cout_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    wgrad_small_cout_kernel<7><<<grid, 256, smem, stream>>>((const __nv_bfloat16*)dz, dzC, (const __nv_bfloat16*)xop, Cout, N, H, W, dw);
+    wgrad_small_cout_kernel<7><<<grid, 256, smem, stream>>>((const __nv_bfloat16*)dz, dzC, (const __nv_bfloat16*)xop, Cout, N, H, W, ws);
   } else {
     cudaFuncSetAttribute(wgrad_small_cout_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    wgrad_small_cout_kernel<3><<<grid, 256, smem, stream>>>((const __nv_bfloat16*)dz, dzC, (const __nv_bfloat16*)xop, Cout, N, H, W, dw);
+    wgrad_small_cout_kernel<3><<<grid, 256, smem, stream>>>((const __nv_bfloat16*)dz, dzC, (const __nv_bfloat16*)xop, Cout, N, H, W, ws);
   }
   SG_CHECK_LAUNCH("sg_wgrad_small_cout");
+  wgrad_small_reduce_kernel<<<sg_cdiv(elems, 256), 256, 0, stream>>>(ws, grid, elems, dw);
+  SG_CHECK_LAUNCH("sg_wgrad_small_cout(reduce)");
   return SG_OK;
 }
 

@@ -203,6 +203,19 @@ def cast_pad(x, ld_dst=None, mask_y=None, slope=0.0):
     return out
 
 
+_parts_cache = {}
+
+
+def _nap_parts(N, H, W, C):
+    """partial-sum slots per image of the norm-backward reduction (sg_norm_act_pad_bwd_parts)"""
+    key = (N, H, W, C)
+    v = _parts_cache.get(key)
+    if v is None:
+        v = _parts_cache[key] = int(_lib.lib().sg_norm_act_pad_bwd_parts(N, H, W, C))
+        assert v > 0
+    return v
+
+
 def _nap_desc(src, scale, shift, act, slope, res, res_strides, up, pad, pad_mode, planes):
     N, H, W, C = src.shape
     d = NapDesc()
@@ -289,17 +302,16 @@ def _conv_forward(x5, wk, bias, spec, Cout):
     else:
         y = torch.empty((N, Cout, Ho, Wo), dtype=torch.float32, device=dev)
         strides = (Cout * Ho * Wo, Wo, 1, Ho * Wo)
-    stats = ARENA.zeros((N, Cout, 2), dev) if spec.stats else None
-    kw = dict(bias=bias, act=spec.act, slope=spec.slope, stats=stats)
+    kw = dict(bias=bias, act=spec.act, slope=spec.slope, stats=spec.stats)
     if spec.kind == 's1':
         taps, off = convspec.conv_s1(spec.k, spec.pad)
-        ops.conv_tc(x5, wk, y, strides, Ho, Wo, taps, in_h0=off, in_w0=off, **kw)
+        r = ops.conv_tc(x5, wk, y, strides, Ho, Wo, taps, in_h0=off, in_w0=off, **kw)
     elif spec.kind == 's2':
-        ops.conv_tc(x5, wk, y, strides, Ho, Wo, convspec.conv_s2(spec.k, spec.pad), **kw)
+        r = ops.conv_tc(x5, wk, y, strides, Ho, Wo, convspec.conv_s2(spec.k, spec.pad), **kw)
     else:
         taps, phases = convspec.convT_s2(spec.k, 1)
-        ops.conv_tc(x5, wk, y, strides, Ho // 2, Wo // 2, taps, phases=phases, oh_mul=2, ow_mul=2, **kw)
-    return y, stats
+        r = ops.conv_tc(x5, wk, y, strides, Ho // 2, Wo // 2, taps, phases=phases, oh_mul=2, ow_mul=2, **kw)
+    return r if spec.stats else (y, None)       # stats: (N, slots, Cout, 2) partial sums of the epilogue
 
 
 class ConvFn(torch.autograd.Function):
@@ -370,9 +382,7 @@ class ConvFn(torch.autograd.Function):
         # ---- bias gradient ----------------------------------------------------------------------
         db = None
         if bias is not None and ctx.needs_input_grad[2]:
-            db = ARENA.zeros((Cout,), dy.device)
-            flat = dz5.reshape(-1, Coutp)
-            _lib.call('sg_colsum_bf16', _ptr(flat), flat.shape[0], Cout, Coutp, _ptr(db), _stream())
+            db = ops.colsum(dz5.reshape(-1, Coutp), Cout)
         # ---- weight gradient ---------------------------------------------------------------------
         dw = None
         if ctx.needs_input_grad[1]:
@@ -382,8 +392,9 @@ class ConvFn(torch.autograd.Function):
                 g3 = torch.empty((N, Cout, taps_n, Cin), dtype=torch.float32, device=dy.device)
             if spec.kind == 's1' and spec.pad == 0 and Cout <= 3 and Cin == 64 and x5.shape[4] == 64 and spec.k in (3, 7) \
                     and dz5.shape[1] == 1:
+                ws = torch.empty(296 * g3.numel(), dtype=torch.float32, device=dy.device)     # SG_WGRAD_SMALL_BLOCKS partials
                 _lib.call('sg_wgrad_small_cout', _ptr(dz5), dz5.shape[4], _ptr(x5), Cout, spec.k, Cin, N, Ho, Wo, _ptr(g3),
-                          _stream())
+                          _ptr(ws), ws.numel(), _stream())
             elif spec.kind == 's1':
                 ops.wgrad_tc(dz5, x5, g3, Ho, Wo, convspec.wgrad_s1(spec.k, spec.pad), Cout, Cin)
             elif spec.kind == 's2':
@@ -473,8 +484,7 @@ class LinearFn(torch.autograd.Function):
             ops.wgrad_tc(dz5, xb.view(1, 1, 1, M, xb.shape[1]), dw, 1, M, ONE_WTAP, Nout, K)
             dw = dw.view(Nout, K)
         if ctx.needs_input_grad[2]:
-            db = ARENA.zeros((Nout,), dy.device)
-            _lib.call('sg_colsum_bf16', _ptr(dz), M, Nout, Np, _ptr(db), _stream())
+            db = ops.colsum(dz, Nout)
         return dx, dw, db, None
 
 
@@ -516,7 +526,8 @@ class NapFn(torch.autograd.Function):
         elif spec.norm is not None:
             scale, shift, mean, rstd = torch.empty((4, N * C), dtype=torch.float32, device=dev).unbind(0)   # one allocation
             rm, rv = (running if running is not None else (None, None))
-            _lib.call('sg_norm_finalize', _ptr(stats), 0 if spec.norm == 'in' else 1, N, C, float(H * W), spec.eps,
+            assert stats.dim() == 4 and stats.shape[0] == N and stats.shape[2] == C     # (N, slots, C, 2)
+            _lib.call('sg_norm_finalize', _ptr(stats), stats.shape[1], 0 if spec.norm == 'in' else 1, N, C, float(H * W), spec.eps,
                       _ptr(gamma), _ptr(beta), _ptr(rm), _ptr(rv), spec.momentum, _ptr(scale), _ptr(shift), _ptr(mean),
                       _ptr(rstd), _stream())
         res_ptr, res_strides = None, (0, 0, 0)
@@ -552,14 +563,16 @@ class NapFn(torch.autograd.Function):
             dres_ptr = dres.data_ptr() + 2 * (p * ctx.res_shape[3] * C + p * C)
         sums = None
         bn = spec.norm == 'bn'
+        parts = 0
         if spec.norm in ('in', 'bn'):
-            sums = torch.empty(((N + 1) * C if bn else N * C, 2), dtype=torch.float32, device=dev)
+            parts = _nap_parts(N, H, W, C)
+            sums = torch.empty(((N * parts + 1) * C, 2), dtype=torch.float32, device=dev)
         count = float(H * W * (N if bn else 1))
         _lib.call('sg_norm_act_pad_bwd', ctypes.byref(d), _ptr(g), _ptr(mean), _ptr(rstd), int(bn), count, _ptr(sums), 0,
                   _ptr(dsrc), dres_ptr, _stream())
         dgamma = dbeta = None
         if bn:
-            dgamma, dbeta = sums[N * C:, 1].contiguous(), sums[N * C:, 0].contiguous()
+            dgamma, dbeta = sums[N * parts * C:, 1].contiguous(), sums[N * parts * C:, 0].contiguous()
         return dsrc, None, dgamma, dbeta, dres, None, None
 
 

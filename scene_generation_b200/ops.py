@@ -58,6 +58,36 @@ def _ptr(t):
     return ctypes.c_void_p(0 if t is None else t.data_ptr())
 
 
+# Per-stream scratch of the fixed-order reductions (include/sg_b200.h: sg_wgrad_desc_t.locks, sg_colsum_bf16): int32
+# turn counters / tickets that are zero between launches (every kernel leaves them zero) followed by f32 partial-sum
+# rows.  Launches of one stream are serialised, so they share a buffer; every stream (graph branch) gets its own.
+N_LOCKS = 8192
+COLSUM_MAX_BLOCKS = 296
+_scratch = {}
+
+
+def stream_scratch(device):
+    """(locks int32 (N_LOCKS + 8,), partial rows f32) of torch's current stream on `device`"""
+    key = (device.index, _stream().value)
+    ent = _scratch.get(key)
+    if ent is None:
+        ent = _scratch[key] = (torch.zeros(N_LOCKS + 8, dtype=torch.int32, device=device),
+                               torch.empty(COLSUM_MAX_BLOCKS * 2048, dtype=torch.float32, device=device))
+    return ent
+
+
+def colsum(x2, C):
+    """f32 (C,) column sums of a bf16 (rows, ld) matrix: bias gradients (fixed summation order)"""
+    rows, ld = x2.shape
+    out = torch.empty((C,), dtype=torch.float32, device=x2.device)
+    locks, ws = stream_scratch(x2.device)
+    if ws.numel() < COLSUM_MAX_BLOCKS * C:
+        ws = torch.empty(COLSUM_MAX_BLOCKS * C, dtype=torch.float32, device=x2.device)
+    _lib.call('sg_colsum_bf16', _ptr(x2), rows, C, ld, _ptr(out), _ptr(ws), ws.numel(),
+              ctypes.c_void_p(locks.data_ptr() + 4 * N_LOCKS), _stream())
+    return out
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -218,7 +248,7 @@ _desc_cache = {}
 
 
 def conv_tc(x5, w3, y, y_strides, Hout, Wout, taps, phases=None, oh_mul=1, ow_mul=1, in_h0=0, in_w0=0,
-            bias=None, act=_lib.ACT_NONE, slope=0.0, stats=None, w_rows=None, mn_cols=None):
+            bias=None, act=_lib.ACT_NONE, slope=0.0, stats=False, w_rows=None, mn_cols=None):
     """x5: bf16 (N,P,H,W,C) contiguous; w3: bf16 (Cout,taps,C) contiguous — or (N,R,taps,C) per-image weights
     (channel-compacted operands), of which rows [w_rows[0], w_rows[1]) of every image are the output channels;
     y: f32/bf16 output storage
@@ -227,6 +257,8 @@ def conv_tc(x5, w3, y, y_strides, Hout, Wout, taps, phases=None, oh_mul=1, ow_mu
     phases: sequence of (tap_begin, ntaps, oh_off, ow_off) or None for a single phase.
     mn_cols=(c0, c1): "transposed" use of an fprop weight tensor (rows, taps, C) — the contraction runs over its rows
     and the output channels are its columns [c0, c1) (dgrad with the same bf16 copy of the weights as fprop).
+    stats=True: also returns the (N, slots, Cout, 2) f32 partial sum / sum-of-squares tensor of the pre-activation
+    output (sg_conv_desc_t.stats; sg_norm_finalize adds the slots).
     The filled descriptor is cached per call-site geometry; only the pointers change per call."""
     key = ('c', x5.shape, w3.shape, y.dtype, tuple(y_strides), Hout, Wout, id(taps), id(phases), oh_mul, ow_mul,
            in_h0, in_w0, act, slope, w_rows, mn_cols)
@@ -262,14 +294,20 @@ def conv_tc(x5, w3, y, y_strides, Hout, Wout, taps, phases=None, oh_mul=1, ow_mu
         for i, tp in enumerate(taps):
             d.taps[i] = Tap(*tp)
         d.act, d.slope = act, slope
+        slots = ctypes.c_int(0)
+        _lib.call('sg_conv_stats_slots', ctypes.byref(d), ctypes.byref(slots))
+        d.stats_slots = slots.value
         ent = (d, taps, phases, ctypes.byref(d))
         _desc_cache[key] = ent
     d = ent[0]
     d.x, d.w, d.y = x5.data_ptr(), w3.data_ptr(), y.data_ptr()
     d.bias = None if bias is None else bias.data_ptr()
-    d.stats = None if stats is None else stats.data_ptr()
+    st = None
+    if stats:
+        st = torch.empty((d.x_N, d.stats_slots, d.w_Cout, 2), dtype=torch.float32, device=x5.device)
+    d.stats = None if st is None else st.data_ptr()
     _lib.call('sg_conv_tc', ent[3], _stream())
-    return y
+    return (y, st) if stats else y
 
 
 def wgrad_tc(dy5, x5, dw, Hred, Wred, taps, Cout, Cin, ksplit=0):
@@ -297,5 +335,6 @@ def wgrad_tc(dy5, x5, dw, Hred, Wred, taps, Cout, Cin, ksplit=0):
         _desc_cache[key] = ent
     d = ent[0]
     d.dy, d.x, d.dw = dy5.data_ptr(), x5.data_ptr(), dw.data_ptr()
+    d.locks, d.n_locks = stream_scratch(dw.device)[0].data_ptr(), N_LOCKS
     _lib.call('sg_wgrad_tc', ent[3], _stream())
     return dw

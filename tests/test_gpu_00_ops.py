@@ -66,6 +66,17 @@ def test_layout_fwd_bwd_vs_oracle(H, W, kmax):
     g16 = gout.to(DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     dv16, _ = ops.masks_to_layout_bwd(vecs.detach().to(DEV), boxes.to(DEV), pm.detach().to(DEV), r, H, W, g16)
     close(dv16, vecs.grad, 2e-2)
+    # gather formulation, fixed summation order: a second launch gives the same bits
+    dv2, dm2 = ops.masks_to_layout_bwd(vecs.detach().to(DEV), boxes.to(DEV), pm.detach().to(DEV), r, H, W, gout.to(DEV),
+                                       need_dmasks=True)
+    assert torch.equal(dv, dv2) and torch.equal(dm, dm2)
+    # align_corners=True adjoint
+    v2, p2 = vecs.detach().clone().requires_grad_(True), pm.detach().clone().requires_grad_(True)
+    R.masks_to_layout(v2, boxes, p2, o2i, H, W, align_corners=True).backward(gout)
+    dva, dma = ops.masks_to_layout_bwd(v2.detach().to(DEV), boxes.to(DEV), p2.detach().to(DEV), r, H, W, gout.to(DEV),
+                                       align_corners=True, need_dmasks=True)
+    close(dva, v2.grad, 1e-4)
+    close(dma, p2.grad, 1e-4)
 
 
 def test_layout_degenerate_boxes_and_empty_image():
@@ -135,5 +146,17 @@ def test_crop_golden_oracle_and_backward():
     ref.backward(gout)
     df = ops.crop_bbox_bwd(gout.to(DEV), boxes.to(DEV), o2i.to(DEV), *imgs.shape)
     close(df, fr.grad, 1e-5)
+    assert torch.equal(df, ops.crop_bbox_bwd(gout.to(DEV), boxes.to(DEV), o2i.to(DEV), *imgs.shape))   # gather: fixed order
+    # non-identity box -> image mapping of the reference's demo (bilinear.py:289-295), bf16 channels-last gradient
+    f2 = feats.clone().requires_grad_(True)
+    ref2 = R.crop_bbox_batch(f2, bb, b2f, 8, 6)
+    g2 = cases.rand(tuple(ref2.shape), 9)
+    ref2.backward(g2)
+    close(ops.crop_bbox_bwd(g2.to(DEV), bb.to(DEV), b2f.to(DEV), *feats.shape), f2.grad, 1e-5)
+    g2n = torch.zeros(g2.shape[0], g2.shape[2], g2.shape[3], 8, dtype=torch.bfloat16)
+    g2n[..., :3] = g2.permute(0, 2, 3, 1).to(torch.bfloat16)
+    f3 = feats.clone().requires_grad_(True)
+    R.crop_bbox_batch(f3, bb, b2f, 8, 6).backward(g2n[..., :3].float().permute(0, 3, 1, 2))
+    close(ops.crop_bbox_bwd(g2n.to(DEV), bb.to(DEV), b2f.to(DEV), *feats.shape, grad_format=ops.NHWC_BF16), f3.grad, 1e-5)
     close(ops.crop_bbox_fwd(imgs.to(DEV), boxes.to(DEV), o2i.to(DEV), 16, 16, align_corners=True),
           R.crop_bbox_batch(imgs, boxes, o2i, 16, align_corners=True))

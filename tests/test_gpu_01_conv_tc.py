@@ -85,11 +85,15 @@ def test_conv_s1_reflect_prepadded(N, C, H, Co, k, out_bf16):
     ref = F.conv2d(xp, r32(w), b)
     taps, off = convspec.conv_s1(k, 0)
     y = torch.full((N, H, H, Co), float('nan'), device=DEV, dtype=torch.bfloat16 if out_bf16 else torch.float32)
-    stats = torch.zeros(N, Co, 2, device=DEV)
-    ops.conv_tc(to_nhwc5(xp), pack_w(w), y, (H * H * Co, H * Co, Co), H, H, taps, bias=b.to(DEV), stats=stats)
+    _, stats = ops.conv_tc(to_nhwc5(xp), pack_w(w), y, (H * H * Co, H * Co, Co), H, H, taps, bias=b.to(DEV), stats=True)
     check(y.permute(0, 3, 1, 2), ref, 1e-2 if out_bf16 else 2e-3)
-    check(stats[..., 0], ref.sum(dim=(2, 3)), 2e-3)
-    check(stats[..., 1], (ref ** 2).sum(dim=(2, 3)), 2e-3)
+    assert stats.shape[0] == N and stats.shape[2:] == (Co, 2)      # (N, slots, Cout, 2) partial sums
+    check(stats.sum(1)[..., 0], ref.sum(dim=(2, 3)), 2e-3)
+    check(stats.sum(1)[..., 1], (ref ** 2).sum(dim=(2, 3)), 2e-3)
+    # fixed-order reductions: a second launch reproduces the statistics bit for bit
+    y2 = torch.empty_like(y)
+    _, stats2 = ops.conv_tc(to_nhwc5(xp), pack_w(w), y2, (H * H * Co, H * Co, Co), H, H, taps, bias=b.to(DEV), stats=True)
+    assert torch.equal(stats, stats2) and torch.equal(y, y2)
 
 
 @pytest.mark.parametrize('N,C,H,W,Co,k,p', [(2, 45, 13, 13, 64, 4, 2), (3, 64, 16, 16, 128, 3, 1), (2, 8, 32, 32, 64, 4, 0),
@@ -123,11 +127,12 @@ def test_convT_phases(N, C, H, Co):
     taps, phases = convspec.convT_s2(3, 1)
     w3 = pack_w(w.permute(1, 0, 2, 3))          # (Cout, Cin, kh, kw) view of the ConvT weight
     y = torch.full((N, Ho, Ho, Co), float('nan'), device=DEV)
-    stats = torch.zeros(N, Co, 2, device=DEV)
-    ops.conv_tc(to_nhwc5(x), w3, y, (Ho * Ho * Co, Ho * Co, Co), H, H, taps, phases=phases, oh_mul=2, ow_mul=2,
-                bias=b.to(DEV), stats=stats)
+    _, stats = ops.conv_tc(to_nhwc5(x), w3, y, (Ho * Ho * Co, Ho * Co, Co), H, H, taps, phases=phases, oh_mul=2, ow_mul=2,
+                           bias=b.to(DEV), stats=True)
     check(y.permute(0, 3, 1, 2), ref)
-    check(stats[..., 0], ref.sum(dim=(2, 3)), 2e-3)
+    assert stats.shape[1] % 4 == 0                 # one slot per (sub-pixel phase, M tile of the image)
+    check(stats.sum(1)[..., 0], ref.sum(dim=(2, 3)), 2e-3)
+    check(stats.sum(1)[..., 1], (ref ** 2).sum(dim=(2, 3)), 2e-3)
 
 
 def test_dgrad_s1_matches_autograd():
@@ -151,10 +156,18 @@ def test_wgrad_s1(N, C, H, Co, k, p):
     dy = rnd(*out.shape, seed=21)
     out.backward(r32(dy))
     Ho = out.shape[2]
-    dw = torch.zeros(Co, k * k, C, device=DEV)
+    dw = torch.full((Co, k * k, C), float('nan'), device=DEV)      # overwritten, split-K included (no zero-fill needed)
     ops.wgrad_tc(to_nhwc5(dy), to_nhwc5(x), dw, Ho, Ho, convspec.wgrad_s1(k, p), Co, C)
     ref = wr.grad.permute(0, 2, 3, 1).reshape(Co, k * k, C)
     check(dw, ref)
+    # the k-splits of a tile are added in split order: bit-reproducible, also with a forced deep split
+    for ksplit in (0, 3):
+        a = torch.full((Co, k * k, C), float('nan'), device=DEV)
+        b = torch.full((Co, k * k, C), float('nan'), device=DEV)
+        ops.wgrad_tc(to_nhwc5(dy), to_nhwc5(x), a, Ho, Ho, convspec.wgrad_s1(k, p), Co, C, ksplit=ksplit)
+        ops.wgrad_tc(to_nhwc5(dy), to_nhwc5(x), b, Ho, Ho, convspec.wgrad_s1(k, p), Co, C, ksplit=ksplit)
+        assert torch.equal(a, b)
+        check(a, ref)
 
 
 def test_wgrad_s2_and_convT():

@@ -26,7 +26,8 @@ def close(a, b, tol=2e-2, name=''):
 
 def stats_of(y_nhwc):
     yf = y_nhwc.float()
-    return torch.stack([yf.sum(dim=(1, 2)), (yf * yf).sum(dim=(1, 2))], dim=-1).contiguous()
+    # (N, slots = 1, C, 2): the partial-sum layout the conv epilogue writes (sg_conv_desc_t.stats)
+    return torch.stack([yf.sum(dim=(1, 2)), (yf * yf).sum(dim=(1, 2))], dim=-1).unsqueeze(1).contiguous()
 
 
 def planes_ref(x_nchw):
@@ -162,3 +163,36 @@ def test_linear_fn_forward_backward():
     close(xd.grad, xr.grad, 2e-2, 'dx')
     close(wd.grad, wr.grad, 2e-2, 'dw')
     close(bd.grad, br.grad, 2e-2, 'db')
+
+
+@pytest.mark.parametrize('N,H,W,C,norm', [(3, 8, 8, 1024, 'in'), (2, 64, 64, 64, 'in'), (5, 33, 17, 128, 'in'),
+                                          (7, 16, 16, 192, 'bn'), (40, 4, 4, 64, 'bn')])
+def test_norm_backward_and_bias_gradient_are_bit_reproducible(N, H, W, C, norm):
+    """No floating-point atomics on the path: two runs of the norm backward (partial sums per CTA added in a fixed
+    order) and of the bias-gradient column sum give identical bits, and several slots of conv-epilogue partial
+    sums finalize to the statistics of their total."""
+    y = (rnd(N, H, W, C, seed=11) * 2 + 0.3).to(torch.bfloat16).to(DEV)
+    g = rnd(N, 1, H, W, C, seed=12).to(torch.bfloat16).to(DEV)
+    gamma = (rnd(C, seed=13) * 0.2 + 1.0).to(DEV).requires_grad_(True) if norm == 'bn' else None
+    beta = (rnd(C, seed=14) * 0.1).to(DEV).requires_grad_(True) if norm == 'bn' else None
+    st = stats_of(y)
+    # the same statistics split into 3 slots must finalize identically up to fp32 rounding of the split
+    st3 = torch.cat([st * 0.25, st * 0.5, st * 0.25], dim=1).contiguous()
+    outs = []
+    for stats in (st, st, st3):
+        yd = y.clone().requires_grad_(True)
+        if gamma is not None:
+            gamma.grad = beta.grad = None
+        out = Fn.nap(yd, stats, gamma, beta, None, None, NapSpec(norm=norm, act=_lib.ACT_LEAKY, slope=0.2))
+        out.backward(g)
+        outs.append((out.detach().clone(), yd.grad.clone(), None if gamma is None else gamma.grad.clone(),
+                     None if beta is None else beta.grad.clone()))
+    for a, b in zip(outs[0], outs[1]):
+        assert (a is None and b is None) or torch.equal(a, b)
+    close(outs[2][0], outs[0][0], 1e-2, 'slots fwd')
+    close(outs[2][1], outs[0][1], 2e-2, 'slots bwd')
+    from scene_generation_b200 import ops
+    x2 = g.reshape(-1, C)
+    s1, s2 = ops.colsum(x2, C), ops.colsum(x2, C)
+    assert torch.equal(s1, s2)
+    close(s1, x2.float().sum(0), 2e-3, 'colsum')

