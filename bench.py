@@ -4,8 +4,11 @@
 synthetic COCO-Stuff-shaped scene graphs, 128x128, batch 32 per GPU (BASELINE.json configs[1]/[2]).
 
     python bench.py --gpus N --steps K --warmup W             # this framework (one process per GPU)
-    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on host cores
-                                                             #   (oracle port; rank 0 only)
+    python bench.py --impl reference --gpus N --steps K ...   # the UNMODIFIED reference's own train loop
+                                                             #   (train.py:190-215) on the host cores, rank 0 only
+    python bench.py --impl reference-gpu ...                  # informational: the same reference loop through stock
+                                                             #   PyTorch eager / cuDNN on one B200
+    python bench.py --config cfg4|cfg5 ...                    # BASELINE.json configs[3] / configs[4] shapes
 Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for how every field is produced.
 """
 import argparse
@@ -21,7 +24,8 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FLOPS_PER_IMAGE_STEP = 224.1e9     # algorithmic FLOPs of one image through one train step
+FLOPS_BY_CONFIG = {'cfg2': 224.1e9, 'cfg4': 826.5e9, 'cfg5': 324.3e9}   # algorithmic FLOPs of one image through one train step
+FLOPS_PER_IMAGE_STEP = FLOPS_BY_CONFIG['cfg2']
 NUM_OBJS = 172
 VGG_FLOPS_PER_IMAGE = 35.5e9       # VGG19 feature loss, fwd on two images + dgrad through one
 
@@ -31,11 +35,18 @@ def parse():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference', 'reference-gpu'])
+    ap.add_argument('--config', default='cfg2', choices=['cfg2', 'cfg4', 'cfg5'],
+                    help='cfg2: 128x128, 3-8 objects (the headline, BASELINE configs[1]/[2]); cfg4: 256x256, 8-15 objects '
+                         '(layout-scatter stress, configs[3]); cfg5: 128x128, 29 objects (graph-conv stress, configs[4])')
     ap.add_argument('--batch', type=int, default=32, help='images per GPU')
-    ap.add_argument('--image-size', type=int, default=128)
-    ap.add_argument('--kmin', type=int, default=3)
-    ap.add_argument('--kmax', type=int, default=8)
+    ap.add_argument('--image-size', type=int, default=None)
+    ap.add_argument('--kmin', type=int, default=None)
+    ap.add_argument('--kmax', type=int, default=None)
+    ap.add_argument('--distinct', type=int, default=0,
+                    help='distinct synthetic batches (geometries) per rank cycled by the timed loop; 0 = max(steps, 24): '
+                         'every timed step sees a batch geometry of its own')
+    ap.add_argument('--no-dropin', action='store_true', help='skip the plain drop-in (no loader metadata, eager) measurement')
     ap.add_argument('--cpu-batch', type=int, default=2, help='images per step of the CPU baseline sample')
     ap.add_argument('--cpu-steps', type=int, default=3)
     ap.add_argument('--cpu-budget', type=int, default=90, help='seconds the CPU baseline may take')
@@ -49,7 +60,12 @@ def parse():
                     help='cProfile 5 steps of the host side (launch path) into gpurun_out/host_profile_*.txt and exit')
     ap.add_argument('--profile-step', action='store_true',
                     help='after warm-up run ONE step between cudaProfilerStart/Stop and exit (use with ncu --profile-from-start off)')
-    return ap.parse_args()
+    a = ap.parse_args()
+    preset = {'cfg2': (128, 3, 8), 'cfg4': (256, 8, 15), 'cfg5': (128, 29, 29)}[a.config]
+    a.image_size = a.image_size or preset[0]
+    a.kmin = a.kmin if a.kmin is not None else preset[1]
+    a.kmax = a.kmax if a.kmax is not None else preset[2]
+    return a
 
 
 # ------------------------------------------------------------------------------------------------
@@ -70,24 +86,46 @@ def host_threads():
     return max(1, min(n, 64))      # torch CPU kernels stop scaling (and oversubscribe) far below the core count of a GPU host
 
 
+def reference_kind():
+    """'reference' when the unmodified reference can be imported (its tree, or the sha256-checked staging copy
+    oracle/_ref that oracle/build_ref.py makes), else 'port' (oracle/restate.py, the CPU restatement)"""
+    try:
+        from oracle import ref_harness
+        return 'reference' if ref_harness.available() else 'port'
+    except Exception:
+        return 'port'
+
+
 def cpu_worker(a):
-    """child process: prints one JSON line per finished step so the parent can stop it at its time budget"""
-    from oracle import restate as R
+    """child process: prints one JSON line per finished step so the parent can stop it at its time budget.  Runs the
+    reference's own loop body (train.py:193-215 via oracle/ref_harness.train_iteration) on its own Trainer; only if
+    the reference cannot be imported, the oracle port."""
     from scene_generation_b200 import synthetic
     import random
     cores = host_threads()
     torch.set_num_threads(cores)
     H = a.image_size
-    cfg = dict(image_size=(H, H), num_objs=NUM_OBJS, rep_size=32, mask_size=32, n_downsample_global=4,
-               gconv_num_layers=5, crop_size=32, ngf=64, n_blocks=9)
-    tr = R.OracleTrainer(R.make_state_dicts(cfg, seed=0), cfg, vgg_sd=R.make_vgg_state_dict(0) if a.vgg else None)
+    kind = reference_kind()
     random.seed(0)
-    print(json.dumps({'ready': True, 'cores': cores}), flush=True)
+    torch.manual_seed(0)
+    if kind == 'reference':
+        from oracle import ref_harness
+        tr, _ = ref_harness.make_trainer(synthetic.make_vocab(NUM_OBJS), image_size=(H, H))
+        step = lambda batch, s: ref_harness.train_iteration(tr, batch, use_gt=(s % 2 == 0))
+        src = ref_harness.which()
+    else:
+        from oracle import restate as R
+        cfg = dict(image_size=(H, H), num_objs=NUM_OBJS, rep_size=32, mask_size=32, n_downsample_global=4,
+                   gconv_num_layers=5, crop_size=32, ngf=64, n_blocks=9)
+        tr = R.OracleTrainer(R.make_state_dicts(cfg, seed=0), cfg, vgg_sd=R.make_vgg_state_dict(0) if a.vgg else None)
+        step = lambda batch, s: tr.step(batch, torch.randn((1, 64)), use_gt=(s % 2 == 0))
+        src = 'oracle/restate.py'
+    print(json.dumps({'ready': True, 'cores': cores, 'kind': kind, 'source': src}), flush=True)
     s = 0
     while True:
         batch = synthetic.make_batch(a.cpu_batch, (H, H), NUM_OBJS, a.kmin, a.kmax, seed=1000 + s)
         t0 = time.perf_counter()
-        tr.step(batch, torch.randn((1, 64)), use_gt=(s % 2 == 0))
+        step(batch, s)
         print(json.dumps({'step': s, 'sec': time.perf_counter() - t0}), flush=True)
         s += 1
 
@@ -102,6 +140,7 @@ def cpu_reference_bounded(a, steps, warmup, budget_s):
     p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env)
     t_end = time.perf_counter() + budget_s
     times, cores = [], host_threads()
+    info = {'kind': 'port', 'source': ''}
     try:
         while len(times) < warmup + steps:
             left = t_end - time.perf_counter()
@@ -113,9 +152,15 @@ def cpu_reference_bounded(a, steps, warmup, budget_s):
             line = p.stdout.readline()
             if not line:
                 break
-            d = json.loads(line)
+            try:
+                d = json.loads(line)
+            except ValueError:
+                continue            # the reference prints to stdout (e.g. its output directory)
+            if not isinstance(d, dict):
+                continue
             if 'cores' in d:
                 cores = d['cores']
+                info = {'kind': d.get('kind', 'port'), 'source': d.get('source', '')}
             if 'sec' in d:
                 times.append(d['sec'])
     finally:
@@ -123,21 +168,21 @@ def cpu_reference_bounded(a, steps, warmup, budget_s):
         p.wait()
     meas = times[warmup:] if len(times) > warmup else times
     if not meas:
-        return None, None, cores, 0
+        return None, None, cores, 0, info
     mean = sum(meas) / len(meas)
-    return a.cpu_batch / mean, mean, cores, len(meas)
+    return a.cpu_batch / mean, mean, cores, len(meas), info
 
 
 def run_reference_arm(a):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    rate, mean, cores, n = cpu_reference_bounded(a, a.steps, max(a.warmup, 1), a.cpu_budget)
+    rate, mean, cores, n, info = cpu_reference_bounded(a, a.steps, max(a.warmup, 1), a.cpu_budget)
     if rate is None:
         print(json.dumps({'impl': 'reference', 'unavailable': 'CPU reference produced no step within %d s' % a.cpu_budget}))
         return
-    sample = '%d images/step x %d measured steps of the %dx%d, <=%d-object workload (fp32, %d host threads, <=%d s budget)' % (
-        a.cpu_batch, n, a.image_size, a.image_size, a.kmax, cores, a.cpu_budget)
+    sample = '%d images/step x %d measured steps of the %dx%d, <=%d-object workload (fp32, %d host threads, <=%d s budget; %s)' % (
+        a.cpu_batch, n, a.image_size, a.image_size, a.kmax, cores, a.cpu_budget, info['source'])
     line = {
         'impl': 'reference', 'metric': 'images/sec (train step, %dx%d, bs32/GPU)' % (a.image_size, a.image_size),
         'value': rate, 'unit': 'images/s', 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': max(a.warmup, 1),
@@ -146,11 +191,51 @@ def run_reference_arm(a):
         'config': {'workload': 'COCO-Stuff-shaped synthetic scene graphs (<=%d obj), %dx%d, full train step '
                                '(no VGG loss: pretrained weights unavailable offline)' % (a.kmax, a.image_size, a.image_size),
                    'global_batch': a.cpu_batch, 'parallelism': 'cpu x%d threads' % cores},
-        'cpu_baseline': {'value': rate, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': rate, 'unit': 'images/s', 'cores': cores, 'kind': info['kind'], 'sample': sample},
         'e2e': {'value': rate, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line))
+
+
+def run_reference_gpu_arm(a):
+    """Informational: the UNMODIFIED reference's train loop (train.py:190-215) through stock
+    PyTorch eager / cuDNN / cuBLAS on ONE B200, fp32 with TF32 off (the reference's own numerics) — the only
+    pre-existing Blackwell path.  Same synthetic workload, batches resident on the device, CUDA events."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from oracle import ref_harness
+    from scene_generation_b200 import synthetic
+    if not ref_harness.available():
+        print(json.dumps({'impl': 'reference-gpu', 'unavailable': 'reference not staged (run python -m oracle.build_ref)'}))
+        return
+    import random
+    torch.cuda.set_device(0)
+    H = a.image_size
+    random.seed(0)
+    torch.manual_seed(0)
+    tr, _ = ref_harness.make_trainer(synthetic.make_vocab(NUM_OBJS), image_size=(H, H), device='cuda')
+    batches = [tuple(t.cuda() for t in synthetic.make_batch(a.batch, (H, H), NUM_OBJS, a.kmin, a.kmax, seed=7919 + i))
+               for i in range(4)]
+    for i in range(max(a.warmup, 3)):
+        ref_harness.train_iteration(tr, batches[i % 4], use_gt=(i % 2 == 0))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(a.steps):
+        ref_harness.train_iteration(tr, batches[i % 4], use_gt=(i % 2 == 0))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps
+    print(json.dumps({
+        'impl': 'reference-gpu', 'metric': 'images/sec (train step, %dx%d, bs%d/GPU)' % (H, H, a.batch),
+        'value': a.batch / (ms / 1e3), 'unit': 'images/s', 'n_gpus': 1, 'steps': a.steps, 'warmup': max(a.warmup, 3),
+        'ms_per_step': ms, 'higher_is_better': True, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'unmodified reference loop (train.py:190-215) on stock PyTorch %s eager, %dx%d, %d-%d objects, '
+                               'no VGG loss; %s' % (torch.__version__, H, H, a.kmin, a.kmax, ref_harness.which()),
+                   'global_batch': a.batch, 'parallelism': 'single GPU (the reference has no data parallelism)'},
+        'gpu_launches': 0}))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -316,6 +401,8 @@ def main():
         return cpu_worker(a)
     if a.impl == 'reference':
         return run_reference_arm(a)
+    if a.impl == 'reference-gpu':
+        return run_reference_gpu_arm(a)
 
     import torch.distributed as dist
     from scene_generation_b200 import _lib, args as sgargs, synthetic
@@ -336,10 +423,12 @@ def main():
     targs = sgargs.default_args(image_size=(H, H), num_objs=NUM_OBJS)
     if a.vgg:
         targs.vgg_features_weight = 10.0
+        targs.vgg_random_init = True      # no pretrained weights offline: same FLOPs, seeded random VGG19
     torch.manual_seed(1234)           # identical replicas; the reducers broadcast rank 0's weights anyway
     tr = Trainer(targs, synthetic.make_vocab(NUM_OBJS), {})
-    # distinct synthetic batches per rank and per step, pre-built in pinned host memory
-    n_distinct = 4
+    # distinct synthetic batches per rank and per step, pre-built in pinned host memory: every step of the timed loop
+    # sees a batch (object / triple counts = graph geometry) of its own, different on every rank
+    n_distinct = a.distinct or max(a.steps, 24)
     host_batches = []
     for i in range(n_distinct):
         hb = synthetic.make_batch(a.batch, (H, H), NUM_OBJS, a.kmin, a.kmax, seed=7919 * rank + i)
@@ -388,11 +477,14 @@ def main():
         torch.cuda.synchronize()
         log('warm-up step %d done' % i)
     if tr.use_graphs and not a.host_profile:
-        # every (batch geometry, use_gt) pair of the timed loop: one more eager sighting at most, then the capture
-        for i in range(2 * n_distinct):
-            step_resident(i)
+        # every (batch geometry, use_gt) pair of the timed loops (step i uses batch i % n_distinct and coin i % 2): an
+        # eager sighting, then the capture — untimed, like a training run's first few hundred iterations
+        period = n_distinct if n_distinct % 2 == 0 else 2 * n_distinct
+        for rep in range(2):
+            for i in range(min(period, max(a.steps, 1) + 1)):
+                step_resident(i)
         torch.cuda.synchronize()
-        log('captured %d iteration graphs (cuda graphs %s)' % (
+        log('captured %d batch geometries (cuda graphs %s)' % (
             sum(1 for v in tr._graphs.values() if not isinstance(v, str)), 'on' if tr.use_graphs else 'FELL BACK to eager'))
     if a.host_profile:
         tr.use_graphs = False
@@ -438,6 +530,32 @@ def main():
         e2e = {'value': images / (ms_e2e / 1e3), 'unit': 'images/s', 'h2d_bytes_per_step': h2d_bytes * world,
                'd2h_bytes_per_step': 4 * world, 'ms_per_step': ms_e2e / a.steps}
 
+    # the PLAIN drop-in configuration: the reference's own loop body calling the mirrors with a batch that carries no
+    # loader metadata (what data/coco.py's coco_collate_fn produces) -> eager launches, dense layouts, the host syncs of
+    # the reference API.  Second number next to the headline, single GPU only.
+    dropin = None
+    if rank == 0 and world == 1 and not a.no_dropin:
+        def step_dropin(i):
+            imgs, objs, boxes, masks, triples, o2i, t2i, attrs = plain_batches[i % len(plain_batches)]
+            use_gt = i % 2 == 0
+            if not use_gt:
+                attrs = torch.zeros_like(attrs)
+            out = tr.model(imgs, objs, triples, o2i, boxes_gt=boxes, masks_gt=masks, attributes=attrs)
+            imgs_pred, boxes_pred, masks_pred, layout, layout_pred, layout_wrong = out
+            tr.train_generator(imgs, imgs_pred, masks, masks_pred, layout, objs, boxes, boxes_pred, o2i, use_gt)
+            tr.train_mask_discriminator(masks, masks_pred.detach(), objs)
+            tr.train_obj_discriminator(imgs, imgs_pred.detach(), objs, boxes, boxes.detach(), o2i)
+            tr.train_image_discriminator(imgs, imgs_pred.detach(), layout.detach(), layout_wrong.detach())
+        plain_batches = [tuple(t.to(dev) for t in hb) for hb in host_batches[:4]]
+        n_drop = min(a.steps, 10)
+        for i in range(2):
+            step_dropin(i)
+        ms_drop = timed(step_dropin, n_drop)
+        dropin = {'value': a.batch * n_drop / (ms_drop / 1e3), 'unit': 'images/s', 'ms_per_step': ms_drop / n_drop,
+                  'steps': n_drop, 'what': 'train.py:190-215 loop body on the mirrors, plain collate batch (no HostMeta): eager '
+                                           'launches, dense 204-channel layouts, host syncs of the reference API'}
+        del plain_batches
+
     # one instrumented (untimed) step: per-launch device time + algorithmic FLOPs of the tensor-core kernels
     roofline, kernels = None, None
     def step_eager(i):
@@ -457,13 +575,19 @@ def main():
         lay = fam.pop('layout_fwd', None)
         dom = max(fam.items(), key=lambda kv: kv[1]['ms'])
         achieved = dom[1]['flops'] / (dom[1]['ms'] * 1e-3) / 1e12
+        # DRAM traffic of the family's heaviest launch from the committed ncu --set full summary (tools/ncu_summary.py
+        # writes profiles/traffic.json from the capture's raw csv): dram__bytes_read.sum + dram__bytes_write.sum of ONE
+        # launch, next to its algorithmic bytes
+        traffic, traffic_sample = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+            traffic_sample = tj.get(dom[0])
+            if traffic_sample:
+                traffic = traffic_sample.get('dram_bytes')
+        except (OSError, ValueError):
+            pass
         roofline = {'kernel': dom[0], 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                    'frac': achieved / peak_tf, 'traffic': None,
-                    # ncu --set full of the family's heaviest shape (profiles/r01_conv_tc_resblock_s.md): DRAM bytes of one
-                    # launch next to its algorithmic bytes (bf16 weights + padded activations; the output stays in L2)
-                    'traffic_sample': {'launch': 'resblock 3x3 conv, GEMM 2048x1024x9216', 'dram_bytes': 25765888,
-                                       'algorithmic_bytes': 25480000, 'tensor_pipe_pct': 36.3,
-                                       'source': 'profiles/r01_conv_tc_resblock_s.md'},
+                    'frac': achieved / peak_tf, 'traffic': traffic, 'traffic_sample': traffic_sample,
                     'peak_source': which,
                     'launches_per_step': dom[1]['launches'], 'ms_per_step': dom[1]['ms']}
         kernels = {k: {'launches': v['launches'], 'ms': round(v['ms'], 3),
@@ -488,14 +612,16 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         log('cpu baseline (<= %d s)' % a.cpu_budget)
-        rate, mean, cores, n = cpu_reference_bounded(a, a.cpu_steps, 1, a.cpu_budget)
-        cpu = {'value': rate, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+        rate, mean, cores, n, info = cpu_reference_bounded(a, a.cpu_steps, 1, a.cpu_budget)
+        cpu = {'value': rate, 'unit': 'images/s', 'cores': cores, 'kind': info['kind'],
                'sample': '%d images/step x %d measured steps (+1 warm-up) of the same workload, fp32, %d host threads, '
-                         '%s s/step, budget %d s' % (a.cpu_batch, n, cores, ('%.2f' % mean) if mean else 'n/a', a.cpu_budget)}
+                         '%s s/step, budget %d s; %s' % (a.cpu_batch, n, cores, ('%.2f' % mean) if mean else 'n/a',
+                                                         a.cpu_budget, info['source'])}
 
     if rank == 0:
         line = {
             'metric': 'images/sec (train step, %dx%d, bs%d/GPU)' % (H, H, a.batch), 'value': value, 'unit': 'images/s',
+            'bench_config': a.config,
             'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3), 'ms_per_step': ms_total / a.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
             'config': {'workload': 'COCO-Stuff-shaped synthetic scene graphs (%d-%d objects + __image__), %dx%d, full '
@@ -504,11 +630,12 @@ def main():
                                        'ON (weight 10, seeded random VGG19 weights: none can be downloaded offline)' if a.vgg
                                        else 'off (no pretrained weights offline)'),
                        'global_batch': a.batch * world, 'parallelism': 'dp%d' % world,
-                       'l2': 'working set (732 MB of f32 weights + activations) >> 126 MB L2; %d distinct batches cycled'
-                             % n_distinct,
-                       'algorithmic_gflop_per_image': (FLOPS_PER_IMAGE_STEP + (VGG_FLOPS_PER_IMAGE if a.vgg else 0)) / 1e9},
-            'model_tflops': value * (FLOPS_PER_IMAGE_STEP + (VGG_FLOPS_PER_IMAGE if a.vgg else 0)) / 1e12,
-            'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'host_enqueue_ms_per_step': round(host_enqueue_ms, 2),
+                       'l2': 'working set (732 MB of f32 weights + activations) >> 126 MB L2; %d distinct batches '
+                             '(graph geometries) per rank, a different one every timed step' % n_distinct,
+                       'algorithmic_gflop_per_image': (FLOPS_BY_CONFIG[a.config] + (VGG_FLOPS_PER_IMAGE if a.vgg else 0)) / 1e9},
+            'model_tflops': value * (FLOPS_BY_CONFIG[a.config] + (VGG_FLOPS_PER_IMAGE if a.vgg else 0)) / 1e12,
+            'clocks': clocks, 'e2e': e2e, 'dropin_eager': dropin, 'gpu_launches': int(launches),
+            'host_enqueue_ms_per_step': round(host_enqueue_ms, 2),
             'cuda_graphs': {'enabled': bool(tr.use_graphs),
                             'captured': sum(1 for v in tr._graphs.values() if not isinstance(v, str))},
             'roofline': roofline, 'kernels': kernels,

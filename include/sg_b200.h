@@ -131,8 +131,9 @@ int sg_conv_stats_slots(const sg_conv_desc_t* desc, int* slots);
 /* Weight gradient (cuDNN wgrad in the reference):
  *   dw[co, wtap, ci] += sum_{img,h,w} dy[img, pa, h+dha, w+dwa, co] * x[img, pb, h+dhb, w+dwb, ci]
  * for every entry of the tap table (a = dy side, b = x side).  dw is f32 [Cout][w_taps][dw_C] and is
- * OVERWRITTEN.  When the reduction over pixels is split across CTAs, the splits add their partial sums
- * one after the other in split order (turn counters in `locks`), so the result is bit-reproducible.
+ * OVERWRITTEN.  When the reduction over pixels is split across CTAs, every split stores its partial sums to a slab
+ * of the workspace `ws` and a second kernel adds the slabs in split order, so the result is bit-reproducible;
+ * without a workspace the reduction is not split.
  * At least one side must have zero tap offsets and extents equal to (Hred, Wred), so that pixels
  * outside the reduction extent read as zero through the TMA fill. */
 typedef struct {
@@ -151,9 +152,9 @@ typedef struct {
   int ksplit;             /* 0 = auto */
   int per_image;          /* 1: dw is f32 [N][Cout][w_taps][dw_C], one slab per image (no reduction over
                              images; the per-image weight gradients of a channel-compacted operand) */
-  int* locks;             /* int32 turn counters, one per (Cout tile, Cin tile, tap) <= n_locks; ZERO on entry and
-                             left zero on return (stream-ordered reuse is fine; never share between streams) */
-  int n_locks;
+  float* ws;              /* f32 scratch for split partial sums: the reduction uses at most ws_floats / (Cout * w_taps *
+                             dw_C) splits; stream-ordered reuse is fine, never share between streams; may be NULL */
+  long long ws_floats;
 } sg_wgrad_desc_t;
 int sg_wgrad_tc(const sg_wgrad_desc_t* desc, sg_stream_t stream);
 
@@ -233,9 +234,9 @@ typedef struct {
 int sg_norm_act_pad_fwd(const sg_nap_desc_t* d, void* out, sg_stream_t stream);
 /* adjoint: grad has the layout of the forward output.  With save_mean != NULL the norm backward
  * dsrc = scale * (g' - mean(g') - xhat * mean(g' xhat)) is applied (bn=1: statistics over all images);
- * sums is f32 scratch of N*parts*C*2 floats, parts = sg_norm_act_pad_bwd_parts(N,H,W,C) <= SG_NAP_MAX_PARTS
- * (partial S1 = sum g', S2 = sum g' xhat per image and reduction CTA, added in a fixed order: no atomics, no zeroing)
- * plus, for bn=1, C*2 more floats behind them that return the batch totals (= d beta, d gamma for BatchNorm).
+ * sums is f32 scratch of (parts + 1)*N*C*2 floats, parts = sg_norm_act_pad_bwd_parts(N,H,W,C) <= SG_NAP_MAX_PARTS
+ * (partial S1 = sum g', S2 = sum g' xhat per reduction CTA and image, then their sums in part order: no atomics, no
+ * zeroing) plus, for bn=1, C*2 more floats behind them that return the batch totals (= d beta, d gamma for BatchNorm).
  * dsrc is plain bf16 NHWC or (out_planes=1) parity planes.
  * dres (optional, bf16, addressed with the residual's res_os_* strides) receives the folded
  * gradient of the residual input. */
@@ -267,11 +268,11 @@ int sg_maxpool2x2_bwd(const void* gy, const void* x, int N, int H, int W, int C,
 int sg_gap_fwd(const void* x, int N, int HW, int C, float* y, sg_stream_t stream);
 int sg_gap_bwd(const float* gy, int N, int HW, int C, void* gx, sg_stream_t stream);
 /* bias gradient: column sums of bf16 [rows][ld] (first C columns) written to f32 out[C].  Fixed-order reduction:
- * ws = f32 scratch of SG_COLSUM_MAX_BLOCKS * C floats (one partial row per CTA), ticket = one uint32 that is ZERO on
- * entry and left zero on return (stream-ordered reuse is fine; never share between streams). */
+ * ws = f32 scratch of SG_COLSUM_MAX_BLOCKS * C floats (one partial row per CTA, added in CTA order by a second
+ * kernel; stream-ordered reuse is fine, never share between streams). */
 #define SG_COLSUM_MAX_BLOCKS 296
 int sg_colsum_bf16(const void* x, long long rows, int C, int ld, float* out, float* ws, long long ws_floats,
-                   unsigned* ticket, sg_stream_t stream);
+                   sg_stream_t stream);
 
 /* ---- trainer.py:60,80,106,133 (torch.optim.Adam.step) + operand refresh ----------------------------------
  * Multi-tensor Adam (no weight decay, no amsgrad) over n_tensors parameter tensors, each given by its dense

@@ -66,7 +66,7 @@ class WgradDesc(ctypes.Structure):
         ('Hred', c_int), ('Wred', c_int),
         ('dw', c_void_p), ('Cout', c_int), ('Cin', c_int), ('w_taps', c_int), ('dw_C', c_int),
         ('ntaps', c_int), ('taps', WTap * SG_MAX_TAPS),
-        ('ksplit', c_int), ('per_image', c_int), ('locks', c_void_p), ('n_locks', c_int),
+        ('ksplit', c_int), ('per_image', c_int), ('ws', c_void_p), ('ws_floats', c_long),
     ]
 
 
@@ -125,7 +125,7 @@ _SIGS = {
     'sg_maxpool2x2_bwd': [_P, _P, c_int, c_int, c_int, c_int, _P, _P],
     'sg_gap_fwd': [_P, c_int, c_int, c_int, _P, _P],
     'sg_gap_bwd': [_P, c_int, c_int, c_int, _P, _P],
-    'sg_colsum_bf16': [_P, c_long, c_int, c_int, _P, _P, c_long, _P, _P],
+    'sg_colsum_bf16': [_P, c_long, c_int, c_int, _P, _P, c_long, _P],
     'sg_norm_act_pad_bwd_parts': [c_int, c_int, c_int, c_int],
     'sg_adam_pack': [c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                      ctypes.c_double, _P],

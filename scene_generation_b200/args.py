@@ -33,8 +33,9 @@ parser.add_argument('--appearance_normalization', default='batch')
 # generator losses
 parser.add_argument('--l1_pixel_loss_weight', default=.0, type=float)
 parser.add_argument('--bbox_pred_loss_weight', default=10, type=float)
-parser.add_argument('--vgg_features_weight', default=0.0, type=float)   # reference default 10: needs pretrained VGG19
-parser.add_argument('--vgg_weights', default=None, type=str)             # torchvision vgg19 state_dict file (no download here)
+parser.add_argument('--vgg_features_weight', default=10.0, type=float)  # args.py:73; needs the ImageNet VGG19 weights:
+parser.add_argument('--vgg_weights', default=None, type=str)             # a torchvision vgg19 state_dict file (nothing is downloaded)
+parser.add_argument('--vgg_random_init', default=False, type=bool_flag)  # throughput runs / tests only: seeded random VGG19
 parser.add_argument('--d_img_weight', default=1.0, type=float)
 parser.add_argument('--d_img_features_weight', default=10.0, type=float)
 parser.add_argument('--d_mask_weight', default=1.0, type=float)
@@ -69,6 +70,8 @@ parser.add_argument('--restore_from_checkpoint', default=False, type=bool_flag)
 parser.add_argument('--layout_dtype', default='bf16', choices=['bf16', 'f32'])
 parser.add_argument('--align_corners', default=False, type=bool_flag)
 parser.add_argument('--num_objs', default=172, type=int)   # synthetic vocabulary size (COCO-Stuff: 172)
+parser.add_argument('--cuda_graphs', default=True, type=bool_flag)   # replay captured iterations (trainer.py)
+parser.add_argument('--graph_cache', default=64, type=int)           # captured batch geometries kept alive
 
 
 def get_args(argv=None):
@@ -76,7 +79,11 @@ def get_args(argv=None):
 
 
 def default_args(**over):
+    """the reference's defaults for offline runs (tests, bench.py): the VGG19 term is off unless asked for, because
+    its pretrained weights cannot be downloaded here (pass vgg_features_weight=10 with vgg_weights=... or
+    vgg_random_init=True to include it)"""
     a = parser.parse_args([])
+    a.vgg_features_weight = 0.0
     for k, v in over.items():
         setattr(a, k, v)
     return a

@@ -29,6 +29,9 @@ void sg_count_launch();
 
 static inline int sg_cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
+// dst[i] = sum over p < parts of src[p * part_stride + i], added in part order (runtime.cu)
+int sg_sum_parts(const float* src, long n, int parts, long part_stride, float* dst, cudaStream_t stream, const char* what);
+
 // torch.linspace(0,1,steps)[i] in fp32, evaluated from both ends like ATen
 // (reference: layout.py:114-115, bilinear.py:263-265).
 __device__ __forceinline__ float sg_linspace01(int i, int steps) {

@@ -358,11 +358,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 struct WgradKParams {
   int tiles_w, tiles_h, BW, BH, BI;
   int ktiles_total, ktiles_per_split;
-  int serial;       // 1: the k-splits of a dw tile add their partial sums one after the other, in split order
+  int serial;       // 1: split-K through per-split workspace slabs, added in split order by sg_sum_parts
   int Cout, Cin, w_taps, dw_C, n_ci_tiles, stages;
   long long dw_split_stride;   // per_image: floats between the dw slabs of consecutive k-splits (= images)
   float* dw;
-  int* locks;       // serial: one turn counter per dw tile (zero on entry, zero again on exit)
+  float* ws;        // serial: [ksplit][Cout * w_taps * dw_C] partial sums
   sg_wtap_t taps[SG_MAX_TAPS];
 };
 
@@ -378,19 +378,8 @@ struct WgradCfg {
   static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 + 256; }
 };
 
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_gpu(int* p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// Split-K is DETERMINISTIC: the k-splits (blockIdx.z) of one dw tile take turns in split order (a turn counter per
-// tile, acquire/release at gpu scope): split 0 stores its partial sums, split z > 0 waits for split z - 1 and adds its
-// own with plain loads and stores; the last split resets the counter.  Thread blocks are dispatched in increasing
-// linear block index (z slowest), so the split a CTA waits for is always resident or finished.
+// Split-K is DETERMINISTIC: every k-split (blockIdx.z) of a dw tile stores its partial sums to its own slab of the
+// workspace; sg_sum_parts then adds the slabs in split order (no atomics, nothing waits).
 template <int BN>
 __global__ void __launch_bounds__(192, 2)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -470,19 +459,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else {
     const int q = warp & 3;
     const int co = co0 + q * 32 + lane;
-    int* lock = p.serial ? p.locks + (blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
-    const bool add = p.serial && blockIdx.z > 0;
+    float* base = p.serial ? p.ws + (long long)blockIdx.z * p.dw_split_stride
+                           : p.dw + (long long)blockIdx.z * p.dw_split_stride;       // per_image: one slab per image
     if (iters > 0) {
       mbar_wait(accum_full, 0);
       tc_fence_after();
-    }
-    if (p.serial) {
-      if (q == 0 && lane == 0) {
-        while (ld_acquire_gpu(lock) != (int)blockIdx.z) __nanosleep(64);
-      }
-      epi_bar();
-    }
-    if (iters > 0) {
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         if (ci0 + c0 >= p.Cin) break;
@@ -490,36 +471,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, raw);
         tmem_ld_wait();
         if (co < p.Cout) {
-          float* dst = p.dw + (long long)(p.serial ? 0 : blockIdx.z) * p.dw_split_stride +
-                       ((long long)co * p.w_taps + tp.wtap) * p.dw_C + ci0 + c0;
+          float* dst = base + ((long long)co * p.w_taps + tp.wtap) * p.dw_C + ci0 + c0;
           const bool vec = (ci0 + c0 + 32 <= p.Cin) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
           if (vec) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 v = make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]), __uint_as_float(raw[j + 2]),
-                                     __uint_as_float(raw[j + 3]));
-              if (add) {
-                const float4 o = __ldcg(reinterpret_cast<const float4*>(dst + j));
-                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-              }
-              __stcg(reinterpret_cast<float4*>(dst + j), v);
-            }
+            for (int j = 0; j < 32; j += 4)
+              __stcg(reinterpret_cast<float4*>(dst + j), make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]),
+                                                                     __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3])));
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (ci0 + c0 + j < p.Cin) {
-                float v = __uint_as_float(raw[j]);
-                if (add) v += __ldcg(dst + j);
-                __stcg(dst + j, v);
-              }
+              if (ci0 + c0 + j < p.Cin) __stcg(dst + j, __uint_as_float(raw[j]));
           }
         }
       }
-    }
-    if (p.serial) {
-      __threadfence();
-      epi_bar();
-      if (q == 0 && lane == 0) st_release_gpu(lock, blockIdx.z + 1 == gridDim.z ? 0 : (int)blockIdx.z + 1);
     }
   }
   tc_fence_before();
@@ -740,22 +705,25 @@ extern "C" int sg_wgrad_tc(const sg_wgrad_desc_t* d, sg_stream_t stream) {
     ksplit = d->N;
     kp.dw_split_stride = (long long)d->Cout * d->w_taps * d->dw_C;
   } else if (ksplit <= 0) {
-    // fill the 2 x 148 co-resident CTA slots once; a grid that (almost) does so unsplit stays unsplit
-    ksplit = (int)((2 * 148 + base_ctas / 2) / base_ctas);
+    // fill the 2 x 148 co-resident CTA slots once
+    ksplit = (int)((2 * 148 + base_ctas - 1) / base_ctas);
     if (ksplit > kp.ktiles_total) ksplit = kp.ktiles_total;
     if (ksplit < 1) ksplit = 1;
     // keep at least 8 k-tiles per split so the pipeline prologue amortises
     while (ksplit > 1 && kp.ktiles_total / ksplit < 8) --ksplit;
   }
+  const long long dw_floats = (long long)d->Cout * d->w_taps * d->dw_C;
+  if (!d->per_image && ksplit > 1) {
+    // the splits leave their partial sums in the caller's workspace: as many splits as it (and the tickets) allow
+    const long long cap = d->ws != nullptr ? d->ws_floats / dw_floats : 1;
+    if (ksplit > cap) ksplit = cap < 1 ? 1 : (int)cap;
+  }
   kp.ktiles_per_split = sg_cdiv(kp.ktiles_total, ksplit);
   ksplit = sg_cdiv(kp.ktiles_total, kp.ktiles_per_split);
   kp.serial = ksplit > 1 && !d->per_image;
   if (kp.serial) {
-    SG_CHECK_ARG(d->locks != nullptr && d->n_locks >= base_ctas,
-                 "sg_wgrad_tc: split reduction needs %ld zero-initialised int32 turn counters (locks / n_locks = %d)",
-                 base_ctas, d->n_locks);
-    SG_CHECK_ARG(base_ctas * ksplit < (1L << 31), "sg_wgrad_tc: grid too large");
-    kp.locks = d->locks;
+    kp.ws = d->ws;
+    kp.dw_split_stride = dw_floats;
   }
   CUtensorMap tmA, tmB;
   long long adims[5] = {d->dy_C, d->dy_W, d->dy_H, d->dy_P, d->N};
@@ -764,12 +732,15 @@ extern "C" int sg_wgrad_tc(const sg_wgrad_desc_t* d, sg_stream_t stream) {
   if (int e = make_tmap(&tmA, d->dy, 5, adims, box)) return e;
   if (int e = make_tmap(&tmB, d->x, 5, bdims, box)) return e;
   dim3 grid(co_tiles * kp.n_ci_tiles, d->ntaps, ksplit);
+  int e;
   switch (BN) {
-    case 256: return launch_wgrad<256>(tmA, tmB, kp, grid, stream);
-    case 192: return launch_wgrad<192>(tmA, tmB, kp, grid, stream);
-    case 128: return launch_wgrad<128>(tmA, tmB, kp, grid, stream);
-    default: return launch_wgrad<64>(tmA, tmB, kp, grid, stream);
+    case 256: e = launch_wgrad<256>(tmA, tmB, kp, grid, stream); break;
+    case 192: e = launch_wgrad<192>(tmA, tmB, kp, grid, stream); break;
+    case 128: e = launch_wgrad<128>(tmA, tmB, kp, grid, stream); break;
+    default: e = launch_wgrad<64>(tmA, tmB, kp, grid, stream); break;
   }
+  if (e != SG_OK || !kp.serial) return e;
+  return sg_sum_parts(d->ws, dw_floats, ksplit, dw_floats, d->dw, stream, "sg_wgrad_tc(split sum)");
 }
 
 

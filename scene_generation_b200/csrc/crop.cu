@@ -63,7 +63,10 @@ __global__ void __launch_bounds__(CROP_BWD_THREADS) crop_bwd_kernel(CropArgs a, 
   extern __shared__ unsigned char crop_smem[];
   SgBilin* sAx = reinterpret_cast<SgBilin*>(crop_smem);      // [WW]
   SgBilin* sAy = sAx + a.WW;                                  // [HH]
+  unsigned char* sMine = reinterpret_cast<unsigned char*>(sAy + a.HH);   // [B]: box b crops this CTA's image
   const int n = blockIdx.y;
+  for (int b = threadIdx.x; b < a.B; b += CROP_BWD_THREADS) sMine[b] = a.map[b] == n;
+  __syncthreads();
   const int p = blockIdx.x * CROP_BWD_THREADS + threadIdx.x;
   const bool live = p < a.H * a.W;
   const int y = live ? p / a.W : -4, x = live ? p % a.W : -4;
@@ -71,7 +74,7 @@ __global__ void __launch_bounds__(CROP_BWD_THREADS) crop_bwd_kernel(CropArgs a, 
 #pragma unroll
   for (int c = 0; c < CROP_MAX_C; ++c) acc[c] = 0.f;
   for (int b = 0; b < a.B; ++b) {
-    if (a.map[b] != n) continue;                              // block-uniform
+    if (!sMine[b]) continue;                                  // block-uniform
     __syncthreads();
     for (int t = threadIdx.x; t < a.WW + a.HH; t += CROP_BWD_THREADS) {
       SgBilin ax, ay;
@@ -137,7 +140,8 @@ extern "C" int sg_crop_bbox_bwd(const float* boxes, const long long* box_to_feat
   SG_CHECK_ARG(C <= CROP_MAX_C, "crop_bbox_bwd: at most %d feature channels (images)", CROP_MAX_C);
   // every pixel of every image is written by exactly one thread (zeros where no crop touches it): B == 0 included
   dim3 grid(sg_cdiv((long)H * W, CROP_BWD_THREADS), N);
-  const size_t smem = sizeof(SgBilin) * (size_t)(HH + WW);
+  const size_t smem = sizeof(SgBilin) * (size_t)(HH + WW) + (size_t)B + 16;
+  SG_CHECK_ARG(smem <= 48 * 1024, "crop_bbox_bwd: too many boxes / too large crops for the shared-memory tables");
   if (grad_format == 1) crop_bwd_kernel<true><<<grid, CROP_BWD_THREADS, smem, stream>>>(a, grad_out, dfeats);
   else crop_bwd_kernel<false><<<grid, CROP_BWD_THREADS, smem, stream>>>(a, grad_out, dfeats);
   SG_CHECK_LAUNCH("sg_crop_bbox_bwd");

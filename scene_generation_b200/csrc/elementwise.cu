@@ -255,9 +255,10 @@ struct NapBwdArgs {
   const float* save_rstd;
   int bn;                 // 1: statistics shared over images (BatchNorm)
   float count;            // elements per statistic
-  float* sums;            // [N][parts][C*2] partial S1 = sum g', S2 = sum g' * xhat per CTA of the reduce kernel
-                          // (+ [C*2] batch totals behind them for BatchNorm)
+  float* sums;            // [parts][N][C*2] partial S1 = sum g', S2 = sum g' * xhat per CTA of the reduce kernel, then
+                          // [N][C*2] their sums in part order, then (BatchNorm) [C*2] batch totals
   int parts;              // partial slots per image
+  const float* sums_final;  // [N][C*2] per-image sums (+ [C*2] batch totals): what the apply kernel reads
   int out_planes;         // dsrc written as parity planes (for transposed-conv producers)
   bf16* dsrc;             // [N][H][W][C] plain, or planes [N][4][ceil(H/2)][ceil(W/2)][C]
   bf16* dres;             // optional: folded grad (no act') in plain source layout
@@ -361,9 +362,9 @@ __global__ void nap_bwd_reduce_kernel(NapBwdArgs b, int pix_per_block) {
     mine[2 * k + 1] = s2[k];
   }
   __syncthreads();
-  // one partial per (image, CTA, channel, sum), lanes added in lane order: no atomics, fixed order.  The apply
-  // kernel (InstanceNorm) / bn_total_kernel (BatchNorm) add the parts of an image in part order.
-  float* dst = b.sums + ((long)n * b.parts + blockIdx.x) * a.C * 2;
+  // one partial per (CTA, image, channel, sum), lanes added in lane order: no atomics, fixed order; sg_sum_parts adds
+  // the parts of an image in part order (a single part is written straight to the final slot)
+  float* dst = b.sums + ((long)(b.parts > 1 ? blockIdx.x : 0) * a.N + n) * a.C * 2;
   for (int t = threadIdx.x; t < nC * 16; t += blockDim.x) {
     float v = 0.f;
     for (int l = 0; l < lanes; ++l) v += red[l * nC * 16 + t];
@@ -371,13 +372,13 @@ __global__ void nap_bwd_reduce_kernel(NapBwdArgs b, int pix_per_block) {
   }
 }
 
-// BatchNorm: totals[c*2+j] = sum over images and parts (in that order) of the partials; stored behind them
-__global__ void bn_total_kernel(float* sums, int rows, int C) {
+// BatchNorm: totals[c*2+j] = sum over images (in image order) of the per-image sums; stored behind them
+__global__ void bn_total_kernel(float* sums, int N, int C) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= C * 2) return;
   float v = 0.f;
-  for (int r = 0; r < rows; ++r) v += sums[(long)r * C * 2 + t];
-  sums[(long)rows * C * 2 + t] = v;
+  for (int n = 0; n < N; ++n) v += sums[(long)n * C * 2 + t];
+  sums[(long)N * C * 2 + t] = v;
 }
 
 // grid.x = source row (n, h), grid.y * blockDim.x covers its (w, channel-chunk) items
@@ -401,22 +402,9 @@ __global__ void nap_bwd_apply_kernel(NapBwdArgs b) {
   if (b.save_mean) {
     float sc[8], s01[8], s23[8];
     load8f(a.scale + pc, sc);                                          // scale = rstd (* gamma)
-    if (b.bn) {                                                          // batch totals behind the partials
-      const float* sm = b.sums + ((long)a.N * b.parts * a.C + ch * 8) * 2;   // (S1,S2) pairs of 8 channels
-      load8f(sm, s01);
-      load8f(sm + 8, s23);
-    } else {                                                             // this image's parts, in part order
-#pragma unroll
-      for (int k = 0; k < 8; ++k) s01[k] = s23[k] = 0.f;
-      for (int part = 0; part < b.parts; ++part) {
-        const float* sm = b.sums + (((long)n * b.parts + part) * a.C + ch * 8) * 2;
-        float t0[8], t1[8];
-        load8f(sm, t0);
-        load8f(sm + 8, t1);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { s01[k] += t0[k]; s23[k] += t1[k]; }
-      }
-    }
+    const float* sm = b.sums_final + ((long)(b.bn ? a.N : n) * a.C + ch * 8) * 2;   // (S1,S2) pairs of 8 channels
+    load8f(sm, s01);
+    load8f(sm + 8, s23);
     const float inv = 1.f / b.count;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -727,14 +715,11 @@ __global__ void gap_bwd_kernel(const float* __restrict__ gy, int N, int HW, int 
   gx[idx] = __float2bfloat16(gy[(long)n * C + c] / (float)HW);
 }
 
-// column sums of a bf16 [rows][ld] matrix (ld % 8 == 0) into f32 [C] (bias gradient).  Deterministic: every CTA
-// leaves one partial row in `ws` (lanes added in lane order); the CTA that finishes last (integer ticket) adds the
-// partial rows in CTA order — the order of the additions never depends on which CTA that is — and resets the ticket.
+// column sums of a bf16 [rows][ld] matrix (ld % 8 == 0) (bias gradient).  Deterministic: every CTA leaves one partial
+// row dst[blockIdx.x][C] (lanes added in lane order); sg_sum_parts adds the partial rows in CTA order.
 // thread = (8-channel chunk, row lane); 16-byte loads.
-__global__ void colsum_kernel(const bf16* __restrict__ x, long rows, int C, int ld, int rows_per_block, float* ws,
-                              unsigned* ticket, float* __restrict__ out) {
+__global__ void colsum_kernel(const bf16* __restrict__ x, long rows, int C, int ld, int rows_per_block, float* __restrict__ dst) {
   extern __shared__ float red[];     // [lanes][nC*8]
-  __shared__ int is_last;
   const int nC = ld / 8;
   const int lanes = blockDim.x / nC;
   const int ch = threadIdx.x % nC, lane = threadIdx.x / nC;
@@ -754,42 +739,11 @@ __global__ void colsum_kernel(const bf16* __restrict__ x, long rows, int C, int 
     for (int k = 0; k < 8; ++k) red[lane * nC * 8 + ch * 8 + k] = acc[k];
   }
   __syncthreads();
-  if (gridDim.x == 1) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      float s = 0.f;
-      for (int l = 0; l < lanes; ++l) s += red[l * nC * 8 + c];
-      out[c] = s;
-    }
-    return;
-  }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = 0.f;
     for (int l = 0; l < lanes; ++l) s += red[l * nC * 8 + c];
-    __stcg(ws + (long)blockIdx.x * C + c, s);
+    dst[(long)blockIdx.x * C + c] = s;
   }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  // last CTA: thread (group g, channel c) adds the partial rows g, g + G, ... in order, then the groups in order
-  const int G = max(1, (int)blockDim.x / C);
-  for (int c0 = 0; c0 < C; c0 += blockDim.x) {
-    const int c = c0 + threadIdx.x % (G > 1 ? C : blockDim.x), g = G > 1 ? threadIdx.x / C : 0;
-    float s = 0.f;
-    if (c < C && g < G)
-      for (int b = g; b < (int)gridDim.x; b += G) s += __ldcg(ws + (long)b * C + c);
-    __syncthreads();
-    red[threadIdx.x] = s;
-    __syncthreads();
-    if (g == 0 && c < C) {
-      float t = 0.f;
-      for (int gg = 0; gg < G; ++gg) t += red[G > 1 ? gg * C + c : threadIdx.x];
-      out[c] = t;
-    }
-  }
-  if (threadIdx.x == 0) *ticket = 0;
 }
 
 }  // namespace
@@ -918,6 +872,7 @@ extern "C" int sg_norm_act_pad_bwd(const sg_nap_desc_t* d, const void* grad, con
   b.f = nap_args(d);
   b.g = (const bf16*)grad; b.save_mean = save_mean; b.save_rstd = save_rstd; b.bn = bn; b.count = count; b.sums = sums;
   b.parts = 1;
+  b.sums_final = sums;
   b.out_planes = out_planes; b.dsrc = (bf16*)dsrc; b.dres = (bf16*)dres;
   const int nC = d->C / 8;
   if (save_mean && !bn && nap_fused_enabled() && (long)d->H * d->W <= 256) {
@@ -936,12 +891,17 @@ extern "C" int sg_norm_act_pad_bwd(const sg_nap_desc_t* d, const void* grad, con
     int threads, pix_per_block, parts;
     nap_reduce_shape(d->N, d->H, d->W, d->C, &threads, &pix_per_block, &parts);
     SG_CHECK_ARG(threads <= 1024, "norm_act_pad_bwd: too many channels");
+    const long per = (long)d->N * d->C * 2;
+    float* fin = sums + (parts > 1 ? (long)parts * per : 0);       // per-image sums: behind the partials
     b.parts = parts;
+    b.sums_final = fin;
     dim3 grid(parts, d->N);
     nap_bwd_reduce_kernel<<<grid, threads, sizeof(float) * 16 * threads, stream>>>(b, pix_per_block);
     SG_CHECK_LAUNCH("sg_norm_act_pad_bwd(reduce)");
+    if (parts > 1)
+      if (int e = sg_sum_parts(sums, per, parts, per, fin, stream, "sg_norm_act_pad_bwd(sum parts)")) return e;
     if (bn) {
-      bn_total_kernel<<<sg_cdiv(2 * d->C, 256), 256, 0, stream>>>(sums, d->N * parts, d->C);
+      bn_total_kernel<<<sg_cdiv(2 * d->C, 256), 256, 0, stream>>>(fin, d->N, d->C);
       SG_CHECK_LAUNCH("sg_norm_act_pad_bwd(bn totals)");
     }
   }
@@ -1045,7 +1005,7 @@ extern "C" int sg_gap_bwd(const float* gy, int N, int HW, int C, void* gx, sg_st
 }
 
 extern "C" int sg_colsum_bf16(const void* x, long long rows, int C, int ld, float* out, float* ws, long long ws_floats,
-                              unsigned* ticket, sg_stream_t stream) {
+                              sg_stream_t stream) {
   SG_CHECK_ARG(x && out && rows > 0 && C > 0 && ld >= C, "colsum: bad arguments");
   SG_CHECK_ARG(ld % 8 == 0 && ld <= 8192, "colsum: ld must be a multiple of 8 (<= 8192)");
   const int nC = ld / 8;
@@ -1053,12 +1013,13 @@ extern "C" int sg_colsum_bf16(const void* x, long long rows, int C, int ld, floa
   SG_CHECK_ARG(threads <= 1024, "colsum: too many channels");
   const int lanes = threads / nC;
   int rpb = (int)((rows + SG_COLSUM_MAX_BLOCKS - 1) / SG_COLSUM_MAX_BLOCKS);
-  if (rpb < lanes * 16) rpb = lanes * 16;                  // few, longer CTAs on small inputs: the last CTA adds one row per CTA
+  if (rpb < lanes * 4) rpb = lanes * 4;
   const int blocks = sg_cdiv(rows, rpb);
-  SG_CHECK_ARG(blocks == 1 || (ws != nullptr && ticket != nullptr && ws_floats >= (long long)blocks * C),
-               "colsum: needs %lld floats of workspace and a zero-initialised ticket", (long long)blocks * C);
-  size_t smem = sizeof(float) * (size_t)(lanes * nC * 8 > threads ? lanes * nC * 8 : threads);
-  colsum_kernel<<<blocks, threads, smem, stream>>>((const bf16*)x, rows, C, ld, rpb, ws, ticket, out);
+  SG_CHECK_ARG(blocks == 1 || (ws != nullptr && ws_floats >= (long long)blocks * C),
+               "colsum: needs %lld floats of workspace", (long long)blocks * C);
+  size_t smem = sizeof(float) * (size_t)lanes * nC * 8;
+  colsum_kernel<<<blocks, threads, smem, stream>>>((const bf16*)x, rows, C, ld, rpb, blocks == 1 ? out : ws);
   SG_CHECK_LAUNCH("sg_colsum_bf16");
-  return SG_OK;
+  if (blocks == 1) return SG_OK;
+  return sg_sum_parts(ws, C, blocks, C, out, stream, "sg_colsum_bf16(sum)");
 }

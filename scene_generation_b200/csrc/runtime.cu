@@ -24,3 +24,34 @@ extern "C" unsigned long long sg_launch_count(void) { return g_launches.load(std
 extern "C" void sg_reset_launch_count(void) { g_launches.store(0, std::memory_order_relaxed); }
 // launches replayed from a captured CUDA graph (the host enqueued them once, at capture): the caller accounts them
 extern "C" void sg_add_launch_count(unsigned long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ------------------------------------------------------------------------------------------------
+// dst[i] = src[0][i] + src[1][i] + ... + src[parts-1][i], added in that order (the second half of every fixed-order
+// reduction of the library: producers leave one partial row per CTA / split, this kernel adds the rows).
+namespace {
+__global__ void sum_parts_kernel(const float* __restrict__ src, long n, int parts, long part_stride, float* __restrict__ dst) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i * 4 >= n) return;
+  if (i * 4 + 4 <= n && (part_stride & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < parts; ++p) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(src + (long)p * part_stride) + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(dst)[i] = acc;
+  } else {
+    for (long e = i * 4; e < n && e < i * 4 + 4; ++e) {
+      float acc = 0.f;
+      for (int p = 0; p < parts; ++p) acc += __ldcg(src + (long)p * part_stride + e);
+      dst[e] = acc;
+    }
+  }
+}
+}  // namespace
+
+int sg_sum_parts(const float* src, long n, int parts, long part_stride, float* dst, cudaStream_t stream, const char* what) {
+  if (n <= 0) return SG_OK;
+  sum_parts_kernel<<<sg_cdiv(sg_cdiv(n, 4), 256), 256, 0, stream>>>(src, n, parts, part_stride, dst);
+  SG_CHECK_LAUNCH(what);
+  return SG_OK;
+}

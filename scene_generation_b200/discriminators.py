@@ -106,6 +106,10 @@ def _run_patch_d(layers, x_plain, cond=None, n_cls=0, need_dx=True, dx_channels=
     x = x_plain
     for j, seq in enumerate(layers):
         conv = seq[0]
+        for mod in seq[1:]:
+            if not isinstance(mod, (nn.InstanceNorm2d, nn.LeakyReLU)):
+                raise NotImplementedError('PatchGAN columns run InstanceNorm2d + LeakyReLU (norm_D / norm_D_mask = '
+                                          "'instance', the reference's default); got %s" % type(mod).__name__)
         k, stride, pad = conv.kernel_size[0], conv.stride[0], conv.padding[0]
         has_norm = len(seq) > 1 and isinstance(seq[1], nn.InstanceNorm2d)
         has_act = any(isinstance(s, nn.LeakyReLU) for s in seq)
@@ -197,7 +201,9 @@ class MultiscaleDiscriminator(nn.Module):
         D = layout.shape[1]                           # cmap already maps channels [D, D+3) to the image inputs
         if raw is None or raw.shape[3] < D + img.shape[1]:
             assert cmap is None
-            return self.forward(torch.cat((layout.float(), img), dim=1))
+            # f32 layouts, or no spare channels behind a dense bf16 layout: materialise the concat — with the layout
+            # DETACHED like on the fast path (trainer.py:249 match_layout = layout.detach(), train.py:211-215)
+            return self.forward(torch.cat((layout.detach().float(), img), dim=1))
         x = Fn.ImageSlotFn.apply(raw.detach(), img, D)
         return self._columns(x, img.requires_grad, (D, D + img.shape[1]), cmap)
 

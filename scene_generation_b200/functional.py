@@ -134,62 +134,6 @@ def invalidate_packed(params):
         _pack_cache.pop((id(p), 'cmap'), None)
 
 
-class ZeroArena:
-    """f32 scratch that reads as zero when handed out.  The conv epilogue statistics, bias gradients and similar
-    accumulators of one training step (several hundred small buffers) come from here: Trainer.train_step calls
-    begin_step(), which clears what the previous step used with ONE fill instead of one fill kernel per buffer.
-    Buffers are only valid until the next begin_step(); outside a training step (or when the arena is full)
-    zeros() falls back to torch.zeros."""
-
-    def __init__(self, nbytes=48 << 20):
-        self.capacity = nbytes // 4
-        self.buf = None
-        self.off = 0
-        self.active = False
-
-    def ensure(self, device):
-        """allocate the backing buffer (must happen outside a CUDA graph capture)"""
-        if self.buf is None or self.buf.device != device:
-            self.buf = torch.zeros(self.capacity, dtype=torch.float32, device=device)
-            self.off = 0
-
-    def begin_step(self, device, force=False):
-        # Off by default for eagerly launched steps: they are host-bound on the launch path (bench.py:
-        # host_enqueue_ms_per_step) and a view per buffer costs the host slightly more than torch.zeros, although it
-        # saves ~300 fill kernels per step on the GPU (measured: -0.7 ms GPU, +0.8 ms host per step).  SG_ZERO_ARENA=1
-        # enables it; captured steps (Trainer.train_step with CUDA graphs) always use it (force=True).
-        if not force and os.environ.get('SG_ZERO_ARENA', '0') != '1':
-            self.active = False
-            return
-        self.ensure(device)
-        if torch.cuda.is_current_stream_capturing():
-            self.buf.zero_()         # the replayed graph cannot know what the step before it used: clear everything
-        elif self.off:
-            self.buf[:self.off].zero_()
-        self.off = 0
-        self.active = True
-
-    def end(self):
-        self.active = False
-
-    def zeros(self, shape, device):
-        if not self.active:
-            return torch.zeros(shape, dtype=torch.float32, device=device)
-        strides, n = [], 1
-        for s in reversed(shape):
-            strides.append(n)
-            n *= s
-        n_al = (n + 63) // 64 * 64                   # 256-byte granules keep every buffer vector-aligned
-        if self.off + n_al > self.capacity or self.buf.device != device:
-            return torch.zeros(shape, dtype=torch.float32, device=device)
-        t = self.buf.as_strided(shape, strides[::-1], self.off)      # one view op per buffer
-        self.off += n_al
-        return t
-
-
-ARENA = ZeroArena()
-
-
 # ---------------------------------------------------------------------------------------------
 # small kernel wrappers
 # ---------------------------------------------------------------------------------------------
@@ -566,13 +510,14 @@ class NapFn(torch.autograd.Function):
         parts = 0
         if spec.norm in ('in', 'bn'):
             parts = _nap_parts(N, H, W, C)
-            sums = torch.empty(((N * parts + 1) * C, 2), dtype=torch.float32, device=dev)
+            # [parts][N][C][2] partials | [N][C][2] per-image sums | [C][2] batch totals (a single part: no partials)
+            sums = torch.empty((((parts + 1 if parts > 1 else 1) * N + 1) * C, 2), dtype=torch.float32, device=dev)
         count = float(H * W * (N if bn else 1))
         _lib.call('sg_norm_act_pad_bwd', ctypes.byref(d), _ptr(g), _ptr(mean), _ptr(rstd), int(bn), count, _ptr(sums), 0,
                   _ptr(dsrc), dres_ptr, _stream())
         dgamma = dbeta = None
         if bn:
-            dgamma, dbeta = sums[N * parts * C:, 1].contiguous(), sums[N * parts * C:, 0].contiguous()
+            dgamma, dbeta = sums[-C:, 1].contiguous(), sums[-C:, 0].contiguous()
         return dsrc, None, dgamma, dbeta, dres, None, None
 
 

@@ -99,10 +99,12 @@ def build_cnn(arch, normalization='batch', activation='relu', padding='same', po
         vals = [int(v) for v in s[1:].split('-')]
         K, next_C, stride = (vals + [1])[:3] if len(vals) == 2 else vals
         if not first:
-            if normalization == 'batch':
-                layers.append(nn.BatchNorm2d(cur_C))
-            elif normalization == 'instance':
-                layers.append(nn.InstanceNorm2d(cur_C))
+            if normalization != 'batch':
+                # the reference also accepts 'instance' / 'none' (layers.py:164-167); only its default, the
+                # BatchNorm2d + LeakyReLU crop CNN (args.py:68,96), is built on the CUDA kernels
+                raise NotImplementedError("crop CNNs (appearance encoder, object discriminator) run with "
+                                          "normalization='batch'; got %r" % (normalization,))
+            layers.append(nn.BatchNorm2d(cur_C))
             layers.append(nn.LeakyReLU(parse_activation(activation)[1]))
         first = False
         P = 0 if padding == 'valid' else (K - 1) // 2

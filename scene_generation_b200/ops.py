@@ -58,33 +58,29 @@ def _ptr(t):
     return ctypes.c_void_p(0 if t is None else t.data_ptr())
 
 
-# Per-stream scratch of the fixed-order reductions (include/sg_b200.h: sg_wgrad_desc_t.locks, sg_colsum_bf16): int32
-# turn counters / tickets that are zero between launches (every kernel leaves them zero) followed by f32 partial-sum
-# rows.  Launches of one stream are serialised, so they share a buffer; every stream (graph branch) gets its own.
-N_LOCKS = 8192
+# Per-stream scratch of the fixed-order reductions (include/sg_b200.h: sg_wgrad_desc_t.ws, sg_colsum_bf16): f32 partial
+# rows / split slabs that a second kernel adds in order.  Launches of one stream are serialised, so they share a
+# buffer; every stream (graph branch) gets its own.
 COLSUM_MAX_BLOCKS = 296
+SCRATCH_FLOATS = 16 << 20          # 64 MB per stream: split-K slabs of the weight gradients, bias-gradient partial rows
 _scratch = {}
 
 
 def stream_scratch(device):
-    """(locks int32 (N_LOCKS + 8,), partial rows f32) of torch's current stream on `device`"""
+    """f32 partial-sum scratch of torch's current stream on `device`"""
     key = (device.index, _stream().value)
-    ent = _scratch.get(key)
-    if ent is None:
-        ent = _scratch[key] = (torch.zeros(N_LOCKS + 8, dtype=torch.int32, device=device),
-                               torch.empty(COLSUM_MAX_BLOCKS * 2048, dtype=torch.float32, device=device))
-    return ent
+    ws = _scratch.get(key)
+    if ws is None:
+        ws = _scratch[key] = torch.empty(SCRATCH_FLOATS, dtype=torch.float32, device=device)
+    return ws
 
 
 def colsum(x2, C):
     """f32 (C,) column sums of a bf16 (rows, ld) matrix: bias gradients (fixed summation order)"""
     rows, ld = x2.shape
     out = torch.empty((C,), dtype=torch.float32, device=x2.device)
-    locks, ws = stream_scratch(x2.device)
-    if ws.numel() < COLSUM_MAX_BLOCKS * C:
-        ws = torch.empty(COLSUM_MAX_BLOCKS * C, dtype=torch.float32, device=x2.device)
-    _lib.call('sg_colsum_bf16', _ptr(x2), rows, C, ld, _ptr(out), _ptr(ws), ws.numel(),
-              ctypes.c_void_p(locks.data_ptr() + 4 * N_LOCKS), _stream())
+    ws = stream_scratch(x2.device)
+    _lib.call('sg_colsum_bf16', _ptr(x2), rows, C, ld, _ptr(out), _ptr(ws), ws.numel(), _stream())
     return out
 
 
@@ -335,6 +331,7 @@ def wgrad_tc(dy5, x5, dw, Hred, Wred, taps, Cout, Cin, ksplit=0):
         _desc_cache[key] = ent
     d = ent[0]
     d.dy, d.x, d.dw = dy5.data_ptr(), x5.data_ptr(), dw.data_ptr()
-    d.locks, d.n_locks = stream_scratch(dw.device)[0].data_ptr(), N_LOCKS
+    ws = stream_scratch(dw.device)
+    d.ws, d.ws_floats = ws.data_ptr(), ws.numel()
     _lib.call('sg_wgrad_tc', ent[3], _stream())
     return dw

@@ -5,11 +5,16 @@ pairs instead of a materialised concat, and with torch.distributed initialised e
 is preceded by a flat-buffer NCCL all-reduce of that network's gradients (DDP semantics).
 
 train_step() launches the ~1900 kernels of one iteration either eagerly (host-bound: ~31 ms of Python/launch
-time per step against ~25 ms of GPU time) or — default — as ONE captured CUDA graph per batch geometry
-(number of objects / triples, the use_gt coin): the first step of a geometry runs eagerly, the second is
-captured, later ones are replayed after copying the batch into the graph's static input buffers.  The only
-per-step host work that survives is the VectorPool replacement policy (python `random`, utils.py:62-90), whose
-index vector is an input of the graph."""
+time per step against ~25 ms of GPU time) or — default — as FOUR captured CUDA graphs per batch geometry
+(number of objects / triples, the use_gt coin): A = Model.forward + generator losses + backward, B = the three
+discriminator forward/backward passes, Cg / Cd = Adam of the generator / of the discriminators.  The first step of
+a geometry runs eagerly, the second is captured, later ones are replayed after copying the batch into the graphs'
+static input buffers.  The gradient all-reduces of data-parallel runs are issued EAGERLY between the graphs (after
+A: generator, after B: discriminators) in the same order on every rank whatever mix of eager / capturing /
+replaying steps the ranks are in — no collective is ever captured, so ranks with different batch geometries cannot
+deadlock — and overlap the next graph on NCCL's own stream.  The only per-step host work that survives is the
+VectorPool replacement policy (python `random`, utils.py:62-90), whose index vector is an input of graph A."""
+import collections
 import os
 import warnings
 
@@ -80,9 +85,26 @@ def _batch_to_device(batch, device):
     return out
 
 
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def _detached(t):
+    """t.detach() that keeps the loader / layout tags (channel map, gradient channels) of the tensor"""
+    d = t.detach()
+    for k, v in getattr(t, '__dict__', {}).items():
+        if k.startswith('_sg_'):
+            setattr(d, k, v)
+    return d
+
+
 class _StepGraph:
-    """One captured training iteration: static input buffers (batch, index metadata, VectorPool plan), the CUDA
-    graph, and the tensors it leaves behind (outputs of Model.forward, the four LossManagers)."""
+    """One captured training iteration: static input buffers (batch, index metadata, VectorPool plan), the four CUDA
+    graphs (A, B, Cg, Cd), and the tensors they leave behind (outputs of Model.forward, the four LossManagers)."""
 
     def __init__(self, batch, meta, plan):
         dev = torch.device('cuda', torch.cuda.current_device())
@@ -90,7 +112,8 @@ class _StepGraph:
         self.meta_tensors = tuple(torch.empty(t.shape, dtype=t.dtype, device=dev) for t in meta.tensors())
         self.pool_idx = None if plan is None else torch.empty(plan.shape, dtype=plan.dtype, device=dev)
         self.slots_used = meta.slots_used
-        self.graph = self.out = self.losses = None
+        self.graphs = None            # {'A','B','Cg','Cd'} -> torch.cuda.CUDAGraph
+        self.out = self.losses = None
         self.launches = 0
 
     def load(self, batch, meta, plan):
@@ -118,12 +141,15 @@ class Trainer:
         self.init_mask_discriminator(args, checkpoint)
         # CUDA-graph replay of whole iterations (SG_CUDA_GRAPH=0 or args.cuda_graphs=False: eager launches)
         self.use_graphs = bool(getattr(args, 'cuda_graphs', True)) and os.environ.get('SG_CUDA_GRAPH', '1') != '0'
-        self._graphs = {}             # batch geometry -> 'warm' (seen once, ran eagerly) | _StepGraph
+        # batch geometry -> 'warm' (seen once, ran eagerly) | _StepGraph, least recently used first; at most
+        # SG_GRAPH_CACHE captured geometries stay alive (each pins its outputs in the shared pool)
+        self._graphs = collections.OrderedDict()
+        self._graph_cache_size = int(os.environ.get('SG_GRAPH_CACHE', getattr(args, 'graph_cache', 64)))
         self._graph_pool = None       # one private memory pool shared by all captured iterations (replayed one at a time)
-        self._side_streams = None     # captured iterations run the mask / object discriminator updates as parallel branches
-        self._defer_g_update = False
-        self._g_update_pending = False
+        self._side_streams = None     # captured iterations run independent sub-steps as parallel graph branches
+        self._branches = None         # the side streams while a capture is running, else None (eager: one stream)
         self._fwd_stream = None
+        self._st = None               # tensors handed from one phase of the iteration to the next
         self.generator_losses = self.d_mask_losses = self.d_obj_losses = self.d_img_losses = None
         self.reducers = {}
         if ddp.world_size() > 1:
@@ -131,9 +157,7 @@ class Trainer:
                               ('mask', self.mask_discriminator)):
                 if net is not None:
                     ddp.broadcast_parameters(net)
-                    # SG_DDP_BUCKET_MB (experimental): bucketed all-reduce launched from gradient hooks during backward
-                    mb = float(os.environ.get('SG_DDP_BUCKET_MB', '0') or 0)
-                    self.reducers[name] = ddp.FlatGradReducer(net, bucket_mb=mb if (mb > 0 and name == 'g') else None)
+                    self.reducers[name] = ddp.FlatGradReducer(net)
 
     # ---- construction (trainer.py:30-134) ------------------------------------------------------
     def init_generator(self, args, checkpoint):
@@ -150,9 +174,14 @@ class Trainer:
         self.criterionVGG = None
         if getattr(args, 'vgg_features_weight', 0) > 0:
             # trainer.py:57.  The ImageNet weights cannot be downloaded here: args.vgg_weights names a torchvision
-            # vgg19 state_dict file; without it the stack keeps a seeded initialisation (throughput runs, tests).
+            # vgg19 state_dict file.  A seeded random VGG19 (same FLOPs, meaningless features) must be asked for.
             from .losses import VGGLoss
-            self.criterionVGG = VGGLoss(getattr(args, 'vgg_weights', None))
+            weights = getattr(args, 'vgg_weights', None)
+            if weights is None and not getattr(args, 'vgg_random_init', False):
+                raise RuntimeError('vgg_features_weight = %g needs the pretrained VGG19 (--vgg_weights <torchvision vgg19 '
+                                   'state_dict>); pass --vgg_features_weight 0 to train without the perceptual term or '
+                                   '--vgg_random_init 1 for throughput runs' % args.vgg_features_weight)
+            self.criterionVGG = VGGLoss(weights)
         self.criterionFeat = torch.nn.L1Loss()
         self.criterionGAN = GANLoss(use_lsgan=not args.no_lsgan)
         self.optimizer = _adam(model.parameters(), lr=args.learning_rate, betas=(args.beta1, 0.999))
@@ -201,6 +230,7 @@ class Trainer:
 
     # ---- checkpoint (trainer.py:136-203) -------------------------------------------------------
     def restore_checkpoint(self, checkpoint):
+        self.release_graphs()         # captured Adam launches hold the addresses of the optimizer state they replace
         self.model.load_state_dict(checkpoint['model_state'])
         self.optimizer.load_state_dict(checkpoint['optim_state'])
         for net, opt, k in ((self.obj_discriminator, self.optimizer_d_obj, 'd_obj'),
@@ -229,9 +259,10 @@ class Trainer:
         return path
 
     # ---- the four sub-steps (trainer.py:205-325) -----------------------------------------------
-    def _step(self, name, optimizer, losses):
-        self._backward(name, optimizer, losses)
-        self._update(name, optimizer)
+    # Each train_* method computes its losses and gradients (zero_grad + backward); the optimizer updates are separate
+    # (_update) so that data-parallel runs can all-reduce in between.  train_generator / train_*_discriminator keep the
+    # reference's one-call semantics (backward AND update) unless a phased iteration is running (self._phased).
+    _phased = False
 
     def _backward(self, name, optimizer, losses):
         from . import ops
@@ -239,18 +270,35 @@ class Trainer:
         if name in self.reducers:
             self.reducers[name].zero()            # .grad tensors are views of one flat buffer
         else:
+            # None gradients: backward then hands its fresh tensors over instead of adding them into zero-filled ones
+            # (257 add kernels per iteration).  A parameter without a gradient in a step (box_net when use_gt is False)
+            # is skipped by Adam, where the reference's pytorch-1.0 zero_grad — and the data-parallel flat buffers —
+            # apply its momentum-only update; DESIGN.md lists the difference.
             optimizer.zero_grad(set_to_none=True)
         losses.total_loss.backward()
         # drop the autograd graph now: a loss kept for logging would keep this iteration's AccumulateGrad nodes (bound
         # to the stream they were created on) alive into the next iteration — fatal for a CUDA graph capture
         losses.total_loss = losses.total_loss.detach()
+        if not self._phased:
+            self._allreduce((name,))
+            self._update(name, optimizer)
+
+    def _allreduce(self, names, async_op=False):
+        """data parallel: average the flat gradient buffers of these networks over the ranks (eager NCCL calls, issued in
+        the same order on every rank).  async_op: returns the work handles; the caller waits before the update."""
+        works = []
+        for name in names:
+            r = self.reducers.get(name)
+            if r is not None:
+                w = r.allreduce(async_op=async_op)
+                if w is not None:
+                    works.append(w)
+        return works
 
     def _update(self, name, optimizer):
-        """gradient all-reduce (data parallel) + Adam"""
+        """Adam step of one network"""
         from . import ops
         ops.refresh_stream()
-        if name in self.reducers:
-            self.reducers[name].allreduce()
         optimizer.step()
         if not isinstance(optimizer, PackedAdam):
             # torch's fused Adam does not bump Tensor._version: tell the bf16 operand cache which masters changed
@@ -262,14 +310,13 @@ class Trainer:
         return oh.scatter_(1, objs.view(-1, 1).long(), 1.0)
 
     def train_generator(self, imgs, imgs_pred, masks, masks_pred, layout, objs, boxes, boxes_pred, obj_to_img, use_gt):
+        from . import ops
         args = self.args
         self.generator_losses = gl = LossManager()
         if use_gt:
             if args.l1_pixel_loss_weight > 0:
                 gl.add_loss(F.l1_loss(imgs_pred, imgs), 'L1_pixel_loss', args.l1_pixel_loss_weight)
             gl.add_loss(F.mse_loss(boxes_pred, boxes), 'bbox_pred', args.bbox_pred_loss_weight)
-        if self.criterionVGG is not None:                           # trainer.py:218-221 (with and without use_gt)
-            gl.add_loss(self.criterionVGG(imgs_pred, imgs), 'g_vgg', args.vgg_features_weight)
         # The G step back-propagates THROUGH the discriminators; the gradients it would deposit in their
         # parameters (trainer.py:262) are cleared by every D step's zero_grad before use, so the D weights are
         # frozen for this graph and their wgrad kernels are skipped.
@@ -277,32 +324,54 @@ class Trainer:
         for net in d_nets:
             for p in net.parameters():
                 p.requires_grad_(False)
+        # Inside a captured iteration the loss branches that only share imgs_pred / masks_pred — the VGG term, the object
+        # discriminator, the mask discriminator — run on side streams next to the image discriminator (forward here,
+        # backward through autograd's stream semantics); their loss terms join the total in the reference's order.
+        br = self._branches
+        main = torch.cuda.current_stream()
+        if br:
+            for st in br:
+                st.wait_stream(main)
+
+        def on(i):
+            return ops.on_stream(br[i]) if br else _NullCtx()
         try:
-            scores_fake, ac_loss, _ = self.obj_discriminator(imgs_pred, objs, boxes, obj_to_img)
-            gl.add_loss(ac_loss, 'ac_loss', args.ac_loss_weight)
-            gl.add_loss(self.gan_g_loss(scores_fake), 'g_gan_obj_loss', args.d_obj_weight)
+            terms = {}
+            if self.criterionVGG is not None:                       # trainer.py:218-221 (with and without use_gt)
+                with on(2):
+                    terms['g_vgg'] = self.criterionVGG(imgs_pred, imgs)
+            with on(0):
+                scores_fake, ac_loss, _ = self.obj_discriminator(imgs_pred, objs, boxes, obj_to_img)
+                terms['ac_loss'] = ac_loss
+                terms['g_gan_obj_loss'] = self.gan_g_loss(scores_fake)
             if self.mask_discriminator is not None:
-                scores_fake = self.mask_discriminator(masks_pred.unsqueeze(1), objs)
-                gl.add_loss(self.criterionGAN(scores_fake, True), 'g_gan_mask_obj_loss', args.d_mask_weight)
-                if args.d_mask_features_weight > 0:
-                    with torch.no_grad():
-                        scores_real = self.mask_discriminator(masks.unsqueeze(1), objs)
-                    gl.add_loss(self.calculate_features_loss(scores_fake, scores_real), 'g_mask_features_loss',
-                                args.d_mask_features_weight)
+                with on(1):
+                    scores_fake = self.mask_discriminator(masks_pred.unsqueeze(1), objs)
+                    terms['g_gan_mask_obj_loss'] = self.criterionGAN(scores_fake, True)
+                    if args.d_mask_features_weight > 0:
+                        with torch.no_grad():
+                            scores_real = self.mask_discriminator(masks.unsqueeze(1), objs)
+                        terms['g_mask_features_loss'] = self.calculate_features_loss(scores_fake, scores_real)
             if self.netD is not None:
                 with torch.no_grad():       # only used detached (trainer.py:246,339)
                     pred_real = self.netD.forward_pair(layout, imgs)
                 img_pred_fake = self.netD.forward_pair(layout, imgs_pred)
-                gl.add_loss(self.criterionGAN(img_pred_fake, True), 'g_gan_img_loss', args.d_img_weight)
+                terms['g_gan_img_loss'] = self.criterionGAN(img_pred_fake, True)
                 if args.d_img_features_weight > 0:
-                    gl.add_loss(self.calculate_features_loss(img_pred_fake, pred_real), 'g_gan_features_loss_img',
-                                args.d_img_features_weight)
+                    terms['g_gan_features_loss_img'] = self.calculate_features_loss(img_pred_fake, pred_real)
+            if br:
+                for st in br:
+                    main.wait_stream(st)
+                ops.refresh_stream()
+            weights = (('g_vgg', args.vgg_features_weight), ('ac_loss', args.ac_loss_weight),
+                       ('g_gan_obj_loss', args.d_obj_weight), ('g_gan_mask_obj_loss', args.d_mask_weight),
+                       ('g_mask_features_loss', args.d_mask_features_weight), ('g_gan_img_loss', args.d_img_weight),
+                       ('g_gan_features_loss_img', args.d_img_features_weight))
+            for name, wgt in weights:
+                if name in terms:
+                    gl.add_loss(terms[name], name, wgt)
             gl._terms['total_loss'] = gl.total_loss.detach()
             self._backward('g', self.optimizer, gl)
-            if self._defer_g_update:          # captured iterations overlap the generator's all-reduce + Adam with the D steps
-                self._g_update_pending = True
-            else:
-                self._update('g', self.optimizer)
         finally:
             for net in d_nets:
                 for p in net.parameters():
@@ -317,7 +386,7 @@ class Trainer:
         dl.add_loss(self.gan_d_loss(scores_real, scores_fake), 'd_obj_gan_loss', 0.5)
         dl.add_loss(ac_real, 'd_ac_loss_real')
         dl.add_loss(ac_fake, 'd_ac_loss_fake')
-        self._step('obj', self.optimizer_d_obj, dl)
+        self._backward('obj', self.optimizer_d_obj, dl)
 
     def train_mask_discriminator(self, masks, masks_pred, objs):
         if self.mask_discriminator is None:
@@ -335,7 +404,7 @@ class Trainer:
             scores_real = self.mask_discriminator(masks.unsqueeze(1), objs)
         dl.add_loss(self.criterionGAN(scores_fake, False), 'fake_loss', 0.5)
         dl.add_loss(self.criterionGAN(scores_real, True), 'real_loss', 0.5)
-        self._step('mask', self.optimizer_d_mask, dl)
+        self._backward('mask', self.optimizer_d_mask, dl)
 
     def train_image_discriminator(self, imgs, imgs_pred, layout, layout_wrong):
         if self.netD is None:
@@ -351,7 +420,7 @@ class Trainer:
         dl.add_loss(self.criterionGAN(fake, False), 'fake_image_loss', alpha)
         dl.add_loss(self.criterionGAN(wrong, False), 'wrong_texture_loss', alpha)
         dl.add_loss(self.criterionGAN(real, True), 'd_img_gan_real_loss', 0.5)
-        self._step('img', self.optimizer_d_img, dl)
+        self._backward('img', self.optimizer_d_img, dl)
 
     def discriminate(self, input_label, test_image):
         return self.netD.forward_pair(input_label, test_image)
@@ -365,6 +434,7 @@ class Trainer:
                 loss = loss + dw * fw * self.criterionFeat(pred_fake[i][j].float(), pred_real[i][j].detach().float())
         return loss
 
+    # ---- one iteration of train.py:190-215 in four phases ------------------------------------------
     def train_step(self, batch, use_gt=True, graph=None):
         """One iteration of train.py:190-215 on a collated batch.  The batch tensors may live on the device or
         (graph replay) in pinned host memory — they are copied into the captured iteration's input buffers.
@@ -374,51 +444,69 @@ class Trainer:
             return self._train_step_graphed(batch, use_gt)
         return self._train_step_eager(batch, use_gt)
 
-    def _train_step_eager(self, batch, use_gt, arena=False):
-        batch = _batch_to_device(batch, 'cuda')
+    def _d_nets(self):
+        return [(n, o) for n, o in (('mask', self.optimizer_d_mask), ('obj', self.optimizer_d_obj), ('img', self.optimizer_d_img))
+                if o is not None]
+
+    def _phase_a(self, batch, use_gt):
+        """Model.forward (model.py:94-124) + generator losses + backward (trainer.py:205-262 without the update)"""
         imgs, objs, boxes, masks, triples, obj_to_img, triple_to_img, attributes = batch
         if not use_gt:
             attributes = torch.zeros_like(attributes)
-        Fn.ARENA.begin_step(imgs.device, force=arena)        # zero-initialised scratch of this iteration (one fill per step)
         out = self.model(imgs, objs, triples, obj_to_img, boxes_gt=boxes, masks_gt=masks, attributes=attributes)
         imgs_pred, boxes_pred, masks_pred, layout, layout_pred, layout_wrong = out
-        side = self._side_streams if (arena and torch.cuda.is_current_stream_capturing()) else None
-        # SG_OVERLAP_G_ALLREDUCE=0: keep the generator's all-reduce + Adam in front of the D steps (A/B switch)
-        self._defer_g_update = bool(side) and os.environ.get('SG_OVERLAP_G_ALLREDUCE', '1') != '0'
-        try:
-            self.train_generator(imgs, imgs_pred, masks, masks_pred, layout, objs, boxes, boxes_pred, obj_to_img, use_gt)
-        finally:
-            self._defer_g_update = False
+        self.train_generator(imgs, imgs_pred, masks, masks_pred, layout, objs, boxes, boxes_pred, obj_to_img, use_gt)
+        self._st = (batch, out)
+        return out
+
+    def _phase_b(self):
+        """the three discriminator passes (train.py:207-215): losses + backward, no update.  They only share read-only
+        inputs, and none of them reads the generator's weights: inside a capture they are parallel graph branches."""
+        from . import ops
+        (imgs, objs, boxes, masks, triples, obj_to_img, _, _), out = self._st
+        imgs_pred, boxes_pred, masks_pred, layout, layout_pred, layout_wrong = out
         masks_fake, imgs_fake = masks_pred.detach(), imgs_pred.detach()
-        if side:
-            # The three discriminator updates only share read-only inputs (train.py:207-215), and none of them reads
-            # the generator's weights (they see imgs_pred / masks_pred of THIS iteration's forward): inside a captured
-            # iteration the generator's gradient all-reduce + Adam and the three D steps become parallel branches of
-            # the graph — the all-reduce (NVLink) and the HBM-bound Adam pass hide under the discriminators' convolutions,
-            # and the small mask / object discriminator kernels fill the SMs the image discriminator leaves idle.
-            # Every tensor that crosses streams stays referenced until the branches are joined (no allocator reuse
-            # while a side stream may still read it).  Collectives are issued in the same host order on every rank.
-            from . import ops
+        # the reference hands layout.detach() / layout_wrong.detach() to the image discriminator (train.py:211-215)
+        lay, lay_wrong = _detached(layout), _detached(layout_wrong)
+        br = self._branches
+        if br:
             main = torch.cuda.current_stream()
-            for s in side:
-                s.wait_stream(main)
-            if self._g_update_pending:
-                with ops.on_stream(side[2]):
-                    self._update('g', self.optimizer)
-                self._g_update_pending = False
-            with ops.on_stream(side[0]):
+            for st in br[:2]:
+                st.wait_stream(main)
+            with ops.on_stream(br[0]):
                 self.train_mask_discriminator(masks, masks_fake, objs)
-            with ops.on_stream(side[1]):
+            with ops.on_stream(br[1]):
                 self.train_obj_discriminator(imgs, imgs_fake, objs, boxes, boxes.detach(), obj_to_img)
-            self.train_image_discriminator(imgs, imgs_fake, layout, layout_wrong)
-            for s in side:
-                main.wait_stream(s)
+            self.train_image_discriminator(imgs, imgs_fake, lay, lay_wrong)
+            for st in br[:2]:
+                main.wait_stream(st)
             ops.refresh_stream()
         else:
             self.train_mask_discriminator(masks, masks_fake, objs)
             self.train_obj_discriminator(imgs, imgs_fake, objs, boxes, boxes.detach(), obj_to_img)
-            self.train_image_discriminator(imgs, imgs_fake, layout, layout_wrong)
-        Fn.ARENA.end()
+            self.train_image_discriminator(imgs, imgs_fake, lay, lay_wrong)
+
+    def _phase_cd(self):
+        for name, opt in self._d_nets():
+            self._update(name, opt)
+
+    def _train_step_eager(self, batch, use_gt):
+        """eager launches on the current stream; data parallel: the generator's all-reduce runs on NCCL's stream next
+        to the discriminator passes"""
+        batch = _batch_to_device(batch, 'cuda')
+        self._phased = True
+        try:
+            out = self._phase_a(batch, use_gt)
+            works = self._allreduce(('g',), async_op=True)
+            self._phase_b()
+            for w in works:
+                w.wait()
+            self._update('g', self.optimizer)
+            self._allreduce([n for n, _ in self._d_nets()])
+            self._phase_cd()
+        finally:
+            self._phased = False
+            self._st = None
         return out
 
     # ---- captured iterations ---------------------------------------------------------------------
@@ -432,15 +520,19 @@ class Trainer:
         ent = self._graphs.get(key)
         if ent is None:               # first sight of this geometry: eager (also warms every lazy initialisation)
             self._graphs[key] = 'warm'
+            self._evict()
             # detached like the outputs of a replay: a caller holding on to this iteration's autograd graph would
             # keep its AccumulateGrad nodes (bound to the eager stream) alive into the capture
             return tuple(o.detach() if torch.is_tensor(o) else o for o in self._train_step_eager(batch, use_gt))
+        self._graphs.move_to_end(key)
         pool = self.model.fake_pool
         plan = None
         if pool.pool_size > 0:        # host half of the VectorPool, exactly once per iteration
             if pool.store is None:
                 return self._train_step_eager(batch, use_gt)
             plan = pool.plan(meta.objs_host)
+        if ent == 'warm' and not self._capturable():
+            return tuple(o.detach() if torch.is_tensor(o) else o for o in self._train_step_eager(batch, use_gt))
         if ent == 'warm':
             ent = _StepGraph(batch, meta, plan)
             ent.load(batch, meta, plan)
@@ -464,25 +556,64 @@ class Trainer:
                 finally:
                     self.model.pool_plan = None
             self._graphs[key] = ent
+            self._evict()
         else:
             ent.load(batch, meta, plan)
-        ent.graph.replay()
+        # replay: A | all-reduce(generator) on NCCL's stream | B | Cg on a side stream behind the all-reduce |
+        # all-reduce(discriminators) | Cd.  The same order of collectives as _train_step_eager.
+        g = ent.graphs
+        main = torch.cuda.current_stream()
+        side = self._side_streams[2]
+        g['A'].replay()
+        works = self._allreduce(('g',), async_op=True)
+        if not works:
+            side.wait_stream(main)    # Cg needs A's gradients only (with an all-reduce it waits for that instead)
+        g['B'].replay()
+        with torch.cuda.stream(side):
+            for w in works:
+                w.wait()              # stream-side wait: `side` waits for NCCL's stream
+            g['Cg'].replay()
+        self._allreduce([n for n, _ in self._d_nets()])
+        g['Cd'].replay()
+        main.wait_stream(side)
         _lib.add_launch_count(ent.launches)
         Fn.drop_unmaintained()        # the replay updated masters behind the version counters of the bf16 operand cache
         self.generator_losses, self.d_mask_losses, self.d_obj_losses, self.d_img_losses = ent.losses
         return ent.out
 
+    def _evict(self):
+        """keep at most _graph_cache_size captured geometries (least recently used go first)"""
+        captured = [k for k, v in self._graphs.items() if not isinstance(v, str)]
+        while len(captured) > max(1, self._graph_cache_size):
+            del self._graphs[captured.pop(0)]
+        warm = [k for k, v in self._graphs.items() if isinstance(v, str)]
+        while len(warm) > 4096:
+            del self._graphs[warm.pop(0)]
+
     def release_graphs(self):
         """forget every captured iteration (and the memory pool they share); the next train_step starts over with eager
-        sightings.  Call before destroying a process group whose collectives were captured."""
+        sightings."""
         self._graphs.clear()
         self._graph_pool = None
         self.generator_losses = self.d_mask_losses = self.d_obj_losses = self.d_img_losses = None
 
+    def _capturable(self):
+        """Adam creates a parameter's state at its first gradient and skips parameters without one (like the
+        reference's optimizer).  A capture would freeze a "no state yet" skip into the graph: wait until every trainable
+        parameter has had a gradient once (box_net gets its first one in the first use_gt iteration, train.py:195)."""
+        for opt in (self.optimizer, self.optimizer_d_obj, self.optimizer_d_mask, self.optimizer_d_img):
+            if opt is None:
+                continue
+            for group in opt.param_groups:
+                for p in group['params']:
+                    if p.requires_grad and len(opt.state.get(p, ())) == 0:
+                        return False
+        return True
+
     def _materialize_optimizer_state(self):
         """Adam creates a parameter's moments lazily at its first gradient (torch/optim/adam.py, _init_group).  Inside a
         capture that creation would be recorded — and the moments re-zeroed by every replay — so parameters that have
-        not had a gradient yet (box_net when every eager iteration so far had use_gt=False) get their state here."""
+        not had a gradient yet get their state here."""
         for opt in (self.optimizer, self.optimizer_d_obj, self.optimizer_d_mask, self.optimizer_d_img):
             if opt is None:
                 continue
@@ -495,40 +626,54 @@ class Trainer:
                         st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
 
     def _capture(self, ent, use_gt):
+        """capture the four graphs of one batch geometry into the shared pool (nothing executes; no collective is
+        captured).  thread_local capture mode: NCCL's watchdog thread may query its events meanwhile."""
         from . import _lib, ops
-        dev = ent.batch[0].device
         self._materialize_optimizer_state()
-        if self._side_streams is None and os.environ.get('SG_PARALLEL_D', '1') != '0':
+        if self._side_streams is None:
             self._side_streams = (torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream())
         Fn.drop_unmaintained()        # operands no optimizer keeps current are re-packed at their first use inside the graph
-        Fn.ARENA.ensure(dev)
         self.model.pool_plan = ent.pool_idx
-        two_branch_fwd = os.environ.get('SG_PARALLEL_FWD', '0') == '1'       # experimental, see Model._forward_train_two_branches
-        if two_branch_fwd:
+        parallel = os.environ.get('SG_PARALLEL_BRANCHES', '1') != '0'
+        if parallel and os.environ.get('SG_PARALLEL_FWD', '1') != '0':     # Model._forward_train_two_branches
             if self._fwd_stream is None:
                 self._fwd_stream = torch.cuda.Stream()
             self.model.graph_branch_stream = self._fwd_stream
-            ops.CACHE_STREAM[0] = False       # backward nodes of the side branch run on the side stream
-        mode = os.environ.get('SG_GRAPH_CAPTURE_MODE', 'global')
-        g = torch.cuda.CUDAGraph()
+        ops.CACHE_STREAM[0] = False   # backward nodes of a side branch run on that branch's stream
+        mode = os.environ.get('SG_GRAPH_CAPTURE_MODE', 'thread_local')
+        torch.cuda.synchronize()      # nothing of an earlier iteration (or of NCCL) in flight while capturing
+        graphs = {}
         n0 = _lib.launch_count()
-        try:
+        self._phased = True
+        self._branches = self._side_streams if parallel else None
+
+        def cap(name, fn):
+            g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=self._graph_pool, capture_error_mode=mode):
-                out = self._train_step_eager(ent.batch, use_gt, arena=True)
-                ent.out = tuple(o.detach() if torch.is_tensor(o) else o for o in out)
-                del out
+                r = fn()
+            if self._graph_pool is None:
+                self._graph_pool = g.pool()
+            graphs[name] = g
+            return r
+        try:
+            out = cap('A', lambda: self._phase_a(ent.batch, use_gt))
+            ent.out = tuple(o.detach() if torch.is_tensor(o) else o for o in out)
+            cap('B', self._phase_b)
+            cap('Cg', lambda: self._update('g', self.optimizer))
+            cap('Cd', self._phase_cd)
+            del out
         finally:
+            self._phased = False
+            self._branches = None
+            self._st = None
             self.model.pool_plan = None
             self.model.graph_branch_stream = None
             ops.CACHE_STREAM[0] = True
-            Fn.ARENA.end()
             ops.refresh_stream()      # the cached stream handle is the capture stream
             Fn.drop_unmaintained()
         ent.launches = _lib.launch_count() - n0
         ent.losses = (self.generator_losses, self.d_mask_losses, self.d_obj_losses, self.d_img_losses)
-        ent.graph = g
-        if self._graph_pool is None:
-            self._graph_pool = g.pool()
+        ent.graphs = graphs
 
     def write_losses(self, checkpoint, t):
         print('t = %d / %d' % (t, self.args.num_iterations))

@@ -29,22 +29,27 @@ def _worker(rank, world, port, ret):
     loss.backward()
     red.allreduce()
     ret[rank] = [p.grad.clone() for p in net.parameters()] + [p.detach().clone() for p in net.parameters()]
-    # bucketed variant: all-reduces launched from post-accumulate-grad hooks while backward is still running; two
-    # steps (the second with a different loss) must give exactly the gradients of the monolithic reducer
-    net2 = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2), torch.nn.Linear(2, 2))
-    net2.load_state_dict(net.state_dict())
-    red2 = ddp.FlatGradReducer(net2, bucket_mb=40 / (1 << 20))      # ~10 floats per bucket -> several buckets
-    assert red2.buckets is not None and len(red2.buckets) >= 3
-    outs = []
-    for step in range(2):
-        for r_, n_ in ((red, net), (red2, net2)):
-            r_.zero()
-            h = n_[1](n_[0](x))
-            loss = h.pow(2).mean() if step == 0 else (h.sum() + n_[2](h).pow(2).sum())
-            loss.backward()
-            r_.allreduce()
-        outs.append(all(torch.equal(a.grad, b.grad) for a, b in zip(net.parameters(), net2.parameters())))
-    ret['bucketed%d' % rank] = outs
+    # ranks with DIFFERENT local batch geometries (rank 0: 3 rows, rank 1: 5 rows) and several networks reduced in the
+    # trainer's fixed order (generator first, then the discriminators): every rank issues the same collectives in the
+    # same order whatever its local shapes are, and gets the mean of the per-rank gradients
+    nets = [torch.nn.Linear(4, 2) for _ in range(3)]
+    for n_ in nets:
+        ddp.broadcast_parameters(n_)
+    reds = [ddp.FlatGradReducer(n_) for n_ in nets]
+    xs = torch.arange(4 * (3 + 2 * rank), dtype=torch.float32).view(-1, 4) / 7 + rank
+    local = []
+    for r_, n_ in zip(reds, nets):
+        r_.zero()
+        n_(xs).pow(2).mean().backward()
+        local.append([p.grad.clone() for p in n_.parameters()])
+    works = [reds[0].allreduce(async_op=True)]          # gloo: finished on return (None), NCCL: a work handle
+    for r_ in reds[1:]:
+        r_.allreduce()
+    for w in works:
+        if w is not None:
+            w.wait()
+    ret['geo_local%d' % rank] = local
+    ret['geo%d' % rank] = [[p.grad.clone() for p in n_.parameters()] for n_ in nets]
     dist.destroy_process_group()
 
 
@@ -55,7 +60,10 @@ def test_flat_grad_allreduce_equals_big_batch_gradient():
     port = 29500 + os.getpid() % 2000
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     g0, g1 = ret[0], ret[1]
-    assert ret['bucketed0'] == [True, True] and ret['bucketed1'] == [True, True]
+    for k in range(3):
+        for j in range(2):
+            mean = (ret['geo_local0'][k][j] + ret['geo_local1'][k][j]) / 2
+            assert torch.allclose(ret['geo0'][k][j], mean, atol=1e-6) and torch.equal(ret['geo0'][k][j], ret['geo1'][k][j])
     assert torch.equal(ret['conv0'], ret['conv1']) and ret['conv0'].stride() == ret['conv1'].stride()
     for a, b in zip(g0, g1):
         assert torch.equal(a, b)                     # identical grads and params on both ranks

@@ -20,7 +20,7 @@ def main(path, out):
     rows = [(r['Kernel Name'], r['Grid Size'], float(r['Metric Value'].replace(',', ''))) for r in csv.DictReader(lines)]
     idx = [i for i, (n, _, _) in enumerate(rows) if 'layout_fwd' in n]
     starts = [i for k, i in enumerate(idx) if k == 0 or i - idx[k - 1] > 3]
-    if len(starts) >= 2:
+    if len(starts) >= 2 and '--whole' not in sys.argv:
         a, b = starts[-2], starts[-1]
     else:                      # capture taken with bench.py --profile-step: the file IS one step
         a, b = 0, len(rows)
