@@ -47,11 +47,39 @@ __global__ void sum_parts_kernel(const float* __restrict__ src, long n, int part
     }
   }
 }
+
+// Many parts, few elements (bias gradients: up to 296 partial rows of C floats): a serial loop per element would be one
+// long latency chain.  G groups of threads add the parts g, g + G, g + 2G, ... of an element each; the G group sums
+// are then added in group order.  The grouping depends only on (parts, G): still a fixed order.
+template <int G>
+__global__ void __launch_bounds__(256) sum_parts_grouped_kernel(const float* __restrict__ src, long n, int parts, long part_stride,
+                                                                float* __restrict__ dst) {
+  constexpr int COLS = 256 / G;
+  __shared__ float red[G][COLS];
+  const int col = threadIdx.x % COLS, g = threadIdx.x / COLS;
+  const long e = (long)blockIdx.x * COLS + col;
+  float acc = 0.f;
+  if (e < n)
+    for (int p = g; p < parts; p += G) acc += __ldcg(src + (long)p * part_stride + e);
+  red[g][col] = acc;
+  __syncthreads();
+  if (g == 0 && e < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < G; ++k) t += red[k][col];
+    dst[e] = t;
+  }
+}
 }  // namespace
 
 int sg_sum_parts(const float* src, long n, int parts, long part_stride, float* dst, cudaStream_t stream, const char* what) {
   if (n <= 0) return SG_OK;
-  sum_parts_kernel<<<sg_cdiv(sg_cdiv(n, 4), 256), 256, 0, stream>>>(src, n, parts, part_stride, dst);
+  if (parts > 64 && n <= 65536)
+    sum_parts_grouped_kernel<32><<<sg_cdiv(n, 8), 256, 0, stream>>>(src, n, parts, part_stride, dst);
+  else if (parts > 8 && n <= 65536)
+    sum_parts_grouped_kernel<8><<<sg_cdiv(n, 32), 256, 0, stream>>>(src, n, parts, part_stride, dst);
+  else
+    sum_parts_kernel<<<sg_cdiv(sg_cdiv(n, 4), 256), 256, 0, stream>>>(src, n, parts, part_stride, dst);
   SG_CHECK_LAUNCH(what);
   return SG_OK;
 }
