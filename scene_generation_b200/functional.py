@@ -28,6 +28,25 @@ ONE_WTAP = ((0, 0, 0, 0, 0, 0, 0),)
 _pack_cache = {}
 
 
+# Data parallel: every parameter's .grad is a view into its network's flat all-reduce buffer (ddp.FlatGradReducer),
+# zero-filled before backward.  AccumulateGrad would ADD each fresh gradient into it (257 add kernels per iteration);
+# instead, while a set is installed here (Trainer._backward), the first weight / bias gradient of a parameter in a
+# backward pass is written by its kernel straight into the view and the Function returns None for it; later
+# contributions to the same parameter (a network applied twice) go through autograd's accumulation as usual.
+DIRECT_GRADS = [None]
+
+
+def _direct_target(param, like):
+    """param.grad if this gradient may be written into it directly (see DIRECT_GRADS), else None"""
+    done = DIRECT_GRADS[0]
+    g = param.grad
+    if done is None or g is None or id(param) in done or g.dtype != torch.float32 or g.shape != param.shape \
+            or g.stride() != param.stride() or not g.is_cuda:
+        return None
+    done.add(id(param))
+    return g
+
+
 def master3(weight, kind):
     """f32 view (Cout, taps, Cin) of a Conv2d / ConvTranspose2d / Linear weight (no copy)."""
     if weight.dim() == 2:
@@ -326,11 +345,15 @@ class ConvFn(torch.autograd.Function):
         # ---- bias gradient ----------------------------------------------------------------------
         db = None
         if bias is not None and ctx.needs_input_grad[2]:
-            db = ops.colsum(dz5.reshape(-1, Coutp), Cout)
+            tgt = _direct_target(bias, None)
+            db = ops.colsum(dz5.reshape(-1, Coutp), Cout, out=tgt)
+            if tgt is not None:
+                db = None
         # ---- weight gradient ---------------------------------------------------------------------
         dw = None
         if ctx.needs_input_grad[1]:
-            g3 = torch.empty_like(m3)
+            tgt = _direct_target(weight, m3)
+            g3 = torch.empty_like(m3) if tgt is None else master3(tgt, spec.kind)
             g3_dense = g3
             if cmap is not None:    # per-image gradients of the gathered weights, scattered back below
                 g3 = torch.empty((N, Cout, taps_n, Cin), dtype=torch.float32, device=dy.device)
@@ -349,7 +372,7 @@ class ConvFn(torch.autograd.Function):
                 _lib.call('sg_wgrad_cmap_scatter', _ptr(g3), _ptr(cmap), N, Cout, taps_n, Cin, m3.shape[2], _ptr(g3_dense),
                           _stream())
                 g3 = g3_dense
-            dw = grad_like_weight(g3, weight, spec.kind)
+            dw = grad_like_weight(g3, weight, spec.kind) if tgt is None else None
         # ---- input gradient (in the operand's own format) ---------------------------------------
         dx = None
         if spec.need_dx and ctx.needs_input_grad[0]:
@@ -403,6 +426,7 @@ class LinearFn(torch.autograd.Function):
         ctx.act = act
         ctx.in_dtype = x.dtype
         ctx.K = K
+        ctx.bias_param = bias           # identity only (direct gradient writes); not needed for the arithmetic
         ctx.save_for_backward(xb, weight, y if act != _lib.ACT_NONE else None)
         return y
 
@@ -424,11 +448,15 @@ class LinearFn(torch.autograd.Function):
             else:
                 ops.conv_tc(dz5, packed_weights(weight, 's1')[0], dx, (0, 0, K, 1), 1, M, ONE_TAP, mn_cols=(0, K))
         if ctx.needs_input_grad[1]:
-            dw = torch.empty((Nout, 1, K), dtype=torch.float32, device=dy.device)
+            tgt = _direct_target(weight, None)
+            dw = torch.empty((Nout, 1, K), dtype=torch.float32, device=dy.device) if tgt is None else tgt.view(Nout, 1, K)
             ops.wgrad_tc(dz5, xb.view(1, 1, 1, M, xb.shape[1]), dw, 1, M, ONE_WTAP, Nout, K)
-            dw = dw.view(Nout, K)
+            dw = dw.view(Nout, K) if tgt is None else None
         if ctx.needs_input_grad[2]:
-            db = ops.colsum(dz, Nout)
+            tgt = _direct_target(ctx.bias_param, None) if ctx.bias_param is not None else None
+            db = ops.colsum(dz, Nout, out=tgt)
+            if tgt is not None:
+                db = None
         return dx, dw, db, None
 
 

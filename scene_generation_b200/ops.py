@@ -75,10 +75,12 @@ def stream_scratch(device):
     return ws
 
 
-def colsum(x2, C):
+def colsum(x2, C, out=None):
     """f32 (C,) column sums of a bf16 (rows, ld) matrix: bias gradients (fixed summation order)"""
     rows, ld = x2.shape
-    out = torch.empty((C,), dtype=torch.float32, device=x2.device)
+    if out is None:
+        out = torch.empty((C,), dtype=torch.float32, device=x2.device)
+    assert out.is_contiguous() and out.numel() == C and out.dtype == torch.float32
     ws = stream_scratch(x2.device)
     _lib.call('sg_colsum_bf16', _ptr(x2), rows, C, ld, _ptr(out), _ptr(ws), ws.numel(), _stream())
     return out

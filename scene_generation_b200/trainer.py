@@ -152,11 +152,13 @@ class Trainer:
         self._st = None               # tensors handed from one phase of the iteration to the next
         self.generator_losses = self.d_mask_losses = self.d_obj_losses = self.d_img_losses = None
         self.reducers = {}
-        if ddp.world_size() > 1:
+        # data parallel (or args.flat_grads, which tests use on one GPU): flat gradient buffers per network
+        if ddp.world_size() > 1 or getattr(args, 'flat_grads', False):
             for name, net in (('g', self.model), ('img', self.netD), ('obj', self.obj_discriminator),
                               ('mask', self.mask_discriminator)):
                 if net is not None:
-                    ddp.broadcast_parameters(net)
+                    if ddp.world_size() > 1:
+                        ddp.broadcast_parameters(net)
                     self.reducers[name] = ddp.FlatGradReducer(net)
 
     # ---- construction (trainer.py:30-134) ------------------------------------------------------
@@ -267,15 +269,21 @@ class Trainer:
     def _backward(self, name, optimizer, losses):
         from . import ops
         ops.refresh_stream()
-        if name in self.reducers:
+        direct = name in self.reducers
+        if direct:
             self.reducers[name].zero()            # .grad tensors are views of one flat buffer
+            Fn.DIRECT_GRADS[0] = set()            # weight / bias gradients are written straight into those views
         else:
             # None gradients: backward then hands its fresh tensors over instead of adding them into zero-filled ones
             # (257 add kernels per iteration).  A parameter without a gradient in a step (box_net when use_gt is False)
             # is skipped by Adam, where the reference's pytorch-1.0 zero_grad — and the data-parallel flat buffers —
             # apply its momentum-only update; DESIGN.md lists the difference.
             optimizer.zero_grad(set_to_none=True)
-        losses.total_loss.backward()
+        try:
+            losses.total_loss.backward()
+        finally:
+            if direct:
+                Fn.DIRECT_GRADS[0] = None
         # drop the autograd graph now: a loss kept for logging would keep this iteration's AccumulateGrad nodes (bound
         # to the stream they were created on) alive into the next iteration — fatal for a CUDA graph capture
         losses.total_loss = losses.total_loss.detach()

@@ -173,6 +173,33 @@ def test_graph_cache_is_bounded_and_restore_checkpoint_drops_graphs():
     _one_step(tr, metas[0].attach(tuple(t.to(DEV) for t in hbs[0])), noise, graph=None)
 
 
+def test_flat_gradient_buffers_give_the_plain_gradients():
+    """data-parallel plumbing on one GPU (args.flat_grads): .grad tensors are views of one flat buffer per network and
+    the weight / bias gradient kernels write into them directly — the iteration must end in the same bits as with
+    ordinary gradients, eagerly launched and replayed from the captured graphs"""
+    cfg = cases.CFG1
+    sds = R.make_state_dicts(cfg, seed=5)
+    H = cfg['image_size'][0]
+    hb = tuple(t.pin_memory() for t in synthetic.make_batch(2, (H, H), cfg['num_objs'], 3, 3, seed=1))
+    meta = synthetic.HostMeta(hb)
+    noise = cases.noise_for(21).to(DEV)
+    finals = []
+    for flat in (False, True, True):
+        a = sgargs.default_args(image_size=cfg['image_size'], num_objs=cfg['num_objs'], flat_grads=flat)
+        a.cuda_graphs = len(finals) == 2
+        tr = Trainer(a, synthetic.make_vocab(cfg['num_objs']), {})
+        for net, k in ((tr.model, 'g'), (tr.obj_discriminator, 'obj'), (tr.mask_discriminator, 'mask'), (tr.netD, 'img')):
+            net.load_state_dict(sds[k])
+        assert bool(tr.reducers) == flat
+        random.seed(5)
+        for i in range(3):               # use_gt every time: every parameter has a gradient (Adam skips None gradients)
+            _one_step(tr, meta.attach(tuple(t.to(DEV) for t in hb)), noise, graph=None)
+        finals.append({n: t.detach().clone() for n, t in _state_tensors(tr)})
+    for other in finals[1:]:
+        bad = [n for n in finals[0] if not torch.equal(finals[0][n], other[n])]
+        assert not bad, bad[:10]
+
+
 def argparse_ns(a):
     import copy, tempfile
     b = copy.copy(a)
