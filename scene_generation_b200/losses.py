@@ -49,8 +49,7 @@ class GANLoss(nn.Module):
 
 
 # ---------------------------------------------------------------------------------------------
-# VGG19 feature matching (losses.py:178-224) — SURVEY.md §8f-2.  NOT yet validated on hardware (written after the
-# round-1 GPU budget was spent): off unless --vgg_features_weight > 0; check with SG_TEST_VGG=1 pytest tests/test_gpu_vgg.py
+# VGG19 feature matching (losses.py:178-224) — SURVEY.md §8f-2; parity: tests/test_gpu_05_vgg.py (reference golden)
 # ---------------------------------------------------------------------------------------------
 _VGG_SLICES = ((0,), (2, 'M', 5), (7, 'M', 10), (12, 14, 16, 'M', 19), (21, 23, 25, 'M', 28))      # losses.py:187-196
 _VGG_CH = {0: (3, 64), 2: (64, 64), 5: (64, 128), 7: (128, 128), 10: (128, 256), 12: (256, 256), 14: (256, 256),

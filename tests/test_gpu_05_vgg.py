@@ -1,6 +1,5 @@
 """VGG19 feature-matching loss (losses.py:178-224) on the tensor-core conv kernel + the 2x2 max-pool kernels vs the
-reference golden (tests/golden/vgg.pt, written by the reference's own Vgg19 / VGGLoss with seeded weights).
-NOT yet validated on hardware (written after the round-1 GPU budget was spent): runs on request, SG_TEST_VGG=1."""
+reference golden (tests/golden/vgg.pt, written by the reference's own Vgg19 / VGGLoss with seeded weights)."""
 import os
 
 import pytest
@@ -10,8 +9,7 @@ import torch.nn.functional as F
 from oracle import restate as R
 from scene_generation_b200 import functional as Fn, losses
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('SG_TEST_VGG') != '1', reason='unvalidated path: set SG_TEST_VGG=1 to run')]
+pytestmark = pytest.mark.gpu
 DEV = 'cuda'
 GOLD = os.path.join(os.path.dirname(__file__), 'golden')
 

@@ -1,6 +1,11 @@
 """Whole training iteration (Model.forward + G step + 3 D steps + Adam) on the GPU vs the committed
-golden of the UNMODIFIED reference (tests/golden/step_cfg1.pt, BASELINE configs[0]).
-Tolerance: bf16 tensor-core path vs fp32 reference -> 6 % on every loss term."""
+golden of the UNMODIFIED reference (tests/golden/step_cfg1.pt, BASELINE configs[0]) and vs the CPU oracle at the
+benchmarked shapes (128x128, 172 classes, D = 204).
+
+Tolerances.  The CUDA path is bit-reproducible (no floating-point atomics), so every bound below is a fixed number set
+from ONE measurement (tests/diag_parity.py on a B200) with a 2x margin: bf16 tensor-core arithmetic vs the fp32
+reference moves the loss terms of one iteration by at most 0.68 % (0.37 % at 64x64, 0.68 % at 128x128; worst term:
+the mask discriminator's fake loss) -> LOSS_TOL = 1.5 %."""
 import os
 import random
 
@@ -14,6 +19,7 @@ from scene_generation_b200.trainer import Trainer
 pytestmark = pytest.mark.gpu
 DEV = 'cuda'
 GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+LOSS_TOL = 0.015
 
 
 def make_trainer(cfg, sds):
@@ -47,7 +53,7 @@ def test_train_step_losses_vs_reference_golden(use_gt, seed):
         mine = lm.all_losses
         for name, ref in g['%s_%s' % (tag, key)].items():
             assert name in mine, name
-            assert abs(mine[name] - ref) <= 0.06 * abs(ref) + 5e-3, (tag, name, mine[name], ref)
+            assert abs(mine[name] - ref) <= LOSS_TOL * abs(ref) + 1e-3, (tag, name, mine[name], ref)
     # one Adam step moves every element by ~lr*sign(grad): compare the update direction with the reference's
     lr = 1e-4
     nets = {'g': tr.model, 'obj': tr.obj_discriminator, 'mask': tr.mask_discriminator, 'img': tr.netD}
@@ -82,13 +88,19 @@ def test_two_steps_run_and_stay_finite_at_128():
                 assert v == v and abs(v) < 1e4, (name, v)
 
 
-def test_generator_step_gradients_vs_oracle_autograd():
+@pytest.mark.parametrize('shapes', ['cfg1', 'cfg2'])
+def test_generator_step_gradients_vs_oracle_autograd(shapes):
     """Gradients of the whole generator loss (through the three discriminators, the generator, the layout
-    scatter, the crop and the graph network) vs CPU autograd of the oracle on the same weights/batch."""
-    cfg = cases.CFG1
+    scatter, the crop and the graph network) vs CPU autograd of the oracle on the same weights/batch, at the
+    plumbing configuration (64x64, 4x4 bottleneck) and at the benchmarked shapes (128x128, D = 204, 8x8 bottleneck)."""
+    if shapes == 'cfg1':
+        cfg = cases.CFG1
+        batch_cpu = cases.cfg1_batch()
+    else:
+        cfg = dict(cases.CFG1, image_size=(128, 128), num_objs=172)
+        batch_cpu = synthetic.make_batch(2, (128, 128), 172, 3, 8, seed=1)
     sds = R.make_state_dicts(cfg, seed=5)
     tr = make_trainer(cfg, sds)
-    batch_cpu = cases.cfg1_batch()
     batch = [t.to(DEV) for t in batch_cpu]
     imgs, objs, boxes, masks, triples, o2i, t2i, attrs = batch
     noise = cases.noise_for(21)
@@ -117,13 +129,21 @@ def test_generator_step_gradients_vs_oracle_autograd():
         a, b = p.grad.detach().float().cpu().reshape(-1), ref.reshape(-1)
         rows.append((name, float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-30)), float(a.norm() / b.norm())))
     print('\n'.join('%-50s cos %.4f ratio %.3f' % r for r in rows))
-    # cfg-1 (64x64, batch 2) is the noisiest setting for a bf16 pipeline: InstanceNorm over 4x4 maps, L1 feature
-    # matching (sign gradients) and 30+ layers of ReLU gates between the loss and the first layers.  Offline analysis
-    # ("Parity") shows every adjoint kernel is exact on its own input; the thresholds bound the drift.
+    # Every adjoint kernel is exact on its own input (tests/diag_gimg.py: the gradient of each loss term w.r.t. a GIVEN
+    # image has cosine 0.993-0.999 and norm ratio 1.000 against autograd); what decays with depth is the agreement of
+    # the bf16 ACTIVATIONS the gradients are formed from (27 generator layers with InstanceNorm over 4x4 / 8x8 maps,
+    # ReLU gate flips, the sign gradient of the L1 feature matching).  Measured (reproducible): last generator layer
+    # 0.984 (cfg-1) / 0.993 (cfg-2 shapes), the four transposed convolutions before it 0.88-0.93 / 0.92-0.96, resblocks
+    # 0.85 / 0.9, minimum 0.75 (repr_net at cfg-2 shapes).
     ws = [r for r in rows if not r[0].endswith('.bias')]
-    bad = [r for r in ws if r[1] < 0.6]
+    by = dict((r[0], r) for r in ws)
+    assert by['layout_to_image.model.38.weight'][1] >= (0.975 if shapes == 'cfg1' else 0.985), by['layout_to_image.model.38.weight']
+    assert by['layout_to_image.model.34.weight'][1] >= (0.90 if shapes == 'cfg1' else 0.94), by['layout_to_image.model.34.weight']
+    for name in ('box_net.2.weight', 'mask_net.20.weight', 'mask_net.1.weight'):
+        assert by[name][1] >= 0.99, by[name]
+    bad = [r for r in ws if r[1] < 0.7]
     assert not bad, bad
-    assert sum(r[1] for r in ws) / len(ws) > 0.85
+    assert sum(r[1] for r in ws) / len(ws) > 0.88
 
 
 def test_inference_path_test_mode_eval_bn_vs_oracle():
@@ -160,6 +180,49 @@ def test_inference_path_test_mode_eval_bn_vs_oracle():
     assert torch.equal(bn.running_mean.cpu(), sds['g']['mask_net.2.running_mean'])     # eval mode must not touch them
 
 
+@pytest.mark.parametrize('compact', [True, False])
+@pytest.mark.parametrize('use_gt', [True, False])
+def test_cfg2_shapes_train_step_vs_oracle(compact, use_gt):
+    """The benchmarked shapes (BASELINE configs[1]: 128x128, COCO-Stuff vocabulary of 172 classes -> D = 204, 3-8
+    objects per image, 8x8 bottleneck) at batch 3, through Trainer.train_step with the channel-compacted layouts the
+    benchmark uses and with dense ones: Model.forward outputs and every loss term of the four sub-steps vs the oracle."""
+    cfg = dict(cases.CFG1, image_size=(128, 128), num_objs=172)
+    sds = R.make_state_dicts(cfg, seed=5)
+    hb = synthetic.make_batch(3, (128, 128), 172, 3, 8, seed=1)
+    meta = synthetic.HostMeta(hb)
+    tr = make_trainer(cfg, sds)
+    tr.use_graphs = False
+    tr.model.compact_layout = compact
+    batch = meta.attach(tuple(t.to(DEV) for t in hb))
+    noise = cases.noise_for(21)
+    oracle = R.OracleTrainer(sds, cfg)
+    random.seed(21)
+    fwd = oracle.step(hb, noise, use_gt=use_gt)
+    random.seed(21)
+    orig = torch.randn
+    torch.randn = lambda *a, **k: noise.to(DEV).clone()
+    try:
+        out = tr.train_step(batch, use_gt=use_gt)
+    finally:
+        torch.randn = orig
+    assert (getattr(out[3], '_sg_cmap', None) is not None) == compact
+    imgs_pred, boxes_pred, masks_pred = out[0].float().cpu(), out[1].float().cpu(), out[2].float().cpu()
+    assert (boxes_pred - fwd[1].detach()).abs().max() <= 2e-2 * fwd[1].detach().abs().max()
+    assert (masks_pred - fwd[2].detach()).abs().max() <= 3e-2                    # sigmoid outputs
+    assert (imgs_pred - fwd[0].detach()).abs().mean() <= 2.5e-2                  # tanh outputs, |x| <= 1 (measured 1.5e-2)
+    from scene_generation_b200 import layout as L
+    lay = L.expand_layout(out[3], 204).float().cpu()
+    ref_lay = fwd[3].detach()
+    assert lay.shape == ref_lay.shape
+    assert (lay - ref_lay).abs().max() <= 2e-2 * ref_lay.abs().max()
+    mine = {'g': tr.generator_losses.all_losses, 'mask': tr.d_mask_losses.all_losses, 'obj': tr.d_obj_losses.all_losses,
+            'img': tr.d_img_losses.all_losses}
+    for net, terms in oracle.losses.items():
+        for name, r in terms.items():
+            if name in mine[net]:
+                assert abs(mine[net][name] - r) <= LOSS_TOL * abs(r) + 1e-3, (net, name, mine[net][name], r)
+
+
 @pytest.mark.parametrize('size,kmin,kmax', [(256, 8, 15), (128, 29, 29)])
 def test_cfg4_cfg5_shapes_run(size, kmin, kmax):
     """BASELINE configs[3] (256x256, <=16 objects) and configs[4] (30-object graphs): shapes, tiles and the
@@ -180,11 +243,13 @@ def test_cfg4_cfg5_shapes_run(size, kmin, kmax):
 
 
 def _traj_tol(i, net, name):
-    """bf16 tensor-core arithmetic vs fp32: 6 % on the first iteration (the golden test's bound), +3 % per further
-    iteration.  The terms of the image-discriminator game are chaotic at batch 2 — two GPU runs of the SAME build were
-    measured 2.5 % below and 7.8 % above the oracle at iteration 1 — so they get 15 % + 5 % per iteration."""
+    """bf16 tensor-core arithmetic vs fp32 along a trajectory (weights, Adam moments, BN statistics and the pool carried
+    over).  Measured on a B200 (the CUDA path is bit-reproducible, so this is THE deviation, not a sample): iteration 0
+    0.4 %, then 1.1 % / 1.4 % / 1.9 % for every term except the image discriminator's own losses, which reach 5.2 % at
+    iteration 3 (two players' sign-like Adam steps feeding back).  Bounds: 1.5 % + 1 % per iteration; image-D terms
+    1.5 % + 3 % per iteration."""
     chaotic = net == 'img' or 'img' in name or name == 'total_loss'
-    return (0.15 + 0.05 * i) if chaotic else (0.06 + 0.03 * i)
+    return 0.015 + (0.03 if chaotic else 0.01) * i
 
 
 @pytest.mark.parametrize('graphs', [False, True])
@@ -232,9 +297,7 @@ def test_four_step_trajectory_vs_oracle(graphs):
     print('\n'.join('step %d %-5s %-26s gpu %.5f oracle %.5f rel %+.3f' % (i, net, name, m, r, (m - r) / (abs(r) + 1e-9))
                     for i, net, name, m, r in rows))
     for i, net, name, m, r in rows:
-        # bf16 tensor-core arithmetic vs fp32: 6 % on the first iteration (the golden test's bound); the adversarial terms
-        # feed back through both players' updates, so the bound widens by 3 % per further iteration
-        assert abs(m - r) <= _traj_tol(i, net, name) * abs(r) + 5e-3, (i, net, name, m, r)
+        assert abs(m - r) <= _traj_tol(i, net, name) * abs(r) + 1e-3, (i, net, name, m, r)
     # the same iterations of the UNMODIFIED reference (tests/golden/traj_cfg1.pt, written by oracle/gen_golden.py)
     gold = torch.load(os.path.join(GOLD, 'traj_cfg1.pt'))
     assert (gold['seed'], gold['noise_seed']) == (9, 21)
@@ -244,7 +307,7 @@ def test_four_step_trajectory_vs_oracle(graphs):
             for name, val in terms.items():
                 if (i, net, name) in mine_by_key:
                     m = mine_by_key[(i, net, name)]
-                    assert abs(m - val) <= (_traj_tol(i, net, name) + 0.01) * abs(val) + 5e-3, ('reference golden', i, net, name, m, val)
+                    assert abs(m - val) <= (_traj_tol(i, net, name) + 0.01) * abs(val) + 1e-3, ('reference golden', i, net, name, m, val)
     if graphs:
         assert tr.use_graphs and sum(1 for v in tr._graphs.values() if not isinstance(v, str)) == 2
     # the bbox loss must actually have moved (it barely does when stale operand weights are used)
