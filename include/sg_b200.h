@@ -37,11 +37,13 @@ void sg_add_launch_count(unsigned long long n); /* account launches replayed fro
 int sg_masks_to_layout_fwd(const float* vecs, const float* boxes, const void* masks, int mask_dtype,
                            const int* img_ranges, int O, int D, int M, int N, int H, int W,
                            int align_corners, int out_format, int Cp, void* out, sg_stream_t stream);
-/* d vecs (O,D) f32 always; d masks (O,M,M) f32 when dmasks != NULL. */
+/* d vecs (O,D) f32 always — columns outside [c_begin, c_end) (c_begin % 8 == 0; pass 0, D for all) are written as
+ * zeros: model.py:165-168 only the appearance part of a layout vector carries a gradient; d masks (O,M,M) f32 when
+ * dmasks != NULL.  ws: optional f32 scratch of 8*O*D floats (per-band partial sums, added in band order). */
 int sg_masks_to_layout_bwd(const float* vecs, const float* boxes, const void* masks, int mask_dtype,
                            const int* img_ranges, int O, int D, int M, int N, int H, int W,
-                           int align_corners, int grad_format, int Cp, const void* grad_out,
-                           float* dvecs, float* dmasks, sg_stream_t stream);
+                           int align_corners, int grad_format, int Cp, const void* grad_out, int c_begin, int c_end,
+                           float* dvecs, float* dmasks, float* ws, long long ws_floats, sg_stream_t stream);
 /* test_mode=True compositing (layout.py:157-169); mass_ws: O floats of workspace. */
 int sg_masks_to_layout_test(const float* vecs, const float* boxes, const void* masks, int mask_dtype,
                             const int* img_ranges, int O, int D, int M, int N, int H, int W,
@@ -171,6 +173,12 @@ int sg_probe_shifted_desc(const void* x, const void* w, float* y, int mode, sg_s
  * [N][H+k-1][W+k-1][Cin].  Cout <= 4, k <= 7, Cin in {32, 64}. */
 int sg_dgrad_small_cout(const void* dz, int dzC, const float* w, int Cout, int k, int Cin, int N, int H, int W,
                         void* dx, sg_stream_t stream);
+
+/* Tap-unrolled copy of the output gradient of a tiny-Cout stride-1 "valid" convolution over the PADDED pixel grid:
+ *   col[n,u,v, co*k*k + kh*k + kw] = dz[n, u-kh, v-kw, co]   (zero outside; bf16 [N][H+k-1][W+k-1][Kp], Kp % 8 == 0)
+ * so that both adjoints of the layer (generators.py:87) are ordinary tensor-core GEMMs: dgrad = sg_conv_tc with one
+ * tap over col (K = Cout*k*k), wgrad = sg_wgrad_tc with one tap (dy side = col, x side = the padded operand). */
+int sg_im2col_dz(const void* dz, int dzC, int Cout, int k, int N, int H, int W, int Kp, void* col, sg_stream_t stream);
 
 /* Weight gradient of the same layer (tiny Cout): dw[co,kh*k+kw,ci] = sum dz[n,h,w,co] * xop[n,h+kh,w+kw,ci]
  * with the pre-padded bf16 operand xop [N][H+k-1][W+k-1][64]; dw f32 [Cout][k*k][64] is overwritten.

@@ -97,7 +97,7 @@ _lib = None
 _P = c_void_p
 _SIGS = {
     'sg_masks_to_layout_fwd': [_P, _P, _P, c_int, _P] + [c_int] * 9 + [_P, _P],
-    'sg_masks_to_layout_bwd': [_P, _P, _P, c_int, _P] + [c_int] * 9 + [_P, _P, _P, _P],
+    'sg_masks_to_layout_bwd': [_P, _P, _P, c_int, _P] + [c_int] * 9 + [_P, c_int, c_int, _P, _P, _P, c_long, _P],
     'sg_masks_to_layout_test': [_P, _P, _P, c_int, _P] + [c_int] * 9 + [_P, _P, _P],
     'sg_gconv_gather_fwd': [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
     'sg_gconv_pool_fwd': [_P, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P],
@@ -131,6 +131,7 @@ _SIGS = {
                      ctypes.c_double, _P],
     'sg_wgrad_tc': [ctypes.POINTER(WgradDesc), _P],
     'sg_probe_shifted_desc': [_P, _P, _P, c_int, _P],
+    'sg_im2col_dz': [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
     'sg_dgrad_small_cout': [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
     'sg_wgrad_small_cout': [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_long, _P],
 }

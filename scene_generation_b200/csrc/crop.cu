@@ -54,16 +54,36 @@ __global__ void crop_fwd_kernel(CropArgs a, void* out) {
 // Adjoint as a GATHER (no atomics, fixed summation order): thread = one pixel (y, x) of image n; the boxes of that
 // image are visited in box order, their crop rows i and columns j in ascending order, and crop pixel (i, j) adds
 // wy * wx * g to the thread's accumulators when one of its four bilinear taps is (y, x).  The axis taps of a box
-// (HH + WW entries, the forward's own sg_axis values) are tabulated in shared memory once per CTA and box.
+// (HH + WW entries, the forward's own sg_axis values with the validity folded into the weights) are tabulated in
+// shared memory once per CTA and box.  The sample coordinate is linear in the crop index, so the crop rows / columns
+// that can touch pixel row y / column x form a short interval: it is estimated from the two end taps of the table
+// (with a margin) and every candidate is then checked against the exact table entry; degenerate boxes scan everything.
 constexpr int CROP_BWD_THREADS = 256;
 constexpr int CROP_MAX_C = 4;
+
+struct CropTap { int i0; float w0, w1; };       // weight 0 where the forward's tap was out of range
+
+// candidate interval [lo, hi) of crop indices whose tap rows can be `y`, from the table's end points (f ~ linear)
+__device__ __forceinline__ void crop_candidates(float f_first, float f_last, int n, int y, int& lo, int& hi) {
+  lo = 0; hi = n;
+  const float span = f_last - f_first;
+  if (n < 2 || !isfinite(span) || !(fabsf(span) > 1e-3f)) return;
+  const float step = span / (float)(n - 1);
+  float a = ((float)(y - 1) - f_first) / step, b = ((float)(y + 1) - f_first) / step;
+  if (a > b) { const float t = a; a = b; b = t; }
+  if (!isfinite(a) || !isfinite(b)) return;
+  lo = max(0, (int)floorf(fminf(a, (float)n)) - 2);
+  hi = min(n, (int)ceilf(fmaxf(b, -1.f)) + 3);
+  if (hi < lo) hi = lo;
+}
 
 template <bool NHWC_BF16>
 __global__ void __launch_bounds__(CROP_BWD_THREADS) crop_bwd_kernel(CropArgs a, const void* grad, float* dfeats) {
   extern __shared__ unsigned char crop_smem[];
-  SgBilin* sAx = reinterpret_cast<SgBilin*>(crop_smem);      // [WW]
-  SgBilin* sAy = sAx + a.WW;                                  // [HH]
-  unsigned char* sMine = reinterpret_cast<unsigned char*>(sAy + a.HH);   // [B]: box b crops this CTA's image
+  CropTap* sAx = reinterpret_cast<CropTap*>(crop_smem);      // [WW]
+  CropTap* sAy = sAx + a.WW;                                  // [HH]
+  float* sF = reinterpret_cast<float*>(sAy + a.HH);           // [4]: un-normalised coordinate of the first / last tap per axis
+  unsigned char* sMine = reinterpret_cast<unsigned char*>(sF + 4);   // [B]: box b crops this CTA's image
   const int n = blockIdx.y;
   for (int b = threadIdx.x; b < a.B; b += CROP_BWD_THREADS) sMine[b] = a.map[b] == n;
   __syncthreads();
@@ -79,21 +99,40 @@ __global__ void __launch_bounds__(CROP_BWD_THREADS) crop_bwd_kernel(CropArgs a, 
     for (int t = threadIdx.x; t < a.WW + a.HH; t += CROP_BWD_THREADS) {
       SgBilin ax, ay;
       crop_axes(a, b, t < a.WW ? 0 : t - a.WW, t < a.WW ? t : 0, ax, ay);
-      if (t < a.WW) sAx[t] = ax; else sAy[t - a.WW] = ay;
+      const SgBilin& s = t < a.WW ? ax : ay;
+      CropTap tap;
+      tap.i0 = s.i0;
+      tap.w0 = s.ok0 ? s.w0 : 0.f;
+      tap.w1 = s.ok1 ? s.w1 : 0.f;
+      if (t < a.WW) sAx[t] = tap; else sAy[t - a.WW] = tap;
+      // i0 + w1 is the un-normalised sample coordinate (w1 = frac) wherever the tap is finite and sg_axis did not clamp
+      // the index (coordinates far outside the image): otherwise no estimate -> every crop index is a candidate
+      const int size = t < a.WW ? a.W : a.H;
+      const bool fin = (s.w0 != 0.f || s.w1 != 0.f) && s.i0 > -2 && s.i0 < size + 1;
+      const float f = fin ? (float)s.i0 + s.w1 : __int_as_float(0x7fc00000);
+      if (t == 0) sF[0] = f;
+      if (t == a.WW - 1) sF[1] = f;
+      if (t == a.WW) sF[2] = f;
+      if (t == a.WW + a.HH - 1) sF[3] = f;
     }
     __syncthreads();
-    for (int i = 0; i < a.HH; ++i) {
-      const SgBilin ay = sAy[i];
-      float wy = 0.f;
-      if (ay.ok0 && ay.i0 == y) wy = ay.w0;
-      else if (ay.ok1 && ay.i0 + 1 == y) wy = ay.w1;
+    int ilo, ihi, jlo, jhi;
+    crop_candidates(sF[2], sF[3], a.HH, y, ilo, ihi);
+    crop_candidates(sF[0], sF[1], a.WW, x, jlo, jhi);
+    for (int i = ilo; i < ihi; ++i) {
+      const CropTap ay = sAy[i];
+      float wy;
+      if (ay.i0 == y) wy = ay.w0;
+      else if (ay.i0 + 1 == y) wy = ay.w1;
       else continue;
-      for (int j = 0; j < a.WW; ++j) {
-        const SgBilin ax = sAx[j];
+      if (wy == 0.f) continue;
+      for (int j = jlo; j < jhi; ++j) {
+        const CropTap ax = sAx[j];
         float wx;
-        if (ax.ok0 && ax.i0 == x) wx = ax.w0;
-        else if (ax.ok1 && ax.i0 + 1 == x) wx = ax.w1;
+        if (ax.i0 == x) wx = ax.w0;
+        else if (ax.i0 + 1 == x) wx = ax.w1;
         else continue;
+        if (wx == 0.f) continue;
         const float wgt = wx * wy;
         if (NHWC_BF16) {
           const __nv_bfloat16* g = (const __nv_bfloat16*)grad + (((long)b * a.HH + i) * a.WW + j) * a.Cp;
@@ -140,7 +179,7 @@ extern "C" int sg_crop_bbox_bwd(const float* boxes, const long long* box_to_feat
   SG_CHECK_ARG(C <= CROP_MAX_C, "crop_bbox_bwd: at most %d feature channels (images)", CROP_MAX_C);
   // every pixel of every image is written by exactly one thread (zeros where no crop touches it): B == 0 included
   dim3 grid(sg_cdiv((long)H * W, CROP_BWD_THREADS), N);
-  const size_t smem = sizeof(SgBilin) * (size_t)(HH + WW) + (size_t)B + 16;
+  const size_t smem = sizeof(CropTap) * (size_t)(HH + WW) + 16 + (size_t)B + 16;
   SG_CHECK_ARG(smem <= 48 * 1024, "crop_bbox_bwd: too many boxes / too large crops for the shared-memory tables");
   if (grad_format == 1) crop_bwd_kernel<true><<<grid, CROP_BWD_THREADS, smem, stream>>>(a, grad_out, dfeats);
   else crop_bwd_kernel<false><<<grid, CROP_BWD_THREADS, smem, stream>>>(a, grad_out, dfeats);

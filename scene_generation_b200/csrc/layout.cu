@@ -6,6 +6,7 @@
 // The reference materialises (O,D,M,M) and (O,D,H,W) tensors; here S_o is evaluated once per
 // (object, pixel) into shared memory and the D channels are produced by FMAs from it, so the only
 // HBM traffic is the output write (fwd) / the gradient read (bwd): N*Cp*H*W*s bytes.
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/sg_b200.h"
 
@@ -366,23 +367,31 @@ __device__ __forceinline__ void object_rect(const LayoutArgs& a, const float* bx
   h_hi = (int)fmaxf(fminf(hu, (float)(a.H - 1)), -1.f);
 }
 
-constexpr int BWD_CW = 16;    // channels per CTA of the dvecs kernel (32 B of an NHWC bf16 pixel)
+constexpr int BWD_CW = 32;    // channels per CTA of the dvecs kernel (64 B of an NHWC bf16 pixel)
+constexpr int BWD_BANDS = 8;  // horizontal bands of an image, one CTA each (partial sums added in band order)
 
-// dvecs.  grid = (channel slabs of BWD_CW, images).  The CTA walks the objects of its image in order; for each, its
-// 256 threads stride over the pixels of the object's rectangle (rows, then columns), each keeping BWD_CW partial sums;
-// these are combined by a shuffle tree inside each warp and then over the 8 warps in warp order.
+// dvecs.  grid = (channel slabs of BWD_CW inside [c_begin, c_end), images, bands).  The CTA walks the objects of its
+// image in order; for each, its 256 threads stride over the pixels of the object's rectangle inside the band (rows,
+// then columns), each keeping BWD_CW partial sums; these are combined by a shuffle tree inside each warp and then
+// over the 8 warps in warp order, and stored to part[band][o][c].  sg_sum_parts adds the bands in band order.
 template <bool NHWC_BF16>
-__global__ void __launch_bounds__(THREADS) layout_bwd_vecs_kernel(LayoutArgs a, const void* grad, float* dvecs) {
+__global__ void __launch_bounds__(THREADS) layout_bwd_vecs_kernel(LayoutArgs a, const void* grad, int c_begin, int bands,
+                                                                  float* part) {
   __shared__ float red[THREADS / 32][BWD_CW];
   const int n = blockIdx.y;
-  const int c0 = blockIdx.x * BWD_CW;
+  const int c0 = c_begin + blockIdx.x * BWD_CW;
   const int HW = a.H * a.W;
+  const int band_h = (a.H + bands - 1) / bands;
+  const int b_lo = blockIdx.z * band_h, b_hi = min(a.H, b_lo + band_h) - 1;
   const int o_begin = a.ranges[2 * n], o_end = a.ranges[2 * n + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* dst = part + (long)blockIdx.z * a.O * a.D;
   for (int o = o_begin; o < o_end; ++o) {
     const float* bx = a.boxes + 4 * o;
     int h_lo, h_hi, w_lo, w_hi;
     object_rect(a, bx, h_lo, h_hi, w_lo, w_hi);
+    h_lo = max(h_lo, b_lo);
+    h_hi = min(h_hi, b_hi);
     const int rw = w_hi - w_lo + 1, rh = h_hi - h_lo + 1;
     float acc[BWD_CW];
 #pragma unroll
@@ -394,17 +403,17 @@ __global__ void __launch_bounds__(THREADS) layout_bwd_vecs_kernel(LayoutArgs a, 
         if (sv == 0.f) continue;
         if (NHWC_BF16) {
           const __nv_bfloat16* g = (const __nv_bfloat16*)grad + ((long)n * HW + (long)h * a.W + w) * a.Cp + c0;
-          const uint4 r0 = *reinterpret_cast<const uint4*>(g);
-          const uint4 r1 = (c0 + 8 < a.Cp) ? *reinterpret_cast<const uint4*>(g + 8) : make_uint4(0, 0, 0, 0);
-          const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
-          const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f0 = __bfloat1622float2(h0[j]), f1 = __bfloat1622float2(h1[j]);
-            acc[2 * j] = __fmaf_rn(sv, f0.x, acc[2 * j]);
-            acc[2 * j + 1] = __fmaf_rn(sv, f0.y, acc[2 * j + 1]);
-            acc[8 + 2 * j] = __fmaf_rn(sv, f1.x, acc[8 + 2 * j]);
-            acc[8 + 2 * j + 1] = __fmaf_rn(sv, f1.y, acc[8 + 2 * j + 1]);
+          for (int q = 0; q < BWD_CW / 8; ++q) {
+            if (c0 + 8 * q >= a.Cp) break;
+            const uint4 r0 = *reinterpret_cast<const uint4*>(g + 8 * q);
+            const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f0 = __bfloat1622float2(h0[j]);
+              acc[8 * q + 2 * j] = __fmaf_rn(sv, f0.x, acc[8 * q + 2 * j]);
+              acc[8 * q + 2 * j + 1] = __fmaf_rn(sv, f0.y, acc[8 * q + 2 * j + 1]);
+            }
           }
         } else {
           const float* g = (const float*)grad + (long)n * a.D * HW + (long)h * a.W + w;
@@ -430,7 +439,7 @@ __global__ void __launch_bounds__(THREADS) layout_bwd_vecs_kernel(LayoutArgs a, 
     if (threadIdx.x < BWD_CW && c0 + threadIdx.x < a.D) {
       float v = 0.f;
       for (int wq = 0; wq < THREADS / 32; ++wq) v += red[wq][threadIdx.x];
-      dvecs[(long)o * a.D + c0 + threadIdx.x] = v;
+      dst[(long)o * a.D + c0 + threadIdx.x] = v;
     }
   }
 }
@@ -620,21 +629,30 @@ extern "C" int sg_masks_to_layout_fwd(const float* vecs, const float* boxes, con
 
 extern "C" int sg_masks_to_layout_bwd(const float* vecs, const float* boxes, const void* masks, int mask_dtype,
                                       const int* img_ranges, int O, int D, int M, int N, int H, int W,
-                                      int align_corners, int grad_format, int Cp, const void* grad_out,
-                                      float* dvecs, float* dmasks, cudaStream_t stream) {
+                                      int align_corners, int grad_format, int Cp, const void* grad_out, int c_begin, int c_end,
+                                      float* dvecs, float* dmasks, float* ws, long long ws_floats, cudaStream_t stream) {
   LayoutArgs a{vecs, boxes, masks, img_ranges, mask_dtype, O, D, M, N, H, W, Cp, align_corners};
   if (int e = check_args(a, grad_format)) return e;
   SG_CHECK_ARG(dvecs != nullptr, "masks_to_layout_bwd: dvecs is null");
   SG_CHECK_ARG(!dmasks || M <= THREADS, "masks_to_layout_bwd: mask size must be <= %d for the mask gradient", THREADS);
   if (O == 0) return SG_OK;
-  // objects outside every image range (none in a well-formed batch) get zero gradients
-  cudaMemsetAsync(dvecs, 0, sizeof(float) * (size_t)O * D, stream);
+  SG_CHECK_ARG(c_begin >= 0 && c_begin % 8 == 0 && c_begin < c_end && c_end <= D,
+               "masks_to_layout_bwd: channel range [%d, %d) must start at a multiple of 8 inside [0, %d]", c_begin, c_end, D);
+  const long per = (long)O * D;
+  // image height bands: more CTAs for the few, large images of a batch (each band leaves one partial row set)
+  int bands = H >= 64 ? BWD_BANDS : 1;
+  if (ws == nullptr || ws_floats < (long long)bands * per) bands = 1;
+  float* part = bands > 1 ? ws : dvecs;
+  // channels outside [c_begin, c_end) and objects outside every image range (none in a well-formed batch): zero
+  cudaMemsetAsync(part, 0, sizeof(float) * (size_t)bands * per, stream);
   if (N > 0) {
-    dim3 grid(sg_cdiv(grad_format == 1 ? Cp : D, BWD_CW), N);
-    if (grad_format == 1) layout_bwd_vecs_kernel<true><<<grid, THREADS, 0, stream>>>(a, grad_out, dvecs);
-    else layout_bwd_vecs_kernel<false><<<grid, THREADS, 0, stream>>>(a, grad_out, dvecs);
+    dim3 grid(sg_cdiv(c_end - c_begin, BWD_CW), N, bands);
+    if (grad_format == 1) layout_bwd_vecs_kernel<true><<<grid, THREADS, 0, stream>>>(a, grad_out, c_begin, bands, part);
+    else layout_bwd_vecs_kernel<false><<<grid, THREADS, 0, stream>>>(a, grad_out, c_begin, bands, part);
     SG_CHECK_LAUNCH("sg_masks_to_layout_bwd");
   }
+  if (bands > 1)
+    if (int e = sg_sum_parts(part, per, bands, per, dvecs, stream, "sg_masks_to_layout_bwd(sum bands)")) return e;
   if (dmasks) {
     size_t smem = sizeof(float) * ((size_t)D + W + (size_t)M * M) + sizeof(SgBilin) * (size_t)W + 16;
     if (grad_format == 1) {

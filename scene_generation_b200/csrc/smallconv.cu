@@ -142,7 +142,50 @@ __global__ void wgrad_small_reduce_kernel(const float* __restrict__ ws, int n_bl
   dw[e] = v;
 }
 
+// Tap-unrolled copy of the output gradient of a tiny-Cout convolution ("im2col along K"):
+//   col[n, u, v, co * k*k + kh * k + kw] = dz[n, u - kh, v - kw, co]     (zero outside, u < H+k-1, v < W+k-1)
+// With it both adjoints of the layer are ordinary tensor-core GEMMs over the PADDED pixel grid:
+//   dgrad  dx[n,u,v,ci]        = sum_K col[n,u,v,K] * wcol[ci][K]                (sg_conv_tc, one tap, K = Cout*k*k)
+//   wgrad  dw[co, tap, ci]     = sum_{n,u,v} col[n,u,v,co*k*k+tap] * xop[n,u,v,ci]   (sg_wgrad_tc, one tap)
+// instead of GEMMs whose contraction (dgrad) or output (wgrad) dimension is 3.  thread = (pixel, 8-channel chunk).
+__global__ void im2col_dz_kernel(const __nv_bfloat16* __restrict__ dz, int dzC, int Cout, int k, int N, int H, int W, int Kp,
+                                 __nv_bfloat16* __restrict__ col) {
+  const int chunks = Kp / 8;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int Hp = H + k - 1, Wp = W + k - 1;
+  const long total = (long)N * Hp * Wp * chunks;
+  if (idx >= total) return;
+  const int ch = (int)(idx % chunks);
+  long r = idx / chunks;
+  const int v = (int)(r % Wp); r /= Wp;
+  const int u = (int)(r % Hp);
+  const int n = (int)(r / Hp);
+  const int taps = k * k;
+  __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int K = ch * 8 + j;
+    __nv_bfloat16 val = __float2bfloat16(0.f);
+    if (K < Cout * taps) {
+      const int co = K / taps, tap = K - co * taps;
+      const int h = u - tap / k, x = v - tap % k;
+      if (h >= 0 && h < H && x >= 0 && x < W) val = dz[(((long)n * H + h) * W + x) * dzC + co];
+    }
+    o[j] = val;
+  }
+  *reinterpret_cast<uint4*>(col + idx * 8) = *reinterpret_cast<const uint4*>(o);
+}
+
 }  // namespace
+
+extern "C" int sg_im2col_dz(const void* dz, int dzC, int Cout, int k, int N, int H, int W, int Kp, void* col, sg_stream_t stream) {
+  SG_CHECK_ARG(dz && col && Cout >= 1 && dzC >= Cout && k >= 1 && N > 0 && H > 0 && W > 0, "im2col_dz: bad arguments");
+  SG_CHECK_ARG(Kp % 8 == 0 && Kp >= Cout * k * k, "im2col_dz: Kp must be a multiple of 8 >= Cout*k*k");
+  const long total = (long)N * (H + k - 1) * (W + k - 1) * (Kp / 8);
+  im2col_dz_kernel<<<sg_cdiv(total, 256), 256, 0, stream>>>((const __nv_bfloat16*)dz, dzC, Cout, k, N, H, W, Kp, (__nv_bfloat16*)col);
+  SG_CHECK_LAUNCH("sg_im2col_dz");
+  return SG_OK;
+}
 
 extern "C" int sg_wgrad_small_cout(const void* dz, int dzC, const void* xop, int Cout, int k, int Cin, int N, int H, int W,
                                    float* dw, float* ws, long long ws_floats, sg_stream_t stream) {

@@ -72,6 +72,9 @@ def grad_like_weight(g3, weight, kind):
 # SG_DGRAD_WT=1: dgrad reads a second, transposed bf16 copy [Cin][taps][Cout] (K-major B operand) instead of the
 # fprop copy through the MN-major-B kernel variant (A/B switch; costs one more pack kernel per weight and step)
 DGRAD_WT = os.environ.get('SG_DGRAD_WT', '0') == '1'
+# SG_SMALL_COUT_TC=0: adjoints of tiny-Cout convolutions as direct CUDA-core kernels instead of tap-unrolled
+# tensor-core GEMMs (A/B switch)
+SMALL_COUT_TC = os.environ.get('SG_SMALL_COUT_TC', '1') != '0'
 
 
 def packed_weights(weight, kind, need_t=False):
@@ -351,13 +354,25 @@ class ConvFn(torch.autograd.Function):
                 db = None
         # ---- weight gradient ---------------------------------------------------------------------
         dw = None
+        col = None                # tap-unrolled dz of a tiny-Cout convolution, shared by its wgrad and dgrad
         if ctx.needs_input_grad[1]:
             tgt = _direct_target(weight, m3)
             g3 = torch.empty_like(m3) if tgt is None else master3(tgt, spec.kind)
             g3_dense = g3
             if cmap is not None:    # per-image gradients of the gathered weights, scattered back below
                 g3 = torch.empty((N, Cout, taps_n, Cin), dtype=torch.float32, device=dy.device)
-            if spec.kind == 's1' and spec.pad == 0 and Cout <= 3 and Cin == 64 and x5.shape[4] == 64 and spec.k in (3, 7) \
+            small = spec.kind == 's1' and spec.pad == 0 and Cout <= 4 and Cin == x5.shape[4] and Cin % 8 == 0 and cmap is None \
+                and dz5.shape[1] == 1 and SMALL_COUT_TC
+            if small:
+                # tiny Cout (the generator's 64 -> 3 output conv): tap-unrolled dz, then ordinary tensor-core GEMMs over
+                # the padded pixel grid for both adjoints (csrc/smallconv.cu)
+                kk = spec.k * spec.k
+                Kp = round_up(Cout * kk, 8)
+                Hp, Wp = x5.shape[2], x5.shape[3]
+                col = torch.empty((N, 1, Hp, Wp, Kp), dtype=BF, device=dy.device)
+                _lib.call('sg_im2col_dz', _ptr(dz5), dz5.shape[4], Cout, spec.k, N, Ho, Wo, Kp, _ptr(col), _stream())
+                ops.wgrad_tc(col, x5, g3.view(Cout * kk, 1, Cin), Hp, Wp, ONE_WTAP, Cout * kk, Cin)
+            elif spec.kind == 's1' and spec.pad == 0 and Cout <= 3 and Cin == 64 and x5.shape[4] == 64 and spec.k in (3, 7) \
                     and dz5.shape[1] == 1:
                 ws = torch.empty(296 * g3.numel(), dtype=torch.float32, device=dy.device)     # SG_WGRAD_SMALL_BLOCKS partials
                 _lib.call('sg_wgrad_small_cout', _ptr(dz5), dz5.shape[4], _ptr(x5), Cout, spec.k, Cin, N, Ho, Wo, _ptr(g3),
@@ -390,7 +405,17 @@ class ConvFn(torch.autograd.Function):
                 wsub, wsel = wt, dict(w_rows=(c0, c1))
             _, P, Hx, Wx, _ = x5.shape
             base = dx.view(-1)[c0:]
-            if spec.kind == 's1' and spec.pad == 0 and Cout <= 4 and Cin in (32, 64) and Cx == Cin and not partial \
+            if spec.kind == 's1' and spec.pad == 0 and Cout <= 4 and Cx == Cin and Cin % 8 == 0 and not partial and cmap is None \
+                    and dz5.shape[1] == 1 and SMALL_COUT_TC:
+                kk = spec.k * spec.k
+                Kp = round_up(Cout * kk, 8)
+                if col is None:
+                    col = torch.empty((N, 1, Hx, Wx, Kp), dtype=BF, device=dy.device)
+                    _lib.call('sg_im2col_dz', _ptr(dz5), dz5.shape[4], Cout, spec.k, N, Ho, Wo, Kp, _ptr(col), _stream())
+                # wcol[ci][co*kk + tap] = w[co][tap][ci]: the (Cin, Cout*kk) transpose of the master, as a 1-tap operand
+                wcol = cast_pad(m3.detach().permute(2, 0, 1).reshape(Cin, Cout * kk), Kp).view(Cin, 1, Kp)
+                ops.conv_tc(col, wcol, base, (Hx * Wx * Cx, Wx * Cx, Cx, 1), Hx, Wx, ONE_TAP)
+            elif spec.kind == 's1' and spec.pad == 0 and Cout <= 4 and Cin in (32, 64) and Cx == Cin and not partial \
                     and dz5.shape[1] == 1:
                 # tiny Cout (the 64 -> 3 output conv): direct CUDA-core dgrad instead of a K=3 tensor-core GEMM
                 _lib.call('sg_dgrad_small_cout', _ptr(dz5), dz5.shape[4], _ptr(m3), Cout, spec.k, Cin, N, Ho, Wo, _ptr(dx),
@@ -412,20 +437,21 @@ def conv(x5, weight, bias, spec, cmap=None):
 
 
 class LinearFn(torch.autograd.Function):
-    """nn.Linear (+ fused ReLU) as a 1-tap tcgen05 GEMM (layers.py:215-231, graph.py:85,120)."""
+    """nn.Linear (+ fused ReLU) as a 1-tap tcgen05 GEMM (layers.py:215-231, graph.py:85,120).  x: f32 (M, K), or a bf16
+    operand (M, Kp >= K) whose pad columns are zero (the graph gather writes that directly)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, act):
         wk, _ = packed_weights(weight, 's1')
-        M, K = x.shape
-        Nout = weight.shape[0]
+        M, Kx = x.shape
+        Nout, K = weight.shape
         xb = cast_pad(x) if x.dtype != BF else x
+        assert xb.shape[1] == wk.shape[2] and Kx in (K, wk.shape[2])
         y = torch.empty((M, Nout), dtype=torch.float32, device=x.device)
         if M > 0:
             ops.conv_tc(xb.view(1, 1, 1, M, xb.shape[1]), wk, y, (0, 0, Nout, 1), 1, M, ONE_TAP, bias=bias, act=act)
         ctx.act = act
-        ctx.in_dtype = x.dtype
-        ctx.K = K
+        ctx.Kx = Kx
         ctx.bias_param = bias           # identity only (direct gradient writes); not needed for the arithmetic
         ctx.save_for_backward(xb, weight, y if act != _lib.ACT_NONE else None)
         return y
@@ -433,20 +459,22 @@ class LinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         xb, weight, y = ctx.saved_tensors
-        M, Nout, K = dy.shape[0], weight.shape[0], ctx.K
+        M, (Nout, K), Kx = dy.shape[0], weight.shape, ctx.Kx
         Np = round_up(Nout, 8)
         dz = cast_pad(dy, Np, mask_y=y, slope=0.0)
         dz5 = dz.view(1, 1, 1, M, Np)
         dx = dw = db = None
         if M == 0:
-            return (torch.zeros((0, K), device=dy.device) if ctx.needs_input_grad[0] else None,
+            return (torch.zeros((0, Kx), device=dy.device) if ctx.needs_input_grad[0] else None,
                     torch.zeros_like(weight), torch.zeros(Nout, device=dy.device), None)
         if ctx.needs_input_grad[0]:
-            dx = torch.empty((M, K), dtype=torch.float32, device=dy.device)
+            # Kx > K (padded bf16 input): the pad columns of the operand weights are zero, so are those of dx
+            dx = torch.empty((M, Kx), dtype=torch.float32, device=dy.device)
             if DGRAD_WT:
+                assert Kx == K
                 ops.conv_tc(dz5, packed_weights(weight, 's1', need_t=True)[1], dx, (0, 0, K, 1), 1, M, ONE_TAP)
             else:
-                ops.conv_tc(dz5, packed_weights(weight, 's1')[0], dx, (0, 0, K, 1), 1, M, ONE_TAP, mn_cols=(0, K))
+                ops.conv_tc(dz5, packed_weights(weight, 's1')[0], dx, (0, 0, Kx, 1), 1, M, ONE_TAP, mn_cols=(0, Kx))
         if ctx.needs_input_grad[1]:
             tgt = _direct_target(weight, None)
             dw = torch.empty((Nout, 1, K), dtype=torch.float32, device=dy.device) if tgt is None else tgt.view(Nout, 1, K)
@@ -574,20 +602,23 @@ class LayoutFn(torch.autograd.Function):
     the reference's (N,D,H,W) f32 tensor."""
 
     @staticmethod
-    def forward(ctx, vecs, boxes, masks, ranges, H, W, align_corners, nhwc_bf16, Cp=None):
+    def forward(ctx, vecs, boxes, masks, ranges, H, W, align_corners, nhwc_bf16, Cp=None, grad_channels=None):
+        """grad_channels=(c0, c1): only these columns of vecs carry a gradient (model.py:165-168: the one-hot part of a
+        layout vector is a constant); the adjoint computes just them, the other columns of d vecs are zero."""
         fmt = ops.NHWC_BF16 if nhwc_bf16 else ops.NCHW_F32
         out = ops.masks_to_layout_fwd(vecs, boxes, masks, ranges, H, W, align_corners, fmt, raw=True, Cp=Cp)
         ctx.save_for_backward(vecs, boxes, masks, ranges)
-        ctx.cfg = (H, W, align_corners)
+        ctx.cfg = (H, W, align_corners, grad_channels)
         return out
 
     @staticmethod
     def backward(ctx, g):
         vecs, boxes, masks, ranges = ctx.saved_tensors
-        H, W, ac = ctx.cfg
+        H, W, ac, chans = ctx.cfg
         need_dm = ctx.needs_input_grad[2] and masks.is_floating_point()
-        dv, dm = ops.masks_to_layout_bwd(vecs, boxes, masks, ranges, H, W, g.contiguous(), ac, need_dmasks=need_dm)
-        return dv, None, dm, None, None, None, None, None, None
+        dv, dm = ops.masks_to_layout_bwd(vecs, boxes, masks, ranges, H, W, g.contiguous(), ac, need_dmasks=need_dm,
+                                         channels=chans)
+        return dv, None, dm, None, None, None, None, None, None, None
 
 
 class CropFn(torch.autograd.Function):

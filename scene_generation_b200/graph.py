@@ -53,7 +53,8 @@ class GraphTripleConv(nn.Module):
         if index is None:
             index = GraphIndex(edges, obj_vecs.size(0))
         H, Dout = self.hidden_dim, self.output_dim
-        cur_t = Fn.GatherFn.apply(obj_vecs, pred_vecs, index.edges, index.seg_ptr, index.seg_src, False)
+        # the gather writes the bf16 operand of net1's first GEMM directly (columns padded to a multiple of 8 with zeros)
+        cur_t = Fn.GatherFn.apply(obj_vecs, pred_vecs, index.edges, index.seg_ptr, index.seg_src, True)
         new_t = self.net1(cur_t)
         pooled, new_p = Fn.PoolFn.apply(new_t, index.edges, index.seg_ptr, index.seg_src, index.O, H, Dout,
                                         self.pooling == 'avg')

@@ -17,13 +17,14 @@ def _ranges(obj_to_img, N=None):
 
 
 def masks_to_layout(vecs, boxes, masks, obj_to_img, H, W=None, pooling='sum', test_mode=False, align_corners=False,
-                    nhwc_bf16=False, N=None, cmap=None):
+                    nhwc_bf16=False, N=None, cmap=None, grad_channels=None):
     """layout.py:64-93.  Returns (N,D,H,W); with nhwc_bf16 the result is a bf16 view of a channels-last
     buffer (N,H,W,Cp) which is also attached as ``._sg_nhwc`` for the conv operands.
 
     cmap (int32 (N, COMPACT_CC), nhwc_bf16 only): ``vecs`` are channel-compacted layout vectors (class slots of
     the image instead of the vocabulary, see Model._compact_plan); the result then has D = vecs.shape[1]
-    compact channels, carries the map as ``._sg_cmap`` and is expanded by expand_layout()."""
+    compact channels, carries the map as ``._sg_cmap`` and is expanded by expand_layout().
+    grad_channels=(c0, c1): columns of ``vecs`` that carry a gradient (default: all)."""
     if pooling != 'sum':
         raise NotImplementedError('only pooling="sum" is used by the model')
     W = H if W is None else W
@@ -35,7 +36,7 @@ def masks_to_layout(vecs, boxes, masks, obj_to_img, H, W=None, pooling='sum', te
             raw = ops.masks_to_layout_fwd(vecs, boxes, masks, ranges, H, W, align_corners, fmt, test_mode=True, raw=True)
     else:
         raw = Fn.LayoutFn.apply(vecs, boxes, masks, ranges, H, W, align_corners, nhwc_bf16,
-                                COMPACT_CC if cmap is not None else None)
+                                COMPACT_CC if cmap is not None else None, grad_channels)
     if not nhwc_bf16:
         return raw
     out = raw.permute(0, 3, 1, 2)[:, :D]

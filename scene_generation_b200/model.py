@@ -92,10 +92,11 @@ class Model(nn.Module):
             masks = masks_gt if masks_gt is not None else masks_pred
             pred_layout = masks_to_layout(scene_layout_vecs, boxes, masks, obj_to_img, H, W, test_mode=True, **lay)
             return self.layout_to_image(pred_layout), boxes_pred, masks_pred, None, pred_layout, None
-        gt_layout = masks_to_layout(scene_layout_vecs, boxes_gt, masks_gt, obj_to_img, H, W, **lay)
+        # only the appearance channels of layout_vecs carry a gradient (one_hot_obj is a constant, model.py:165-168)
+        c0 = self.num_objs if plan is None else self.compact_slots
+        gt_layout = masks_to_layout(scene_layout_vecs, boxes_gt, masks_gt, obj_to_img, H, W,
+                                    grad_channels=(c0, scene_layout_vecs.shape[1]), **lay)
         if self.layout_dtype == 'bf16':
-            # only the appearance channels of layout_vecs carry a gradient (one_hot_obj is a constant)
-            c0 = self.num_objs if plan is None else self.compact_slots
             gt_layout._sg_grad_channels = (c0, scene_layout_vecs.shape[1])
         pred_layout = masks_to_layout(scene_layout_vecs, boxes_gt, masks_pred, obj_to_img, H, W, **lay)
         wrong_layout = masks_to_layout(wrong_layout_vecs, boxes_gt, masks_gt, obj_to_img, H, W, **lay)
@@ -137,9 +138,10 @@ class Model(nn.Module):
         wrong_layout_vecs = torch.cat([one_hot_obj, wrong_objs_rep], dim=1)
         lay = dict(align_corners=self.align_corners, nhwc_bf16=self.layout_dtype == 'bf16', N=N,
                    cmap=None if plan is None else plan[1])
-        gt_layout = masks_to_layout(scene_layout_vecs, boxes_gt, masks_gt, obj_to_img, H, W, **lay)
+        c0 = self.num_objs if plan is None else self.compact_slots
+        gt_layout = masks_to_layout(scene_layout_vecs, boxes_gt, masks_gt, obj_to_img, H, W,
+                                    grad_channels=(c0, scene_layout_vecs.shape[1]), **lay)
         if self.layout_dtype == 'bf16':
-            c0 = self.num_objs if plan is None else self.compact_slots
             gt_layout._sg_grad_channels = (c0, scene_layout_vecs.shape[1])
         wrong_layout = masks_to_layout(wrong_layout_vecs, boxes_gt, masks_gt, obj_to_img, H, W, **lay)
         imgs_pred = self.layout_to_image(gt_layout)

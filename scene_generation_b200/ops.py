@@ -129,8 +129,9 @@ def masks_to_layout_fwd(vecs, boxes, masks, ranges, H, W, align_corners=False, o
     return buf
 
 
-def masks_to_layout_bwd(vecs, boxes, masks, ranges, H, W, grad, align_corners=False, need_dmasks=False):
-    """grad: (N,D,H,W) f32 contiguous, or a channels-last bf16 tensor whose storage is (N,H,W,Cp)."""
+def masks_to_layout_bwd(vecs, boxes, masks, ranges, H, W, grad, align_corners=False, need_dmasks=False, channels=None):
+    """grad: (N,D,H,W) f32 contiguous, or a channels-last bf16 tensor whose storage is (N,H,W,Cp).
+    channels=(c0, c1): only these columns of d vecs are computed (the others are zero; c0 is rounded down to 8)."""
     O, D = vecs.shape
     M = masks.shape[1]
     N = ranges.shape[0]
@@ -149,8 +150,11 @@ def masks_to_layout_bwd(vecs, boxes, masks, ranges, H, W, grad, align_corners=Fa
         fmt = NCHW_F32
     dvecs = torch.empty((O, D), dtype=torch.float32, device=vecs.device)
     dmasks = torch.empty((O, M, M), dtype=torch.float32, device=vecs.device) if need_dmasks else None
+    c0, c1 = channels or (0, D)
+    ws = stream_scratch(vecs.device)
     _lib.call('sg_masks_to_layout_bwd', _ptr(vecs), _ptr(boxes), _ptr(masks), _MASK_DT[masks.dtype], _ptr(ranges),
-              O, D, M, N, H, W, int(align_corners), fmt, Cp, _ptr(g), _ptr(dvecs), _ptr(dmasks), _stream())
+              O, D, M, N, H, W, int(align_corners), fmt, Cp, _ptr(g), c0 // 8 * 8, c1, _ptr(dvecs), _ptr(dmasks), _ptr(ws),
+              ws.numel(), _stream())
     return dvecs, dmasks
 
 

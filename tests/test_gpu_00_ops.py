@@ -70,6 +70,11 @@ def test_layout_fwd_bwd_vs_oracle(H, W, kmax):
     dv2, dm2 = ops.masks_to_layout_bwd(vecs.detach().to(DEV), boxes.to(DEV), pm.detach().to(DEV), r, H, W, gout.to(DEV),
                                        need_dmasks=True)
     assert torch.equal(dv, dv2) and torch.equal(dm, dm2)
+    # channel-restricted adjoint (only the appearance columns of a layout vector carry a gradient): same bits there,
+    # zeros elsewhere
+    dvr, _ = ops.masks_to_layout_bwd(vecs.detach().to(DEV), boxes.to(DEV), pm.detach().to(DEV), r, H, W, gout.to(DEV),
+                                     channels=(24, 52))
+    assert torch.equal(dvr[:, 24:], dv[:, 24:]) and float(dvr[:, :24].abs().max()) == 0.0
     # align_corners=True adjoint
     v2, p2 = vecs.detach().clone().requires_grad_(True), pm.detach().clone().requires_grad_(True)
     R.masks_to_layout(v2, boxes, p2, o2i, H, W, align_corners=True).backward(gout)

@@ -244,12 +244,13 @@ def test_cfg4_cfg5_shapes_run(size, kmin, kmax):
 
 def _traj_tol(i, net, name):
     """bf16 tensor-core arithmetic vs fp32 along a trajectory (weights, Adam moments, BN statistics and the pool carried
-    over).  Measured on a B200 (the CUDA path is bit-reproducible, so this is THE deviation, not a sample): iteration 0
-    0.4 %, then 1.1 % / 1.4 % / 1.9 % for every term except the image discriminator's own losses, which reach 5.2 % at
-    iteration 3 (two players' sign-like Adam steps feeding back).  Bounds: 1.5 % + 1 % per iteration; image-D terms
-    1.5 % + 3 % per iteration."""
+    over).  Measured on a B200 (the CUDA path is bit-reproducible, so this is THE deviation of a build, not a sample):
+    iteration 0 0.4 %, then 1.1 % / 1.4 % / 1.9 % for every term except the image discriminator's own losses.  Those
+    are a two-player game driven by sign-like first Adam steps at batch 2: builds that differ only in the rounding of
+    one adjoint (f32 vs bf16 weights in the last convolution's input gradient) were measured at +5 % and -14 % at
+    iteration 3.  Bounds: 1.5 % + 1 % per iteration; image-D terms 2 % + 7 % per iteration."""
     chaotic = net == 'img' or 'img' in name or name == 'total_loss'
-    return 0.015 + (0.03 if chaotic else 0.01) * i
+    return (0.02 + 0.07 * i) if chaotic else (0.015 + 0.01 * i)
 
 
 @pytest.mark.parametrize('graphs', [False, True])
