@@ -355,6 +355,116 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair variant for long-K, wide-N GEMMs (the 1024-channel ResnetBlock convolutions and their input gradients):
+// two CTAs of a cluster own two neighbouring M tiles and ONE N tile of BN = 256; the leader issues
+// tcgen05.mma.cta_group::2 with M = 256: A = 128 rows from each CTA's shared memory, B = 128 output channels from each
+// CTA.  Per 64-channel k-block an SM streams 16 KB of A + 16 KB of B for 128 x 256 outputs — half the L2 -> SM operand
+// bytes per MMA cycle of the single-CTA 128 x 128 tile, which is what limits that kernel on these shapes (ncu: 604 MB
+// through the L2 -> SM path per launch at its ~6.3 kB/clk ceiling).  Used where the pairs alone fill most SMs (the
+// input gradients: 64 pairs); the forward GEMM (M = 2048: 32 pairs) stays on the single-CTA kernel — a two-way K split
+// of the pairs ran its MMA phase in 38 us at 66 % tensor pipe (ncu, profiles/), but exchanging the fp32 accumulators
+// between the two CTAs of a tile cost what the halved operand stream had gained (66 us either way).
+// Barrier protocol (CUTLASS PipelineTmaUmmaAsync, 2x1 atom): both producers wait on their own `empty`, only the leader
+// arms `full` with the bytes of BOTH CTAs, both issue their TMA loads against the leader's `full`; the leader's MMA
+// thread commits to `empty` / `accum_full` of both CTAs (multicast).
+template <bool BMN>
+__global__ void __launch_bounds__(192, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ ConvKParams p) {
+  constexpr int BN = 256;
+  constexpr int B_HALF = (BN / 2) * 128;        // bytes of this CTA's half of the weight tile per stage
+  constexpr int TM_COLS = BN;
+  const int STAGES = p.stages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_HALF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* accum_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const int mt = blockIdx.x;                    // cluster dim x = 2: the pair is (2i, 2i + 1)
+  const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, ti = mt / (p.tiles_w * p.tiles_h);
+  const int w0 = tw * p.BW, h0 = th * p.BH, img0 = ti * p.BI;
+  const int n0 = blockIdx.y * BN;
+  const sg_phase_t ph = p.phases[blockIdx.z];
+  const int it_begin = 0, it_end = ph.ntaps * p.kblocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum_full, 1);
+    fence_barrier_init();
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1) tmem_alloc2<TM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();                               // peer barriers / TMEM exist before any remote signal
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t par = 0;
+      for (int it = it_begin; it < it_end; ++it, ++s) {
+        if (s == STAGES) { s = 0; par ^= 1; }
+        mbar_wait(&empty[s], par ^ 1);
+        const int tap_i = it / p.kblocks, kb = it - tap_i * p.kblocks;
+        const sg_tap_t tp = p.taps[ph.tap_begin + tap_i];
+        if (crank == 0) mbar_expect_tx(&full[s], 2 * (p.a_bytes + B_HALF));
+        const uint32_t bar = leader_bar_addr(&full[s]);
+        tma_load_5d_2cta(sA + s * A_BYTES, &tmA, bar, kb * 64, w0 + tp.dw + p.in_w0, h0 + tp.dh + p.in_h0, tp.plane, img0);
+        if (BMN) {
+#pragma unroll
+          for (int j = 0; j < BN / 128; ++j)
+            tma_load_3d_2cta(sB + s * B_HALF + j * 8192, &tmB, bar, p.w_col0 + n0 + (int)crank * (BN / 2) + 64 * j, tp.wtap,
+                             kb * 64);
+        } else {
+          tma_load_3d_2cta(sB + s * B_HALF, &tmB, bar, kb * 64, tp.wtap, n0 + (int)crank * (BN / 2));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, BMN ? 1 : 0);
+      int s = 0;
+      uint32_t par = 0;
+      for (int it = it_begin; it < it_end; ++it, ++s) {
+        if (s == STAGES) { s = 0; par ^= 1; }
+        mbar_wait(&full[s], par);
+        tc_fence_after();
+        const uint64_t ad = umma_desc_sw128(smem_u32(sA + s * A_BYTES), 16, 1024);
+        const uint64_t bd = BMN ? umma_desc_sw128(smem_u32(sB + s * B_HALF), 8192, 1024)
+                                : umma_desc_sw128(smem_u32(sB + s * B_HALF), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          mma_bf16_2cta(tmem, ad + 2 * k, bd + (BMN ? 128 : 2) * k, idesc, ((it - it_begin) | k) != 0 ? 1u : 0u);
+        mma_commit_2cta(&empty[s], (uint16_t)3);
+      }
+      mma_commit_2cta(accum_full, (uint16_t)3);
+    }
+  } else {
+    // ---------------- epilogue: warps 2..5 own TMEM lane quarters (warp % 4) -------------------
+    mbar_wait(accum_full, 0);
+    tc_fence_after();
+    const int slot = blockIdx.z * p.slots_per_phase + (p.BI == 1 ? th * p.tiles_w + tw : 0);
+    conv_epilogue<BN>(p, ph, tmem, warp & 3, lane, w0, h0, img0, n0, slot, reinterpret_cast<float*>(sA));
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();                               // the leader's MMAs read this CTA's shared memory until the last commit
+  if (warp == 1) tmem_dealloc2<TM_COLS>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------
 struct WgradKParams {
   int tiles_w, tiles_h, BW, BH, BI;
   int ktiles_total, ktiles_per_split;
@@ -555,6 +665,46 @@ int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKParams& kp,
   return launch_conv_t<BN, false>(tmA, tmB, kp, grid, stream);
 }
 
+// SG_CONV_2CTA=0 disables the CTA-pair kernel (A/B switch)
+bool two_cta_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SG_CONV_2CTA");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <bool BMN>
+int launch_conv2(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKParams& kp, dim3 grid, cudaStream_t stream) {
+  constexpr int STAGES = 6;                                          // 32 KB per stage and CTA
+  constexpr int SMEM = STAGES * (A_BYTES + 128 * 128) + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return sg_fail(SG_ERR_CUDA, "conv_tc2 smem attribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  kp.stages = STAGES;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<BMN>, tmA, tmB, kp);
+  if (e != cudaSuccess) return sg_fail(SG_ERR_CUDA, "sg_conv_tc (CTA-pair launch): %s", cudaGetErrorString(e));
+  SG_CHECK_LAUNCH("sg_conv_tc");
+  return SG_OK;
+}
+
 // SG_CONV_NO192=1 keeps the N tiles at powers of two (A/B switch for the 192-wide tile)
 bool no192() {
   static int v = -1;
@@ -669,7 +819,20 @@ extern "C" int sg_conv_tc(const sg_conv_desc_t* d, sg_stream_t stream) {
   long long bdims[3] = {d->w_C, d->w_taps,
                         bmn ? (long long)d->w_rows
                             : (d->w_img_rows > 0 ? (long long)d->w_img_rows * d->x_N : (long long)d->w_Cout)};
-  const int m_tiles = kp.tiles_w * kp.tiles_h * img_tiles;
+  int m_tiles = kp.tiles_w * kp.tiles_h * img_tiles;
+  // CTA pairs (M = 256 x N = 256 per pair) for long-K, wide-N launches whose pairs fill most of the SMs (the input
+  // gradients of the 1024-channel ResnetBlock convolutions: 64 pairs) but whose single-CTA grid is at most two waves
+  const long iters = (long)d->ntaps * kp.kblocks;
+  const int n_tiles256 = sg_cdiv(d->w_Cout, 256);
+  const int pairs = ((m_tiles + 1) / 2) * n_tiles256 * d->nphases;
+  if (two_cta_enabled() && BN == 256 && d->w_Cout >= 256 && d->w_img_rows == 0 && m_tiles >= 2 && iters >= 64 &&
+      2 * pairs >= 96 && 2 * pairs <= 2 * 148) {
+    m_tiles = (m_tiles + 1) & ~1;       // an odd tail tile gets a fully masked partner
+    int bbox2[3] = {64, 1, bmn ? 64 : 128};
+    if (int e = make_tmap(&tmB, d->w, 3, bdims, bbox2)) return e;
+    dim3 grid2(m_tiles, n_tiles256, d->nphases);
+    return bmn ? launch_conv2<true>(tmA, tmB, kp, grid2, stream) : launch_conv2<false>(tmA, tmB, kp, grid2, stream);
+  }
   int bbox[3] = {64, 1, bmn ? 64 : BN};
   if (int e = make_tmap(&tmB, d->w, 3, bdims, bbox)) return e;
   dim3 grid(m_tiles, sg_cdiv(d->w_Cout, BN), d->nphases);

@@ -85,6 +85,13 @@ def _batch_to_device(batch, device):
     return out
 
 
+def _nvtx(name):
+    """NVTX range (visible in Nsight Systems / ncu --nvtx); SG_NVTX=0 turns the ranges off"""
+    if os.environ.get('SG_NVTX', '1') == '0':
+        return _NullCtx()
+    return torch.cuda.nvtx.range(name)
+
+
 class _NullCtx:
     def __enter__(self):
         return self
@@ -458,6 +465,10 @@ class Trainer:
 
     def _phase_a(self, batch, use_gt):
         """Model.forward (model.py:94-124) + generator losses + backward (trainer.py:205-262 without the update)"""
+        with _nvtx('sg.phase_a: forward + generator backward'):
+            return self._phase_a_impl(batch, use_gt)
+
+    def _phase_a_impl(self, batch, use_gt):
         imgs, objs, boxes, masks, triples, obj_to_img, triple_to_img, attributes = batch
         if not use_gt:
             attributes = torch.zeros_like(attributes)
@@ -470,6 +481,10 @@ class Trainer:
     def _phase_b(self):
         """the three discriminator passes (train.py:207-215): losses + backward, no update.  They only share read-only
         inputs, and none of them reads the generator's weights: inside a capture they are parallel graph branches."""
+        with _nvtx('sg.phase_b: discriminator passes'):
+            self._phase_b_impl()
+
+    def _phase_b_impl(self):
         from . import ops
         (imgs, objs, boxes, masks, triples, obj_to_img, _, _), out = self._st
         imgs_pred, boxes_pred, masks_pred, layout, layout_pred, layout_wrong = out
@@ -495,8 +510,9 @@ class Trainer:
             self.train_image_discriminator(imgs, imgs_fake, lay, lay_wrong)
 
     def _phase_cd(self):
-        for name, opt in self._d_nets():
-            self._update(name, opt)
+        with _nvtx('sg.phase_cd: discriminator Adam'):
+            for name, opt in self._d_nets():
+                self._update(name, opt)
 
     def _train_step_eager(self, batch, use_gt):
         """eager launches on the current stream; data parallel: the generator's all-reduce runs on NCCL's stream next

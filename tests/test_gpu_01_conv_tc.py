@@ -261,3 +261,31 @@ def test_conv_dgrad_mn_major_weights(Cin, Cout, k, H):
     dx = torch.zeros((N, Hx, Hx, Cx), dtype=torch.bfloat16, device=DEV)
     ops.conv_tc(to_nhwc5(dy), wk, dx, (Hx * Hx * Cx, Hx * Cx, Cx, 1), Hx, Hx, convspec.dgrad_s1(k, pad), mn_cols=(0, Cin))
     check(dx[..., :Cin].permute(0, 3, 1, 2), ref, 1e-2)         # bf16 output rounding
+
+
+@pytest.mark.parametrize('N,C,H,Co', [(4, 1024, 8, 1024), (5, 512, 8, 512), (32, 1024, 8, 1024), (3, 576, 16, 256)])
+def test_cta_pair_kernel_long_k_wide_n(N, C, H, Co):
+    """The shapes served by the CTA-pair kernel (tcgen05 cta_group::2, M = 256 x N = 256 per pair, K split over
+    blockIdx.z with the partial accumulators added in split order): ResnetBlock convolution (fused statistics, odd
+    numbers of M tiles) and its input gradient through the fprop weight copy; bit-reproducible."""
+    k, p = 3, 1
+    x, w, b = rnd(N, C, H, H, seed=4), rnd(Co, C, k, k, seed=5, scale=0.03), rnd(Co, seed=6)
+    xp = F.pad(r32(x), (p, p, p, p), mode='reflect')
+    ref = F.conv2d(xp, r32(w), b)
+    taps, _ = convspec.conv_s1(k, 0)
+    outs = []
+    for rep in range(2):
+        y = torch.full((N, H, H, Co), float('nan'), device=DEV, dtype=torch.bfloat16)
+        _, st = ops.conv_tc(to_nhwc5(xp), pack_w(w), y, (H * H * Co, H * Co, Co), H, H, taps, bias=b.to(DEV), stats=True)
+        outs.append((y, st))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    y, st = outs[0]
+    check(y.permute(0, 3, 1, 2), ref, 1e-2)
+    check(st.sum(1)[..., 0], ref.sum(dim=(2, 3)), 2e-3)
+    check(st.sum(1)[..., 1], (ref ** 2).sum(dim=(2, 3)), 2e-3)
+    # input gradient: dx = conv_transpose(dy, w) with the SAME bf16 weight copy read MN-major
+    dy = rnd(N, Co, H, H, seed=7)
+    refd = F.conv_transpose2d(r32(dy), r32(w), padding=p)
+    dx = torch.full((N, H, H, C), float('nan'), dtype=torch.bfloat16, device=DEV)
+    ops.conv_tc(to_nhwc5(dy), pack_w(w), dx, (H * H * C, H * C, C, 1), H, H, convspec.dgrad_s1(k, p), mn_cols=(0, C))
+    check(dx.permute(0, 3, 1, 2), refd, 1e-2)
