@@ -390,8 +390,24 @@ def time_dense_layout(model, batch, H, peak_hbm, reps=10):
             times.append(e0.elapsed_time(e1))
     ms = sorted(times)[len(times) // 2]
     gbs = out.numel() * 2 / (ms * 1e-3) / 1e9
+    # the scatter only WRITES: next to the copy figure of MEASURED_PEAKS.json (read + write bytes) the pure-write rate of
+    # this GPU, measured here the same way on a 1 GiB memset
+    big = torch.empty(1 << 30, dtype=torch.uint8, device=objs.device)
+    wt = []
+    for r in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        big.zero_()
+        e1.record()
+        torch.cuda.synchronize()
+        if r >= 2:
+            wt.append(e0.elapsed_time(e1))
+    wpeak = (1 << 30) / (min(wt) * 1e-3) / 1e9
+    del big
     return {'launches': 1, 'ms': round(ms, 4), 'bound': 'hbm', 'bytes': out.numel() * 2, 'achieved_gbs': round(gbs, 1),
-            'peak_gbs': peak_hbm, 'frac': round(gbs / peak_hbm, 3)}
+            'peak_gbs': peak_hbm, 'frac': round(gbs / peak_hbm, 3), 'write_peak_gbs': round(wpeak, 1),
+            'frac_of_write_peak': round(gbs / wpeak, 3),
+            'note': 'write-only kernel: a 1 GiB memset reaches write_peak_gbs on this GPU; peak_gbs is the read + write copy rate'}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -565,12 +581,18 @@ def main():
         step_eager(0)             # the probe step contains the gradient all-reduces: every rank must take part
         torch.cuda.synchronize()
     if rank == 0:
-        with KernelProbe() as probe:
-            # let the host run ahead of the device so that event intervals of small launches measure the kernel,
-            # not the host's launch gap: park the stream on a ~100 ms spin first
-            torch.cuda._sleep(int(2e8))
-            step_eager(0)         # launched eagerly: the probe wraps the Python entry points
-            fam, top = probe.summary()
+        best = None
+        for rep in range(3 if world == 1 else 1):     # every rank takes part in a probe step's all-reduces: one at N > 1
+            with KernelProbe() as probe:
+                # let the host run ahead of the device so that event intervals of small launches measure the kernel,
+                # not the host's launch gap: park the stream on a ~100 ms spin first
+                torch.cuda._sleep(int(2e8))
+                step_eager(0)         # launched eagerly: the probe wraps the Python entry points
+                fam_r, top_r = probe.summary()
+            tot = sum(v['ms'] for k, v in fam_r.items() if k != 'layout_fwd')
+            if best is None or tot < best[0]:         # the repetition least disturbed by host launch gaps
+                best = (tot, fam_r, top_r)
+        fam, top = best[1], best[2]
         peak_tf, peak_hbm, which = load_peaks()
         lay = fam.pop('layout_fwd', None)
         dom = max(fam.items(), key=lambda kv: kv[1]['ms'])
