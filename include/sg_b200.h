@@ -248,7 +248,7 @@ int sg_norm_act_pad_fwd(const sg_nap_desc_t* d, void* out, sg_stream_t stream);
  * dsrc is plain bf16 NHWC or (out_planes=1) parity planes.
  * dres (optional, bf16, addressed with the residual's res_os_* strides) receives the folded
  * gradient of the residual input. */
-#define SG_NAP_MAX_PARTS 8
+#define SG_NAP_MAX_PARTS 32
 int sg_norm_act_pad_bwd(const sg_nap_desc_t* d, const void* grad, const float* save_mean, const float* save_rstd,
                         int bn, float count, float* sums, int out_planes, void* dsrc, void* dres,
                         sg_stream_t stream);

@@ -36,16 +36,6 @@ __device__ __forceinline__ void store8(bf16* p, const float* f) {
   for (int j = 0; j < 4; ++j) pk[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
   *reinterpret_cast<uint4*>(p) = *reinterpret_cast<uint4*>(pk);
 }
-__device__ __forceinline__ float act_fwd(float v, int act, float slope) {
-  if (act == SG_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == SG_ACT_LEAKY) return v >= 0.f ? v : v * slope;
-  return v;
-}
-__device__ __forceinline__ float act_grad(float z, int act, float slope) {
-  if (act == SG_ACT_RELU) return z > 0.f ? 1.f : 0.f;
-  if (act == SG_ACT_LEAKY) return z >= 0.f ? 1.f : slope;
-  return 1.f;
-}
 
 // ---------------------------------------------------------------------------------------------
 // cast / pack
@@ -199,50 +189,90 @@ __device__ __forceinline__ int src_coord(int hp, int pad, int pad_mode, int Hu) 
   return hu;
 }
 
-// grid.x = output row (n, plane, i), grid.y * blockDim.x covers the (j, channel-chunk) items of a row: the row
-// decomposition is block-uniform and the only per-thread division is by the chunk count
-__global__ void nap_fwd_kernel(NapArgs a, bf16* __restrict__ out) {
-  const int nC = a.C / 8;
+template <int ACT>
+__device__ __forceinline__ float act_fwd_t(float v, float slope) {
+  if (ACT == SG_ACT_RELU) return fmaxf(v, 0.f);
+  if (ACT == SG_ACT_LEAKY) return v >= 0.f ? v : v * slope;
+  return v;
+}
+template <int ACT>
+__device__ __forceinline__ float act_grad_t(float z, float slope) {
+  if (ACT == SG_ACT_RELU) return z > 0.f ? 1.f : 0.f;
+  if (ACT == SG_ACT_LEAKY) return z >= 0.f ? 1.f : slope;
+  return 1.f;
+}
+__device__ __forceinline__ int div_up_factor(int v, int up) { return up == 1 ? v : (up == 2 ? v >> 1 : v / up); }
+__device__ __forceinline__ void unpack8(const uint4& raw, float* f) {
+  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { const float2 v = __bfloat1622float2(h2[q]); f[2 * q] = v.x; f[2 * q + 1] = v.y; }
+}
+
+// These kernels stream 2 B in and 2 B out per element; what bounds them is the instruction issue rate, so the index
+// arithmetic is kept out of the per-item path: blockDim.x = the C/8 channel chunks (a thread's chunk, its scale /
+// shift vectors and its row base pointers are loop constants), blockDim.y = pixel lanes of ONE output row,
+// blockIdx = (pixel group, output row i, image * planes + plane): no division by a run-time value except the
+// upsampling factor.  Each thread issues the 16-byte loads of its ITEMS pixels before the first use.
+template <int ACT, int ITEMS>
+__global__ void __launch_bounds__(256) nap_fwd_kernel(NapArgs a, bf16* __restrict__ out) {
   const int Hu = a.H * a.up, Wu = a.W * a.up;
   const int Hp = Hu + 2 * a.pad, Wp = Wu + 2 * a.pad;
   const int Ho = a.planes ? (Hp + 1) / 2 : Hp, Wo = a.planes ? (Wp + 1) / 2 : Wp;
-  const int P = a.planes ? 4 : 1;
-  const unsigned item = blockIdx.y * blockDim.x + threadIdx.x;
-  if (item >= (unsigned)(Wo * nC)) return;
-  const int j = item / (unsigned)nC, ch = item - j * nC;
-  const unsigned row = blockIdx.x;
-  const int i = row % (unsigned)Ho;
-  const unsigned rp = row / (unsigned)Ho;
-  const int pl = rp % (unsigned)P, n = rp / (unsigned)P;
-  const long idx = (long)row * (Wo * nC) + item;
-  int hp = a.planes ? 2 * i + (pl >> 1) : i;
-  int wp = a.planes ? 2 * j + (pl & 1) : j;
-  float f[8];
+  const int ch8 = threadIdx.x * 8;
+  const int i = blockIdx.y;
+  const int pl = a.planes ? (int)(blockIdx.z & 3) : 0;
+  const int n = a.planes ? (int)(blockIdx.z >> 2) : (int)blockIdx.z;
+  const int hp = a.planes ? 2 * i + (pl >> 1) : i;
+  const int hu = hp < Hp ? src_coord(hp, a.pad, a.pad_mode, Hu) : -1;
+  const bool row_ok = hu >= 0 && hu < Hu;
+  const int h = row_ok ? div_up_factor(hu, a.up) : 0;
+  const bf16* srow = a.src + ((long)n * a.H + h) * a.W * a.C + ch8;
+  const bf16* rrow = a.res ? a.res + (long)n * a.res_os_img + (long)h * a.res_os_h + ch8 : nullptr;
+  bf16* orow = out + ((long)blockIdx.z * Ho + i) * Wo * a.C + ch8;
+  const int j0 = blockIdx.x * (blockDim.y * ITEMS) + threadIdx.y;
+  uint4 raw[ITEMS], rres[ITEMS];
+  bool ok[ITEMS];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) f[k] = 0.f;
-  if (hp < Hp && wp < Wp) {
-    int hu = src_coord(hp, a.pad, a.pad_mode, Hu), wu = src_coord(wp, a.pad, a.pad_mode, Wu);
-    if (hu >= 0 && wu >= 0 && hu < Hu && wu < Wu) {
-      int h = hu / a.up, w = wu / a.up;
-      load8(a.src + (((long)n * a.H + h) * a.W + w) * a.C + ch * 8, f);
-      if (a.scale) {
-        const float4* sc = reinterpret_cast<const float4*>(a.scale + (long)n * a.C + ch * 8);
-        const float4* sh = reinterpret_cast<const float4*>(a.shift + (long)n * a.C + ch * 8);
-        float4 s0 = sc[0], s1 = sc[1], h0 = sh[0], h1 = sh[1];
-        f[0] = fmaf(f[0], s0.x, h0.x); f[1] = fmaf(f[1], s0.y, h0.y); f[2] = fmaf(f[2], s0.z, h0.z); f[3] = fmaf(f[3], s0.w, h0.w);
-        f[4] = fmaf(f[4], s1.x, h1.x); f[5] = fmaf(f[5], s1.y, h1.y); f[6] = fmaf(f[6], s1.z, h1.z); f[7] = fmaf(f[7], s1.w, h1.w);
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) f[k] = act_fwd(f[k], a.act, a.slope);
-      if (a.res) {
-        float rr[8];
-        load8(a.res + (long)n * a.res_os_img + (long)h * a.res_os_h + (long)w * a.res_os_w + ch * 8, rr);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] += rr[k];
-      }
+  for (int k = 0; k < ITEMS; ++k) {
+    const int j = j0 + k * blockDim.y;
+    const int wp = a.planes ? 2 * j + (pl & 1) : j;
+    const int wu = (j < Wo && wp < Wp) ? src_coord(wp, a.pad, a.pad_mode, Wu) : -1;
+    ok[k] = row_ok && wu >= 0 && wu < Wu;
+    raw[k] = make_uint4(0u, 0u, 0u, 0u);
+    rres[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (ok[k]) {
+      const int w = div_up_factor(wu, a.up);
+      raw[k] = *reinterpret_cast<const uint4*>(srow + w * a.C);
+      if (rrow) rres[k] = *reinterpret_cast<const uint4*>(rrow + (long)w * a.res_os_w);
     }
   }
-  store8(out + idx * 8, f);
+  float sc[8], sh[8];
+  if (a.scale) {
+    load8f(a.scale + (long)n * a.C + ch8, sc);
+    load8f(a.shift + (long)n * a.C + ch8, sh);
+  }
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    const int j = j0 + k * blockDim.y;
+    if (j >= Wo) continue;
+    float f[8];
+    unpack8(raw[k], f);
+    if (ok[k]) {
+      if (a.scale) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) f[q] = fmaf(f[q], sc[q], sh[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) f[q] = act_fwd_t<ACT>(f[q], a.slope);
+      if (rrow) {
+        float r[8];
+        unpack8(rres[k], r);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) f[q] += r[q];
+      }
+    }
+    store8(orow + j * a.C, f);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -264,98 +294,178 @@ struct NapBwdArgs {
   bf16* dres;             // optional: folded grad (no act') in plain source layout
 };
 
-// accumulate the folded output-gradient for source pixel (n,h,w), channels ch*8..+8
-__device__ __forceinline__ void fold_grad(const NapArgs& a, const bf16* g, int n, int h, int w, int ch, float* acc) {
+// accumulate the folded output-gradient for source pixel (h,w) of one image; gimg = the image's operand gradient
+// already offset to the thread's 8 channels; offsets inside an image fit 32 bits (checked by the host)
+__device__ __forceinline__ int operand_off(const NapArgs& a, int Ho, int Wo, int hp, int wp) {
+  return a.planes ? ((((hp & 1) * 2 + (wp & 1)) * Ho + (hp >> 1)) * Wo + (wp >> 1)) * a.C : (hp * Wo + wp) * a.C;
+}
+__device__ __forceinline__ void add8(const bf16* p, float* acc) {
+  float t[8];
+  load8(p, t);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] += t[k];
+}
+// The taps are always added in the same order (operand rows: own, top mirror, bottom mirror; columns likewise; the
+// up x up block row-major), so every variant below produces the same bits.  The first tap is loaded unconditionally:
+// in the common cases it is the only one, and its load can be issued early.
+__device__ __forceinline__ void fold_grad_img(const NapArgs& a, const bf16* gimg, int Ho, int Wo, int h, int w, float* acc) {
   const int Hu = a.H * a.up, Wu = a.W * a.up;
-  const int Hp = Hu + 2 * a.pad, Wp = Wu + 2 * a.pad;
-  const int Ho = a.planes ? (Hp + 1) / 2 : Hp, Wo = a.planes ? (Wp + 1) / 2 : Wp;
+  const bool reflect = a.pad_mode && a.pad > 0;
+  if (a.up == 1) {
+    load8(gimg + operand_off(a, Ho, Wo, h + a.pad, w + a.pad), acc);
+    if (!reflect) return;
+    // a source pixel has mirror images in the halo only within pad of a border (and not ON the border)
+    const int r1 = (h >= 1 && h <= a.pad) ? a.pad - h : -1;
+    const int r2 = (h <= Hu - 2 && h >= Hu - 1 - a.pad) ? a.pad + 2 * (Hu - 1) - h : -1;
+    const int c1 = (w >= 1 && w <= a.pad) ? a.pad - w : -1;
+    const int c2 = (w <= Wu - 2 && w >= Wu - 1 - a.pad) ? a.pad + 2 * (Wu - 1) - w : -1;
+    if ((r1 & r2 & c1 & c2) < 0) return;          // all four are -1: no mirror
+    const int r0 = h + a.pad, c0 = w + a.pad;
+#pragma unroll
+    for (int ri = 0; ri < 3; ++ri) {
+      const int hp = ri == 0 ? r0 : (ri == 1 ? r1 : r2);
+      if (hp < 0) continue;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const int wp = ci == 0 ? c0 : (ci == 1 ? c1 : c2);
+        if (wp < 0 || (ri == 0 && ci == 0)) continue;
+        add8(gimg + operand_off(a, Ho, Wo, hp, wp), acc);
+      }
+    }
+    return;
+  }
+  if (a.up == 2 && !reflect) {
+    // nearest x2: the 2 x 2 operand pixels of the source pixel
+    const int hp = 2 * h + a.pad, wp = 2 * w + a.pad;
+    float t1[8], t2[8], t3[8];
+    load8(gimg + operand_off(a, Ho, Wo, hp, wp), acc);
+    load8(gimg + operand_off(a, Ho, Wo, hp, wp + 1), t1);
+    load8(gimg + operand_off(a, Ho, Wo, hp + 1, wp), t2);
+    load8(gimg + operand_off(a, Ho, Wo, hp + 1, wp + 1), t3);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = ((acc[k] + t1[k]) + t2[k]) + t3[k];
+    return;
+  }
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
   for (int uh = 0; uh < a.up; ++uh) {
     const int hu = h * a.up + uh;
-    int rows[3];
-    int nr = 0;
-    rows[nr++] = hu + a.pad;
-    if (a.pad_mode && a.pad > 0) {
-      if (hu >= 1 && hu <= a.pad) rows[nr++] = a.pad - hu;
-      if (hu <= Hu - 2 && hu >= Hu - 1 - a.pad) rows[nr++] = a.pad + 2 * (Hu - 1) - hu;
-    }
+    const int r0 = hu + a.pad;
+    const int r1 = (reflect && hu >= 1 && hu <= a.pad) ? a.pad - hu : -1;
+    const int r2 = (reflect && hu <= Hu - 2 && hu >= Hu - 1 - a.pad) ? a.pad + 2 * (Hu - 1) - hu : -1;
     for (int uw = 0; uw < a.up; ++uw) {
       const int wu = w * a.up + uw;
-      int cols[3];
-      int nc = 0;
-      cols[nc++] = wu + a.pad;
-      if (a.pad_mode && a.pad > 0) {
-        if (wu >= 1 && wu <= a.pad) cols[nc++] = a.pad - wu;
-        if (wu <= Wu - 2 && wu >= Wu - 1 - a.pad) cols[nc++] = a.pad + 2 * (Wu - 1) - wu;
-      }
-      for (int ri = 0; ri < nr; ++ri)
-        for (int ci = 0; ci < nc; ++ci) {
-          int hp = rows[ri], wp = cols[ci];
-          long off;
-          if (a.planes) off = ((((long)n * 4 + (hp & 1) * 2 + (wp & 1)) * Ho + (hp >> 1)) * Wo + (wp >> 1)) * a.C;
-          else off = (((long)n * Ho + hp) * Wo + wp) * a.C;
-          float t[8];
-          load8(g + off + ch * 8, t);
+      const int c0 = wu + a.pad;
+      const int c1 = (reflect && wu >= 1 && wu <= a.pad) ? a.pad - wu : -1;
+      const int c2 = (reflect && wu <= Wu - 2 && wu >= Wu - 1 - a.pad) ? a.pad + 2 * (Wu - 1) - wu : -1;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc[k] += t[k];
+      for (int ri = 0; ri < 3; ++ri) {
+        const int hp = ri == 0 ? r0 : (ri == 1 ? r1 : r2);
+        if (hp < 0) continue;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+          const int wp = ci == 0 ? c0 : (ci == 1 ? c1 : c2);
+          if (wp < 0) continue;
+          add8(gimg + operand_off(a, Ho, Wo, hp, wp), acc);
         }
+      }
     }
   }
 }
 
-// g' = fold(g) * act'(z), xhat; returns both
-__device__ __forceinline__ void gprime(const NapBwdArgs& b, int n, int h, int w, int ch, float* gp, float* xh) {
+// SINGLE: no upsampling and no reflection halo, every source pixel has exactly one operand pixel
+template <bool SINGLE>
+__device__ __forceinline__ uint4 fold_load(const NapArgs& a, const bf16* gimg, int Ho, int Wo, int h, int w) {
+  return *reinterpret_cast<const uint4*>(gimg + operand_off(a, Ho, Wo, h + a.pad, w + a.pad));
+}
+
+__device__ __forceinline__ void operand_dims(const NapArgs& a, int* Ho, int* Wo) {
+  const int Hp = a.H * a.up + 2 * a.pad, Wp = a.W * a.up + 2 * a.pad;
+  *Ho = a.planes ? (Hp + 1) / 2 : Hp;
+  *Wo = a.planes ? (Wp + 1) / 2 : Wp;
+}
+
+// per-thread constants of the backward kernels (the thread's 8 channels of its image)
+struct NapChan {
+  float sc[8], sh[8], mu[8], rs[8];
+};
+template <int ACT>
+__device__ __forceinline__ void nap_chan_load(const NapBwdArgs& b, int n, int ch8, NapChan& c) {
   const NapArgs& a = b.f;
-  fold_grad(a, b.g, n, h, w, ch, gp);
-  float x[8];
-  load8(a.src + (((long)n * a.H + h) * a.W + w) * a.C + ch * 8, x);
-  const long pc = (long)n * a.C + ch * 8;
-  if (a.scale && a.act != SG_ACT_NONE) {
-    float sc[8], sh[8];
-    load8f(a.scale + pc, sc);
-    load8f(a.shift + pc, sh);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) gp[k] *= act_grad(fmaf(x[k], sc[k], sh[k]), a.act, a.slope);
-  } else if (a.act != SG_ACT_NONE) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) gp[k] *= act_grad(x[k], a.act, a.slope);
+  const long pc = (long)n * a.C + ch8;
+  if (a.scale && ACT != SG_ACT_NONE) {
+    load8f(a.scale + pc, c.sc);
+    load8f(a.shift + pc, c.sh);
   }
   if (b.save_mean) {
-    float mu[8], rs[8];
-    load8f(b.save_mean + pc, mu);
-    load8f(b.save_rstd + pc, rs);
+    load8f(b.save_mean + pc, c.mu);
+    load8f(b.save_rstd + pc, c.rs);
+  }
+}
+// gp = folded gradient (in) -> g' = gp * act'(z) (out); xh = xhat (0 without a norm)
+template <int ACT>
+__device__ __forceinline__ void gprime_apply(const NapBwdArgs& b, const NapChan& c, const float* x, float* gp, float* xh) {
+  const NapArgs& a = b.f;
+  if (ACT != SG_ACT_NONE) {
+    if (a.scale) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) xh[k] = (x[k] - mu[k]) * rs[k];
+      for (int k = 0; k < 8; ++k) gp[k] *= act_grad_t<ACT>(fmaf(x[k], c.sc[k], c.sh[k]), a.slope);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) gp[k] *= act_grad_t<ACT>(x[k], a.slope);
+    }
+  }
+  if (b.save_mean) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) xh[k] = (x[k] - c.mu[k]) * c.rs[k];
   } else {
 #pragma unroll
     for (int k = 0; k < 8; ++k) xh[k] = 0.f;
   }
 }
 
-__global__ void nap_bwd_reduce_kernel(NapBwdArgs b, int pix_per_block) {
+// grid (parts, N), block (C/8 chunks, pixel lanes): a CTA sums its pixel range of one image; (h, w) of a lane's
+// pixels advance incrementally (one division per thread)
+template <int ACT, bool SINGLE>
+__global__ void __launch_bounds__(256, 2) nap_bwd_reduce_kernel(NapBwdArgs b, int pix_per_block) {
   extern __shared__ float red[];                // [lanes][nC*16]: (S1,S2) pairs per channel
   const NapArgs& a = b.f;
-  const int nC = a.C / 8;
-  const int lanes = blockDim.x / nC;            // pixel lanes per block
-  const int ch = threadIdx.x % nC, lane = threadIdx.x / nC;
+  const int nC = blockDim.x, lanes = blockDim.y;
+  const int ch = threadIdx.x, lane = threadIdx.y;
   const int n = blockIdx.y;
   const int HW = a.H * a.W;
+  int Ho, Wo;
+  operand_dims(a, &Ho, &Wo);
+  const bf16* gimg = b.g + (long)n * (a.planes ? 4 : 1) * Ho * Wo * a.C + ch * 8;
+  const bf16* simg = a.src + (long)n * HW * a.C + ch * 8;
+  NapChan c;
+  nap_chan_load<ACT>(b, n, ch * 8, c);
   const int p_begin = blockIdx.x * pix_per_block;
   const int p_end = min(p_begin + pix_per_block, HW);
+  const int dh = lanes / a.W, dw = lanes - dh * a.W;
+  int p = p_begin + lane;
+  int h = p / a.W, w = p - h * a.W;
   float s1[8], s2[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
-  for (int p = p_begin + lane; p < p_end; p += lanes) {
-    float gp[8], xh[8];
-    gprime(b, n, p / a.W, p % a.W, ch, gp, xh);
+#pragma unroll 2
+  for (; p < p_end; p += lanes) {
+    float gp[8], xh[8], x[8];
+    if (SINGLE) unpack8(fold_load<true>(a, gimg, Ho, Wo, h, w), gp);
+    else fold_grad_img(a, gimg, Ho, Wo, h, w, gp);
+    load8(simg + p * a.C, x);
+    gprime_apply<ACT>(b, c, x, gp, xh);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       s1[k] += gp[k];
       s2[k] += gp[k] * xh[k];
     }
+    h += dh;
+    w += dw;
+    if (w >= a.W) { w -= a.W; ++h; }
   }
-  float* mine = red + (lane * nC + ch) * 16;
+  const int tid = lane * nC + ch;
+  float* mine = red + tid * 16;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     mine[2 * k] = s1[k];
@@ -365,7 +475,7 @@ __global__ void nap_bwd_reduce_kernel(NapBwdArgs b, int pix_per_block) {
   // one partial per (CTA, image, channel, sum), lanes added in lane order: no atomics, fixed order; sg_sum_parts adds
   // the parts of an image in part order (a single part is written straight to the final slot)
   float* dst = b.sums + ((long)(b.parts > 1 ? blockIdx.x : 0) * a.N + n) * a.C * 2;
-  for (int t = threadIdx.x; t < nC * 16; t += blockDim.x) {
+  for (int t = tid; t < nC * 16; t += nC * lanes) {
     float v = 0.f;
     for (int l = 0; l < lanes; ++l) v += red[l * nC * 16 + t];
     dst[t] = v;
@@ -381,54 +491,82 @@ __global__ void bn_total_kernel(float* sums, int N, int C) {
   sums[(long)N * C * 2 + t] = v;
 }
 
-// grid.x = source row (n, h), grid.y * blockDim.x covers its (w, channel-chunk) items
-__global__ void nap_bwd_apply_kernel(NapBwdArgs b) {
+// grid (pixel group, h, n), block (C/8 chunks, pixel lanes of the source row); a thread loads the gradient taps and the
+// source of its ITEMS pixels before the first store
+template <int ACT, bool SINGLE, int ITEMS>
+__global__ void __launch_bounds__(256, 2) nap_bwd_apply_kernel(NapBwdArgs b) {
   const NapArgs& a = b.f;
-  const int nC = a.C / 8;
-  const unsigned item = blockIdx.y * blockDim.x + threadIdx.x;
-  if (item >= (unsigned)(a.W * nC)) return;
-  const int w = item / (unsigned)nC, ch = item - w * nC;
-  const int h = blockIdx.x % (unsigned)a.H, n = blockIdx.x / (unsigned)a.H;
-  const long idx = (long)blockIdx.x * (a.W * nC) + item;
-  float gp[8], xh[8];
-  if (b.dres) {
-    float fg[8];
-    fold_grad(a, b.g, n, h, w, ch, fg);
-    store8(b.dres + (long)n * a.res_os_img + (long)h * a.res_os_h + (long)w * a.res_os_w + ch * 8, fg);
+  const int ch8 = threadIdx.x * 8;
+  const int h = blockIdx.y, n = blockIdx.z;
+  int Ho, Wo;
+  operand_dims(a, &Ho, &Wo);
+  const bf16* gimg = b.g + (long)n * (a.planes ? 4 : 1) * Ho * Wo * a.C + ch8;
+  const bf16* srow = a.src + ((long)n * a.H + h) * a.W * a.C + ch8;
+  const int w0 = blockIdx.x * (blockDim.y * ITEMS) + threadIdx.y;
+  uint4 graw[ITEMS], xraw[ITEMS];
+  float gp[ITEMS][8];
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const int w = w0 + j * blockDim.y;
+    graw[j] = make_uint4(0u, 0u, 0u, 0u);
+    xraw[j] = make_uint4(0u, 0u, 0u, 0u);
+    if (w < a.W) {
+      if (SINGLE) graw[j] = fold_load<true>(a, gimg, Ho, Wo, h, w);
+      else fold_grad_img(a, gimg, Ho, Wo, h, w, gp[j]);
+      xraw[j] = *reinterpret_cast<const uint4*>(srow + w * a.C);
+    }
   }
-  gprime(b, n, h, w, ch, gp, xh);
-  float o[8];
-  const long pc = (long)n * a.C + ch * 8;
+  NapChan c;
+  nap_chan_load<ACT>(b, n, ch8, c);
+  float osc[8], m1[8], m2[8];
+  if (a.scale) load8f(a.scale + (long)n * a.C + ch8, osc);          // scale = rstd (* gamma)
   if (b.save_mean) {
-    float sc[8], s01[8], s23[8];
-    load8f(a.scale + pc, sc);                                          // scale = rstd (* gamma)
-    const float* sm = b.sums_final + ((long)(b.bn ? a.N : n) * a.C + ch * 8) * 2;   // (S1,S2) pairs of 8 channels
+    float s01[8], s23[8];
+    const float* sm = b.sums_final + ((long)(b.bn ? a.N : n) * a.C + ch8) * 2;   // (S1,S2) pairs of 8 channels
     load8f(sm, s01);
     load8f(sm + 8, s23);
     const float inv = 1.f / b.count;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      float m1 = (k < 4 ? s01[2 * k] : s23[2 * k - 8]) * inv;
-      float m2 = (k < 4 ? s01[2 * k + 1] : s23[2 * k - 7]) * inv;
-      o[k] = sc[k] * (gp[k] - m1 - xh[k] * m2);
+      m1[k] = (k < 4 ? s01[2 * k] : s23[2 * k - 8]) * inv;
+      m2[k] = (k < 4 ? s01[2 * k + 1] : s23[2 * k - 7]) * inv;
     }
-  } else if (a.scale) {
-    float sc[8];
-    load8f(a.scale + pc, sc);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = gp[k] * sc[k];
-  } else {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = gp[k];
   }
-  long off;
+  bf16* drow;
   if (b.out_planes) {
     const int Hh = (a.H + 1) / 2, Wh = (a.W + 1) / 2;
-    off = ((((long)n * 4 + (h & 1) * 2 + (w & 1)) * Hh + (h >> 1)) * Wh + (w >> 1)) * a.C + ch * 8;
+    drow = b.dsrc + (((long)n * 4 + (h & 1) * 2) * Hh + (h >> 1)) * Wh * a.C + ch8;
   } else {
-    off = idx * 8;
+    drow = b.dsrc + ((long)n * a.H + h) * a.W * a.C + ch8;
   }
-  store8(b.dsrc + off, o);
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const int w = w0 + j * blockDim.y;
+    if (w >= a.W) continue;
+    if (SINGLE) unpack8(graw[j], gp[j]);
+    if (b.dres) store8(b.dres + (long)n * a.res_os_img + (long)h * a.res_os_h + (long)w * a.res_os_w + ch8, gp[j]);
+    float x[8], xh[8], o[8];
+    unpack8(xraw[j], x);
+    gprime_apply<ACT>(b, c, x, gp[j], xh);
+    if (b.save_mean) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = osc[k] * (gp[j][k] - m1[k] - xh[k] * m2[k]);
+    } else if (a.scale) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = gp[j][k] * osc[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = gp[j][k];
+    }
+    int off;
+    if (b.out_planes) {
+      const int Hh = (a.H + 1) / 2, Wh = (a.W + 1) / 2;
+      off = ((w & 1) * Hh * Wh + (w >> 1)) * a.C;
+    } else {
+      off = w * a.C;
+    }
+    store8(drow + off, o);
+  }
 }
 
 // InstanceNorm backward of SMALL maps (H*W <= 256) in one kernel (SG_NAP_FUSED=0 falls back to reduce + apply).  nap_bwd_reduce + nap_bwd_apply read the gradient operand and the source twice, need a memset and — on the
@@ -438,7 +576,8 @@ __global__ void nap_bwd_apply_kernel(NapBwdArgs b) {
 constexpr int NAPF_THREADS = 256;
 constexpr int NAPF_MAX_ITEMS = 4;      // items per thread: H*W*SC <= 1024
 
-__global__ void __launch_bounds__(NAPF_THREADS) nap_bwd_fused_kernel(NapBwdArgs b, int SC) {
+template <int ACT, bool SINGLE>
+__global__ void __launch_bounds__(NAPF_THREADS, 2) nap_bwd_fused_kernel(NapBwdArgs b, int SC, int sc_shift) {
   __shared__ float part[NAPF_THREADS][17];        // per-thread partial (S1,S2) x 8 channels (+1: bank spread)
   __shared__ float stat[32][16];                  // per chunk of the slab: m1[8], m2[8]
   const NapArgs& a = b.f;
@@ -446,19 +585,30 @@ __global__ void __launch_bounds__(NAPF_THREADS) nap_bwd_fused_kernel(NapBwdArgs 
   const int HW = a.H * a.W;
   const int n = blockIdx.y;
   const int ch0 = blockIdx.x * SC;
-  const int c = threadIdx.x % SC;                 // NAPF_THREADS % SC == 0: a thread's items all have this chunk
+  const int c = threadIdx.x & (SC - 1);           // SC is a power of two dividing NAPF_THREADS: one chunk per thread
   const int ch = ch0 + c;
-  const int items = HW * SC;
+  const bool live = ch < nC;
+  int Ho, Wo;
+  operand_dims(a, &Ho, &Wo);
+  const bf16* gimg = b.g + (long)n * (a.planes ? 4 : 1) * Ho * Wo * a.C + ch * 8;
+  const bf16* simg = a.src + (long)n * HW * a.C + ch * 8;
+  NapChan cst;
+  if (live) nap_chan_load<ACT>(b, n, ch * 8, cst);
   float gp[NAPF_MAX_ITEMS][8], xh[NAPF_MAX_ITEMS][8];
   float s1[8], s2[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
 #pragma unroll
   for (int j = 0; j < NAPF_MAX_ITEMS; ++j) {
-    const int i = threadIdx.x + j * NAPF_THREADS;
-    if (i < items && ch < nC) {
-      const int p = i / SC;
-      gprime(b, n, p / a.W, p % a.W, ch, gp[j], xh[j]);
+    const int p = (threadIdx.x + j * NAPF_THREADS) >> sc_shift;
+    if (p < HW && live) {
+      const int h = p / a.W, w = p - h * a.W;
+      float x[8];
+      if (SINGLE) unpack8(fold_load<true>(a, gimg, Ho, Wo, h, w), gp[j]);
+      else fold_grad_img(a, gimg, Ho, Wo, h, w, gp[j]);
+      load8(simg + p * a.C, x);
+      if (b.dres) store8(b.dres + (long)n * a.res_os_img + (long)h * a.res_os_h + (long)w * a.res_os_w + ch * 8, gp[j]);
+      gprime_apply<ACT>(b, cst, x, gp[j], xh[j]);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         s1[k] += gp[j][k];
@@ -479,31 +629,26 @@ __global__ void __launch_bounds__(NAPF_THREADS) nap_bwd_fused_kernel(NapBwdArgs 
     stat[cc][e] = v / b.count;
   }
   __syncthreads();
-  if (ch >= nC) return;
+  if (!live) return;
   float sc[8];
   load8f(a.scale + (long)n * a.C + ch * 8, sc);
+  const int Hh = (a.H + 1) / 2, Wh = (a.W + 1) / 2;
+  bf16* dimg = b.dsrc + (long)n * (b.out_planes ? 4 * Hh * Wh : HW) * a.C + ch * 8;
 #pragma unroll
   for (int j = 0; j < NAPF_MAX_ITEMS; ++j) {
-    const int i = threadIdx.x + j * NAPF_THREADS;
-    if (i >= items) continue;
-    const int p = i / SC;
-    const int h = p / a.W, w = p % a.W;
-    if (b.dres) {
-      float fg[8];
-      fold_grad(a, b.g, n, h, w, ch, fg);
-      store8(b.dres + (long)n * a.res_os_img + (long)h * a.res_os_h + (long)w * a.res_os_w + ch * 8, fg);
-    }
+    const int p = (threadIdx.x + j * NAPF_THREADS) >> sc_shift;
+    if (p >= HW) continue;
     float o[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) o[k] = sc[k] * (gp[j][k] - stat[c][2 * k] - xh[j][k] * stat[c][2 * k + 1]);
-    long off;
+    int off;
     if (b.out_planes) {
-      const int Hh = (a.H + 1) / 2, Wh = (a.W + 1) / 2;
-      off = ((((long)n * 4 + (h & 1) * 2 + (w & 1)) * Hh + (h >> 1)) * Wh + (w >> 1)) * a.C + ch * 8;
+      const int h = p / a.W, w = p - h * a.W;
+      off = ((((h & 1) * 2 + (w & 1)) * Hh + (h >> 1)) * Wh + (w >> 1)) * a.C;
     } else {
-      off = (((long)n * a.H + h) * a.W + w) * a.C + ch * 8;
+      off = p * a.C;
     }
-    store8(b.dsrc + off, o);
+    store8(dimg + off, o);
   }
 }
 
@@ -802,35 +947,40 @@ static bool nap_fused_enabled() {
 }
 
 // launch shape of the norm-backward reduction: threads per CTA, pixels per CTA, CTAs (= partial slots) per image
-static void nap_reduce_shape(int N, int H, int W, int C, int* threads_out, int* pix_per_block_out, int* parts_out) {
+static void nap_reduce_shape(int N, int H, int W, int C, int* lanes_out, int* pix_per_block_out, int* parts_out) {
   const int nC = C / 8;
-  int threads = nC >= 256 ? nC : 256;
-  threads = (threads / nC) * nC;
-  const int lanes = threads / nC;
   const long HW = (long)H * W;
-  // ~8 CTAs per SM over all images, at most SG_NAP_MAX_PARTS per image (the apply kernel adds an image's parts
-  // itself), at least 2 pixels per thread
-  long parts = (1184 + N - 1) / N;
+  int lanes = nC >= 256 ? 1 : 256 / nC;
+  if (lanes > HW) lanes = (int)HW;
+  // ~16 CTAs per SM over all images, at most SG_NAP_MAX_PARTS per image, at least 2 pixels per thread
+  long parts = (2368 + N - 1) / N;
   if (parts > SG_NAP_MAX_PARTS) parts = SG_NAP_MAX_PARTS;
   if (parts < 1) parts = 1;
   long ppb = (HW + parts - 1) / parts;
   if (ppb < lanes * 2) ppb = lanes * 2;
   ppb = ((ppb + lanes - 1) / lanes) * lanes;
-  *threads_out = threads;
+  *lanes_out = lanes;
   *pix_per_block_out = (int)ppb;
   *parts_out = (int)((HW + ppb - 1) / ppb);
 }
 
 extern "C" int sg_norm_act_pad_bwd_parts(int N, int H, int W, int C) {
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 != 0) return 0;
-  int threads, ppb, parts;
-  nap_reduce_shape(N, H, W, C, &threads, &ppb, &parts);
+  int lanes, ppb, parts;
+  nap_reduce_shape(N, H, W, C, &lanes, &ppb, &parts);
   return parts;
 }
 
 static int nap_check(const sg_nap_desc_t* d) {
   SG_CHECK_ARG(d && d->src, "norm_act_pad: null pointer");
   SG_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0 && d->C > 0 && d->C % 8 == 0, "norm_act_pad: bad sizes (C must be a multiple of 8)");
+  SG_CHECK_ARG(d->C <= 2048, "norm_act_pad: at most 2048 channels (one thread per 8 channels, 256 threads)");
+  SG_CHECK_ARG(d->up >= 1 && d->pad >= 0, "norm_act_pad: bad up / pad");
+  {
+    const long Hp = (long)d->H * d->up + 2 * d->pad + 1, Wp = (long)d->W * d->up + 2 * d->pad + 1;
+    SG_CHECK_ARG(Hp * Wp * d->C < (1L << 31), "norm_act_pad: one image's operand must stay below 2^31 elements");
+    SG_CHECK_ARG(Hp < 65536 && (long)d->N * 4 < 65536, "norm_act_pad: grid limits (rows, images * 4 < 65536)");
+  }
   SG_CHECK_ARG(d->up == 1 || d->up == 2, "norm_act_pad: up must be 1 or 2");
   SG_CHECK_ARG(d->pad >= 0 && (d->pad_mode == 0 || d->pad_mode == 1), "norm_act_pad: bad padding");
   SG_CHECK_ARG(!(d->pad_mode == 1 && d->pad >= d->H * d->up), "norm_act_pad: reflection pad must be smaller than the input");
@@ -851,13 +1001,23 @@ extern "C" int sg_norm_act_pad_fwd(const sg_nap_desc_t* d, void* out, sg_stream_
   SG_CHECK_ARG(out != nullptr, "norm_act_pad_fwd: null output");
   NapArgs a = nap_args(d);
   const int Hp = d->H * d->up + 2 * d->pad, Wp = d->W * d->up + 2 * d->pad;
-  const long per_img = d->planes ? 4L * ((Hp + 1) / 2) * ((Wp + 1) / 2) : (long)Hp * Wp;
-  const long rows = d->N * (d->planes ? 4L * ((Hp + 1) / 2) : (long)Hp);
-  const int row_items = (d->planes ? (Wp + 1) / 2 : Wp) * (d->C / 8);
-  (void)per_img;
-  SG_CHECK_ARG(rows < (1L << 31), "norm_act_pad_fwd: too many rows");
-  const int threads = row_items >= 256 ? 256 : ((row_items + 31) / 32) * 32;
-  nap_fwd_kernel<<<dim3((unsigned)rows, sg_cdiv(row_items, threads)), threads, 0, stream>>>(a, (bf16*)out);
+  const int Ho = d->planes ? (Hp + 1) / 2 : Hp, Wo = d->planes ? (Wp + 1) / 2 : Wp;
+  const int nC = d->C / 8;
+  int lanes = 256 / nC;
+  if (lanes > Wo) lanes = Wo;
+  const int per_lane = sg_cdiv(Wo, lanes);
+  const int items = per_lane >= 4 ? 4 : (per_lane >= 2 ? 2 : 1);
+  const dim3 block(nC, lanes), grid(sg_cdiv(Wo, lanes * items), Ho, d->N * (d->planes ? 4 : 1));
+#define NAP_FWD_LAUNCH(ACT)                                                                      \
+  do {                                                                                           \
+    if (items == 4) nap_fwd_kernel<ACT, 4><<<grid, block, 0, stream>>>(a, (bf16*)out);           \
+    else if (items == 2) nap_fwd_kernel<ACT, 2><<<grid, block, 0, stream>>>(a, (bf16*)out);      \
+    else nap_fwd_kernel<ACT, 1><<<grid, block, 0, stream>>>(a, (bf16*)out);                      \
+  } while (0)
+  if (d->act == SG_ACT_RELU) NAP_FWD_LAUNCH(SG_ACT_RELU);
+  else if (d->act == SG_ACT_LEAKY) NAP_FWD_LAUNCH(SG_ACT_LEAKY);
+  else NAP_FWD_LAUNCH(SG_ACT_NONE);
+#undef NAP_FWD_LAUNCH
   SG_CHECK_LAUNCH("sg_norm_act_pad_fwd");
   return SG_OK;
 }
@@ -875,6 +1035,7 @@ extern "C" int sg_norm_act_pad_bwd(const sg_nap_desc_t* d, const void* grad, con
   b.sums_final = sums;
   b.out_planes = out_planes; b.dsrc = (bf16*)dsrc; b.dres = (bf16*)dres;
   const int nC = d->C / 8;
+  const bool single = d->up == 1 && !(d->pad_mode && d->pad > 0);
   if (save_mean && !bn && nap_fused_enabled() && (long)d->H * d->W <= 256) {
     // experimental single-kernel path for small InstanceNorm maps: SC chunks per CTA with H*W*SC <= 1024 items
     int SC = 8;
@@ -882,21 +1043,40 @@ extern "C" int sg_norm_act_pad_bwd(const sg_nap_desc_t* d, const void* grad, con
     if ((long)d->H * d->W * SC <= (long)NAPF_THREADS * NAPF_MAX_ITEMS) {
       if (out_planes && ((d->H & 1) || (d->W & 1)))
         cudaMemsetAsync(dsrc, 0, sizeof(bf16) * 4 * (size_t)d->N * ((d->H + 1) / 2) * ((d->W + 1) / 2) * d->C, stream);
-      nap_bwd_fused_kernel<<<dim3(sg_cdiv(nC, SC), d->N), NAPF_THREADS, 0, stream>>>(b, SC);
+      int sc_shift = 0;
+      while ((1 << sc_shift) < SC) ++sc_shift;
+      const dim3 grid(sg_cdiv(nC, SC), d->N);
+#define NAP_FUSED_LAUNCH(ACT)                                                                                  \
+  do {                                                                                                         \
+    if (single) nap_bwd_fused_kernel<ACT, true><<<grid, NAPF_THREADS, 0, stream>>>(b, SC, sc_shift);           \
+    else nap_bwd_fused_kernel<ACT, false><<<grid, NAPF_THREADS, 0, stream>>>(b, SC, sc_shift);                 \
+  } while (0)
+      if (d->act == SG_ACT_RELU) NAP_FUSED_LAUNCH(SG_ACT_RELU);
+      else if (d->act == SG_ACT_LEAKY) NAP_FUSED_LAUNCH(SG_ACT_LEAKY);
+      else NAP_FUSED_LAUNCH(SG_ACT_NONE);
+#undef NAP_FUSED_LAUNCH
       SG_CHECK_LAUNCH("sg_norm_act_pad_bwd(fused)");
       return SG_OK;
     }
   }
   if (save_mean) {
-    int threads, pix_per_block, parts;
-    nap_reduce_shape(d->N, d->H, d->W, d->C, &threads, &pix_per_block, &parts);
-    SG_CHECK_ARG(threads <= 1024, "norm_act_pad_bwd: too many channels");
+    int lanes, pix_per_block, parts;
+    nap_reduce_shape(d->N, d->H, d->W, d->C, &lanes, &pix_per_block, &parts);
     const long per = (long)d->N * d->C * 2;
     float* fin = sums + (parts > 1 ? (long)parts * per : 0);       // per-image sums: behind the partials
     b.parts = parts;
     b.sums_final = fin;
-    dim3 grid(parts, d->N);
-    nap_bwd_reduce_kernel<<<grid, threads, sizeof(float) * 16 * threads, stream>>>(b, pix_per_block);
+    const dim3 grid(parts, d->N), block(nC, lanes);
+    const size_t smem = sizeof(float) * 16 * nC * lanes;
+#define NAP_RED_LAUNCH(ACT)                                                                                     \
+  do {                                                                                                          \
+    if (single) nap_bwd_reduce_kernel<ACT, true><<<grid, block, smem, stream>>>(b, pix_per_block);              \
+    else nap_bwd_reduce_kernel<ACT, false><<<grid, block, smem, stream>>>(b, pix_per_block);                    \
+  } while (0)
+    if (d->act == SG_ACT_RELU) NAP_RED_LAUNCH(SG_ACT_RELU);
+    else if (d->act == SG_ACT_LEAKY) NAP_RED_LAUNCH(SG_ACT_LEAKY);
+    else NAP_RED_LAUNCH(SG_ACT_NONE);
+#undef NAP_RED_LAUNCH
     SG_CHECK_LAUNCH("sg_norm_act_pad_bwd(reduce)");
     if (parts > 1)
       if (int e = sg_sum_parts(sums, per, parts, per, fin, stream, "sg_norm_act_pad_bwd(sum parts)")) return e;
@@ -911,9 +1091,21 @@ extern "C" int sg_norm_act_pad_bwd(const sg_nap_desc_t* d, const void* grad, con
       cudaMemsetAsync(dsrc, 0, sizeof(bf16) * 4 * (size_t)d->N * ((d->H + 1) / 2) * ((d->W + 1) / 2) * d->C, stream);
   }
   {
-    const int row_items = d->W * nC;
-    const int threads = row_items >= 256 ? 256 : ((row_items + 31) / 32) * 32;
-    nap_bwd_apply_kernel<<<dim3((unsigned)(d->N * d->H), sg_cdiv(row_items, threads)), threads, 0, stream>>>(b);
+    int lanes = 256 / nC;
+    if (lanes > d->W) lanes = d->W;
+    const int items = sg_cdiv(d->W, lanes) >= 2 ? 2 : 1;
+    const dim3 block(nC, lanes), grid(sg_cdiv(d->W, lanes * items), d->H, d->N);
+#define NAP_APPLY_LAUNCH(ACT)                                                                     \
+  do {                                                                                            \
+    if (single && items == 2) nap_bwd_apply_kernel<ACT, true, 2><<<grid, block, 0, stream>>>(b);  \
+    else if (single) nap_bwd_apply_kernel<ACT, true, 1><<<grid, block, 0, stream>>>(b);           \
+    else if (items == 2) nap_bwd_apply_kernel<ACT, false, 2><<<grid, block, 0, stream>>>(b);      \
+    else nap_bwd_apply_kernel<ACT, false, 1><<<grid, block, 0, stream>>>(b);                      \
+  } while (0)
+    if (d->act == SG_ACT_RELU) NAP_APPLY_LAUNCH(SG_ACT_RELU);
+    else if (d->act == SG_ACT_LEAKY) NAP_APPLY_LAUNCH(SG_ACT_LEAKY);
+    else NAP_APPLY_LAUNCH(SG_ACT_NONE);
+#undef NAP_APPLY_LAUNCH
   }
   SG_CHECK_LAUNCH("sg_norm_act_pad_bwd(apply)");
   return SG_OK;
