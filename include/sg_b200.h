@@ -160,6 +160,10 @@ typedef struct {
 } sg_wgrad_desc_t;
 int sg_wgrad_tc(const sg_wgrad_desc_t* desc, sg_stream_t stream);
 
+/* Hardware probe (not on any product path): clocks per tcgen05.mma (M = 128, K = 16, N = BN in {16, 64, 128, 256})
+ * issued back to back by one thread over fixed shared-memory operands; mode 0 = the four K steps of a k-block into one
+ * accumulator, 1 = the same K step, 2 = four accumulators round robin.  out: one float on the device. */
+int sg_probe_mma_rate(int BN, int iters, int mode, float* out, sg_stream_t stream);
 /* Hardware probe (groundwork for an smem-resident halo tile, not on any product path): a 3x3 convolution of one
  * 16x8-pixel tile, 64 -> 64 channels, whose nine taps read ONE halo tile through tap-shifted UMMA descriptors.
  * x: bf16 [1][1][18][10][64], w: bf16 [64][9][64], y: f32 [128][64]; mode 0 / 1 = descriptor base_offset 0 / derived

@@ -131,6 +131,7 @@ _SIGS = {
                      ctypes.c_double, _P],
     'sg_wgrad_tc': [ctypes.POINTER(WgradDesc), _P],
     'sg_probe_shifted_desc': [_P, _P, _P, c_int, _P],
+    'sg_probe_mma_rate': [c_int, c_int, c_int, _P, _P],
     'sg_im2col_dz': [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
     'sg_dgrad_small_cout': [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
     'sg_wgrad_small_cout': [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_long, _P],

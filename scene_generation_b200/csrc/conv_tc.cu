@@ -62,16 +62,6 @@ int make_tmap(CUtensorMap* m, const void* base, int rank, const long long* dims,
   return SG_OK;
 }
 
-__device__ __forceinline__ float apply_act(float v, int act, float slope) {
-  switch (act) {
-    case SG_ACT_RELU: return fmaxf(v, 0.f);
-    case SG_ACT_LEAKY: return v >= 0.f ? v : v * slope;
-    case SG_ACT_TANH: return tanhf(v);
-    case SG_ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
-    default: return v;
-  }
-}
-
 // lane l ends up with the sum over the warp of v[l]
 __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
 #pragma unroll
@@ -158,18 +148,15 @@ __device__ __forceinline__ void conv_epilogue(const ConvKParams& p, const sg_pha
     uint32_t raw[32];
     if (CH == 32) tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, raw);
     else tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c0, raw);
-    tmem_ld_wait();
     float f[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (j < CH) {
-        const int c = n0 + c0 + j;
-        float b = (p.bias != nullptr && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
-        f[j] = __uint_as_float(raw[j]) + b;
-      } else {
-        f[j] = 0.f;
-      }
+    for (int j = 0; j < 32; ++j) {                      // the bias loads overlap the TMEM read
+      const int c = n0 + c0 + j;
+      f[j] = (j < CH && p.bias != nullptr && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
     }
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < CH; ++j) f[j] += __uint_as_float(raw[j]);
     if (p.stats != nullptr) {
       if (seg_full) {
         float s1[32], s2[32];
@@ -204,8 +191,21 @@ __device__ __forceinline__ void conv_epilogue(const ConvKParams& p, const sg_pha
       }
     }
     if (valid) {
+      // one CTA-uniform branch per chunk, not one jump table per element (the epilogue warps run one per scheduler:
+      // every taken indirect branch is an exposed refetch)
+      if (p.act == SG_ACT_RELU) {
 #pragma unroll
-      for (int j = 0; j < CH; ++j) f[j] = apply_act(f[j], p.act, p.slope);
+        for (int j = 0; j < CH; ++j) f[j] = fmaxf(f[j], 0.f);
+      } else if (p.act == SG_ACT_LEAKY) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) f[j] = f[j] >= 0.f ? f[j] : f[j] * p.slope;
+      } else if (p.act == SG_ACT_TANH) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) f[j] = tanhf(f[j]);
+      } else if (p.act == SG_ACT_SIGMOID) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) f[j] = 1.f / (1.f + __expf(-f[j]));
+      }
       const bool full_chunk = (n0 + c0 + CH <= p.Cout) && p.vec_ok;
       if (p.y_dtype == 1) {
         __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + off + (long long)(n0 + c0) * p.os_c;
@@ -974,6 +974,77 @@ __global__ void __launch_bounds__(128) probe_shift_kernel(const __grid_constant_
 }
 
 }  // namespace
+
+// PROBE: issue rate of tcgen05.mma (M = 128, K = 16, N = BN) from one thread over fixed shared-memory operands —
+// the floor under every kernel of this file.  mode 0: the four K steps of one 64-wide k-block, one accumulator;
+// mode 1: the same K step every time; mode 2: four accumulators round robin.  out[0] = clocks per MMA.
+namespace {
+template <int BN>
+__global__ void __launch_bounds__(128) probe_mma_rate_kernel(int iters, int mode, float* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 2 * A_BYTES;              // A region: 32 KB (modes 3 / 4 read 16 groups 1792 B apart)
+  uint64_t* done = reinterpret_cast<uint64_t*>(sB + 256 * 128);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  for (int i = threadIdx.x; i < (2 * A_BYTES + 256 * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+  if (threadIdx.x == 0) {
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 32) tmem_alloc<512>(tmem_slot);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (threadIdx.x == 0) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+    // modes 3 / 4: the A operand as a tap-shifted view of a halo tile (start 3 rows into a swizzle atom / aligned
+    // start, 8-row groups 14 rows apart): groups that straddle two 1024-byte swizzle atoms
+    const uint64_t ad = mode == 3 ? umma_desc_sw128(smem_u32(sA) + 3 * 128, 16, 14 * 128)
+                      : mode == 4 ? umma_desc_sw128(smem_u32(sA), 16, 14 * 128)
+                                  : umma_desc_sw128(smem_u32(sA), 16, 1024);
+    const uint64_t bd = umma_desc_sw128(smem_u32(sB), 16, 1024);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int kk = mode == 1 ? 0 : k;   // (modes 3 / 4 step through K like mode 0)
+        const uint32_t acc = mode == 2 ? (uint32_t)(((it * 4 + k) & (BN > 128 ? 1 : 3)) * BN) : 0u;
+        mma_bf16(tmem + acc, ad + 2 * kk, bd + 2 * kk, idesc, 1u);
+      }
+    }
+    mma_commit(done);
+    mbar_wait(done, 0);
+    const long long t1 = clock64();
+    out[0] = (float)(t1 - t0) / (4.f * iters);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc<512>(tmem);
+}
+}  // namespace
+
+extern "C" int sg_probe_mma_rate(int BN, int iters, int mode, float* out, sg_stream_t stream) {
+  SG_CHECK_ARG(out && iters > 0 && mode >= 0 && mode <= 4, "sg_probe_mma_rate: bad arguments");
+  const int smem = 2 * A_BYTES + 256 * 128 + 1024 + 256;
+#define SG_PROBE_RATE(N)                                                                                           \
+  do {                                                                                                             \
+    cudaFuncSetAttribute(probe_mma_rate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);             \
+    probe_mma_rate_kernel<N><<<1, 128, smem, stream>>>(iters, mode, out);                                          \
+  } while (0)
+  switch (BN) {
+    case 16: SG_PROBE_RATE(16); break;
+    case 64: SG_PROBE_RATE(64); break;
+    case 128: SG_PROBE_RATE(128); break;
+    case 256: SG_PROBE_RATE(256); break;
+    default: return sg_fail(SG_ERR_ARG, "sg_probe_mma_rate: BN must be 16, 64, 128 or 256");
+  }
+#undef SG_PROBE_RATE
+  SG_CHECK_LAUNCH("sg_probe_mma_rate");
+  return SG_OK;
+}
 
 /* x: bf16 [1][1][18][10][64] (reflection / zero halo already materialised), w: bf16 [64][9][64], y: f32 [128][64]
  * (pixel = h * 8 + w of the 16 x 8 tile, then output channel). */

@@ -289,3 +289,4 @@ def test_cta_pair_kernel_long_k_wide_n(N, C, H, Co):
     dx = torch.full((N, H, H, C), float('nan'), dtype=torch.bfloat16, device=DEV)
     ops.conv_tc(to_nhwc5(dy), pack_w(w), dx, (H * H * C, H * C, C, 1), H, H, convspec.dgrad_s1(k, p), mn_cols=(0, C))
     check(dx.permute(0, 3, 1, 2), refd, 1e-2)
+
