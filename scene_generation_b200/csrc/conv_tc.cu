@@ -470,6 +470,8 @@ struct WgradKParams {
   int ktiles_total, ktiles_per_split;
   int serial;       // 1: split-K through per-split workspace slabs, added in split order by sg_sum_parts
   int Cout, Cin, w_taps, dw_C, n_ci_tiles, stages;
+  int tap_group;    // > 1 (Cin <= 64 only): blockIdx.y owns tap_group taps, tap j in columns [64 j, 64 j + 64) of the N tile
+  int ntaps;
   long long dw_split_stride;   // per_image: floats between the dw slabs of consecutive k-splits (= images)
   float* dw;
   float* ws;        // serial: [ksplit][Cout * w_taps * dw_C] partial sums
@@ -490,6 +492,9 @@ struct WgradCfg {
 
 // Split-K is DETERMINISTIC: every k-split (blockIdx.z) of a dw tile stores its partial sums to its own slab of the
 // workspace; sg_sum_parts then adds the slabs in split order (no atomics, nothing waits).
+// Tap stacking (tap_group > 1, layers with at most 64 input channels): the N tile holds the SAME 64 input channels of
+// tap_group different taps — the dy box is loaded once per k-tile for all of them and the MMAs are N = 64 * tap_group
+// wide (an N = 64 MMA occupies the tensor pipe for 54 clocks, an N = 256 one for 128: sg_probe_mma_rate).
 template <int BN>
 __global__ void __launch_bounds__(192, 2)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -505,8 +510,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ci_tile = blockIdx.x % p.n_ci_tiles, co_tile = blockIdx.x / p.n_ci_tiles;
-  const int co0 = co_tile * 128, ci0 = ci_tile * BN;
-  const sg_wtap_t tp = p.taps[blockIdx.y];
+  const int TG = p.tap_group;
+  const int co0 = co_tile * 128, ci0 = TG > 1 ? 0 : ci_tile * BN;
+  const int tap0 = blockIdx.y * TG;                          // first tap of this CTA
+  const int ntap = min(TG, p.ntaps - tap0);                  // taps of this CTA that exist
+  const sg_wtap_t tp = p.taps[tap0];
   const int kt_begin = blockIdx.z * p.ktiles_per_split;
   const int kt_end = min(kt_begin + p.ktiles_per_split, p.ktiles_total);
   const int iters = max(kt_end - kt_begin, 0);
@@ -538,6 +546,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int tw = kt % p.tiles_w, th = (kt / p.tiles_w) % p.tiles_h, ti = kt / (p.tiles_w * p.tiles_h);
         const int w0 = tw * p.BW, h0 = th * p.BH, img0 = ti * p.BI;
         uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+        if (TG > 1) {
+          // columns of taps that do not exist keep stale shared memory: their accumulator columns are never stored
+          mbar_expect_tx(&full[s], (2 + ntap) * WG_BOX_BYTES);
+          tma_load_5d(st, &tmA, &full[s], co0, w0 + tp.dwa, h0 + tp.dha, tp.pa, img0);
+          tma_load_5d(st + WG_BOX_BYTES, &tmA, &full[s], co0 + 64, w0 + tp.dwa, h0 + tp.dha, tp.pa, img0);
+#pragma unroll
+          for (int j = 0; j < Cfg::NB; ++j) {
+            if (j < ntap) {
+              const sg_wtap_t tj = p.taps[tap0 + j];
+              tma_load_5d(st + (2 + j) * WG_BOX_BYTES, &tmB, &full[s], 0, w0 + tj.dwb, h0 + tj.dhb, tj.pb, img0);
+            }
+          }
+          continue;
+        }
         mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
         tma_load_5d(st, &tmA, &full[s], co0, w0 + tp.dwa, h0 + tp.dha, tp.pa, img0);
         tma_load_5d(st + WG_BOX_BYTES, &tmA, &full[s], co0 + 64, w0 + tp.dwa, h0 + tp.dha, tp.pa, img0);
@@ -576,13 +598,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (ci0 + c0 >= p.Cin) break;
+        // tap stacking: column block j = c0 / 64 is tap tap0 + j, its columns are input channels c0 % 64 ...
+        const int tj = TG > 1 ? c0 >> 6 : 0;
+        const int cc = TG > 1 ? (c0 & 63) : ci0 + c0;        // first input channel of this chunk
+        if (TG > 1 ? tj >= ntap : cc >= p.Cin) break;
+        if (cc >= p.Cin) continue;
+        const int wtap = p.taps[tap0 + tj].wtap;
         uint32_t raw[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, raw);
         tmem_ld_wait();
         if (co < p.Cout) {
-          float* dst = base + ((long long)co * p.w_taps + tp.wtap) * p.dw_C + ci0 + c0;
-          const bool vec = (ci0 + c0 + 32 <= p.Cin) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+          float* dst = base + ((long long)co * p.w_taps + wtap) * p.dw_C + cc;
+          const bool vec = (cc + 32 <= p.Cin) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
           if (vec) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
@@ -591,7 +618,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (ci0 + c0 + j < p.Cin) __stcg(dst + j, __uint_as_float(raw[j]));
+              if (cc + j < p.Cin) __stcg(dst + j, __uint_as_float(raw[j]));
           }
         }
       }
@@ -711,6 +738,16 @@ bool no192() {
   if (v < 0) {
     const char* e = getenv("SG_CONV_NO192");
     v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+// SG_WGRAD_TAPSTACK=0 disables tap stacking in sg_wgrad_tc (A/B switch)
+bool tap_stack_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SG_WGRAD_TAPSTACK");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
 }
@@ -857,11 +894,24 @@ extern "C" int sg_wgrad_tc(const sg_wgrad_desc_t* d, sg_stream_t stream) {
   kp.ktiles_total = kp.tiles_w * kp.tiles_h * sg_cdiv(d->N, kp.BI);
   kp.Cout = d->Cout; kp.Cin = d->Cin; kp.w_taps = d->w_taps; kp.dw_C = d->dw_C; kp.dw = d->dw;
   for (int i = 0; i < d->ntaps; ++i) kp.taps[i] = d->taps[i];
-  const int BN = (d->Cin > 128 && d->Cin <= 192 && !no192()) ? 192 : (d->Cin > 128 ? 256 : (d->Cin > 64 ? 128 : 64));
-  kp.n_ci_tiles = sg_cdiv(d->Cin, BN);
+  int BN = (d->Cin > 128 && d->Cin <= 192 && !no192()) ? 192 : (d->Cin > 128 ? 256 : (d->Cin > 64 ? 128 : 64));
+  // tap stacking for layers with at most 64 input channels: taps whose dy box is the same share an N tile
+  kp.tap_group = 1;
+  kp.ntaps = d->ntaps;
+  if (d->Cin <= 64 && d->ntaps >= 3 && tap_stack_enabled()) {
+    bool same_a = true;
+    for (int i = 1; i < d->ntaps; ++i)
+      same_a = same_a && d->taps[i].dha == d->taps[0].dha && d->taps[i].dwa == d->taps[0].dwa && d->taps[i].pa == d->taps[0].pa;
+    if (same_a) {
+      kp.tap_group = (d->ntaps % 4 != 0 && d->ntaps % 3 == 0 && !no192()) ? 3 : 4;
+      BN = 64 * kp.tap_group;
+    }
+  }
+  const int tap_groups = sg_cdiv(d->ntaps, kp.tap_group);
+  kp.n_ci_tiles = kp.tap_group > 1 ? 1 : sg_cdiv(d->Cin, BN);
   const int co_tiles = sg_cdiv(d->Cout, 128);
   int ksplit = d->ksplit;
-  const long base_ctas = (long)co_tiles * kp.n_ci_tiles * d->ntaps;
+  const long base_ctas = (long)co_tiles * kp.n_ci_tiles * tap_groups;
   if (d->per_image) {
     // one k-split per image: dw is [N][Cout][w_taps][dw_C], every slab is owned by the CTAs of one image
     SG_CHECK_ARG(kp.BI == 1, "sg_wgrad_tc: per_image needs reduction tiles within one image (Hred*Wred >= 64)");
@@ -894,7 +944,7 @@ extern "C" int sg_wgrad_tc(const sg_wgrad_desc_t* d, sg_stream_t stream) {
   int box[5] = {64, kp.BW, kp.BH, 1, kp.BI};
   if (int e = make_tmap(&tmA, d->dy, 5, adims, box)) return e;
   if (int e = make_tmap(&tmB, d->x, 5, bdims, box)) return e;
-  dim3 grid(co_tiles * kp.n_ci_tiles, d->ntaps, ksplit);
+  dim3 grid(co_tiles * kp.n_ci_tiles, tap_groups, ksplit);
   int e;
   switch (BN) {
     case 256: e = launch_wgrad<256>(tmA, tmB, kp, grid, stream); break;

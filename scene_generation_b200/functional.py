@@ -786,16 +786,21 @@ class ToNhwcFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, Cp):
         N, C, H, W = x.shape
-        out = torch.zeros((N, H, W, Cp), dtype=BF, device=x.device)
+        ctx.dims = (N, C, H, W, Cp)
         dt = 1 if x.dtype == torch.int64 else 0
         xs = x.contiguous() if dt else x.contiguous().float()
+        if H * W == 1 and dt == 0:
+            # vectors: NCHW == NHWC, a padded cast (the pixel-per-thread kernel below would run one block)
+            return cast_pad(xs.reshape(N, C), Cp).view(N, 1, 1, Cp)
+        out = torch.zeros((N, H, W, Cp), dtype=BF, device=x.device)
         _lib.call('sg_nchw_to_nhwc', _ptr(xs), dt, N, C, H, W, Cp, 0, _ptr(out), _stream())
-        ctx.dims = (N, C, H, W, Cp)
         return out
 
     @staticmethod
     def backward(ctx, g):
         N, C, H, W, Cp = ctx.dims
+        if H * W == 1:
+            return g.reshape(N, Cp)[:, :C].float().reshape(N, C, 1, 1), None
         gi = torch.empty((N, C, H, W), dtype=torch.float32, device=g.device)
         _lib.call('sg_nhwc_to_nchw', _ptr(g.contiguous()), N, C, H, W, Cp, 0, _ptr(gi), _stream())
         return gi, None

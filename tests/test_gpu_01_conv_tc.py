@@ -148,8 +148,10 @@ def test_dgrad_s1_matches_autograd():
 
 
 @pytest.mark.parametrize('N,C,H,Co,k,p', [(2, 64, 8, 128, 3, 1), (4, 128, 8, 256, 3, 0), (2, 204, 16, 64, 7, 0),
-                                          (3, 40, 12, 72, 3, 1)])
+                                          (3, 40, 12, 72, 3, 1), (2, 64, 20, 64, 7, 3), (3, 8, 17, 64, 4, 2),
+                                          (2, 24, 16, 200, 5, 2)])
 def test_wgrad_s1(N, C, H, Co, k, p):
+    # C <= 64: the taps are stacked in the N tile (3 or 4 per CTA; 49 and 25 taps leave a last group of one tap)
     x, w = rnd(N, C, H + 2 * (k // 2 - p), H + 2 * (k // 2 - p), seed=19), rnd(Co, C, k, k, seed=20, scale=0.05)
     wr = r32(w).requires_grad_(True)
     out = F.conv2d(r32(x), wr, padding=p)
