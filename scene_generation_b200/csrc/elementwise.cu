@@ -482,13 +482,22 @@ __global__ void __launch_bounds__(256, 2) nap_bwd_reduce_kernel(NapBwdArgs b, in
   }
 }
 
-// BatchNorm: totals[c*2+j] = sum over images (in image order) of the per-image sums; stored behind them
-__global__ void bn_total_kernel(float* sums, int N, int C) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= C * 2) return;
+// BatchNorm: totals[c*2+j] = sum over images of the per-image sums, stored behind them.  Block = 32 columns x 32 image
+// lanes: lane r adds images r, r + 32, ... in order, the 32 lane sums are then added in lane order (fixed order).
+__global__ void __launch_bounds__(1024) bn_total_kernel(float* sums, int N, int C) {
+  __shared__ float part[32][33];
+  const int t = blockIdx.x * 32 + threadIdx.x;
   float v = 0.f;
-  for (int n = 0; n < N; ++n) v += sums[(long)n * C * 2 + t];
-  sums[(long)N * C * 2 + t] = v;
+  if (t < C * 2)
+    for (int n = threadIdx.y; n < N; n += 32) v += sums[(long)n * C * 2 + t];
+  part[threadIdx.y][threadIdx.x] = v;
+  __syncthreads();
+  if (threadIdx.y == 0 && t < C * 2) {
+    float a = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) a += part[r][threadIdx.x];
+    sums[(long)N * C * 2 + t] = a;
+  }
 }
 
 // grid (pixel group, h, n), block (C/8 chunks, pixel lanes of the source row); a thread loads the gradient taps and the
@@ -1081,7 +1090,7 @@ extern "C" int sg_norm_act_pad_bwd(const sg_nap_desc_t* d, const void* grad, con
     if (parts > 1)
       if (int e = sg_sum_parts(sums, per, parts, per, fin, stream, "sg_norm_act_pad_bwd(sum parts)")) return e;
     if (bn) {
-      bn_total_kernel<<<sg_cdiv(2 * d->C, 256), 256, 0, stream>>>(fin, d->N, d->C);
+      bn_total_kernel<<<sg_cdiv(2 * d->C, 32), dim3(32, 32), 0, stream>>>(fin, d->N, d->C);
       SG_CHECK_LAUNCH("sg_norm_act_pad_bwd(bn totals)");
     }
   }

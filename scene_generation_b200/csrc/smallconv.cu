@@ -148,32 +148,40 @@ __global__ void wgrad_small_reduce_kernel(const float* __restrict__ ws, int n_bl
 //   dgrad  dx[n,u,v,ci]        = sum_K col[n,u,v,K] * wcol[ci][K]                (sg_conv_tc, one tap, K = Cout*k*k)
 //   wgrad  dw[co, tap, ci]     = sum_{n,u,v} col[n,u,v,co*k*k+tap] * xop[n,u,v,ci]   (sg_wgrad_tc, one tap)
 // instead of GEMMs whose contraction (dgrad) or output (wgrad) dimension is 3.  thread = (pixel, 8-channel chunk).
-__global__ void im2col_dz_kernel(const __nv_bfloat16* __restrict__ dz, int dzC, int Cout, int k, int N, int H, int W, int Kp,
-                                 __nv_bfloat16* __restrict__ col) {
-  const int chunks = Kp / 8;
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int Hp = H + k - 1, Wp = W + k - 1;
-  const long total = (long)N * Hp * Wp * chunks;
-  if (idx >= total) return;
-  const int ch = (int)(idx % chunks);
-  long r = idx / chunks;
-  const int v = (int)(r % Wp); r /= Wp;
-  const int u = (int)(r % Hp);
-  const int n = (int)(r / Hp);
+// KS > 0: kernel size known at compile time (the tap decomposition of a column is then a few multiplies and is
+// computed once per thread, not per pixel); KS = 0: any k.
+template <int KS>
+__global__ void __launch_bounds__(256) im2col_dz_kernel(const __nv_bfloat16* __restrict__ dz, int dzC, int Cout, int k_rt, int N, int H,
+                                                        int W, int Kp, __nv_bfloat16* __restrict__ col) {
+  // grid.x = padded output row (n, u); block = (8-column chunks of K, lanes over the row's pixels v)
+  const int k = KS > 0 ? KS : k_rt;
   const int taps = k * k;
-  __align__(16) __nv_bfloat16 o[8];
+  const int Hp = H + k - 1, Wp = W + k - 1;
+  const int n = blockIdx.x / Hp, u = blockIdx.x - n * Hp;
+  const int ch = threadIdx.x;
+  int kw[8];
+  bool row_ok[8];
+  long rbase[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int K = ch * 8 + j;
-    __nv_bfloat16 val = __float2bfloat16(0.f);
-    if (K < Cout * taps) {
-      const int co = K / taps, tap = K - co * taps;
-      const int h = u - tap / k, x = v - tap % k;
-      if (h >= 0 && h < H && x >= 0 && x < W) val = dz[(((long)n * H + h) * W + x) * dzC + co];
-    }
-    o[j] = val;
+    const int c = K / taps, tap = K - c * taps;
+    const int kh = tap / k;
+    kw[j] = tap - kh * k;
+    const int h = u - kh;
+    row_ok[j] = K < Cout * taps && h >= 0 && h < H;
+    rbase[j] = ((long)n * H + (row_ok[j] ? h : 0)) * W * dzC + c;
   }
-  *reinterpret_cast<uint4*>(col + idx * 8) = *reinterpret_cast<const uint4*>(o);
+  __nv_bfloat16* crow = col + ((long)blockIdx.x * Wp) * Kp + ch * 8;
+  for (int v = threadIdx.y; v < Wp; v += blockDim.y) {
+    __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int x = v - kw[j];
+      o[j] = (row_ok[j] && x >= 0 && x < W) ? dz[rbase[j] + (long)x * dzC] : __float2bfloat16(0.f);
+    }
+    *reinterpret_cast<uint4*>(crow + (long)v * Kp) = *reinterpret_cast<const uint4*>(o);
+  }
 }
 
 }  // namespace
@@ -181,8 +189,14 @@ __global__ void im2col_dz_kernel(const __nv_bfloat16* __restrict__ dz, int dzC, 
 extern "C" int sg_im2col_dz(const void* dz, int dzC, int Cout, int k, int N, int H, int W, int Kp, void* col, sg_stream_t stream) {
   SG_CHECK_ARG(dz && col && Cout >= 1 && dzC >= Cout && k >= 1 && N > 0 && H > 0 && W > 0, "im2col_dz: bad arguments");
   SG_CHECK_ARG(Kp % 8 == 0 && Kp >= Cout * k * k, "im2col_dz: Kp must be a multiple of 8 >= Cout*k*k");
-  const long total = (long)N * (H + k - 1) * (W + k - 1) * (Kp / 8);
-  im2col_dz_kernel<<<sg_cdiv(total, 256), 256, 0, stream>>>((const __nv_bfloat16*)dz, dzC, Cout, k, N, H, W, Kp, (__nv_bfloat16*)col);
+  const int chunks = Kp / 8;
+  SG_CHECK_ARG(chunks <= 256, "im2col_dz: Kp must be <= 2048");
+  int lanes = 256 / chunks;
+  if (lanes > W + k - 1) lanes = W + k - 1;
+  const dim3 block(chunks, lanes), grid((unsigned)(N * (H + k - 1)));
+  if (k == 7) im2col_dz_kernel<7><<<grid, block, 0, stream>>>((const __nv_bfloat16*)dz, dzC, Cout, k, N, H, W, Kp, (__nv_bfloat16*)col);
+  else if (k == 3) im2col_dz_kernel<3><<<grid, block, 0, stream>>>((const __nv_bfloat16*)dz, dzC, Cout, k, N, H, W, Kp, (__nv_bfloat16*)col);
+  else im2col_dz_kernel<0><<<grid, block, 0, stream>>>((const __nv_bfloat16*)dz, dzC, Cout, k, N, H, W, Kp, (__nv_bfloat16*)col);
   SG_CHECK_LAUNCH("sg_im2col_dz");
   return SG_OK;
 }
