@@ -3,8 +3,7 @@
 around the entry point, the inputs as L2-warm or -cold as the step leaves them) and prints the total per operand
 shape with its algorithmic bytes:
 
-    python tools/nap_insitu.py                       # the defaults of the library
-    SG_NAP_ITEMS=1 SG_NAP_APPLY_ITEMS=1 python tools/nap_insitu.py   # A/B of the items-per-thread variants
+    python tools/nap_insitu.py
 """
 import collections
 import ctypes
