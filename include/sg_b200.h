@@ -230,7 +230,8 @@ int sg_norm_finalize(const float* stats, int n_slots, int mode, int n_img, int C
                      const float* beta, float* running_mean, float* running_var, float momentum, float* scale,
                      float* shift, float* save_mean, float* save_rstd, sg_stream_t stream);
 typedef struct {
-  const void* src;        /* bf16 NHWC [N][H][W][C], C % 8 == 0 (raw conv output) */
+  const void* src;        /* bf16 NHWC [N][H][W][C], C % 8 == 0, C <= 2048 (one thread per 8 channels), 4 N < 65536,
+                             one image's padded operand below 2^31 elements (raw conv output) */
   int N, H, W, C;
   const float* scale;     /* (N*C) or NULL (identity) */
   const float* shift;
