@@ -277,3 +277,28 @@ def test_batch_meta_geometry_keys_the_iteration_graphs():
     assert m1.objs_host == b1[1].tolist() and m1.slots_used >= 1
     assert [tuple(t.shape) for t in m1.tensors()] == [(3, 2), (b1[1].numel() + 1,), (2 * b1[4].shape[0],), (b1[1].numel(),),
                                                       (3, synthetic.MAX_CLASS_SLOTS)]
+
+
+def test_entry_points_validate_arguments_before_any_launch():
+    """Argument errors come back as an error code + message through the C ABI (no kernel is launched, so this runs
+    without a GPU): size limits of the norm/act/pad writers, malformed convolution descriptors, probe arguments."""
+    d = _lib.NapDesc()
+    d.src, d.N, d.H, d.W, d.C = 1 << 20, 2, 8, 8, 4096          # never dereferenced: validation comes first
+    d.up, d.pad = 1, 0
+    with pytest.raises(RuntimeError, match='2048 channels'):
+        _lib.call('sg_norm_act_pad_fwd', ctypes.byref(d), ctypes.c_void_p(1 << 21), None)
+    d.C = 12                                                     # not a multiple of 8
+    with pytest.raises(RuntimeError, match='multiple of 8'):
+        _lib.call('sg_norm_act_pad_fwd', ctypes.byref(d), ctypes.c_void_p(1 << 21), None)
+    d.C, d.N = 64, 20000                                         # 4 N must stay below the grid limit
+    with pytest.raises(RuntimeError, match='grid limits'):
+        _lib.call('sg_norm_act_pad_fwd', ctypes.byref(d), ctypes.c_void_p(1 << 21), None)
+    assert _lib.lib().sg_norm_act_pad_bwd_parts(2, 8, 8, 12) == 0                    # invalid sizes: no parts
+    parts = _lib.lib().sg_norm_act_pad_bwd_parts(32, 128, 128, 64)
+    assert 1 <= parts <= 32
+    c = _lib.ConvDesc()
+    c.nphases = 7
+    with pytest.raises(RuntimeError, match='nphases'):
+        _lib.call('sg_conv_tc', ctypes.byref(c), None)
+    with pytest.raises(RuntimeError, match='sg_probe_mma_rate'):
+        _lib.call('sg_probe_mma_rate', 48, 16, 0, ctypes.c_void_p(1 << 20), None)
